@@ -1,0 +1,334 @@
+"""
+Benchmark of the FFTLog hot path (BASELINE.json metric: FFTLog transforms/s, fp64, nk=2048).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload = BASELINE.json configs[1]: batched P(k) -> xi multipoles ell=0,2,4, nk=2048 (padded N=4096), 4096 synthetic
+Eisenstein-Hu cosmologies (Latin hypercube, seed 42 + rank) => 12288 transforms per step and per GPU.
+One step = one pass of the fused kernel over that batch.  Input + output (2 x 201 MB) exceed the 126 MB L2, so every
+step streams from HBM (no explicit flush needed).
+
+`value`  : transforms/s with inputs resident in HBM, CUDA-event timed on the launching stream, max over ranks.
+`e2e`    : the same through the public API with pinned HOST arrays in and out (H2D + D2H inside the timed region).
+`roofline`: achieved vs the binding roofline of BASELINE.md §3, max(bytes/BW_HBM, flops/F_fp64); HBM peak from
+            MEASURED_PEAKS.json, fp64 peak measured here by a DFMA microbenchmark (cpf_measure_fp64_peak) because
+            MEASURED_PEAKS.json has no fp64 entry.
+`cpu_baseline`: the numpy restatement of the reference path (oracle/, kind "port"; it calls numpy.fft exactly as
+            cosmoprimo's NumpyFFTEngine does) on all host cores, bounded sample, rank 0 at N=1 only.
+`--impl reference` times that CPU path alone with the same JSON schema.
+"""
+
+import os
+import sys
+import json
+import time
+import argparse
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+NK = 2048
+NCOSMO = 4096
+ELLS = [0, 2, 4]
+METRIC = 'fftlog_transforms_per_sec_fp64_nk2048'
+UNIT = 'transforms/s'
+# algorithmic work per transform, SURVEY.md §8(d) / BASELINE.md §3
+BYTES_PER_TRANSFORM = 16 * NK
+FLOPS_PER_TRANSFORM = 2 * 2.5 * (2 * NK) * np.log2(2 * NK) + 2 * NK + 6 * (NK + 1) + NK     # = 264198
+CPU_SAMPLE_COSMO = 256     # cosmologies per worker and repetition in the CPU legs
+QUICK = bool(os.environ.get('CPF_BENCH_QUICK'))   # profiler runs: no time-based warm-up / sustain loops
+
+
+def make_inputs(ncosmo, seed):
+    from cosmoprimo_b200 import synthetic
+    k = np.geomspace(1e-5, 1e2, NK)
+    pk = synthetic.eh_pk(k, synthetic.lhs_cosmologies(ncosmo, seed=seed))
+    return k, synthetic.kaiser_multipoles(pk, np.full(ncosmo, 0.76))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU legs (oracle port of the reference path).  Workers are spawned processes that import numpy + oracle only.
+# ---------------------------------------------------------------------------------------------------------------
+_W = {}
+
+
+def _cpu_init(root, seed_base):
+    os.environ['OMP_NUM_THREADS'] = '1'
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    from oracle import fftlog_oracle as O
+    k, fun = make_inputs(CPU_SAMPLE_COSMO, seed_base + os.getpid() % 1000)
+    _W['O'], _W['plan'], _W['fun'] = O, O.plan_power_to_correlation(k, ell=ELLS), fun
+
+
+def _cpu_step(reps):
+    O, plan, fun = _W['O'], _W['plan'], _W['fun']
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        O.execute(plan, fun)
+    return reps * fun.shape[0] * fun.shape[1], time.perf_counter() - t0
+
+
+class CpuPool(object):
+
+    def __init__(self, cores=None):
+        import multiprocessing as mp
+        from concurrent.futures import ProcessPoolExecutor
+        self.cores = cores or len(os.sched_getaffinity(0))
+        self.pool = ProcessPoolExecutor(max_workers=self.cores, mp_context=mp.get_context('spawn'),
+                                        initializer=_cpu_init, initargs=(ROOT, 1000))
+        self.step(1)   # start every worker
+
+    def step(self, reps):
+        """All workers transform their sample `reps` times concurrently; returns (transforms, wall seconds)."""
+        t0 = time.perf_counter()
+        res = list(self.pool.map(_cpu_step, [reps] * self.cores))
+        return sum(r[0] for r in res), time.perf_counter() - t0
+
+    def close(self):
+        self.pool.shutdown()
+
+
+def cpu_sample_desc(cores, reps):
+    return ('oracle port of cosmoprimo numpy engine (numpy {} pocketfft, 1 thread/process): {} processes x {} reps x '
+            '({} cosmologies x 3 ell, nk={}) per step').format(np.__version__, cores, reps, CPU_SAMPLE_COSMO, NK)
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', 0))
+    if rank != 0:
+        return
+    reps = 2
+    pool = CpuPool()
+    for _ in range(max(args.warmup, 1)):
+        pool.step(reps)
+    total, t0 = 0, time.perf_counter()
+    for _ in range(args.steps):
+        total += pool.step(reps)[0]
+    elapsed = time.perf_counter() - t0
+    pool.close()
+    value = total / elapsed
+    out = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+           'warmup': args.warmup, 'ms_per_step': 1e3 * elapsed / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+           'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+           'config': {'workload': 'P(k)->xi multipoles ell=0,2,4, nk=2048, synthetic EH cosmologies (BASELINE configs[1])',
+                      'batch': '{} cosmologies x 3 ell per worker and rep'.format(CPU_SAMPLE_COSMO), 'nk': NK, 'padded_size': 2 * NK},
+           'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': pool.cores, 'kind': 'port', 'sample': cpu_sample_desc(pool.cores, reps)},
+           'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+           'gpu_launches': 0}
+    print(json.dumps(out))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    QUERY = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, device):
+        self.device, self.proc = device, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '--query-gpu=' + self.QUERY, '--format=csv,noheader,nounits', '-lms', '50',
+                                          '-i', str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            text = self.proc.communicate(timeout=5)[0]
+        except Exception:
+            self.proc.kill()
+            text = ''
+        sm, smmax, power, reasons = [], [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for line in text.strip().splitlines():
+            f = [x.strip() for x in line.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smmax.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, flag in zip(names, f[5:9]):
+                if flag.lower().startswith('active'):
+                    reasons.add(name)
+        if not sm:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['no samples']}
+        # samples under load = the upper half by power draw (the sampler also sees idle gaps around the run)
+        order = np.argsort(power)[len(power) // 2:]
+        return {'sm_mhz': float(np.median(np.asarray(sm)[order])), 'sm_max_mhz': float(np.max(smmax)),
+                'power_w_max': float(np.max(power)), 'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+def measured_peaks():
+    fn = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.isfile(fn):
+        with open(fn) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    return 6650., 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+def run_ours(args):
+    import ctypes
+    import torch
+    from cosmoprimo_b200 import _lib
+    from cosmoprimo_b200.fftlog import PowerToCorrelation
+
+    rank = int(os.environ.get('RANK', 0))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    _lib.require_device()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # rows are independent: each rank owns its own 4096 cosmologies (weak scaling, no data-path collective)
+    k, fun = make_inputs(NCOSMO, seed=42 + rank)
+    per_step = fun.shape[0] * fun.shape[1]
+    fftlog = PowerToCorrelation(k, ell=ELLS, engine='cuda', device=local_rank)
+    d_fun = torch.from_numpy(fun).to(dev)
+
+    def step():
+        return fftlog(d_fun)[1]
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    # warm-up: at least W steps and at least 0.3 s of the same load so that clocks settle
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    while time.perf_counter() - t0 < (0. if QUICK else 0.3):
+        for _ in range(20):
+            step()
+        torch.cuda.synchronize()
+
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = step()
+    e1.record()
+    barrier()
+    elapsed = max_over_ranks(e0.elapsed_time(e1) * 1e-3)
+    # keep the same load running ~1 s longer so that the 50 ms clock sampler sees it (the timed region is only a few ms)
+    t0 = time.perf_counter()
+    while time.perf_counter() - t0 < (0. if QUICK else 1.0):
+        for _ in range(20):
+            step()
+        torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * per_step * args.steps / elapsed
+
+    # end to end through the public API with pinned host arrays (H2D + D2H inside the timed region)
+    h_fun = torch.from_numpy(fun).pin_memory().numpy()
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        fftlog(h_fun)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        h_out = fftlog(h_fun)[1]
+    torch.cuda.synchronize()
+    e2e_elapsed = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = world * per_step * e2e_steps / e2e_elapsed
+    assert np.array_equal(h_out, out.cpu().numpy())   # both paths ran the same kernel on the same data
+
+    if rank != 0:
+        return
+
+    # roofline of the fused kernel: one launch per step
+    hbm_gbs, hbm_src = measured_peaks()
+    f64 = ctypes.c_double(0.)
+    _lib.check(_lib.load().cpf_measure_fp64_peak(local_rank, ctypes.byref(f64)))
+    f64_tflops = f64.value / 1e12
+    t_launch = elapsed / args.steps
+    ach_tflops = per_step * FLOPS_PER_TRANSFORM / t_launch / 1e12
+    ach_gbs = per_step * BYTES_PER_TRANSFORM / t_launch / 1e9
+    t_fp64, t_hbm = FLOPS_PER_TRANSFORM / (f64_tflops * 1e12), BYTES_PER_TRANSFORM / (hbm_gbs * 1e9)
+    if t_fp64 >= t_hbm:
+        roof = {'bound': 'fp64', 'achieved': ach_tflops, 'peak': f64_tflops, 'unit': 'TFLOP/s', 'frac': ach_tflops / f64_tflops}
+    else:
+        roof = {'bound': 'hbm', 'achieved': ach_gbs, 'peak': hbm_gbs, 'unit': 'GB/s', 'frac': ach_gbs / hbm_gbs}
+    roof.update({'traffic': None, 'kernel': 'fftlog_fast_kernel<16,pruned>', 'launch_ms': 1e3 * t_launch,
+                 'algorithmic_flops_per_launch': per_step * FLOPS_PER_TRANSFORM, 'algorithmic_bytes_per_launch': per_step * BYTES_PER_TRANSFORM,
+                 'peak_source': 'fp64: DFMA microbenchmark in this run (cpf_measure_fp64_peak); hbm: ' + hbm_src,
+                 'hbm': {'achieved': ach_gbs, 'peak': hbm_gbs, 'unit': 'GB/s', 'frac': ach_gbs / hbm_gbs},
+                 'roofline_transforms_per_s': 1. / max(t_fp64, t_hbm)})
+
+    result = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': warm,
+              'ms_per_step': 1e3 * elapsed / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+              'dtype': 'f64', 'data': 'synthetic',
+              'config': {'workload': 'P(k)->xi multipoles ell=0,2,4, nk=2048, 4096 synthetic EH cosmologies per GPU (BASELINE configs[1])',
+                         'transforms_per_step_per_gpu': per_step, 'nk': NK, 'padded_size': 2 * NK,
+                         'l2': 'inputs+outputs (403 MB/step) larger than L2, no flush', 'partition': 'rows split over ranks, no collective'},
+              'clocks': clocks,
+              'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(fun.nbytes), 'd2h_bytes_per_step': int(h_out.nbytes), 'steps': e2e_steps},
+              'gpu_launches': args.steps, 'roofline': roof}
+
+    if world == 1 and not args.no_cpu_baseline:
+        # CPU baseline + parity of the GPU result against the oracle on the same sample
+        from oracle import fftlog_oracle as O
+        ref = O.execute(O.plan_power_to_correlation(k, ell=ELLS), fun[:64])[1]
+        post = fftlog.padded_postfactor[:, fftlog.padded_size_out_left:fftlog.padded_size_out_left + NK]
+        result['parity'] = {'scale_aware_max_err': float(np.max(O.scale_aware_error(h_out[:64], ref, post))), 'rows': 64 * 3, 'tol': 1e-10}
+        pool = CpuPool()
+        reps = 2
+        pool.step(reps)
+        best = 0.
+        for _ in range(5):
+            n, t = pool.step(reps)
+            best = max(best, n / t)
+        pool.close()
+        single = CpuPool(cores=1)
+        n, t = single.step(reps)
+        single.close()
+        result['cpu_baseline'] = {'value': best, 'unit': UNIT, 'cores': pool.cores, 'kind': 'port', 'sample': cpu_sample_desc(pool.cores, reps),
+                                  'value_1core': n / t}
+    print(json.dumps(result))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    parser = argparse.ArgumentParser()
+    parser.add_argument('--gpus', type=int, default=1)
+    parser.add_argument('--steps', type=int, default=200)
+    parser.add_argument('--warmup', type=int, default=10)
+    parser.add_argument('--impl', type=str, default='ours', choices=['ours', 'reference'])
+    parser.add_argument('--no-cpu-baseline', action='store_true')
+    args = parser.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,701 @@
+// cpf_fftlog.cu — fused FFTLog kernels (sm_100a), plan object and the cpf_fftlog / cpf_rfft / cpf_irfft_conj entry
+// points of include/cpfftlog.h.
+//
+// What the kernels compute (cosmoprimo/fftlog.py:198-241), for one input row f:
+//     a = pad(f) * pre ;  A = rfft(a) ;  g = irfft(conj(A * u), n=N) ;  G = g * post ;  crop
+// Reformulation used here:
+//   * the map a -> g is REAL-linear: g = FFT_fwd( ut .* FFT_fwd(a) ) / N, where ut is u extended to N bins by
+//     Hermitian symmetry with Im dropped at DC and Nyquist (numpy's irfft ignores them).  `conj` + inverse FFT is a
+//     second forward FFT, so one forward routine serves both.
+//   * two independent rows are packed as z = a + i b; Re/Im of the result are the two outputs.  No real-FFT
+//     split/merge passes are needed at all.
+//   * with zero extrapolation the non-zero input window and the cropped output window both sit inside
+//     [N/4, 3N/4).  Rotating both by N/4 multiplies ut by (-1)^k and leaves an input whose upper half is zero and an
+//     output whose upper half is not needed: the first radix stage of FFT#1 and the last of FFT#2 are pruned.
+//
+// One CTA handles one pair of rows (T = N/16 threads, 16 complex values per thread in registers, three register
+// passes per FFT, two shared-memory exchanges per FFT); nothing but the input rows and the output rows touches HBM.
+#include <math.h>
+#include <stdarg.h>
+#include <mutex>
+#include <vector>
+
+#include "cpf_common.h"
+#include "cpf_fft_core.h"
+
+namespace cpf {
+
+// ---------------------------------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+void set_error(const std::string& msg) { g_last_error = msg; }
+
+int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// kernel arguments
+// ---------------------------------------------------------------------------------------------------------------
+struct FftlogArgs {
+  const double* in;
+  double* out;
+  const double* pre;       // [P, N]
+  const double2* ut;       // fast: [P, N/2+1] u/N with Im dropped at DC/Nyquist (times (-1)^k for the pruned kernels);
+                           // generic: [P, N] the same, Hermitian-extended to all N bins
+  const double* post_re;   // [P, N]
+  const double* post_im;   // [P, N] or null
+  const double2* tw1;      // fast: [6, 256] factored twiddles (cpf_fft_core.h) ; generic: [N/2]
+  const double2* tw2;      // fast: [6, 16]
+  long long pairs_per_p;   // ceil(batch / 2)
+  long long batch;
+  int P, in_has_P, n, N, log2N, in_left, out_left, n_out, keep_padding;
+  int ex_l_mode, ex_r_mode;
+  double ex_l_val, ex_r_val;
+};
+
+// value of the padded input at unpadded index i (i < 0 or i >= n is the extrapolated part) — fftlog.py:466-505
+__device__ __forceinline__ double padded_value(const double* __restrict__ row, const int i, const FftlogArgs& a) {
+  if ((unsigned)i < (unsigned)a.n) return __ldcs(row + i);
+  if (i < 0) {
+    if (a.ex_l_mode == CPF_EXTRAP_CONST) return a.ex_l_val;
+    const double f0 = __ldg(row);
+    if (a.ex_l_mode == CPF_EXTRAP_EDGE) return f0;
+    return f0 * pow(__ldg(row + 1) / f0, (double)i);                    // :486-490
+  }
+  if (a.ex_r_mode == CPF_EXTRAP_CONST) return a.ex_r_val;
+  const double fl = __ldg(row + a.n - 1);
+  if (a.ex_r_mode == CPF_EXTRAP_EDGE) return fl;
+  return fl / pow(__ldg(row + a.n - 2) / fl, (double)(i - (a.n - 1)));   // :497-501
+}
+
+__device__ __forceinline__ void store_out(const FftlogArgs& a, double* __restrict__ orow, const int o, const double g,
+                                          const double pr, const double pi, const bool cpost) {
+  if (cpost) {
+    double2 r;
+    r.x = g * pr;
+    r.y = g * pi;
+    __stcs(reinterpret_cast<double2*>(orow) + o, r);
+  } else {
+    __stcs(orow + o, g * pr);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// fast path: N = 256*R1, one CTA of T = 16*R1 threads per pair of rows
+// ---------------------------------------------------------------------------------------------------------------
+template <int R1, bool PRUNED, bool CPOST>
+__global__ void __launch_bounds__(16 * R1, 512 / (16 * R1)) fftlog_fast_kernel(const FftlogArgs a) {
+  typedef Geo<R1> G;
+  extern __shared__ double2 S[];
+  constexpr int T = G::T, N = G::N;
+  constexpr int NR = PRUNED ? 8 : 16;       // live registers rows on the pruned side
+  constexpr int SHIFT = PRUNED ? N / 4 : 0;
+
+  const int t = threadIdx.x;
+  const long long q = blockIdx.x;
+  const int p = (int)(q / a.pairs_per_p);            // p-major: CTAs resident together share one plan row's tables
+  const long long b0 = 2 * (q - p * a.pairs_per_p), b1 = b0 + 1;
+  const bool has1 = b1 < a.batch;
+  const double* rowA = a.in + (a.in_has_P ? (b0 * a.P + p) : b0) * (long long)a.n;
+  const double* rowB = has1 ? a.in + (a.in_has_P ? (b1 * a.P + p) : b1) * (long long)a.n : rowA;
+  const double* pre = a.pre + (size_t)p * N;
+
+  double2 v[16];
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+    const int j = t + T * r + SHIFT;
+    const int i = j - a.in_left;
+    double x, y;
+    if (PRUNED) {
+      const bool ok = (unsigned)i < (unsigned)a.n;
+      x = ok ? __ldcs(rowA + i) : 0.;
+      y = (ok && has1) ? __ldcs(rowB + i) : 0.;
+    } else {
+      x = padded_value(rowA, i, a);
+      y = has1 ? padded_value(rowB, i, a) : 0.;
+    }
+    const double pr = pre[j];
+    v[r] = mk2(x * pr, y * pr);
+  }
+#pragma unroll
+  for (int r = NR; r < 16; ++r) v[r] = mk2(0., 0.);
+
+  // FFT #1
+  fft_pass1<R1, PRUNED>(t, v, S, a.tw1);
+  __syncthreads();
+  fft_pass2<R1>(t, S, a.tw2);
+  __syncthreads();
+  fft_pass3<R1, false>(t, v, S);
+
+  // kernel multiply: thread t holds bins k = t + T*r.  Only bins 0..N/2 are stored; k > N/2 uses conj(u[N-k]).
+  // (plain loads, not __ldg: read-only-path loads may be hoisted above the barriers and then spill)
+  const double2* uh = a.ut + (size_t)p * (N / 2 + 1);
+#pragma unroll
+  for (int r = 0; r < 8; ++r) v[r] = cmul(v[r], uh[t + T * r]);
+#pragma unroll
+  for (int r = 8; r < 16; ++r) v[r] = cmul_conj(v[r], uh[T * (16 - r) - t]);
+  __syncthreads();   // pass-3 reads of S are done before FFT #2 overwrites it
+
+  // FFT #2
+  fft_pass1<R1, false>(t, v, S, a.tw1);
+  __syncthreads();
+  fft_pass2<R1>(t, S, a.tw2);
+  __syncthreads();
+  fft_pass3<R1, PRUNED>(t, v, S);
+
+  // un-bias, crop, store
+  const size_t osz = (size_t)a.n_out * (CPOST ? 2 : 1);
+  double* outA = a.out + (size_t)(b0 * a.P + p) * osz;
+  double* outB = a.out + (size_t)(b1 * a.P + p) * osz;
+  const double* post_re = a.post_re + (size_t)p * N;
+  const double* post_im = CPOST ? a.post_im + (size_t)p * N : nullptr;
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+    const int j = t + T * r + SHIFT;
+    const int o = a.keep_padding ? j : j - a.out_left;
+    if ((unsigned)o < (unsigned)a.n_out) {
+      const double pr = post_re[j];
+      const double pi = CPOST ? post_im[j] : 0.;
+      store_out(a, outA, o, v[r].x, pr, pi, CPOST);
+      if (has1) store_out(a, outB, o, v[r].y, pr, pi, CPOST);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// generic path: any power-of-two N <= CPF_MAX_N, whole transform in shared memory, radix-2
+// ---------------------------------------------------------------------------------------------------------------
+// forward FFT, natural order in and out; tw[k] = exp(-2 pi i k/N), k < N/2
+__device__ void block_fft_forward(double2* S, const int N, const int log2N, const double2* __restrict__ tw) {
+  const int half = N >> 1;
+  for (int h = half; h >= 1; h >>= 1) {       // decimation in frequency
+    const int step = half / h;
+    for (int i = threadIdx.x; i < half; i += blockDim.x) {
+      const int lo = i & (h - 1);
+      const int j = ((i - lo) << 1) | lo;
+      const double2 x0 = S[j], x1 = S[j + h];
+      S[j] = mk2(x0.x + x1.x, x0.y + x1.y);
+      S[j + h] = cmul(mk2(x0.x - x1.x, x0.y - x1.y), __ldg(tw + lo * step));
+    }
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {   // undo the bit reversal
+    const int r = (int)(__brev((unsigned)i) >> (32 - log2N));
+    if (i < r) {
+      const double2 tmp = S[i];
+      S[i] = S[r];
+      S[r] = tmp;
+    }
+  }
+  __syncthreads();
+}
+
+template <bool CPOST>
+__global__ void fftlog_generic_kernel(const FftlogArgs a) {
+  extern __shared__ double2 S[];
+  const int N = a.N;
+  const long long q = blockIdx.x;
+  const int p = (int)(q / a.pairs_per_p);            // p-major: CTAs resident together share one plan row's tables
+  const long long b0 = 2 * (q - p * a.pairs_per_p), b1 = b0 + 1;
+  const bool has1 = b1 < a.batch;
+  const double* rowA = a.in + (a.in_has_P ? (b0 * a.P + p) : b0) * (long long)a.n;
+  const double* rowB = has1 ? a.in + (a.in_has_P ? (b1 * a.P + p) : b1) * (long long)a.n : rowA;
+  const double* pre = a.pre + (size_t)p * N;
+  for (int j = threadIdx.x; j < N; j += blockDim.x) {
+    const int i = j - a.in_left;
+    const double pr = pre[j];
+    S[j] = mk2(padded_value(rowA, i, a) * pr, has1 ? padded_value(rowB, i, a) * pr : 0.);
+  }
+  __syncthreads();
+  block_fft_forward(S, N, a.log2N, a.tw1);
+  const double2* ut = a.ut + (size_t)p * N;
+  for (int j = threadIdx.x; j < N; j += blockDim.x) S[j] = cmul(S[j], __ldg(ut + j));
+  __syncthreads();
+  block_fft_forward(S, N, a.log2N, a.tw1);
+  const size_t osz = (size_t)a.n_out * (CPOST ? 2 : 1);
+  double* outA = a.out + (size_t)(b0 * a.P + p) * osz;
+  double* outB = a.out + (size_t)(b1 * a.P + p) * osz;
+  const double* post_re = a.post_re + (size_t)p * N;
+  const double* post_im = CPOST ? a.post_im + (size_t)p * N : nullptr;
+  const int off = a.keep_padding ? 0 : a.out_left;
+  for (int o = threadIdx.x; o < a.n_out; o += blockDim.x) {
+    const int j = o + off;
+    const double pr = __ldg(post_re + j);
+    const double pi = CPOST ? __ldg(post_im + j) : 0.;
+    store_out(a, outA, o, S[j].x, pr, pi, CPOST);
+    if (has1) store_out(a, outB, o, S[j].y, pr, pi, CPOST);
+  }
+}
+
+// ---- unfused engine duck type (NumpyFFTEngine.forward/backward, fftlog.py:538-544) ----------------------------
+// rfft of two packed rows: Z = FFT(a + i b); A[m] = (Z[m] + conj Z[N-m])/2, B[m] = (Z[m] - conj Z[N-m])/(2i)
+__global__ void rfft_pair_kernel(const double* __restrict__ in, double2* __restrict__ out, const long long rows,
+                                 const int N, const int log2N, const double2* __restrict__ tw) {
+  extern __shared__ double2 S[];
+  const long long b0 = 2LL * blockIdx.x, b1 = b0 + 1;
+  const bool has1 = b1 < rows;
+  const double* rowA = in + b0 * N;
+  const double* rowB = in + (has1 ? b1 : b0) * N;
+  for (int j = threadIdx.x; j < N; j += blockDim.x) S[j] = mk2(rowA[j], has1 ? rowB[j] : 0.);
+  __syncthreads();
+  block_fft_forward(S, N, log2N, tw);
+  const int nb = N / 2 + 1;
+  for (int m = threadIdx.x; m < nb; m += blockDim.x) {
+    const double2 z = S[m], zc = S[(N - m) & (N - 1)];
+    out[b0 * nb + m] = mk2(0.5 * (z.x + zc.x), 0.5 * (z.y - zc.y));
+    if (has1) out[b1 * nb + m] = mk2(0.5 * (z.y + zc.y), 0.5 * (zc.x - z.x));
+  }
+}
+
+// irfft(conj(X), n=N) of two packed rows: W = Xa~ + i Xb~ (Hermitian extensions, Im dropped at DC/Nyquist);
+// FFT_fwd(W)/N = ga + i gb
+__global__ void irfft_conj_pair_kernel(const double2* __restrict__ in, double* __restrict__ out, const long long rows,
+                                       const int N, const int log2N, const double2* __restrict__ tw) {
+  extern __shared__ double2 S[];
+  const long long b0 = 2LL * blockIdx.x, b1 = b0 + 1;
+  const bool has1 = b1 < rows;
+  const int nb = N / 2 + 1;
+  const double2* rowA = in + b0 * nb;
+  const double2* rowB = in + (has1 ? b1 : b0) * nb;
+  for (int k = threadIdx.x; k < N; k += blockDim.x) {
+    const int m = k <= N / 2 ? k : N - k;
+    double2 xa = rowA[m], xb = has1 ? rowB[m] : mk2(0., 0.);
+    if (k > N / 2) { xa.y = -xa.y; xb.y = -xb.y; }
+    if (m == 0 || m == N / 2) { xa.y = 0.; xb.y = 0.; }
+    S[k] = mk2(xa.x - xb.y, xa.y + xb.x);
+  }
+  __syncthreads();
+  block_fft_forward(S, N, log2N, tw);
+  const double inv = 1. / N;
+  for (int j = threadIdx.x; j < N; j += blockDim.x) {
+    out[b0 * N + j] = S[j].x * inv;
+    if (has1) out[b1 * N + j] = S[j].y * inv;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+static double2 unit_root(long long num, long long den) {   // exp(-2 pi i num/den), long double evaluation
+  num %= den;
+  const long double ang = -2.0L * acosl(-1.0L) * (long double)num / (long double)den;
+  double2 r;
+  r.x = (double)cosl(ang);
+  r.y = (double)sinl(ang);
+  // exact values on the axes
+  if ((4 * num) % den == 0) {
+    const long long qd = (4 * num) / den;
+    r.x = qd == 0 ? 1. : (qd == 2 ? -1. : 0.);
+    r.y = qd == 1 ? -1. : (qd == 3 ? 1. : 0.);
+  }
+  return r;
+}
+
+int upload(void** dptr, const void* src, size_t bytes) {
+  CPF_CUDA(cudaMalloc(dptr, bytes ? bytes : 1));
+  CPF_CUDA(cudaMemcpy(*dptr, src, bytes, cudaMemcpyHostToDevice));
+  return CPF_OK;
+}
+
+static int fast_radix(int N) { return N == 4096 ? 16 : N == 2048 ? 8 : N == 1024 ? 4 : 0; }
+
+// per-device twiddle cache for the unfused engine entry points
+struct GenericTw {
+  int device, N;
+  double2* d_tw;
+};
+static std::mutex g_tw_mutex;
+static std::vector<GenericTw> g_tw_cache;
+
+static int generic_twiddles(int device, int N, double2** out) {
+  std::lock_guard<std::mutex> lock(g_tw_mutex);
+  for (auto& e : g_tw_cache)
+    if (e.device == device && e.N == N) { *out = e.d_tw; return CPF_OK; }
+  std::vector<double2> tw(N / 2 > 0 ? N / 2 : 1);
+  for (int k = 0; k < N / 2; ++k) tw[k] = unit_root(k, N);
+  if (N < 2) tw[0] = unit_root(0, 1);
+  double2* d = nullptr;
+  CPF_TRY(upload((void**)&d, tw.data(), tw.size() * sizeof(double2)));
+  g_tw_cache.push_back({device, N, d});
+  *out = d;
+  return CPF_OK;
+}
+
+// staging streams for host-pointer calls (H2D / kernel / D2H of successive chunks overlap)
+static const int kNumStage = 3;
+struct StagePool {
+  int device;
+  cudaStream_t s[kNumStage];
+  cudaEvent_t done[kNumStage];
+  cudaEvent_t start;
+};
+static std::mutex g_stage_mutex;
+static std::vector<StagePool*> g_stage_pools;
+
+static int stage_pool(int device, StagePool** out) {
+  std::lock_guard<std::mutex> lock(g_stage_mutex);
+  for (auto* e : g_stage_pools)
+    if (e->device == device) { *out = e; return CPF_OK; }
+  StagePool* sp = new StagePool();
+  sp->device = device;
+  for (int i = 0; i < kNumStage; ++i) {
+    CPF_CUDA(cudaStreamCreateWithFlags(&sp->s[i], cudaStreamNonBlocking));
+    CPF_CUDA(cudaEventCreateWithFlags(&sp->done[i], cudaEventDisableTiming));
+  }
+  CPF_CUDA(cudaEventCreateWithFlags(&sp->start, cudaEventDisableTiming));
+  // keep freed scratch in the pool instead of returning it to the OS after every call
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    uint64_t thr = UINT64_MAX;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  g_stage_pools.push_back(sp);
+  *out = sp;
+  return CPF_OK;
+}
+
+}  // namespace cpf
+
+using namespace cpf;
+
+struct cpf_plan {
+  int n, N, P, in_left, out_left, device, log2N;
+  bool post_complex;
+  int fast_R1;
+  bool window_prunable;
+  double* d_pre = nullptr;
+  double2* d_ut = nullptr;    // generic plans: [P,N] Hermitian-extended; fast plans: [P,N/2+1]
+  double2* d_uts = nullptr;   // fast plans: (-1)^k u/N  (input and output windows rotated by N/4)
+  double* d_post_re = nullptr;
+  double* d_post_im = nullptr;
+  double2* d_tw = nullptr;    // generic [N/2]
+  double2* d_tw1 = nullptr;   // fast [6,256]
+  double2* d_tw2 = nullptr;   // fast [6,16]
+};
+
+extern "C" {
+
+int cpf_version(void) { return CPF_VERSION; }
+
+const char* cpf_last_error(void) { return g_last_error.c_str(); }
+
+int cpf_device_count(int* count) {
+  if (!count) return fail(CPF_EINVAL, "cpf_device_count: null pointer");
+  *count = 0;
+  int c = 0;
+  cudaError_t e = cudaGetDeviceCount(&c);
+  if (e != cudaSuccess) return fail(CPF_ECUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+  *count = c;
+  return CPF_OK;
+}
+
+int cpf_plan_destroy(cpf_plan* plan) {
+  if (!plan) return CPF_OK;
+  DeviceGuard guard(plan->device);
+  cudaFree(plan->d_pre);
+  cudaFree(plan->d_ut);
+  cudaFree(plan->d_uts);
+  cudaFree(plan->d_post_re);
+  cudaFree(plan->d_post_im);
+  cudaFree(plan->d_tw);
+  cudaFree(plan->d_tw1);
+  cudaFree(plan->d_tw2);
+  delete plan;
+  return CPF_OK;
+}
+
+int cpf_plan_create(cpf_plan** out, int n, int N, int P, int in_left, int out_left, const double* pre,
+                    const double* u_ri, const double* post_re, const double* post_im, int device) {
+  if (!out) return fail(CPF_EINVAL, "cpf_plan_create: null plan pointer");
+  *out = nullptr;
+  if (!pre || !u_ri || !post_re) return fail(CPF_EINVAL, "cpf_plan_create: null table pointer");
+  if (n < 1 || P < 1) return fail(CPF_EINVAL, "cpf_plan_create: n=%d, P=%d must be positive", n, P);
+  if (!is_pow2(N) || N < 2) return fail(CPF_EINVAL, "cpf_plan_create: padded size N=%d must be a power of two >= 2", N);
+  if (N > CPF_MAX_N) return fail(CPF_EUNSUPPORTED, "cpf_plan_create: padded size N=%d exceeds CPF_MAX_N=%d", N, CPF_MAX_N);
+  if (n > N || in_left < 0 || out_left < 0 || in_left + n > N || out_left + n > N)
+    return fail(CPF_EINVAL, "cpf_plan_create: inconsistent sizes n=%d N=%d in_left=%d out_left=%d", n, N, in_left, out_left);
+  int ndev = 0;
+  CPF_TRY(cpf_device_count(&ndev));
+  if (device < 0 || device >= ndev) return fail(CPF_EINVAL, "cpf_plan_create: device %d out of range (%d visible)", device, ndev);
+  DeviceGuard guard(device);
+  if (guard.err != cudaSuccess) return fail(CPF_ECUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(guard.err));
+
+  cpf_plan* pl = new cpf_plan();
+  pl->n = n; pl->N = N; pl->P = P; pl->in_left = in_left; pl->out_left = out_left; pl->device = device;
+  pl->log2N = ilog2(N);
+  pl->post_complex = post_im != nullptr;
+  pl->fast_R1 = fast_radix(N);
+  pl->window_prunable = in_left >= N / 4 && in_left + n <= 3 * (N / 4) && out_left >= N / 4 && out_left + n <= 3 * (N / 4);
+
+  const size_t PN = (size_t)P * N;
+  const int nb = N / 2 + 1;
+  const double inv = 1. / N;
+  // u/N with the imaginary parts that numpy.fft.irfft discards (DC, Nyquist) removed
+  std::vector<double2> uh((size_t)P * nb);
+  for (int p = 0; p < P; ++p)
+    for (int m = 0; m < nb; ++m) {
+      double2 v;
+      v.x = u_ri[2 * ((size_t)p * nb + m)] * inv;
+      v.y = (m == 0 || m == N / 2) ? 0. : u_ri[2 * ((size_t)p * nb + m) + 1] * inv;
+      uh[(size_t)p * nb + m] = v;
+    }
+  int rc = CPF_OK;
+  do {
+    if ((rc = upload((void**)&pl->d_pre, pre, PN * sizeof(double)))) break;
+    if ((rc = upload((void**)&pl->d_post_re, post_re, PN * sizeof(double)))) break;
+    if (post_im && (rc = upload((void**)&pl->d_post_im, post_im, PN * sizeof(double)))) break;
+    if (pl->fast_R1) {
+      std::vector<double2> uhs(uh);
+      for (int p = 0; p < P; ++p)
+        for (int m = 1; m < nb; m += 2) { uhs[(size_t)p * nb + m].x = -uhs[(size_t)p * nb + m].x; uhs[(size_t)p * nb + m].y = -uhs[(size_t)p * nb + m].y; }
+      if ((rc = upload((void**)&pl->d_ut, uh.data(), uh.size() * sizeof(double2)))) break;
+      if ((rc = upload((void**)&pl->d_uts, uhs.data(), uhs.size() * sizeof(double2)))) break;
+      static const int expo[6] = {1, 2, 3, 4, 8, 12};
+      std::vector<double2> tw1(6 * 256), tw2(6 * 16);
+      for (int e = 0; e < 6; ++e) {
+        for (int n2 = 0; n2 < 256; ++n2) tw1[e * 256 + n2] = unit_root((long long)expo[e] * n2, N);
+        for (int m2 = 0; m2 < 16; ++m2) tw2[e * 16 + m2] = unit_root(expo[e] * m2, 256);
+      }
+      if ((rc = upload((void**)&pl->d_tw1, tw1.data(), tw1.size() * sizeof(double2)))) break;
+      if ((rc = upload((void**)&pl->d_tw2, tw2.data(), tw2.size() * sizeof(double2)))) break;
+    } else {
+      std::vector<double2> ut(PN);
+      for (int p = 0; p < P; ++p)
+        for (int k = 0; k < N; ++k) {
+          double2 v = uh[(size_t)p * nb + (k <= N / 2 ? k : N - k)];
+          if (k > N / 2) v.y = -v.y;
+          ut[(size_t)p * N + k] = v;
+        }
+      if ((rc = upload((void**)&pl->d_ut, ut.data(), ut.size() * sizeof(double2)))) break;
+      std::vector<double2> tw(N / 2);
+      for (int k = 0; k < N / 2; ++k) tw[k] = unit_root(k, N);
+      if ((rc = upload((void**)&pl->d_tw, tw.data(), tw.size() * sizeof(double2)))) break;
+    }
+  } while (0);
+  if (rc != CPF_OK) {
+    std::string keep = g_last_error;
+    cpf_plan_destroy(pl);
+    g_last_error = keep;
+    return rc;
+  }
+  *out = pl;
+  return CPF_OK;
+}
+
+static bool use_pruned(const cpf_plan* pl, int ex_l_mode, double ex_l_val, int ex_r_mode, double ex_r_val, int keep_padding) {
+  return pl->fast_R1 && pl->window_prunable && !keep_padding && ex_l_mode == CPF_EXTRAP_CONST && ex_r_mode == CPF_EXTRAP_CONST &&
+         ex_l_val == 0. && ex_r_val == 0.;
+}
+
+int cpf_plan_kernel_family(const cpf_plan* plan, int ex_l_mode, double ex_l_val, int ex_r_mode, double ex_r_val, int keep_padding) {
+  if (!plan) return -1;
+  if (!plan->fast_R1) return 0;
+  return use_pruned(plan, ex_l_mode, ex_l_val, ex_r_mode, ex_r_val, keep_padding) ? 2 : 1;
+}
+
+}  // extern "C"
+
+namespace cpf {
+
+template <int R1, bool PRUNED, bool CPOST>
+static int launch_fast(const FftlogArgs& a, long long nblocks, cudaStream_t stream) {
+  typedef Geo<R1> G;
+  const size_t smem = (size_t)G::SMEM_ELEMS * sizeof(double2);
+  auto kern = fftlog_fast_kernel<R1, PRUNED, CPOST>;
+  CPF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<(unsigned)nblocks, G::T, smem, stream>>>(a);
+  CPF_CUDA(cudaGetLastError());
+  return CPF_OK;
+}
+
+template <int R1>
+static int launch_fast_r(const FftlogArgs& a, bool pruned, bool cpost, long long nblocks, cudaStream_t stream) {
+  if (pruned) return cpost ? launch_fast<R1, true, true>(a, nblocks, stream) : launch_fast<R1, true, false>(a, nblocks, stream);
+  return cpost ? launch_fast<R1, false, true>(a, nblocks, stream) : launch_fast<R1, false, false>(a, nblocks, stream);
+}
+
+static int generic_threads(int N) {
+  int t = N / 2;
+  if (t < 32) t = 32;
+  if (t > 512) t = 512;
+  return t;
+}
+
+// one launch over `batch` device-resident rows
+static int launch_fftlog(const cpf_plan* pl, FftlogArgs a, bool pruned, cudaStream_t stream) {
+  if (a.batch <= 0) return CPF_OK;
+  a.pairs_per_p = (a.batch + 1) / 2;
+  const long long nblocks = (long long)pl->P * a.pairs_per_p;
+  if (nblocks > 2147483647LL) return fail(CPF_EUNSUPPORTED, "cpf_fftlog: batch too large for one launch");
+  if (pl->fast_R1) {
+    a.ut = pruned ? pl->d_uts : pl->d_ut;
+    a.tw1 = pl->d_tw1;
+    a.tw2 = pl->d_tw2;
+    switch (pl->fast_R1) {
+      case 16: return launch_fast_r<16>(a, pruned, pl->post_complex, nblocks, stream);
+      case 8: return launch_fast_r<8>(a, pruned, pl->post_complex, nblocks, stream);
+      default: return launch_fast_r<4>(a, pruned, pl->post_complex, nblocks, stream);
+    }
+  }
+  a.ut = pl->d_ut;
+  a.tw1 = pl->d_tw;
+  a.tw2 = nullptr;
+  const size_t smem = (size_t)pl->N * sizeof(double2);
+  if (pl->post_complex) {
+    CPF_CUDA(cudaFuncSetAttribute(fftlog_generic_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fftlog_generic_kernel<true><<<(unsigned)nblocks, generic_threads(pl->N), smem, stream>>>(a);
+  } else {
+    CPF_CUDA(cudaFuncSetAttribute(fftlog_generic_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fftlog_generic_kernel<false><<<(unsigned)nblocks, generic_threads(pl->N), smem, stream>>>(a);
+  }
+  CPF_CUDA(cudaGetLastError());
+  return CPF_OK;
+}
+
+// Runs `body(chunk_first_row, chunk_rows, d_in_chunk, d_out_chunk, stream)` over the batch.  Device-resident calls
+// are one chunk on the caller's stream.  Host-pointer calls are split into chunks that are copied in, processed and
+// copied back on rotating internal streams so that H2D, compute and D2H overlap; the call returns when all chunks
+// are back in the caller's buffer.
+template <typename Body>
+static int run_staged(int device, const double* in, size_t in_row_doubles, double* out, size_t out_row_doubles,
+                      long long rows, bool in_dev, bool out_dev, cudaStream_t user_stream, Body body) {
+  if (rows <= 0) return CPF_OK;
+  if (in_dev && out_dev) return body(0LL, rows, in, out, user_stream);
+  StagePool* sp = nullptr;
+  CPF_TRY(stage_pool(device, &sp));
+  const size_t row_bytes = (in_row_doubles > out_row_doubles ? in_row_doubles : out_row_doubles) * sizeof(double);
+  long long chunk = (long long)((32u << 20) / (row_bytes ? row_bytes : 1));
+  chunk = chunk < 2 ? 2 : (chunk & ~1LL);           // even, so that row pairs never straddle chunks
+  if (chunk > rows) chunk = rows;
+  const int nbuf = rows > chunk ? kNumStage : 1;
+  ScratchBuf din[kNumStage], dout[kNumStage];
+  CPF_CUDA(cudaEventRecord(sp->start, user_stream));
+  for (int i = 0; i < nbuf; ++i) {
+    CPF_CUDA(cudaStreamWaitEvent(sp->s[i], sp->start, 0));
+    if (!in_dev) CPF_CUDA(din[i].alloc((size_t)chunk * in_row_doubles * sizeof(double), sp->s[i]));
+    if (!out_dev) CPF_CUDA(dout[i].alloc((size_t)chunk * out_row_doubles * sizeof(double), sp->s[i]));
+  }
+  int rc = CPF_OK;
+  long long c = 0;
+  for (long long first = 0; first < rows && rc == CPF_OK; first += chunk, ++c) {
+    const int i = (int)(c % nbuf);
+    const long long cnt = rows - first < chunk ? rows - first : chunk;
+    const double* src = in + (size_t)first * in_row_doubles;
+    double* dst = out + (size_t)first * out_row_doubles;
+    const double* d_in = src;
+    double* d_out = dst;
+    if (!in_dev) {
+      d_in = (const double*)din[i].p;
+      cudaError_t e = cudaMemcpyAsync(din[i].p, src, (size_t)cnt * in_row_doubles * sizeof(double), cudaMemcpyHostToDevice, sp->s[i]);
+      if (e != cudaSuccess) { rc = fail(CPF_ECUDA, "H2D copy: %s", cudaGetErrorString(e)); break; }
+    }
+    if (!out_dev) d_out = (double*)dout[i].p;
+    rc = body(first, cnt, d_in, d_out, sp->s[i]);
+    if (rc != CPF_OK) break;
+    if (!out_dev) {
+      cudaError_t e = cudaMemcpyAsync(dst, d_out, (size_t)cnt * out_row_doubles * sizeof(double), cudaMemcpyDeviceToHost, sp->s[i]);
+      if (e != cudaSuccess) { rc = fail(CPF_ECUDA, "D2H copy: %s", cudaGetErrorString(e)); break; }
+    }
+  }
+  for (int i = 0; i < nbuf; ++i) {
+    cudaError_t e = cudaStreamSynchronize(sp->s[i]);
+    if (e != cudaSuccess && rc == CPF_OK) rc = fail(CPF_ECUDA, "stream sync: %s", cudaGetErrorString(e));
+  }
+  return rc;
+}
+
+}  // namespace cpf
+
+extern "C" {
+
+int cpf_fftlog(const cpf_plan* pl, const double* in, int64_t batch, int in_has_P, int ex_l_mode, double ex_l_val,
+               int ex_r_mode, double ex_r_val, int keep_padding, double* out, int in_on_device, int out_on_device,
+               void* stream) {
+  if (!pl) return fail(CPF_EINVAL, "cpf_fftlog: null plan");
+  if (batch < 0) return fail(CPF_EINVAL, "cpf_fftlog: negative batch");
+  if (batch == 0) return CPF_OK;
+  if (!in || !out) return fail(CPF_EINVAL, "cpf_fftlog: null buffer");
+  for (int m : {ex_l_mode, ex_r_mode})
+    if (m != CPF_EXTRAP_CONST && m != CPF_EXTRAP_EDGE && m != CPF_EXTRAP_LOG) return fail(CPF_EINVAL, "cpf_fftlog: unknown extrapolation mode %d", m);
+  if ((ex_l_mode == CPF_EXTRAP_LOG || ex_r_mode == CPF_EXTRAP_LOG) && pl->n < 2)
+    return fail(CPF_EINVAL, "cpf_fftlog: 'log' extrapolation needs at least two samples");
+  DeviceGuard guard(pl->device);
+  if (guard.err != cudaSuccess) return fail(CPF_ECUDA, "cudaSetDevice(%d): %s", pl->device, cudaGetErrorString(guard.err));
+
+  FftlogArgs a;
+  a.pre = pl->d_pre;
+  a.post_re = pl->d_post_re;
+  a.post_im = pl->d_post_im;
+  a.P = pl->P; a.in_has_P = in_has_P ? 1 : 0; a.n = pl->n; a.N = pl->N; a.log2N = pl->log2N;
+  a.in_left = pl->in_left; a.out_left = pl->out_left;
+  a.keep_padding = keep_padding ? 1 : 0;
+  a.n_out = keep_padding ? pl->N : pl->n;
+  a.ex_l_mode = ex_l_mode; a.ex_r_mode = ex_r_mode; a.ex_l_val = ex_l_val; a.ex_r_val = ex_r_val;
+  const bool pruned = use_pruned(pl, ex_l_mode, ex_l_val, ex_r_mode, ex_r_val, keep_padding);
+  const size_t in_row = (size_t)pl->n * (in_has_P ? pl->P : 1);
+  const size_t out_row = (size_t)a.n_out * pl->P * (pl->post_complex ? 2 : 1);
+  return run_staged(pl->device, in, in_row, out, out_row, batch, in_on_device != 0, out_on_device != 0, (cudaStream_t)stream,
+                    [&](long long, long long cnt, const double* d_in, double* d_out, cudaStream_t s) {
+                      FftlogArgs c = a;
+                      c.in = d_in; c.out = d_out; c.batch = cnt;
+                      return launch_fftlog(pl, c, pruned, s);
+                    });
+}
+
+static int check_fft_size(const char* who, int size, int device) {
+  if (!is_pow2(size) || size < 2) return fail(CPF_EINVAL, "%s: size=%d must be a power of two >= 2", who, size);
+  if (size > CPF_MAX_N) return fail(CPF_EUNSUPPORTED, "%s: size=%d exceeds CPF_MAX_N=%d", who, size, CPF_MAX_N);
+  int ndev = 0;
+  CPF_TRY(cpf_device_count(&ndev));
+  if (device < 0 || device >= ndev) return fail(CPF_EINVAL, "%s: device %d out of range (%d visible)", who, device, ndev);
+  return CPF_OK;
+}
+
+int cpf_rfft(int size, const double* in, int64_t rows, double* out, int in_on_device, int out_on_device, int device,
+             void* stream) {
+  CPF_TRY(check_fft_size("cpf_rfft", size, device));
+  if (rows <= 0) return rows < 0 ? fail(CPF_EINVAL, "cpf_rfft: negative rows") : CPF_OK;
+  if (!in || !out) return fail(CPF_EINVAL, "cpf_rfft: null buffer");
+  DeviceGuard guard(device);
+  double2* tw = nullptr;
+  CPF_TRY(generic_twiddles(device, size, &tw));
+  const size_t smem = (size_t)size * sizeof(double2);
+  CPF_CUDA(cudaFuncSetAttribute(rfft_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int l2 = ilog2(size);
+  return run_staged(device, in, (size_t)size, out, (size_t)(size / 2 + 1) * 2, rows, in_on_device != 0, out_on_device != 0,
+                    (cudaStream_t)stream, [&](long long, long long cnt, const double* d_in, double* d_out, cudaStream_t s) {
+                      rfft_pair_kernel<<<(unsigned)((cnt + 1) / 2), generic_threads(size), smem, s>>>(d_in, (double2*)d_out, cnt, size, l2, tw);
+                      CPF_CUDA(cudaGetLastError());
+                      return (int)CPF_OK;
+                    });
+}
+
+int cpf_irfft_conj(int size, const double* in, int64_t rows, double* out, int in_on_device, int out_on_device,
+                   int device, void* stream) {
+  CPF_TRY(check_fft_size("cpf_irfft_conj", size, device));
+  if (rows <= 0) return rows < 0 ? fail(CPF_EINVAL, "cpf_irfft_conj: negative rows") : CPF_OK;
+  if (!in || !out) return fail(CPF_EINVAL, "cpf_irfft_conj: null buffer");
+  DeviceGuard guard(device);
+  double2* tw = nullptr;
+  CPF_TRY(generic_twiddles(device, size, &tw));
+  const size_t smem = (size_t)size * sizeof(double2);
+  CPF_CUDA(cudaFuncSetAttribute(irfft_conj_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int l2 = ilog2(size);
+  return run_staged(device, in, (size_t)(size / 2 + 1) * 2, out, (size_t)size, rows, in_on_device != 0, out_on_device != 0,
+                    (cudaStream_t)stream, [&](long long, long long cnt, const double* d_in, double* d_out, cudaStream_t s) {
+                      irfft_conj_pair_kernel<<<(unsigned)((cnt + 1) / 2), generic_threads(size), smem, s>>>((const double2*)d_in, d_out, cnt, size, l2, tw);
+                      CPF_CUDA(cudaGetLastError());
+                      return (int)CPF_OK;
+                    });
+}
+
+}  // extern "C"

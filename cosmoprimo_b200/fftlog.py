@@ -1,0 +1,546 @@
+"""
+B200 engine for cosmoprimo's FFTLog transforms: same classes, call signatures, output grids and
+padding/extrapolation semantics as ``cosmoprimo/fftlog.py`` (cited below as ``ref:LINE``), with the execute step
+``pad -> *prefactor -> rfft -> *u -> conj -> irfft -> *postfactor -> crop`` (ref:230-231) running as ONE fused CUDA
+kernel per batch (``csrc/cpf_fftlog.cu``) behind the C ABI of ``include/cpfftlog.h``.
+
+What stays on the host, by design (BASELINE.json north_star): the plan tables.  They are evaluated once per plan with
+scipy's complex ``loggamma`` exactly as ``FFTlog._setup`` does (ref:144-184), cached per (grid, kernel, q, lowring,
+minfolds, xy), and uploaded once per distinct table set.
+
+The engine is ``engine='cuda'`` (:class:`CudaFFTEngine`).  There is no numpy/fftw engine here and no CPU fallback: use
+the reference for those.  A :class:`CudaFFTEngine` instance is also accepted by the UNMODIFIED reference as
+``cosmoprimo.fftlog.FFTlog(..., engine=instance)`` (ref:663) through its ``forward`` / ``backward`` methods.
+"""
+
+import ctypes
+import threading
+import collections
+
+import numpy as np
+from scipy.special import loggamma as _loggamma, gamma as _gamma
+
+from . import _lib
+from . import _buffers as _buf
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Mellin transforms of the kernels, U_K(z) = int_0^inf t^(z-1) K(t) dt              (ref:666-766)
+# ------------------------------------------------------------------------------------------------------------------
+
+class BaseKernel(object):
+    """Mellin-transformed kernel; instances with equal parameters compare (and hash) equal (ref:673-685, 715-716)."""
+
+    _params = ()
+
+    def __call__(self, z):
+        return self.eval(np.asarray(z))
+
+    def key(self):
+        return (type(self).__name__,) + tuple(getattr(self, name) for name in self._params)
+
+    def __eq__(self, other):
+        return isinstance(other, BaseKernel) and other.key() == self.key()
+
+    def __hash__(self):
+        return hash(self.key())
+
+    def __repr__(self):
+        return '{}({})'.format(type(self).__name__, ', '.join('{}={}'.format(n, getattr(self, n)) for n in self._params))
+
+
+class BaseBesselKernel(BaseKernel):
+
+    _params = ('nu',)
+
+    def __init__(self, nu):
+        self.nu = nu
+
+
+class BesselJKernel(BaseBesselKernel):
+    """J_nu: 2^(z-1) Gamma((nu+z)/2) / Gamma((2+nu-z)/2)   (ref:695)."""
+
+    def eval(self, z):
+        return np.exp(np.log(2) * (z - 1) + _loggamma(0.5 * (self.nu + z)) - _loggamma(0.5 * (2 + self.nu - z)))
+
+
+class SphericalBesselJKernel(BaseBesselKernel):
+    """j_nu: 2^(z-1.5) Gamma((nu+z)/2) / Gamma((3+nu-z)/2)   (ref:705)."""
+
+    def eval(self, z):
+        return np.exp(np.log(2) * (z - 1.5) + _loggamma(0.5 * (self.nu + z)) - _loggamma(0.5 * (3 + self.nu - z)))
+
+
+class BaseTophatKernel(BaseKernel):
+
+    _params = ('ndim',)
+
+    def __init__(self, ndim=1):
+        self.ndim = ndim
+
+
+class TophatKernel(BaseTophatKernel):
+    """Top-hat window in ``ndim`` dimensions (ref:726)."""
+
+    def eval(self, z):
+        d = self.ndim
+        return np.exp(np.log(2) * (z - 1) + _loggamma(1 + 0.5 * d) + _loggamma(0.5 * z) - _loggamma(0.5 * (2 + d - z)))
+
+
+class TophatSqKernel(BaseTophatKernel):
+    """Square of the top-hat window (ref:739-746)."""
+
+    def eval(self, z):
+        d = self.ndim
+        if d == 1:
+            return -0.25 * np.sqrt(np.pi) * np.exp(_loggamma(0.5 * (z - 2)) - _loggamma(0.5 * (3 - z)))
+        if d == 3:
+            return 2.25 * np.sqrt(np.pi) * (z - 2) / (z - 6) * np.exp(_loggamma(0.5 * (z - 4)) - _loggamma(0.5 * (5 - z)))
+        lg = (np.log(2) * (d - 1) + 2 * _loggamma(1 + 0.5 * d) + _loggamma(0.5 * (1 + d - z)) + _loggamma(0.5 * z)
+              - _loggamma(1 + d - 0.5 * z) - _loggamma(0.5 * (2 + d - z)))
+        return np.exp(lg) / np.sqrt(np.pi)
+
+
+class GaussianKernel(BaseKernel):
+    """Gaussian window (ref:756)."""
+
+    def eval(self, z):
+        return 2**(0.5 * z - 1) * _gamma(0.5 * z)
+
+
+class GaussianSqKernel(BaseKernel):
+    """Square of the Gaussian window (ref:766)."""
+
+    def eval(self, z):
+        return 0.5 * _gamma(0.5 * z)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# pad (host version, used for the plan grids and exposed like the reference's)     (ref:436-505)
+# ------------------------------------------------------------------------------------------------------------------
+
+def _split_pair(value):
+    """(left, right) from a scalar-or-pair argument, with the reference's unpacking rule (ref:466-474)."""
+    try:
+        left, right = value
+    except (TypeError, ValueError):
+        left = right = value
+    return left, right
+
+
+def pad(array, pad_width, axis=-1, extrap=0):
+    """
+    Pad ``array`` along ``axis`` by ``pad_width`` (int or (left, right)) samples.
+    ``extrap``: 'log' (geometric continuation of the two edge samples), 'edge' (repeat the edge sample) or a fill
+    value; a 2-tuple sets the two sides independently.  Same contract as ``cosmoprimo.fftlog.pad``.
+    """
+    array = np.asarray(array)
+    nleft, nright = _split_pair(pad_width)
+    modes = _split_pair(extrap)
+    a = np.moveaxis(array, axis, -1)
+    pieces = []
+    for side, (count, mode) in enumerate(zip((nleft, nright), modes)):
+        edge = a[..., :1] if side == 0 else a[..., -1:]
+        if isinstance(mode, str) and mode == 'edge':
+            piece = np.repeat(edge, count, axis=-1)
+        elif isinstance(mode, str) and mode == 'log':
+            if side == 0:
+                piece = edge * (a[..., 1:2] / edge) ** np.arange(-count, 0)
+            else:
+                piece = edge / (a[..., -2:-1] / edge) ** np.arange(1, count + 1)
+        else:
+            piece = np.full(a.shape[:-1] + (count,), mode)
+        pieces.append(piece)
+    out = np.concatenate([pieces[0], a, pieces[1]], axis=-1)
+    return np.moveaxis(out, -1, axis)
+
+
+def _extrap_codes(extrap):
+    """Translate the reference's ``extrap`` argument into (mode_l, val_l, mode_r, val_r) for the C ABI."""
+    out = []
+    for mode in _split_pair(extrap):
+        if isinstance(mode, str):
+            if mode == 'edge':
+                out += [_lib.EXTRAP_EDGE, 0.]
+            elif mode == 'log':
+                out += [_lib.EXTRAP_LOG, 0.]
+            else:
+                raise ValueError('unknown extrapolation {!r}, expected "log", "edge" or a fill value'.format(mode))
+        else:
+            out += [_lib.EXTRAP_CONST, float(mode)]
+    return tuple(out)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# engines                                                                            (ref:508-663)
+# ------------------------------------------------------------------------------------------------------------------
+
+class _DevicePlan(object):
+    """Owner of a ``cpf_plan*`` (device copies of the tables + derived twiddles)."""
+
+    def __init__(self, n, N, P, in_left, out_left, pre, u, post, device):
+        lib = _lib.load()
+        _lib.require_device()
+        pre = np.ascontiguousarray(pre, dtype='f8')
+        u = np.ascontiguousarray(u, dtype='c16')
+        self.complex_post = bool(np.iscomplexobj(post))
+        post = np.asarray(post)
+        post_re = np.ascontiguousarray(post.real, dtype='f8')
+        post_im = np.ascontiguousarray(post.imag, dtype='f8') if self.complex_post else None
+        handle = ctypes.c_void_p()
+        rc = lib.cpf_plan_create(ctypes.byref(handle), n, N, P, in_left, out_left, pre.ctypes.data, u.ctypes.data,
+                                 post_re.ctypes.data, post_im.ctypes.data if post_im is not None else None, device)
+        _lib.check(rc)
+        self.handle, self.device = handle, device
+        self.n, self.N, self.P = n, N, P
+
+    def __del__(self):
+        handle, self.handle = getattr(self, 'handle', None), None
+        if handle:
+            try:
+                _lib.load().cpf_plan_destroy(handle)
+            except Exception:
+                pass
+
+
+class CudaFFTEngine(object):
+    """
+    FFT engine running on a CUDA device; the ``engine='cuda'`` counterpart of ``NumpyFFTEngine`` / ``FFTWEngine``
+    (ref:534-638).  Same duck type (``size``, ``nparallel``, ``nthreads``, ``forward``, ``backward``) plus the fused
+    entry point :meth:`fftlog` that :class:`FFTlog` uses.  Unlike ``BaseFFTEngine`` (ref:529-531) it never touches
+    ``os.environ``.
+
+    Parameters
+    ----------
+    size : int
+        Padded array size.
+    nparallel : int, default=1
+        Number of transforms performed in parallel (plan rows).
+    nthreads : ignored (kept for signature compatibility).
+    device : int, default=None
+        CUDA device index for host-array calls; device arrays are processed on the device they live on.
+    """
+    name = 'cuda'
+
+    def __init__(self, size, nparallel=1, nthreads=None, device=None):
+        self.size = int(size)
+        self.nparallel = int(nparallel)
+        self.nthreads = 1
+        self.device = device
+        _lib.load()   # fail now, loudly, if the CUDA library is not built
+
+    def __eq__(self, other):
+        return isinstance(other, CudaFFTEngine) and (other.size, other.nparallel, other.device) == (self.size, self.nparallel, self.device)
+
+    def __hash__(self):
+        return hash((type(self).__name__, self.size, self.nparallel, self.device))
+
+    def __repr__(self):
+        return 'CudaFFTEngine(size={}, nparallel={}, device={})'.format(self.size, self.nparallel, self.device)
+
+    def _device_for(self, buf):
+        if buf.on_device:
+            return buf.device
+        return self.device if self.device is not None else _buf.default_device()
+
+    def _unfused(self, fun, name, in_dtype, in_last, out_dtype, out_last):
+        lib = _lib.load()
+        _lib.require_device()
+        src = _buf.as_input(fun, dtype=in_dtype)
+        if src.shape[-1] != in_last:
+            raise ValueError('last dimension of input is {}, expected {}'.format(src.shape[-1], in_last))
+        rows = int(np.prod(src.shape[:-1], dtype='i8'))
+        dst = _buf.empty_like_kind(src, src.shape[:-1] + (out_last,), dtype=out_dtype)
+        device = self._device_for(src)
+        stream = _buf.current_stream(device) if src.on_device else None
+        rc = getattr(lib, name)(self.size, src.ptr, rows, dst.ptr, int(src.on_device), int(dst.on_device), device, stream)
+        _lib.check(rc)
+        return dst.obj
+
+    def forward(self, fun):
+        """``rfft(fun, axis=-1)`` (ref:538-540)."""
+        return self._unfused(fun, 'cpf_rfft', 'f8', self.size, 'c16', self.size // 2 + 1)
+
+    def backward(self, fun):
+        """``irfft(conj(fun), n=size, axis=-1)`` (ref:542-544)."""
+        return self._unfused(fun, 'cpf_irfft_conj', 'c16', self.size // 2 + 1, 'f8', self.size)
+
+    def fftlog(self, plan, fun, batch, in_has_p, extrap, keep_padding, out_shape):
+        """
+        Fused execute of ``plan`` (a :class:`_DevicePlan` factory, see :meth:`FFTlog._device_plan`) on ``batch`` rows.
+        Returns a numpy array for host input, a ``torch`` tensor for device input.
+        """
+        lib = _lib.load()
+        src = _buf.as_input(fun, dtype='f8')
+        device = self._device_for(src)
+        dplan = plan(device)
+        dst = _buf.empty_like_kind(src, out_shape, dtype='c16' if dplan.complex_post else 'f8')
+        stream = _buf.current_stream(device) if src.on_device else None
+        ml, vl, mr, vr = _extrap_codes(extrap)
+        rc = lib.cpf_fftlog(dplan.handle, src.ptr, batch, int(in_has_p), ml, vl, mr, vr, int(bool(keep_padding)),
+                            dst.ptr, int(src.on_device), int(dst.on_device), stream)
+        _lib.check(rc)
+        return dst.obj
+
+
+def get_fft_engine(engine, *args, **kwargs):
+    """
+    Return the FFT engine (ref:641-663).  ``'cuda'`` builds a :class:`CudaFFTEngine`; an engine *instance* is returned
+    unchanged, as in the reference; the reference's CPU engines ('numpy', 'fftw') are not provided by this package.
+    """
+    if isinstance(engine, str):
+        if engine.lower() == 'cuda':
+            return CudaFFTEngine(*args, **kwargs)
+        if engine.lower() in ('numpy', 'fftw'):
+            raise ValueError('FFT engine {} is provided by cosmoprimo itself, cosmoprimo_b200 only implements "cuda"'.format(engine))
+        raise ValueError('FFT engine {} is unknown'.format(engine))
+    return engine
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# host plan cache: tables are rebuilt on every sigma_r / to_xi call in the reference (interpolator.py:288, 602, 983)
+# ------------------------------------------------------------------------------------------------------------------
+
+_TABLE_CACHE = collections.OrderedDict()
+_TABLE_CACHE_SIZE = 32
+_TABLE_LOCK = threading.Lock()
+
+
+def _cached_tables(key, builder):
+    with _TABLE_LOCK:
+        hit = _TABLE_CACHE.get(key, None)
+        if hit is not None:
+            _TABLE_CACHE.move_to_end(key)
+    if hit is None:
+        hit = builder()
+        with _TABLE_LOCK:
+            _TABLE_CACHE[key] = hit
+            while len(_TABLE_CACHE) > _TABLE_CACHE_SIZE:
+                _TABLE_CACHE.popitem(last=False)
+    return hit
+
+
+def clear_plan_cache():
+    with _TABLE_LOCK:
+        _TABLE_CACHE.clear()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# FFTlog                                                                              (ref:31-248)
+# ------------------------------------------------------------------------------------------------------------------
+
+class FFTlog(object):
+    r"""
+    FFTLog evaluation of :math:`G(y) = \int_0^\infty x dx F(x) K(xy)` on logarithmic grids, for one or several
+    kernels at once.  Drop-in for ``cosmoprimo.fftlog.FFTlog`` with ``engine='cuda'``.
+
+    Parameters are those of the reference (ref:49-92): ``x`` log-spaced abscissae (1D, or one row per kernel),
+    ``kernel`` a Mellin-transformed kernel or a list of them, ``q`` power-law tilt(s), ``minfolds`` padding factor,
+    ``lowring`` low-ringing output grid, ``xy`` reciprocal product when ``lowring`` is False, ``check_level``,
+    ``engine`` ('cuda' or an engine instance) and engine keyword arguments (``device``).
+    """
+
+    def __init__(self, x, kernel, q=0, minfolds=2, lowring=True, xy=1, check_level=0, engine='cuda', **engine_kwargs):
+        self.inparallel = isinstance(kernel, (tuple, list))
+        kernels = list(kernel) if self.inparallel else [kernel]
+        nker = len(kernels)
+        qs = list(q) if np.ndim(q) else [q] * nker
+        xys = list(xy) if np.ndim(xy) else [xy] * nker
+        x = np.asarray(x, dtype='f8')
+        if not self.inparallel:
+            x = x[None, :]
+        elif x.ndim == 1:
+            x = np.tile(x[None, :], (nker, 1))
+        self.x = x
+        if check_level:
+            if len(self.x) != nker:
+                raise ValueError('x and kernel must of same length')
+            if len(qs) != nker:
+                raise ValueError('q and kernel must be lists of same length')
+            if len(xys) != nker:
+                raise ValueError('xy and kernel must be lists of same length')
+        self._setup(kernels, qs, minfolds=minfolds, lowring=lowring, xy=xys, check_level=check_level)
+        self.set_fft_engine(engine, **engine_kwargs)
+
+    # -- geometry ----------------------------------------------------------------------------------------------
+    @property
+    def nparallel(self):
+        """Number of transforms performed in parallel."""
+        return self.x.shape[0]
+
+    @property
+    def size(self):
+        """Size of x-coordinates."""
+        return self.x.shape[-1]
+
+    def set_fft_engine(self, engine='cuda', **engine_kwargs):
+        """Set up the FFT engine, see :func:`get_fft_engine` (ref:119-132)."""
+        self._engine = get_fft_engine(engine, size=self.padded_size, nparallel=self.nparallel, **engine_kwargs)
+        if not hasattr(self._engine, 'fftlog'):
+            raise TypeError('engine {!r} has no fused fftlog entry point; cosmoprimo_b200 runs on CudaFFTEngine only '
+                            '(use cosmoprimo.fftlog.FFTlog for CPU engines)'.format(self._engine))
+        self._dev_plans = {}
+
+    def _setup(self, kernels, qs, minfolds=2, lowring=True, xy=1., check_level=0):
+        """Sizes, output grid and the three tables ``padded_prefactor``, ``padded_u``, ``padded_postfactor`` (ref:144-184)."""
+        n = self.size
+        self.delta = np.log(self.x[:, -1] / self.x[:, 0]) / (n - 1)
+        self.padded_size = 1 << (n * minfolds - 1).bit_length()       # smallest power of two >= n * minfolds
+        npad = self.padded_size - n
+        self.padded_size_in_left, self.padded_size_in_right = npad // 2, npad - npad // 2
+        self.padded_size_out_left, self.padded_size_out_right = npad - npad // 2, npad // 2
+        if check_level:
+            if not np.allclose(np.log(self.x[:, 1:] / self.x[:, :-1]), self.delta[:, None], rtol=1e-3):
+                raise ValueError('Input x must be log-spaced')
+            if self.padded_size < n:
+                raise ValueError('Convolution size must be larger than input x size')
+
+        key = (self.x.tobytes(), self.x.shape, tuple(k.key() if isinstance(k, BaseKernel) else id(k) for k in kernels),
+               tuple(float(q) for q in qs), int(minfolds), bool(lowring), tuple(float(v) for v in xy))
+        cacheable = all(isinstance(k, BaseKernel) for k in kernels)
+
+        def build():
+            N = self.padded_size
+            if lowring:   # ref:162
+                lnxy = np.array([d / np.pi * np.angle(k(q + 1j * np.pi / d)) for k, d, q in zip(kernels, self.delta, qs)], dtype='f8')
+            else:         # ref:164
+                lnxy = np.log(xy) + self.delta
+            y = np.exp(lnxy - self.delta)[:, None] / self.x[:, ::-1]
+            padded_x = pad(self.x, (self.padded_size_in_left, self.padded_size_in_right), axis=-1, extrap='log')
+            padded_y = pad(y, (self.padded_size_out_left, self.padded_size_out_right), axis=-1, extrap='log')
+            m = np.arange(0, N // 2 + 1)
+            us, memo = [], {}
+            for ker, d, q, lxy in zip(kernels, self.delta, qs, lnxy):
+                ident = (ker.key() if isinstance(ker, BaseKernel) else id(ker), float(q), float(d))
+                if ident not in memo:   # U(z) evaluated once per distinct (kernel, q, delta)  (ref:176-179)
+                    memo[ident] = ker(q + 2j * np.pi / N / d * m)
+                us.append(memo[ident] * np.exp(-2j * np.pi * lxy / N / d * m))
+            pre = np.array([px ** (-q) for px, q in zip(padded_x, qs)])
+            post = np.array([py ** (-q) for py, q in zip(padded_y, qs)])
+            return lnxy, y, padded_x, padded_y, np.array(us), pre, post
+
+        tables = _cached_tables(key, build) if cacheable else build()
+        # copies: subclasses rescale the factors in place after construction (ref:280, 319, 405, 433)
+        self.lnxy, self.y, self.padded_x, self.padded_y, self.padded_u, self.padded_prefactor, self.padded_postfactor = (t.copy() for t in tables)
+
+    # -- device plan, built lazily and re-validated against the (public, mutable) tables on every call ---------
+    def _device_plan(self, device):
+        """
+        The tables are public attributes that subclasses rescale after the engine exists (ref:117 then 280, 319, 330,
+        369, 377, 405, 433) and that :meth:`inv` rewrites (ref:243-248), so the device copy is made at first use and
+        refreshed whenever the host arrays no longer match the snapshot it was built from.
+        """
+        pre, u, post = (np.asarray(t) for t in (self.padded_prefactor, self.padded_u, self.padded_postfactor))
+        entry = self._dev_plans.get(device, None)
+        if entry is not None:
+            snap, dplan = entry
+            if all(s.shape == t.shape and s.dtype == t.dtype and np.array_equal(s, t) for s, t in zip(snap, (pre, u, post))):
+                return dplan
+        P, N = self.nparallel, self.padded_size
+        if pre.shape != (P, N) or post.shape != (P, N) or u.shape != (P, N // 2 + 1):
+            raise ValueError('plan tables have shapes {}, {}, {}; expected {}, {}, {}'.format(pre.shape, u.shape, post.shape, (P, N), (P, N // 2 + 1), (P, N)))
+        if np.iscomplexobj(pre):
+            raise ValueError('complex padded_prefactor is not supported')
+        dplan = _DevicePlan(self.size, N, P, self.padded_size_in_left, self.padded_size_out_left, pre, u, post, device)
+        self._dev_plans[device] = ((pre.copy(), u.copy(), post.copy()), dplan)
+        return dplan
+
+    def __call__(self, fun, extrap=0, keep_padding=False):
+        """
+        Perform the transforms (ref:198-241).
+
+        Parameters
+        ----------
+        fun : array_like (numpy -> numpy result) or CUDA array (torch / ``__cuda_array_interface__`` / DLPack -> torch result)
+            Function to be transformed; last dimensions ``(nparallel, len(x))`` or, broadcasting over the kernels,
+            ``(len(x),)`` / ``(..., 1, len(x))``; any leading batch dimensions.
+        extrap : float, 'log', 'edge' or a (left, right) pair, default=0
+        keep_padding : bool, default=False
+
+        Returns
+        -------
+        y, fftloged
+        """
+        shape = tuple(fun.shape) if hasattr(fun, 'shape') else np.shape(fun)
+        n, P, N = self.size, self.nparallel, self.padded_size
+        if len(shape) < 1 or shape[-1] != n:
+            raise ValueError('last dimension of input is {}, expected len(x) = {}'.format(shape[-1] if shape else None, n))
+        lead = shape[:-1]
+        # numpy broadcasting of fun[..., n] against the (P, N) tables (ref:231): the output carries
+        # broadcast(lead, (P,)); an input whose second-to-last dimension is 1 (or absent) feeds every kernel
+        out_lead = tuple(np.broadcast_shapes(lead, (P,)))
+        if P == 1:
+            in_has_p, batch_shape = True, lead
+        else:
+            in_has_p = len(lead) > 0 and lead[-1] == P
+            batch_shape = lead[:-1]
+        batch = int(np.prod(batch_shape, dtype='i8')) if len(batch_shape) else 1
+        n_out = N if keep_padding else n
+        out = self._engine.fftlog(self._device_plan, fun, batch, in_has_p, extrap, keep_padding, out_lead + (n_out,))
+        y = self.padded_y if keep_padding else self.y
+        if not self.inparallel:
+            y = y[0]
+            out = out.reshape(lead + (n_out,))
+        return y, out
+
+    def inv(self):
+        """Inverse the transform, in place (ref:243-248, including the unpadded ``padded_x/padded_y`` of ref:246)."""
+        self.x, self.y = self.y, self.x
+        self.padded_x, self.padded_y = self.y, self.x
+        self.padded_prefactor, self.padded_postfactor = 1 / self.padded_postfactor, 1 / self.padded_prefactor
+        self.padded_u = 1 / self.padded_u.conj()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# transforms                                                                          (ref:251-433)
+# ------------------------------------------------------------------------------------------------------------------
+
+def _per_ell(cls, ell):
+    return cls(ell) if np.ndim(ell) == 0 else [cls(one) for one in ell]
+
+
+class HankelTransform(FFTlog):
+    """Hankel transform of order(s) ``nu`` (ref:252-280)."""
+
+    def __init__(self, x, nu=0, **kwargs):
+        FFTlog.__init__(self, x, _per_ell(BesselJKernel, nu), **kwargs)
+        self.padded_prefactor *= self.padded_x**2
+
+
+class PowerToCorrelation(FFTlog):
+    r""":math:`\xi_\ell(s) = \frac{(-i)^\ell}{2\pi^2} \int dk k^2 P_\ell(k) j_\ell(ks)` (ref:284-330)."""
+
+    def __init__(self, k, ell=0, q=0, complex=False, **kwargs):
+        FFTlog.__init__(self, k, _per_ell(SphericalBesselJKernel, ell), q=1.5 + np.asarray(q) if np.ndim(q) else 1.5 + q, **kwargs)
+        self.padded_prefactor *= self.padded_x**3 / (2 * np.pi)**1.5
+        ell = np.atleast_1d(ell)
+        # (-i)^ell; with complex=False the input is the imaginary part of odd multipoles, hence (-1)^(ell//2)
+        phase = (-1j)**ell if complex else (-1)**(ell // 2)
+        self.padded_postfactor = self.padded_postfactor * phase[:, None]
+
+
+class CorrelationToPower(FFTlog):
+    r""":math:`P_\ell(k) = 4\pi i^\ell \int ds s^2 \xi_\ell(s) j_\ell(ks)` (ref:334-377)."""
+
+    def __init__(self, s, ell=0, q=0, complex=False, **kwargs):
+        FFTlog.__init__(self, s, _per_ell(SphericalBesselJKernel, ell), q=1.5 + np.asarray(q) if np.ndim(q) else 1.5 + q, **kwargs)
+        self.padded_prefactor *= self.padded_x**3 * (2 * np.pi)**1.5
+        ell = np.atleast_1d(ell)
+        phase = (1j)**ell if complex else (-1)**(ell // 2)
+        self.padded_postfactor = self.padded_postfactor * phase[:, None]
+
+
+class TophatVariance(FFTlog):
+    """Variance in a top-hat window, sigma^2(r) (ref:381-405)."""
+
+    def __init__(self, k, q=0, **kwargs):
+        FFTlog.__init__(self, k, TophatSqKernel(ndim=3), q=1.5 + q, **kwargs)
+        self.padded_prefactor *= self.padded_x**3 / (2 * np.pi**2)
+
+
+class GaussianVariance(FFTlog):
+    """Variance in a Gaussian window (ref:409-433)."""
+
+    def __init__(self, k, q=0, **kwargs):
+        FFTlog.__init__(self, k, GaussianSqKernel(), q=1.5 + q, **kwargs)
+        self.padded_prefactor *= self.padded_x**3 / (2 * np.pi**2)

@@ -1,0 +1,127 @@
+/*
+ * cpfftlog.h — C ABI of libcpfftlog.so, the B200 (sm_100a) engine for cosmoprimo's FFTLog hot path.
+ *
+ * Every entry point names the reference interface it replaces (paths relative to cosmodesi/cosmoprimo,
+ * `cosmoprimo/...`).  The reference is pure Python and has no FFI for this path; the binding a maintainer would
+ * add is the ctypes stub shown in INTEGRATION.md (it is what cosmoprimo_b200/_lib.py does).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all floating-point data is IEEE fp64, row-major, densely packed;
+ *   - a pointer is a HOST pointer unless the matching `*_on_device` flag is non-zero, in which case it is a
+ *     device pointer on the plan's device (numpy vs DLPack/__cuda_array_interface__ callers);
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).  Host-pointer calls return after the
+ *     result is in the caller's buffer; device-pointer calls are asynchronous on `stream`;
+ *   - return value: 0 on success, otherwise one of CPF_E*; cpf_last_error() gives the message (thread-local);
+ *   - plans are immutable after creation and may be shared between threads; the caller owns all in/out buffers.
+ */
+#ifndef CPFFTLOG_H
+#define CPFFTLOG_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CPF_VERSION 100
+
+enum cpf_status {
+  CPF_OK = 0,
+  CPF_EINVAL = 1,        /* bad argument / shape  -> Python ValueError */
+  CPF_ECUDA = 2,         /* CUDA runtime failure  -> Python RuntimeError */
+  CPF_ENOMEM = 3,
+  CPF_EUNSUPPORTED = 4   /* size outside what the kernels cover -> Python NotImplementedError */
+};
+
+/* extrapolation modes of cosmoprimo/fftlog.py:466-505 (`pad`): constant fill, 'edge', 'log' */
+enum cpf_extrap { CPF_EXTRAP_CONST = 0, CPF_EXTRAP_EDGE = 1, CPF_EXTRAP_LOG = 2 };
+
+typedef struct cpf_plan cpf_plan;
+
+/* ---- library ------------------------------------------------------------------------------------------------ */
+int cpf_version(void);
+const char* cpf_last_error(void);
+/* number of visible CUDA devices; *count = 0 with CPF_ECUDA when no driver/GPU is present */
+int cpf_device_count(int* count);
+
+/* ---- FFTLog plan: replaces the tables FFTlog._setup builds and the engine get_fft_engine returns -------------
+ * (fftlog.py:144-184, 119-132, 641-663).  The host computes the tables exactly as the reference does (scipy
+ * loggamma) and hands them over once; the plan keeps device copies plus everything derived from them
+ * (Hermitian-extended kernel spectrum, twiddles).
+ *   n, N            : unpadded / padded sizes (fftlog.py:149-150), N a power of two, 2 <= N <= CPF_MAX_N
+ *   P               : nparallel (fftlog.py:134-137)
+ *   in_left,out_left: padded_size_in_left / padded_size_out_left (fftlog.py:152-153)
+ *   pre     [P*N]        padded_prefactor
+ *   u_ri    [P*(N/2+1)*2] padded_u, interleaved (re,im)
+ *   post_re [P*N]        padded_postfactor (real part)
+ *   post_im [P*N] or NULL imaginary part when the post-factor is complex (`complex=True`, fftlog.py:322-330)
+ */
+#define CPF_MAX_N 8192
+int cpf_plan_create(cpf_plan** plan, int n, int N, int P, int in_left, int out_left,
+                    const double* pre, const double* u_ri, const double* post_re, const double* post_im,
+                    int device);
+int cpf_plan_destroy(cpf_plan* plan);
+/* introspection used by the tests: which kernel family a call with these options would run
+ * (0 = generic shared-memory radix-2, 1 = register radix-16 fast path) */
+int cpf_plan_kernel_family(const cpf_plan* plan, int ex_l_mode, double ex_l_val, int ex_r_mode, double ex_r_val,
+                           int keep_padding);
+
+/* ---- FFTLog execute: replaces FFTlog.__call__ (fftlog.py:198-241), i.e. pad -> *pre -> rfft -> *u -> conj ->
+ * irfft -> *post -> crop, fused in one launch.
+ *   in   : [batch, P, n] if in_has_P else [batch, n] (the same row is fed to all P kernels, fftlog.py:231 broadcast)
+ *   out  : [batch, P, n_out] doubles, n_out = keep_padding ? N : n; when the plan has a complex post-factor the
+ *          element type is interleaved complex128, i.e. [batch, P, n_out, 2]
+ *   ex_*_mode/val : left/right extrapolation (cpf_extrap); val only for CPF_EXTRAP_CONST
+ */
+int cpf_fftlog(const cpf_plan* plan, const double* in, int64_t batch, int in_has_P,
+               int ex_l_mode, double ex_l_val, int ex_r_mode, double ex_r_val, int keep_padding,
+               double* out, int in_on_device, int out_on_device, void* stream);
+
+/* ---- unfused engine duck type: replaces NumpyFFTEngine.forward / .backward (fftlog.py:538-544) so that an
+ * instance can be handed to the unmodified reference as FFTlog(..., engine=instance) (fftlog.py:663).
+ *   cpf_rfft        : in [rows, size] real      -> out [rows, size/2+1, 2]
+ *   cpf_irfft_conj  : in [rows, size/2+1, 2]    -> out [rows, size] = irfft(conj(in), n=size)
+ */
+int cpf_rfft(int size, const double* in, int64_t rows, double* out, int in_on_device, int out_on_device,
+             int device, void* stream);
+int cpf_irfft_conj(int size, const double* in, int64_t rows, double* out, int in_on_device, int out_on_device,
+                   int device, void* stream);
+
+/* ---- batched cubic splines: replaces scipy.interpolate.CubicSpline as used by Interpolator1D (jax.py:169-196)
+ * and by the Wallish2018 filter (bao_filter.py:377-382, 400-402, 420).
+ * Column layout as in the reference (axis 0 = knots): y [nx, ncols] row-major, shared abscissae x [nx].
+ *   bc       : 0 = natural (y''=0 at both ends), 1 = clamped (y'=0 at both ends)
+ *   cpf_spline_fit  : slopes [nx, ncols] = dy/dx at the knots (scipy's `c[2]`)
+ *   cpf_spline_eval : out [nq, ncols] = nu-th derivative (0,1,2) at xq [nq]; outside [x0, x_last]: NaN unless extrap
+ */
+int cpf_spline_fit(const double* x, const double* y, int nx, int64_t ncols, int bc, double* slopes,
+                   int on_device, int device, void* stream);
+int cpf_spline_eval(const double* x, const double* y, const double* slopes, int nx, int64_t ncols,
+                    const double* xq, int nq, int nu, int extrap, double* out,
+                    int on_device, int device, void* stream);
+
+/* ---- DST-II / DST-III (orthonormal) along axis 0: replaces scipy.fftpack.dst(type=2, norm='ortho', axis=0) and
+ * idst(type=2, norm='ortho', axis=0) at bao_filter.py:372, 412.  data [nx, ncols] row-major, nx a power of two.
+ */
+int cpf_dst(int type /*2 or 3*/, const double* in, int nx, int64_t ncols, double* out,
+            int on_device, int device, void* stream);
+
+/* ---- Wallish2018 no-wiggle filter: replaces Wallish2018PowerSpectrumBAOFilter._compute (bao_filter.py:361-423)
+ * given the two spline evaluations of the input spectrum that the reference makes:
+ *   klin [nlin] (= linspace(extrap_kmin, 2, 4096)), pklin [nlin, ncols]    (bao_filter.py:364-369)
+ *   kout [nk]   (= self.k),                         pkout [nk, ncols]      (bao_filter.py:90-102)
+ *   pknow [nk, ncols]  result (bao_filter.py:423)
+ *   boxes [ncols, 4] (optional, may be NULL): the even/odd cut boxes (ibox_even, ibox_odd, bao_filter.py:394-395)
+ */
+int cpf_wallish2018(const double* klin, const double* pklin, int nlin, const double* kout, const double* pkout,
+                    int nk, int64_t ncols, double* pknow, int32_t* boxes,
+                    int on_device, int device, void* stream);
+
+/* ---- measurement helper: peak fp64 FMA rate of the device (DFMA chains), in FLOP/s; used by bench.py for the
+ * fp64 roofline denominator that MEASURED_PEAKS.json lacks. */
+int cpf_measure_fp64_peak(int device, double* flops_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CPFFTLOG_H */

@@ -1,0 +1,14 @@
+"""CPU thread-emulation of the register FFT passes the CUDA kernels are built from (tests/emul/emul_fft.cpp)."""
+import os
+import subprocess
+import tempfile
+
+
+def test_three_pass_fft_emulation():
+    here = os.path.dirname(os.path.abspath(__file__))
+    with tempfile.TemporaryDirectory() as tmp:
+        exe = os.path.join(tmp, 'emul_fft')
+        subprocess.run(['g++', '-O2', '-std=c++17', '-o', exe, os.path.join(here, 'emul', 'emul_fft.cpp')], check=True)
+        res = subprocess.run([exe], capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout
+    assert 'OK' in res.stdout

@@ -1,0 +1,253 @@
+"""Parity of the CUDA FFTLog path (through the ctypes C ABI) with the reference: golden vectors produced by the
+unmodified reference, the oracle on seeded inputs, and size-independent properties at BASELINE sizes."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from conftest import load_golden, Golden, scale_aware_error
+from cosmoprimo_b200 import fftlog as F, _lib, synthetic as S
+from oracle import fftlog_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-10   # BASELINE.json north_star: max relative error <= 1e-10, scale-aware form of SURVEY.md §8(d)
+CASES = list(range(len(load_golden().cases)))
+
+
+def cropped_post(obj, g_ref):
+    post = np.asarray(obj.padded_postfactor)
+    if post.shape[-1] != g_ref.shape[-1]:
+        post = post[..., obj.padded_size_out_left:obj.padded_size_out_left + obj.size]
+    if post.shape[-1] != g_ref.shape[-1]:
+        post = np.ones(g_ref.shape[-1])
+    return post
+
+
+def build(golden, idx):
+    case = golden.cases[idx]
+    obj = getattr(F, case['cls'])(golden.inp(case['grid']), **Golden.ctor_kwargs(case))
+    if case['inv']:
+        obj.inv()
+    return obj
+
+
+@pytest.mark.parametrize('idx', CASES)
+def test_golden(fftlog_golden, idx):
+    case = fftlog_golden.cases[idx]
+    obj = build(fftlog_golden, idx)
+    y, g = obj(fftlog_golden.fun(idx), **Golden.call_kwargs(case))
+    y_ref, g_ref = fftlog_golden.get(idx, 'y'), fftlog_golden.get(idx, 'g')
+    assert isinstance(g, np.ndarray) and g.shape == g_ref.shape and g.dtype == g_ref.dtype, case
+    np.testing.assert_allclose(y, y_ref, rtol=1e-14, atol=0)
+    err = scale_aware_error(g, g_ref, cropped_post(obj, g_ref))
+    assert err < TOL, (case, err)
+    assert err < 1e-13, (case, err)   # what two correct fp64 FFTs actually agree to (SURVEY finding 2)
+
+
+def test_analytic_hankel_pair():
+    """Reference KAT (tests/test_fftlog.py:56-89) through the cuda engine, incl. inv() and a batched (3, 60) input."""
+    ffun = lambda x: 1 / (1 + x**2)**1.5
+    gfun = lambda y: np.exp(-y)
+    x = np.logspace(-3, 3, num=60, endpoint=False)
+    f = ffun(x)
+    hf = F.HankelTransform(x, nu=0, q=1, lowring=True, engine='cuda')
+    y, g = hf(f, extrap='log')
+    assert np.allclose(g, gfun(y), rtol=1e-8, atol=1e-8)
+    hf.inv()
+    x2, f2 = hf(g, extrap='log')
+    assert np.allclose(f2, f, rtol=1e-7, atol=1e-7)
+    y = np.logspace(-4, 2, num=60, endpoint=False)
+    hg = F.HankelTransform(y, nu=0, q=1, lowring=True)
+    x, f = hg(gfun(y), extrap='log')
+    assert np.allclose(f, ffun(x), rtol=1e-10, atol=1e-10)
+    yy = np.array([y] * 3)
+    scales = np.linspace(1., 3., 3)
+    x, f = hg(gfun(yy) * scales[:, None], extrap='log')
+    assert x.shape == (60, ) and f.shape == (3, 60)
+    assert np.allclose(f / scales[:, None], ffun(x), rtol=1e-10, atol=1e-10)
+
+
+def test_power_to_correlation_roundtrip(fftlog_golden):
+    """Mirror of the reference's test_power_to_correlation (tests/test_fftlog.py:92-109)."""
+    k, pk = fftlog_golden.inp('k1000'), fftlog_golden.inp('pk1000')
+    multipoles = []
+    ells = [0, 1, 2, 3, 4]
+    for ell in ells:
+        s, xi = F.PowerToCorrelation(k, ell=ell, lowring=True, complex=False)(pk)
+        assert xi.shape == (1000, )
+        k2, pk2 = F.CorrelationToPower(s, ell=ell, lowring=True, complex=False)(xi)
+        idx = (1e-2 < k2) & (k2 < 10.)
+        assert np.allclose(pk2[idx], np.interp(k2[idx], k, pk), rtol=1e-2)
+        multipoles.append(xi)
+    assert np.allclose(F.PowerToCorrelation(k, ell=ells, lowring=True, q=0, complex=False)(pk)[-1], multipoles, rtol=1e-9, atol=0)
+    s, xi = F.PowerToCorrelation(k, ell=0, lowring=False)(pk)
+    assert np.allclose(s[::-1] * k, 1.)
+
+
+def lhs_pk(B, n):
+    k = np.geomspace(1e-5, 1e2, n)
+    return k, S.eh_pk(k, S.lhs_cosmologies(B, seed=42))
+
+
+@pytest.mark.parametrize('n,B', [(2048, 257), (1024, 64), (1000, 33), (512, 7), (300, 5), (4096, 9), (100, 3)])
+def test_oracle_seeded_batch(n, B):
+    """Odd batches of Latin-hypercube EH spectra vs the oracle on the same inputs; covers the three fast-path radices
+    (N = 1024, 2048, 4096), windows narrower than N/2 (n = 1000, 300) and the generic kernel (N = 8192, 256)."""
+    k, pk = lhs_pk(B, n)
+    for cls, planner, kw in [(F.PowerToCorrelation, O.plan_power_to_correlation, dict(ell=2)),
+                             (F.TophatVariance, O.plan_tophat_variance, dict())]:
+        obj = cls(k, **kw)
+        y, g = obj(pk)
+        pl = planner(k, **kw)
+        y_ref, g_ref = O.execute(pl, pk)
+        assert g.shape == (B, n)
+        assert np.allclose(y, y_ref, rtol=1e-14, atol=0)
+        assert scale_aware_error(g, g_ref, cropped_post(obj, g_ref)) < 1e-13
+
+
+def test_multipoles_config2_shapes():
+    """BASELINE config 2 at reduced batch: (B,3,n) per-ell inputs and the broadcast forms (B,1,n), (n,)."""
+    B, n = 17, 2048
+    k, pk = lhs_pk(B, n)
+    multi = S.kaiser_multipoles(pk, np.full(B, 0.76))
+    obj = F.PowerToCorrelation(k, ell=[0, 2, 4])
+    pl = O.plan_power_to_correlation(k, ell=[0, 2, 4])
+    post = obj.padded_postfactor[:, obj.padded_size_out_left:obj.padded_size_out_left + n]
+    for fun in [multi, pk[:, None, :], pk[0], multi[0], pk[:1][:, None, :], pk.reshape(1, B, 1, n)]:
+        s, xi = obj(fun)
+        s_ref, xi_ref = O.execute(pl, fun)
+        assert s.shape == (3, n) and xi.shape == xi_ref.shape
+        assert scale_aware_error(xi, xi_ref, post) < 1e-13
+    # multi-ell == per-ell (tests/test_fftlog.py:107)
+    xi = obj(multi)[1]
+    for i, ell in enumerate([0, 2, 4]):
+        one = F.PowerToCorrelation(k, ell=ell)(multi[:, i])[1]
+        assert scale_aware_error(one, xi[:, i], post[i]) < 1e-14
+
+
+def test_kernel_family_selection():
+    lib = _lib.load()
+    k = np.geomspace(1e-5, 1e2, 2048)
+    fam = lambda obj, *a: lib.cpf_plan_kernel_family(obj._device_plan(0).handle, *a)
+    obj = F.PowerToCorrelation(k)
+    assert fam(obj, 0, 0., 0, 0., 0) == 2              # zero padding, cropped: pruned register kernel
+    assert fam(obj, _lib.EXTRAP_LOG, 0., 0, 0., 0) == 1  # any other option: full register kernel
+    assert fam(obj, 0, 0., 0, 0., 1) == 1
+    assert fam(obj, 0, 1., 0, 0., 0) == 1
+    assert fam(F.PowerToCorrelation(np.geomspace(1e-5, 1e2, 1000)), 0, 0., 0, 0., 0) == 2
+    assert fam(F.PowerToCorrelation(np.geomspace(1e-5, 1e2, 4096)), 0, 0., 0, 0., 0) == 0   # N=8192: generic kernel
+    assert fam(F.PowerToCorrelation(np.geomspace(1e-5, 1e2, 60)), 0, 0., 0, 0., 0) == 0
+
+
+def test_device_buffers_match_host_path():
+    torch = pytest.importorskip('torch')
+    B, n = 31, 2048
+    k, pk = lhs_pk(B, n)
+    obj = F.PowerToCorrelation(k, ell=[0, 2, 4])
+    fun = S.kaiser_multipoles(pk, np.full(B, 0.76))
+    s, xi = obj(fun)
+    s2, xi2 = obj(torch.from_numpy(fun).cuda())
+    assert isinstance(xi2, torch.Tensor) and xi2.is_cuda and xi2.dtype == torch.float64 and tuple(xi2.shape) == xi.shape
+    assert np.array_equal(xi2.cpu().numpy(), xi)       # same kernel, same bits
+    # non-contiguous / float32 device input is promoted like the reference promotes numpy input
+    x32 = torch.from_numpy(fun.astype('f4')).cuda()
+    xi3 = obj(x32)[1]
+    xi3_ref = O.execute(O.plan_power_to_correlation(k, ell=[0, 2, 4]), fun.astype('f4'))[1]
+    assert xi3.dtype == torch.float64
+    post = obj.padded_postfactor[:, obj.padded_size_out_left:obj.padded_size_out_left + n]
+    assert scale_aware_error(xi3.cpu().numpy(), xi3_ref, post) < 1e-13
+    # __cuda_array_interface__ producer that is not a torch tensor
+
+    class CAI(object):
+        def __init__(self, t):
+            self.t = t
+            self.__cuda_array_interface__ = t.__cuda_array_interface__
+    xi4 = obj(CAI(torch.from_numpy(fun).cuda()))[1]
+    assert np.array_equal(xi4.cpu().numpy(), xi)
+    # complex post-factor on device buffers
+    objc = F.PowerToCorrelation(k, ell=[0, 1], complex=True)
+    xc = objc(torch.from_numpy(pk).cuda()[:, None, :])[1]
+    xc_ref = O.execute(O.plan_power_to_correlation(k, ell=[0, 1], complex=True), pk[:, None, :])[1]
+    assert xc.dtype == torch.complex128
+    postc = objc.padded_postfactor[:, objc.padded_size_out_left:objc.padded_size_out_left + n]
+    assert scale_aware_error(xc.cpu().numpy(), xc_ref, postc) < 1e-13
+
+
+def test_empty_and_single():
+    k, pk = lhs_pk(2, 1024)
+    obj = F.PowerToCorrelation(k)
+    s, xi = obj(np.empty((0, 1024)))
+    assert xi.shape == (0, 1024)
+    s, xi = obj(pk[:1])
+    assert xi.shape == (1, 1024)
+    assert scale_aware_error(xi[0], O.execute(O.plan_power_to_correlation(k), pk[0])[1], cropped_post(obj, xi[0])) < 1e-13
+
+
+def test_tables_are_revalidated_after_mutation():
+    """Subclasses and inv() rewrite the public tables after the engine exists (fftlog.py:117, 243-248, 319-330): the
+    device plan must follow."""
+    k, pk = lhs_pk(3, 1024)
+    obj = F.PowerToCorrelation(k)
+    xi = obj(pk)[1]
+    obj.padded_prefactor *= 2.
+    assert np.allclose(obj(pk)[1], 2 * xi, rtol=1e-14, atol=0)
+    obj.padded_prefactor /= 2.
+    s = obj.y[0].copy()
+    obj.inv()
+    k2, pk2 = obj(xi)
+    ref = O.plan_power_to_correlation(k)
+    O.invert_plan(ref)
+    assert scale_aware_error(pk2, O.execute(ref, xi)[1], np.ones(1024)) < 1e-12
+
+
+def test_linearity_and_roundtrip_full_size():
+    """BASELINE config 2 at full size (4096 cosmologies x ell=0,2,4, nk=2048), through size-independent properties:
+    linearity of the transform, and xi -> P -> xi round trip (config 5's pattern)."""
+    B, n = 4096, 2048
+    k, pk = lhs_pk(B, n)
+    fun = S.kaiser_multipoles(pk, np.full(B, 0.76))
+    obj = F.PowerToCorrelation(k, ell=[0, 2, 4])
+    s, xi = obj(fun)
+    assert xi.shape == (B, 3, n) and np.isfinite(xi).all()
+    post = obj.padded_postfactor[:, obj.padded_size_out_left:obj.padded_size_out_left + n]
+    perm = np.random.default_rng(0).permutation(B)
+    a, b = 0.37, -1.83
+    lin = obj(a * fun + b * fun[perm])[1]
+    assert scale_aware_error(lin, a * xi + b * xi[perm], post) < 1e-13
+    # spot-check rows against the oracle
+    rows = [0, 1, 2047, 4095]
+    ref = O.execute(O.plan_power_to_correlation(k, ell=[0, 2, 4]), fun[rows])[1]
+    assert scale_aware_error(xi[rows], ref, post) < 1e-13
+    back = F.CorrelationToPower(s, ell=[0, 2, 4])
+    k2, pk2 = back(xi)
+    idx = (1e-2 < k2[0]) & (k2[0] < 10.)
+    for i in range(3):
+        interp = np.array([np.interp(k2[i][idx], k, fun[r, i]) for r in rows])
+        assert np.allclose(pk2[rows, i][:, idx], interp, rtol=1e-2)
+
+
+def test_unfused_engine_duck_type():
+    """CudaFFTEngine.forward/backward == NumpyFFTEngine's (fftlog.py:538-544)."""
+    rng = np.random.default_rng(1)
+    for size in [8, 128, 2048, 4096, 8192]:
+        eng = F.CudaFFTEngine(size)
+        x = rng.standard_normal((5, size))
+        X = eng.forward(x)
+        assert X.shape == (5, size // 2 + 1) and X.dtype == np.complex128
+        Xr = np.fft.rfft(x, axis=-1)
+        assert np.max(np.abs(X - Xr)) < 1e-13 * np.max(np.abs(Xr))
+        c = rng.standard_normal((3, 2, size // 2 + 1)) + 1j * rng.standard_normal((3, 2, size // 2 + 1))
+        g = eng.backward(c)
+        gr = np.fft.irfft(c.conj(), n=size, axis=-1)
+        assert g.shape == (3, 2, size) and np.max(np.abs(g - gr)) < 1e-13 * np.max(np.abs(gr))
+
+
+def test_reference_accepts_engine_instance():
+    """Zero-patch route: the unmodified reference takes an engine instance (fftlog.py:663)."""
+    ref = pytest.importorskip('cosmoprimo.fftlog')
+    k, pk = lhs_pk(4, 1024)
+    eng = F.CudaFFTEngine(2048)
+    s, xi = ref.PowerToCorrelation(k, engine=eng)(pk)
+    s2, xi2 = ref.PowerToCorrelation(k, engine='numpy')(pk)
+    assert np.allclose(xi, xi2, rtol=1e-9, atol=1e-12 * np.abs(xi2).max())

@@ -1,0 +1,153 @@
+"""
+Generate the golden vectors of tests/golden/ by running the UNMODIFIED reference (cosmodesi/cosmoprimo, mounted
+read-only at /root/reference) with its numpy engine.  The reference cannot travel to the GPU box, the vectors can.
+
+    PYTHONDONTWRITEBYTECODE=1 python tools/make_golden.py
+
+(The reference imports through the 3-line dist-info shim in tools/refshim)
+Outputs: tests/golden/fftlog_golden.npz (+ spline / wallish files written by the other functions below).
+"""
+
+import os
+import sys
+import json
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.dont_write_bytecode = True
+sys.path.insert(0, '/root/reference')
+sys.path.insert(0, os.path.join(HERE, 'refshim'))
+
+import numpy as np
+
+import cosmoprimo
+from cosmoprimo import fftlog as ref
+from cosmoprimo.fiducial import DESI
+
+GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+
+
+def desi_pk(k, z=0.):
+    cosmo = DESI(engine='eisenstein_hu')
+    return cosmo.get_fourier().pk_interpolator()(k, z=z)
+
+
+def class_table_pk(k, fn):
+    """One of the reference's CLASS P(k) tables (real spectrum with BAO), log-log interpolated onto ``k``."""
+    kt, pt = np.loadtxt(fn, unpack=True)[:2]
+    return np.exp(np.interp(np.log(k), np.log(kt), np.log(pt)))
+
+
+def make_fftlog():
+    arrays, cases = {}, []
+
+    def add_input(name, arr):
+        arrays['in_' + name] = np.asarray(arr)
+
+    def add_case(cls, grid, fun, ckw=None, callkw=None, tables=False, inv=False, tag=''):
+        ckw, callkw = dict(ckw or {}), dict(callkw or {})
+        run_kw = {k: (np.asarray(v) if k == 'q' and isinstance(v, list) else v) for k, v in ckw.items()}   # q lists must be arrays (fftlog.py:318)
+        obj = getattr(ref, cls)(arrays['in_' + grid], engine='numpy', **run_kw)
+        if inv:
+            # transform forward first (its output is the inverse's input), then invert in place
+            y0, g0 = obj(arrays['in_' + fun], **callkw)
+            obj.inv()
+            f_in = g0
+            idx = len(cases)
+            arrays['c{}_fun'.format(idx)] = f_in
+        else:
+            f_in = arrays['in_' + fun]
+        y, g = obj(f_in, **callkw)
+        idx = len(cases)
+        arrays['c{}_y'.format(idx)] = y
+        arrays['c{}_g'.format(idx)] = g
+        if tables:
+            arrays['c{}_pre'.format(idx)] = obj.padded_prefactor
+            arrays['c{}_u'.format(idx)] = obj.padded_u
+            arrays['c{}_post'.format(idx)] = obj.padded_postfactor
+            arrays['c{}_padded_x'.format(idx)] = obj.padded_x
+            arrays['c{}_padded_y'.format(idx)] = obj.padded_y
+        jkw = {k: (list(v) if isinstance(v, (tuple, list)) else v) for k, v in callkw.items()}
+        cases.append(dict(cls=cls, grid=grid, fun=fun, ckw=ckw, callkw=jkw, tables=tables, inv=inv, tag=tag,
+                          N=int(obj.padded_size), n=int(obj.size), P=int(obj.nparallel)))
+
+    # ---- inputs ------------------------------------------------------------------------------------------------
+    for n in [1000, 1024, 2048, 4096]:
+        k = np.geomspace(1e-5, 1e2, n) if n != 1000 else np.logspace(-5, 2, 1000)   # 1000: grid of the reference tests
+        add_input('k{}'.format(n), k)
+        add_input('pk{}'.format(n), desi_pk(k))
+    k = arrays['in_k2048']
+    pk = arrays['in_pk2048']
+    # Kaiser multipoles (BASELINE config 2), f = Omega_m(z=0.5)^0.55
+    f = 0.76
+    add_input('pkmulti2048', np.array([(1 + 2 * f / 3 + f**2 / 5) * pk, (4 * f / 3 + 4 * f**2 / 7) * pk, (8 * f**2 / 35) * pk]))
+    rng = np.random.default_rng(42)
+    scales = 1. + 0.5 * rng.uniform(size=(4, 1))
+    add_input('pkbatch1000', arrays['in_pk1000'][None, :] * np.linspace(1., 3., 5)[:, None])
+    add_input('pkbatch2048_b1', (arrays['in_pk2048'][None, :] * scales)[:, None, :])                    # (4,1,n)
+    add_input('pkbatch2048_b3', arrays['in_pkmulti2048'][None, :, :] * scales[:, :, None])              # (4,3,n)
+    fid = '/root/reference/cosmoprimo/tests/fiducial'
+    add_input('pkclass2048', np.array([class_table_pk(k[(k > 2e-5) & (k < 50)], os.path.join(fid, 'abacus_cosm000_CLASSv3.1.1.00_z{}_pk.dat'.format(i))) for i in (1, 3)]))
+    add_input('kclass2048', k[(k > 2e-5) & (k < 50)])
+    x60 = np.logspace(-3, 3, num=60, endpoint=False)
+    add_input('x60', x60)
+    add_input('f60', 1 / (1 + x60**2)**1.5)
+    add_input('x7', np.logspace(-3, 3, num=7, endpoint=True))
+    add_input('f7', 1 / (1 + arrays['in_x7']**2)**1.5)
+
+    # ---- cases -------------------------------------------------------------------------------------------------
+    # A: analytic Hankel pair of the reference tests (test_fftlog.py:56-89)
+    add_case('HankelTransform', 'x60', 'f60', dict(nu=0, q=1, lowring=True), dict(extrap='log'), tables=True, tag='hankel analytic')
+    add_case('HankelTransform', 'x60', 'f60', dict(nu=0, q=1, lowring=True), dict(extrap='log'), inv=True, tag='hankel inv')
+    add_case('HankelTransform', 'x7', 'f7', dict(nu=0, q=1, minfolds=3, xy=1, lowring=False), dict(extrap='log'), tables=True, tag='odd padding (test_pad)')
+    add_case('HankelTransform', 'x7', 'f7', dict(nu=[0, 1], q=1, minfolds=3, lowring=True), dict(extrap='edge', keep_padding=True), tag='odd padding, P=2, keep')
+    # B: n = 1000 (N = 2048), the grid of test_power_to_correlation
+    for ell in range(5):
+        add_case('PowerToCorrelation', 'k1000', 'pk1000', dict(ell=ell, lowring=True, complex=False), tables=(ell == 2), tag='P2xi ell')
+    add_case('PowerToCorrelation', 'k1000', 'pk1000', dict(ell=[0, 1, 2, 3, 4], lowring=True, q=0, complex=False), tag='multi ell')
+    add_case('PowerToCorrelation', 'k1000', 'pk1000', dict(ell=0, lowring=False), tag='lowring False')
+    add_case('PowerToCorrelation', 'k1000', 'pk1000', dict(ell=0, lowring=False, xy=2.5), tag='xy')
+    add_case('PowerToCorrelation', 'k1000', 'pk1000', dict(ell=2, q=0.5), tag='q')
+    add_case('PowerToCorrelation', 'k1000', 'pk1000', dict(ell=[0, 2], q=[0., 0.5]), tag='q list')
+    add_case('PowerToCorrelation', 'k1000', 'pk1000', dict(ell=[0, 1, 2], complex=True), tables=True, tag='complex post')
+    for extrap in ['log', 'edge', (0, 'log'), ('edge', 1e3), 2.5]:
+        add_case('PowerToCorrelation', 'k1000', 'pk1000', dict(ell=0), dict(extrap=extrap), tag='extrap')
+    add_case('PowerToCorrelation', 'k1000', 'pk1000', dict(ell=0), dict(keep_padding=True), tag='keep_padding')
+    add_case('PowerToCorrelation', 'k1000', 'pk1000', dict(ell=[0, 2]), dict(extrap='log', keep_padding=True), tag='keep_padding log P=2')
+    add_case('PowerToCorrelation', 'k1000', 'pkbatch1000', dict(ell=0), tag='batch (5,n)')
+    add_case('PowerToCorrelation', 'k1000', 'pk1000', dict(ell=1), inv=True, tag='inv')
+    add_case('TophatVariance', 'k1000', 'pk1000', dict(lowring=True), tables=True, tag='sigma_r')
+    add_case('GaussianVariance', 'k1000', 'pk1000', dict(), tag='gaussian')
+    add_case('HankelTransform', 'k1000', 'pk1000', dict(nu=[0, 2], q=1), dict(extrap='log'), tag='hankel P=2')
+    # C: n = 1024 (N = 2048) and n = 2048 (N = 4096), the BASELINE grids
+    add_case('PowerToCorrelation', 'k1024', 'pk1024', dict(ell=0), tables=True, tag='config 1')
+    add_case('TophatVariance', 'k1024', 'pk1024', dict(), tag='sigma_r 1024')
+    add_case('PowerToCorrelation', 'k2048', 'pk2048', dict(ell=0), tables=True, tag='nk=2048 ell=0')
+    add_case('PowerToCorrelation', 'k2048', 'pkmulti2048', dict(ell=[0, 2, 4]), tables=True, tag='config 2 (3,n)')
+    add_case('PowerToCorrelation', 'k2048', 'pk2048', dict(ell=[0, 2, 4]), tag='config 2 broadcast (n,)')
+    add_case('PowerToCorrelation', 'k2048', 'pkbatch2048_b1', dict(ell=[0, 2, 4]), tag='config 2 broadcast (4,1,n)')
+    add_case('PowerToCorrelation', 'k2048', 'pkbatch2048_b3', dict(ell=[0, 2, 4]), tag='config 2 (4,3,n)')
+    add_case('PowerToCorrelation', 'k2048', 'pk2048', dict(ell=0), dict(extrap='log', keep_padding=True), tag='nk=2048 full variant')
+    add_case('TophatVariance', 'k2048', 'pk2048', dict(), tag='config 3')
+    add_case('PowerToCorrelation', 'k2048', 'pk2048', dict(ell=0), inv=True, tag='config 5 round trip')
+    add_case('PowerToCorrelation', 'kclass2048', 'pkclass2048', dict(ell=0), tag='CLASS tables, n=1919')
+    # D: n = 4096 (N = 8192)
+    add_case('PowerToCorrelation', 'k4096', 'pk4096', dict(ell=0), tag='nk=4096')
+    add_case('CorrelationToPower', 'k4096', 'pk4096', dict(ell=2, complex=True), dict(extrap='edge'), tag='xi2P complex 4096')
+
+    arrays['manifest'] = np.array(json.dumps(cases))
+    os.makedirs(GOLDEN, exist_ok=True)
+    fn = os.path.join(GOLDEN, 'fftlog_golden.npz')
+    np.savez_compressed(fn, **arrays)
+    print('wrote {} ({} cases, {:.2f} MB)'.format(fn, len(cases), os.path.getsize(fn) / 1e6))
+
+
+if __name__ == '__main__':
+    which = sys.argv[1:] or ['fftlog', 'spline', 'wallish']
+    print('reference: cosmoprimo {} from {}; numpy {}'.format(cosmoprimo.__version__, os.path.dirname(cosmoprimo.__file__), np.__version__))
+    for name in which:
+        fn = globals().get('make_' + name, None)
+        if fn is None:
+            print('skipping {} (no generator yet)'.format(name))
+            continue
+        fn()
