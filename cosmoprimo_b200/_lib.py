@@ -36,14 +36,15 @@ SIGNATURES = {
     'cpf_fftlog': (_i, [_vp, _vp, _i64, _i, _i, _d, _i, _d, _i, _vp, _i, _i, _vp]),
     'cpf_rfft': (_i, [_i, _vp, _i64, _vp, _i, _i, _i, _vp]),
     'cpf_irfft_conj': (_i, [_i, _vp, _i64, _vp, _i, _i, _i, _vp]),
-    'cpf_spline_fit': (_i, [_vp, _vp, _i, _i64, _i, _vp, _i, _i, _vp]),
-    'cpf_spline_eval': (_i, [_vp, _vp, _vp, _i, _i64, _vp, _i, _i, _i, _vp, _i, _i, _vp]),
+    'cpf_spline_create': (_i, [ctypes.POINTER(_vp), _vp, _vp, _i, _i64, _i, _i, _i, _i, _i, _i, _vp]),
+    'cpf_spline_eval': (_i, [_vp, _vp, _i, _i, _vp, _i, _vp]),
+    'cpf_spline_destroy': (_i, [_vp]),
     'cpf_dst': (_i, [_i, _vp, _i, _i64, _vp, _i, _i, _vp]),
     'cpf_wallish2018': (_i, [_vp, _vp, _i, _vp, _vp, _i, _i64, _vp, _vp, _i, _i, _vp]),
     'cpf_measure_fp64_peak': (_i, [_i, ctypes.POINTER(_d)]),
 }
 
-NVCC_FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
+NVCC_FLAGS = ['-O3', '-std=c++17', '--threads', '4', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
               '-Xcompiler', '-fPIC', '-shared']
 
 _lock = threading.Lock()

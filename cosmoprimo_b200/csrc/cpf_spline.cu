@@ -1,0 +1,217 @@
+// cpf_spline.cu — batched cubic splines on a shared abscissa grid: fit (natural / clamped) and evaluation of the
+// value or a derivative.  Replaces scipy.interpolate.CubicSpline + PPoly.__call__ as used by
+// cosmoprimo/jax.py:139-196 (Interpolator1D, numpy path) and cosmoprimo/bao_filter.py:377-382, 400-402, 420.
+//
+// Layout is the reference's: knots along axis 0, one column per spline, y[nx, ncols] row-major.  One thread owns one
+// column, so every load/store of a warp is a contiguous 256-byte run.  HBM-bound: the fit streams y once and the slope
+// array twice (forward elimination writes the reduced right-hand side into it, back substitution rewrites it).
+//
+// Mathematics (same system scipy assembles, scipy/interpolate/_cubic.py): slopes s_i = y'(x_i) solve
+//     dx_i s_{i-1} + 2 (dx_{i-1} + dx_i) s_i + dx_{i-1} s_{i+1} = 3 (dx_i m_{i-1} + dx_{i-1} m_i),  m_i = (y_{i+1}-y_i)/dx_i
+// with end rows   natural: 2 dx_0 s_0 + dx_0 s_1 = 3 (y_1 - y_0)   |   clamped: s_0 = 0   (mirrored at the other end).
+// The matrix depends on x only, so its LU factors are computed once per grid and shared by all columns; it is strictly
+// diagonally dominant by rows, so elimination without pivoting is stable (LAPACK's dgtsv, which scipy calls, only
+// pivots when dominance fails).
+#include <vector>
+
+#include "cpf_common.h"
+#include "cpf_spline_core.h"
+
+namespace cpf {
+
+// ---- factorisation: one thread, O(nx) ------------------------------------------------------------------------------
+// fac[0*nx + i] = lower_i (coefficient of s_{i-1}), fac[1*nx + i] = 1/pivot_i, fac[2*nx + i] = upper_i / pivot_i
+__global__ void spline_factor_kernel(const double* __restrict__ x, const int nx, const int bc, double* __restrict__ fac) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  double* lower = fac;
+  double* winv = fac + nx;
+  double* cp = fac + 2 * nx;
+  double cprev = 0.;
+  for (int i = 0; i < nx; ++i) {
+    double lo, di, up;
+    spline_row(x, nx, bc, i, lo, di, up);
+    const double w = 1. / (di - lo * cprev);
+    lower[i] = lo;
+    winv[i] = w;
+    cprev = up * w;
+    cp[i] = cprev;
+  }
+}
+
+// optional log10 of the abscissae / ordinates (Interpolator1D's interp_x='log' / interp_fun='log', jax.py:152-153)
+__global__ void log10_kernel(const double* __restrict__ in, double* __restrict__ out, const long long count, const int apply) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < count) out[i] = apply ? log10(in[i]) : in[i];
+}
+
+// ---- per-column forward elimination + back substitution ------------------------------------------------------------
+__global__ void __launch_bounds__(128) spline_solve_kernel(const double* __restrict__ x, const double* __restrict__ y,
+                                                            const double* __restrict__ fac, const int nx, const long long ncols,
+                                                            const int bc, double* __restrict__ s) {
+  const long long col = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (col >= ncols) return;
+  const double* lower = fac;
+  const double* winv = fac + nx;
+  const double* cp = fac + 2 * nx;
+  // forward: dp_i = (rhs_i - lower_i dp_{i-1}) / pivot_i, stored in s
+  double ym = 0., y0 = y[col], yp = nx > 1 ? y[ncols + col] : 0.;
+  double dprev = 0.;
+  for (int i = 0; i < nx; ++i) {
+    const double rhs = spline_rhs(x, nx, bc, i, ym, y0, yp);
+    dprev = (rhs - lower[i] * dprev) * winv[i];
+    s[(long long)i * ncols + col] = dprev;
+    ym = y0;
+    y0 = yp;
+    if (i + 2 < nx) yp = y[(long long)(i + 2) * ncols + col];
+  }
+  // backward: s_i = dp_i - cp_i s_{i+1}
+  double snext = dprev;
+  for (int i = nx - 2; i >= 0; --i) {
+    snext = s[(long long)i * ncols + col] - cp[i] * snext;
+    s[(long long)i * ncols + col] = snext;
+  }
+}
+
+// ---- evaluation: block = (column tile, query); the interval search is done once per block --------------------------
+__global__ void __launch_bounds__(128) spline_eval_kernel(const double* __restrict__ x, const double* __restrict__ y,
+                                                           const double* __restrict__ s, const int nx, const long long ncols,
+                                                           const double* __restrict__ xq, const int nq, const int nu,
+                                                           const int extrap, const int log_x, const int log_y,
+                                                           const double xmin_raw, const double xmax_raw, double* __restrict__ out) {
+  const int q = blockIdx.y;
+  const long long col = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (col >= ncols) return;
+  const double raw = xq[q];
+  // bounds are tested on the raw abscissa, before the log10 (jax.py:188-189)
+  const bool inside = raw >= xmin_raw && raw <= xmax_raw;
+  const double xv = log_x ? log10(raw) : raw;
+  double r;
+  if ((!inside && !extrap) || !(xv == xv)) {
+    r = nan("");
+  } else {
+    const int i = spline_interval(x, nx, xv);
+    const long long o = (long long)i * ncols + col;
+    r = spline_poly(x[i], x[i + 1], y[o], y[o + ncols], s[o], s[o + ncols], xv, nu);
+    if (log_y) r = pow(10., r);   // jax.py:191
+  }
+  out[(long long)q * ncols + col] = r;
+}
+
+}  // namespace cpf
+
+using namespace cpf;
+
+struct cpf_spline {
+  int nx, bc, log_x, log_y, extrap, device;
+  long long ncols;
+  double xmin_raw, xmax_raw;
+  double* d_x = nullptr;   // (log10 of) abscissae
+  double* d_y = nullptr;   // (log10 of) ordinates [nx, ncols]
+  double* d_s = nullptr;   // slopes [nx, ncols]
+};
+
+extern "C" {
+
+int cpf_spline_destroy(cpf_spline* sp) {
+  if (!sp) return CPF_OK;
+  DeviceGuard guard(sp->device);
+  cudaFree(sp->d_x);
+  cudaFree(sp->d_y);
+  cudaFree(sp->d_s);
+  delete sp;
+  return CPF_OK;
+}
+
+int cpf_spline_create(cpf_spline** out, const double* x, const double* y, int nx, int64_t ncols, int bc, int log_x, int log_y,
+                      int extrap, int on_device, int device, void* stream_) {
+  if (!out) return fail(CPF_EINVAL, "cpf_spline_create: null handle pointer");
+  *out = nullptr;
+  if (!x || (!y && ncols > 0)) return fail(CPF_EINVAL, "cpf_spline_create: null buffer");
+  if (nx < 2) return fail(CPF_EINVAL, "cpf_spline_create: need at least 2 knots, got %d", nx);
+  if (ncols < 0) return fail(CPF_EINVAL, "cpf_spline_create: negative column count");
+  if (bc != 0 && bc != 1) return fail(CPF_EINVAL, "cpf_spline_create: bc must be 0 (natural) or 1 (clamped)");
+  int ndev = 0;
+  CPF_TRY(cpf_device_count(&ndev));
+  if (device < 0 || device >= ndev) return fail(CPF_EINVAL, "cpf_spline_create: device %d out of range (%d visible)", device, ndev);
+  DeviceGuard guard(device);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  cpf_spline* sp = new cpf_spline();
+  sp->nx = nx; sp->bc = bc; sp->log_x = log_x ? 1 : 0; sp->log_y = log_y ? 1 : 0; sp->extrap = extrap ? 1 : 0;
+  sp->device = device; sp->ncols = ncols;
+  const size_t cells = (size_t)nx * (size_t)ncols;
+  int rc = CPF_OK;
+  ScratchBuf fac, stage_x, stage_y;
+  do {
+    cudaError_t e;
+#define SP_CUDA(call) if ((e = (call)) != cudaSuccess) { rc = fail(CPF_ECUDA, "%s: %s", #call, cudaGetErrorString(e)); break; }
+    SP_CUDA(cudaMalloc(&sp->d_x, nx * sizeof(double)));
+    SP_CUDA(cudaMalloc(&sp->d_y, (cells ? cells : 1) * sizeof(double)));
+    SP_CUDA(cudaMalloc(&sp->d_s, (cells ? cells : 1) * sizeof(double)));
+    const double* src_x = x;
+    const double* src_y = y;
+    double ends[2];
+    if (!on_device) {
+      SP_CUDA(stage_x.alloc(nx * sizeof(double), stream));
+      SP_CUDA(cudaMemcpyAsync(stage_x.p, x, nx * sizeof(double), cudaMemcpyHostToDevice, stream));
+      src_x = (const double*)stage_x.p;
+      if (cells) {
+        SP_CUDA(stage_y.alloc(cells * sizeof(double), stream));
+        SP_CUDA(cudaMemcpyAsync(stage_y.p, y, cells * sizeof(double), cudaMemcpyHostToDevice, stream));
+        src_y = (const double*)stage_y.p;
+      }
+      ends[0] = x[0]; ends[1] = x[nx - 1];
+    } else {
+      SP_CUDA(cudaMemcpyAsync(&ends[0], x, sizeof(double), cudaMemcpyDeviceToHost, stream));
+      SP_CUDA(cudaMemcpyAsync(&ends[1], x + nx - 1, sizeof(double), cudaMemcpyDeviceToHost, stream));
+      SP_CUDA(cudaStreamSynchronize(stream));
+    }
+    sp->xmin_raw = ends[0]; sp->xmax_raw = ends[1];
+    log10_kernel<<<(nx + 255) / 256, 256, 0, stream>>>(src_x, sp->d_x, nx, sp->log_x);
+    if (cells) log10_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, stream>>>(src_y, sp->d_y, (long long)cells, sp->log_y);
+    SP_CUDA(fac.alloc(3 * (size_t)nx * sizeof(double), stream));
+    spline_factor_kernel<<<1, 32, 0, stream>>>(sp->d_x, nx, bc, (double*)fac.p);
+    if (cells) spline_solve_kernel<<<(unsigned)((ncols + 127) / 128), 128, 0, stream>>>(sp->d_x, sp->d_y, (const double*)fac.p, nx, ncols, bc, sp->d_s);
+    SP_CUDA(cudaGetLastError());
+    if (!on_device) SP_CUDA(cudaStreamSynchronize(stream));   // staging buffers of the caller may go away
+#undef SP_CUDA
+  } while (0);
+  if (rc != CPF_OK) {
+    cpf_spline_destroy(sp);
+    return rc;
+  }
+  *out = sp;
+  return CPF_OK;
+}
+
+int cpf_spline_eval(const cpf_spline* sp, const double* xq, int nq, int nu, double* out, int on_device, void* stream_) {
+  if (!sp) return fail(CPF_EINVAL, "cpf_spline_eval: null spline");
+  if (nq < 0) return fail(CPF_EINVAL, "cpf_spline_eval: negative query count");
+  if (nu < 0 || nu > 3) return fail(CPF_EINVAL, "cpf_spline_eval: derivative order %d not in 0..3", nu);
+  if (nq == 0 || sp->ncols == 0) return CPF_OK;
+  if (!xq || !out) return fail(CPF_EINVAL, "cpf_spline_eval: null buffer");
+  if (nq > 65535) return fail(CPF_EUNSUPPORTED, "cpf_spline_eval: more than 65535 query points in one call");
+  DeviceGuard guard(sp->device);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const size_t cells = (size_t)nq * (size_t)sp->ncols;
+  ScratchBuf dq, dout;
+  const double* d_xq = xq;
+  double* d_out = out;
+  if (!on_device) {
+    CPF_CUDA(dq.alloc(nq * sizeof(double), stream));
+    CPF_CUDA(dout.alloc(cells * sizeof(double), stream));
+    CPF_CUDA(cudaMemcpyAsync(dq.p, xq, nq * sizeof(double), cudaMemcpyHostToDevice, stream));
+    d_xq = (const double*)dq.p;
+    d_out = (double*)dout.p;
+  }
+  dim3 grid((unsigned)((sp->ncols + 127) / 128), (unsigned)nq);
+  spline_eval_kernel<<<grid, 128, 0, stream>>>(sp->d_x, sp->d_y, sp->d_s, sp->nx, sp->ncols, d_xq, nq, nu, sp->extrap, sp->log_x,
+                                               sp->log_y, sp->xmin_raw, sp->xmax_raw, d_out);
+  CPF_CUDA(cudaGetLastError());
+  if (!on_device) {
+    CPF_CUDA(cudaMemcpyAsync(out, d_out, cells * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    CPF_CUDA(cudaStreamSynchronize(stream));
+  }
+  return CPF_OK;
+}
+
+}  // extern "C"

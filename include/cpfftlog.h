@@ -87,18 +87,22 @@ int cpf_rfft(int size, const double* in, int64_t rows, double* out, int in_on_de
 int cpf_irfft_conj(int size, const double* in, int64_t rows, double* out, int in_on_device, int out_on_device,
                    int device, void* stream);
 
-/* ---- batched cubic splines: replaces scipy.interpolate.CubicSpline as used by Interpolator1D (jax.py:169-196)
- * and by the Wallish2018 filter (bao_filter.py:377-382, 400-402, 420).
- * Column layout as in the reference (axis 0 = knots): y [nx, ncols] row-major, shared abscissae x [nx].
- *   bc       : 0 = natural (y''=0 at both ends), 1 = clamped (y'=0 at both ends)
- *   cpf_spline_fit  : slopes [nx, ncols] = dy/dx at the knots (scipy's `c[2]`)
- *   cpf_spline_eval : out [nq, ncols] = nu-th derivative (0,1,2) at xq [nq]; outside [x0, x_last]: NaN unless extrap
+/* ---- batched cubic splines: replaces Interpolator1D.__init__ / __call__ on its numpy path (jax.py:139-196), i.e.
+ * scipy.interpolate.CubicSpline(x, fun, axis=0, bc_type='natural') + PPoly evaluation, and the clamped splines of the
+ * Wallish2018 filter (bao_filter.py:377-382, 400-402, 420).
+ * Column layout as in the reference (axis 0 = knots): y [nx, ncols] row-major, shared strictly increasing x [nx].
+ *   bc            : 0 = natural (y''=0 at both ends), 1 = clamped (y'=0 at both ends)
+ *   log_x, log_y  : fit in log10(x) / log10(y) and return 10**spline (interp_x='log' / interp_fun='log', jax.py:152-153,189-191)
+ *   extrap        : 0 => NaN outside [x[0], x[nx-1]] (jax.py:188-192), 1 => extend the end polynomials
+ * The handle owns device copies of the (transformed) knots and the fitted slopes.
+ *   cpf_spline_eval : out [nq, ncols] = nu-th derivative (0..3) of the spline at xq [nq]
  */
-int cpf_spline_fit(const double* x, const double* y, int nx, int64_t ncols, int bc, double* slopes,
-                   int on_device, int device, void* stream);
-int cpf_spline_eval(const double* x, const double* y, const double* slopes, int nx, int64_t ncols,
-                    const double* xq, int nq, int nu, int extrap, double* out,
-                    int on_device, int device, void* stream);
+typedef struct cpf_spline cpf_spline;
+int cpf_spline_create(cpf_spline** spline, const double* x, const double* y, int nx, int64_t ncols, int bc,
+                      int log_x, int log_y, int extrap, int on_device, int device, void* stream);
+int cpf_spline_eval(const cpf_spline* spline, const double* xq, int nq, int nu, double* out, int on_device,
+                    void* stream);
+int cpf_spline_destroy(cpf_spline* spline);
 
 /* ---- DST-II / DST-III (orthonormal) along axis 0: replaces scipy.fftpack.dst(type=2, norm='ortho', axis=0) and
  * idst(type=2, norm='ortho', axis=0) at bao_filter.py:372, 412.  data [nx, ncols] row-major, nx a power of two.
