@@ -97,6 +97,16 @@ __global__ void __launch_bounds__(128) spline_eval_kernel(const double* __restri
   out[(long long)q * ncols + col] = r;
 }
 
+// device-resident fit, shared with cpf_wallish.cu: slopes s[nx, ncols] of the splines through y[nx, ncols] on the
+// knots x[nx]; fac is scratch of 3*nx doubles
+int spline_fit_device(const double* d_x, const double* d_y, int nx, long long ncols, int bc, double* d_s, double* d_fac,
+                      cudaStream_t stream) {
+  spline_factor_kernel<<<1, 32, 0, stream>>>(d_x, nx, bc, d_fac);
+  if (ncols > 0) spline_solve_kernel<<<(unsigned)((ncols + 127) / 128), 128, 0, stream>>>(d_x, d_y, d_fac, nx, ncols, bc, d_s);
+  CPF_CUDA(cudaGetLastError());
+  return CPF_OK;
+}
+
 }  // namespace cpf
 
 using namespace cpf;
@@ -169,9 +179,7 @@ int cpf_spline_create(cpf_spline** out, const double* x, const double* y, int nx
     log10_kernel<<<(nx + 255) / 256, 256, 0, stream>>>(src_x, sp->d_x, nx, sp->log_x);
     if (cells) log10_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, stream>>>(src_y, sp->d_y, (long long)cells, sp->log_y);
     SP_CUDA(fac.alloc(3 * (size_t)nx * sizeof(double), stream));
-    spline_factor_kernel<<<1, 32, 0, stream>>>(sp->d_x, nx, bc, (double*)fac.p);
-    if (cells) spline_solve_kernel<<<(unsigned)((ncols + 127) / 128), 128, 0, stream>>>(sp->d_x, sp->d_y, (const double*)fac.p, nx, ncols, bc, sp->d_s);
-    SP_CUDA(cudaGetLastError());
+    if ((rc = spline_fit_device(sp->d_x, sp->d_y, nx, ncols, bc, sp->d_s, (double*)fac.p, stream)) != CPF_OK) break;
     if (!on_device) SP_CUDA(cudaStreamSynchronize(stream));   // staging buffers of the caller may go away
 #undef SP_CUDA
   } while (0);

@@ -1,0 +1,247 @@
+// cpf_wallish_core.h — per-thread phase functions of the fused Wallish2018 kernel (cosmoprimo/bao_filter.py:361-413):
+// log(k P) -> DST-II -> even/odd second derivatives -> argmax boxes -> cut + re-spline -> DST-III -> exp(.)/k.
+// One CTA of 256 threads processes TWO spectra (columns) at once, packed as the real and imaginary parts of one
+// complex sequence, entirely in shared memory.  Host + device code: tests/emul/emul_wallish.cpp runs the same
+// functions thread by thread on the CPU.
+//
+// Mathematics:
+//  * DST-II of x (N = 4096) = DCT-II of x'_n = (-1)^n x_n read backwards; DCT-II by Makhoul's N-point FFT of
+//    v[n] = x'[2n], v[N-1-n] = x'[2n+1]:  C_k = 2 Re(e^{-i pi k/2N} V_k).  Two columns share one complex FFT
+//    (z = v_a + i v_b, V_a = (Z_k + conj Z_{N-k})/2, V_b = (Z_k - conj Z_{N-k})/2i).  Orthonormal scaling
+//    sqrt(1/2N), last coefficient sqrt(1/4N) (scipy norm='ortho').  DST-III is the exact inverse of these steps.
+//  * clamped cubic spline on the uniform knots 1..n: slopes solve s_{i-1} + 4 s_i + s_{i+1} = 3 (y_{i+1} - y_{i-1}),
+//    s_0 = s_{n-1} = 0.  The Thomas pivots depend on i only (and converge to 2 - sqrt 3 within 20 rows); influence of a
+//    right-hand side decays by 0.27 per knot, so each thread eliminates its own 16-knot chunk after a 48-knot warm-up
+//    (error < 1e-27): fully parallel, no scratch beyond one array.
+//  * cut + re-spline: the second spline (bao_filter.py:400-402) differs from the first only by the removed box, so
+//    only the two slopes at the knots bounding the box are needed: two short one-sided eliminations + a 2x2 solve.
+#pragma once
+
+#include "cpf_fft_core.h"
+
+namespace cpf {
+
+struct WallishGeo {
+  static constexpr int N = 4096;            // DST length (bao_filter.py:364)
+  static constexpr int H = 2048;            // even / odd sequence length
+  static constexpr int T = 256;             // threads per CTA
+  static constexpr int CH = 16;             // knots per thread in the chunked eliminations
+  static constexpr int WARM = 48;           // warm-up knots
+  static constexpr int HP = H + H / CH;     // padded half length (one pad element per 16: conflict-free chunk access)
+  static constexpr int BUF = 2 * HP;        // elements of one shared-memory array (>= 16*257 exchange elements)
+  static constexpr int MARGIN_FIRST = 20, MARGIN_SECOND = 5, OFF_LO = -10, OFF_HI = 20;   // bao_filter.py:387-389
+};
+
+#define CPF_LAMBDA 0.26794919243112270647   // 2 - sqrt(3): limit of the Thomas pivots 1/(4 - w)
+// scipy norm='ortho' scaling of the DST-II of length N = 4096: sqrt(1/2N), last coefficient sqrt(1/4N)
+#define CPF_DST_S 0.011048543456039806
+#define CPF_DST_S_LAST 0.0078125
+
+// padded position of knot i of parity h
+CPF_HD int wpos(const int h, const int i) { return h * WallishGeo::HP + i + (i >> 4); }
+
+// Thomas pivot w_i = 1/(d_i - l_i c_{i-1}) of the clamped uniform system, rows 0..n-1 (row 0 and n-1: s = 0)
+CPF_HD double wpivot(const double* wtab, const int i, const int n) {
+  if (i == 0 || i == n - 1) return 1.;
+  return i < 32 ? wtab[i] : CPF_LAMBDA;
+}
+// c_i = u_i w_i with u_0 = u_{n-1} = 0
+CPF_HD double wcp(const double* wtab, const int i, const int n) {
+  if (i == 0 || i == n - 1) return 0.;
+  return i < 32 ? wtab[i] : CPF_LAMBDA;
+}
+
+// ---- DST-II post-processing: Z (natural order, in A) -> orthonormal DST-II coefficients, de-interleaved + padded ----
+// thread t owns bins k = t + 256 r (zk[r] in registers); tw[k] = exp(-i pi k / 2N)
+CPF_HD void wallish_dst2_post(const int t, const double2 (&zk)[16], const double2* A, double2* X, const double2* tw) {
+  typedef WallishGeo G;
+#pragma unroll
+  for (int r = 0; r < 16; ++r) {
+    const int k = t + G::T * r;
+    const double2 z = zk[r], zm = A[(G::N - k) & (G::N - 1)];
+    // V_a = (z + conj zm)/2, V_b = (z - conj zm)/(2i)
+    const double2 va = mk2(0.5 * (z.x + zm.x), 0.5 * (z.y - zm.y));
+    const double2 vb = mk2(0.5 * (z.y + zm.y), 0.5 * (zm.x - z.x));
+    const double2 w = CPF_LDG(tw + k);
+    const int kk = G::N - 1 - k;                       // DST-II index
+    const double sc = 2. * (kk == G::N - 1 ? CPF_DST_S_LAST : CPF_DST_S);
+    const double ca = sc * (w.x * va.x - w.y * va.y), cb = sc * (w.x * vb.x - w.y * vb.y);
+    X[wpos(kk & 1, kk >> 1)] = mk2(ca, cb);
+  }
+}
+
+// ---- forward elimination of one chunk (both columns at once) -----------------------------------------------------
+// Y: knot values (padded layout, parity h), D: reduced right-hand sides.  sq != 0: the values are y_i * x_i^2.
+CPF_HD double2 wallish_y(const double2* Y, const int h, const int i, const int sq) {
+  double2 y = Y[wpos(h, i)];
+  if (sq) { const double x2 = (double)(i + 1) * (double)(i + 1); y.x *= x2; y.y *= x2; }
+  return y;
+}
+
+CPF_HD void wallish_forward(const int t, const double2* X, double2* D, const double* wtab) {
+  typedef WallishGeo G;
+  const int h = t >> 7, c = t & 127;
+  const int first = c * G::CH, start = first - G::WARM > 0 ? first - G::WARM : 0;
+  double2 d = mk2(0., 0.);
+  double2 ym = start > 0 ? X[wpos(h, start - 1)] : mk2(0., 0.), y0 = X[wpos(h, start)];
+  for (int i = start; i < first + G::CH; ++i) {
+    const double2 yp = i + 1 < G::H ? X[wpos(h, i + 1)] : mk2(0., 0.);
+    const bool edge = (i == 0 || i == G::H - 1);
+    const double w = wpivot(wtab, i, G::H);
+    const double rx = edge ? 0. : 3. * (yp.x - ym.x), ry = edge ? 0. : 3. * (yp.y - ym.y);
+    const double lo = edge ? 0. : 1.;
+    d = mk2((rx - lo * d.x) * w, (ry - lo * d.y) * w);
+    if (i >= first) D[wpos(h, i)] = d;
+    ym = y0; y0 = yp;
+  }
+}
+
+// ---- back substitution of one chunk, fused with the second derivative at the knots (bao_filter.py:379, 382) ----
+// dd_i = 2 c1 = 2 (3 m_i - 2 s_i - s_{i+1}), m_i = y_{i+1} - y_i; last knot: -6 m_{n-2} + 2 s_{n-2} + 4 s_{n-1}
+CPF_HD void wallish_backward_dd(const int t, const double2* X, const double2* D, double2* DD, const double* wtab) {
+  typedef WallishGeo G;
+  const int h = t >> 7, c = t & 127;
+  const int first = c * G::CH, last = first + G::CH - 1;
+  const int end = last + G::WARM < G::H - 1 ? last + G::WARM : G::H - 1;
+  double2 s = D[wpos(h, end)];          // exact when end = n-1, otherwise forgotten after WARM steps
+  double2 yn = X[wpos(h, end)];
+  double2 s_last = s;
+  for (int i = end - 1; i >= first; --i) {
+    const double cp = wcp(wtab, i, G::H);
+    const double2 di = D[wpos(h, i)], yi = X[wpos(h, i)];
+    const double2 sn = s;
+    s = mk2(di.x - cp * sn.x, di.y - cp * sn.y);
+    if (i <= last) {
+      const double mx = yn.x - yi.x, my = yn.y - yi.y;
+      DD[wpos(h, i)] = mk2(2. * (3. * mx - 2. * s.x - sn.x), 2. * (3. * my - 2. * s.y - sn.y));
+      if (i == G::H - 2) DD[wpos(h, G::H - 1)] = mk2(-6. * mx + 2. * s.x + 4. * sn.x, -6. * my + 2. * s.y + 4. * sn.y);
+    }
+    yn = yi;
+  }
+  (void)s_last;
+}
+
+// ---- argmax over [lo, hi) of one (parity, column) sequence, numpy semantics (first maximum) ------------------------
+// 64 threads per sequence; sequence q = t / 64 = 2*h + col.  Partial results go to red (val) / redi (idx).
+CPF_HD void wallish_argmax_local(const int t, const double2* DD, const int lo, const int hi, double* red, int* redi) {
+  const int q = t >> 6, l = t & 63, h = q >> 1, col = q & 1;
+  double best = 0.;
+  int bi = -1;
+  for (int i = lo + l; i < hi; i += 64) {
+    const double2 v = DD[wpos(h, i)];
+    const double x = col ? v.y : v.x;
+    if (bi < 0 || x > best) { best = x; bi = i; }
+  }
+  red[t] = best;
+  redi[t] = bi;
+}
+
+CPF_HD int wallish_argmax_final(const int q, const double* red, const int* redi) {
+  double best = 0.;
+  int bi = -1;
+  for (int l = 0; l < 64; ++l) {
+    const int i = redi[q * 64 + l];
+    if (i < 0) continue;
+    const double x = red[q * 64 + l];
+    if (bi < 0 || x > best || (x == best && i < bi)) { best = x; bi = i; }
+  }
+  return bi;
+}
+
+// ---- cut + re-spline: slopes at the knots L = b0-1 and R = b1+1 bounding the removed box (values y x^2) ------------
+struct WallishGap {
+  int b0, b1;          // removed index range [b0, b1]
+  double sL, sR;       // slopes at L and R
+  double yL, m, G;     // value at L, chord slope over the gap, gap width
+  int ok;              // 0: box reaches the end of the array (reference yields NaN there)
+};
+
+CPF_HD WallishGap wallish_gap_solve(const double2* X, const int h, const int col, const int b0, const int b1, const double* wtab) {
+  typedef WallishGeo Gm;
+  WallishGap g;
+  g.b0 = b0; g.b1 = b1;
+  const int n = Gm::H, L = b0 - 1, R = b1 + 1;
+  g.ok = (L >= 1 && R <= n - 2) ? 1 : 0;
+  g.sL = g.sR = g.yL = g.m = 0.; g.G = 1.;
+  if (!g.ok) return g;
+#define WY(i) (col ? wallish_y(X, h, (i), 1).y : wallish_y(X, h, (i), 1).x)
+  // left elimination over rows < L (unaffected by the cut)
+  double d = 0.;
+  for (int i = (L - Gm::WARM > 0 ? L - Gm::WARM : 0); i < L; ++i) {
+    const bool edge = i == 0;
+    const double r = edge ? 0. : 3. * (WY(i + 1) - WY(i - 1));
+    d = (r - (edge ? 0. : 1.) * d) * wpivot(wtab, i, n);
+  }
+  const double cpL = wcp(wtab, L - 1, n), dpL = d;
+  // right elimination over rows > R, mirrored (pivots of the mirrored system are those of row n-1-i)
+  d = 0.;
+  for (int i = (R + Gm::WARM < n - 1 ? R + Gm::WARM : n - 1); i > R; --i) {
+    const bool edge = i == n - 1;
+    const double r = edge ? 0. : 3. * (WY(i + 1) - WY(i - 1));
+    d = (r - (edge ? 0. : 1.) * d) * wpivot(wtab, n - 1 - i, n);
+  }
+  const double cqR = wcp(wtab, n - 1 - (R + 1), n), dqR = d;
+  const double G = (double)(R - L);
+  const double yL = WY(L), yR = WY(R);
+  const double mleft = yL - WY(L - 1), mgap = (yR - yL) / G, mright = WY(R + 1) - yR;
+#undef WY
+  const double rhsL = 3. * (G * mleft + mgap), rhsR = 3. * (mgap + G * mright);
+  const double a11 = 2. * (1. + G) - G * cpL, a22 = 2. * (G + 1.) - G * cqR;
+  const double b1_ = rhsL - G * dpL, b2_ = rhsR - G * dqR;
+  const double det = a11 * a22 - 1.;
+  g.sL = (b1_ * a22 - b2_) / det;
+  g.sR = (a11 * b2_ - b1_) / det;
+  g.yL = yL; g.m = mgap; g.G = G;
+  return g;
+}
+
+// new value of knot i of a sequence after cut + re-spline: spline(x_i)/x_i^2 (bao_filter.py:402)
+CPF_HD double wallish_fill(const double y, const int i, const WallishGap& g) {
+  const double x = (double)(i + 1), x2 = x * x;
+  if (!g.ok) {
+    // box reaches the array end: the reference's spline is not defined beyond its last knot (extrapolate=False)
+    return i >= g.b0 ? nan("") : (y * x2) / x2;
+  }
+  if (i < g.b0 || i > g.b1) return (y * x2) / x2;
+  const double t = (g.sL + g.sR - 2. * g.m) / g.G;
+  const double c0 = t / g.G, c1 = (g.m - g.sL) / g.G - t;
+  const double d = (double)(i - (g.b0 - 1));
+  return (g.yL + d * (g.sL + d * (c1 + d * c0))) / x2;
+}
+
+// ---- DST-III pre-processing: orthonormal coefficients X -> FFT input Z for bins k = t + 256 r -----------------------
+CPF_HD void wallish_dst3_pre(const int t, const double2* X, double2 (&zk)[16], const double2* tw) {
+  typedef WallishGeo G;
+#pragma unroll
+  for (int r = 0; r < 16; ++r) {
+    const int k = t + G::T * r;
+    // C'_k = X[N-1-k]/s, C'_{N-k} = X[k-1]/s (0 for k = 0)
+    const int k1 = G::N - 1 - k, k2 = k - 1;
+    const double f1 = 0.5 / (k1 == G::N - 1 ? CPF_DST_S_LAST : CPF_DST_S);     // the 0.5 of V_k folded in
+    double2 c1 = X[wpos(k1 & 1, k1 >> 1)];
+    c1.x *= f1; c1.y *= f1;
+    double2 c2 = mk2(0., 0.);
+    if (k2 >= 0) {
+      const double f2 = 0.5 / (k2 == G::N - 1 ? CPF_DST_S_LAST : CPF_DST_S);
+      c2 = X[wpos(k2 & 1, k2 >> 1)];
+      c2.x *= f2; c2.y *= f2;
+    }
+    const double2 w = CPF_LDG(tw + k);                 // exp(-i pi k/2N); need 0.5 * conj(w) * (C'_k - i C'_{N-k})
+    // column a: (c1.x - i c2.x) * conj(w) ; column b: (c1.y - i c2.y) * conj(w)   [0.5 folded into c1, c2]
+    const double var = w.x * c1.x - w.y * c2.x, vai = -w.x * c2.x - w.y * c1.x;   // conj(w) = (w.x, -w.y)
+    const double vbr = w.x * c1.y - w.y * c2.y, vbi = -w.x * c2.y - w.y * c1.y;
+    zk[r] = mk2(var - vbi, vai + vbr);                  // Z = V_a + i V_b
+  }
+}
+
+// output index of FFT bin m of the DST-III transform and its sign (x = (-1)^j x'_j, x'[2n] = v[n], x'[2n+1] = v[N-1-n],
+// v[n] = F[(N-n) mod N] / N)
+CPF_HD int wallish_dst3_out_index(const int m, double& sign) {
+  typedef WallishGeo G;
+  if (m == 0) { sign = 1.; return 0; }
+  if (m <= G::N / 2) { sign = -1.; return 2 * m - 1; }
+  sign = 1.;
+  return 2 * (G::N - m);
+}
+
+}  // namespace cpf

@@ -1,0 +1,175 @@
+"""
+Batched 1-D cubic-spline interpolation on the GPU: drop-in for the numpy path of ``cosmoprimo.jax.Interpolator1D``
+(``cosmoprimo/jax.py:134-196``, cited as ``ref:LINE``): natural cubic spline along axis 0 of ``fun``, optional log10
+abscissa / ordinate, NaN outside the fitted range unless ``extrap``, all-NaN columns passed through, float32 output
+only for float32 queries.
+
+Fit (tridiagonal slope system, one thread per column) and evaluation run in ``csrc/cpf_spline.cu`` behind
+``cpf_spline_create`` / ``cpf_spline_eval``; the fitted spline lives on the device.  numpy in -> numpy out; CUDA
+arrays (torch / ``__cuda_array_interface__`` / DLPack) in -> torch tensors out.
+"""
+
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from . import _buffers as _buf
+
+
+def _bcast_dtype(*args):
+    """float32 only if every array argument is float32, else float64 (``cosmoprimo/utils.py:88-95``)."""
+    dtypes = [np.dtype(str(a.dtype).replace('torch.', '')) for a in args if hasattr(a, 'dtype')]
+    if not dtypes:
+        return np.dtype('f8')
+    out = np.result_type(*dtypes)
+    return out if np.issubdtype(out, np.floating) else np.dtype('f8')
+
+
+class _DeviceSpline(object):
+    """Owner of a ``cpf_spline*``."""
+
+    def __init__(self, xbuf, ybuf, nx, ncols, bc, log_x, log_y, extrap, device, stream):
+        handle = ctypes.c_void_p()
+        rc = _lib.load().cpf_spline_create(ctypes.byref(handle), xbuf.ptr, ybuf.ptr, nx, ncols, bc, int(log_x), int(log_y), int(extrap),
+                                           int(ybuf.on_device), device, stream)
+        _lib.check(rc)
+        self.handle, self.device = handle, device
+
+    def __del__(self):
+        handle, self.handle = getattr(self, 'handle', None), None
+        if handle:
+            try:
+                _lib.load().cpf_spline_destroy(handle)
+            except Exception:
+                pass
+
+
+class Interpolator1D(object):
+    """
+    1-D cubic-spline interpolation along axis 0 of ``fun`` on a CUDA device.
+
+    Parameters
+    ----------
+    x : array (nx,)
+        Abscissae (sorted unless ``assume_sorted`` is False, in which case they are sorted here, ref:147-149).
+    fun : array (nx, ...)
+        Ordinates; numpy array or CUDA array.
+    k : int, default=3
+        Spline order; only the cubic spline of the hot path is implemented.
+    interp_x, interp_fun : 'lin' or 'log'
+        Interpolate in log10 of the abscissa / ordinate (ref:152-153, 189-191).
+    extrap : bool, default=False
+        If False, NaN outside ``[x.min(), x.max()]``.
+    bc_type : 'natural' (the reference's choice, ref:172) or 'clamped' (used by the Wallish2018 filter).
+    device : int, default=None
+        CUDA device for host input.
+    """
+
+    def __init__(self, x, fun, k=3, interp_x='lin', interp_fun='lin', extrap=False, assume_sorted=False, bc_type='natural', device=None):
+        if k != 3:
+            raise NotImplementedError('cosmoprimo_b200.Interpolator1D implements the cubic spline (k=3) only')
+        if bc_type not in ('natural', 'clamped'):
+            raise ValueError('bc_type must be "natural" or "clamped"')
+        _lib.load()
+        self.interp_x, self.interp_fun = str(interp_x), str(interp_fun)
+        self.extrap = bool(extrap)
+        x = np.array(x, dtype='f8').ravel()
+        on_device = _buf.is_device_array(fun)
+        if on_device:
+            ybuf = _buf.as_input(fun, dtype='f8')
+            fun_t = ybuf.obj
+        else:
+            fun_t = np.array(fun, dtype='f8')
+        if fun_t.shape[0] != x.size:
+            raise ValueError('fun has {} samples along axis 0, x has {}'.format(fun_t.shape[0], x.size))
+        self.shape = tuple(fun_t.shape[1:])
+        if not assume_sorted:
+            ix = np.argsort(x)
+            if not np.array_equal(ix, np.arange(x.size)):
+                x = x[ix]
+                fun_t = fun_t[ix] if not on_device else fun_t[_buf._torch().as_tensor(ix, device=fun_t.device)]
+        self.xmin, self.xmax = x[0], x[-1]
+        flat = fun_t.reshape(x.size, -1)
+        # all-NaN columns are passed through as NaN, any other NaN poisons the whole fit (ref:161-172)
+        if on_device:
+            torch = _buf._torch()
+            isnan = torch.isnan(flat)
+            if self.interp_fun == 'log':
+                isnan = isnan | (flat < 0)
+            self._mask_nan = (~isnan.all(dim=0)).cpu().numpy()
+            poisoned = bool(isnan[:, torch.as_tensor(self._mask_nan, device=flat.device)].any().item()) if self._mask_nan.any() else False
+        else:
+            with np.errstate(invalid='ignore'):
+                isnan = np.isnan(flat) | ((flat < 0) if self.interp_fun == 'log' else False)
+            self._mask_nan = ~isnan.all(axis=0)
+            poisoned = bool(isnan[:, self._mask_nan].any())
+        self._ncols = int(flat.shape[1])
+        self._spline = None
+        self._on_device = on_device
+        if x.size < 2:
+            raise ValueError('need at least two knots')
+        if self._mask_nan.any() and not poisoned:
+            _lib.require_device()
+            ybuf = _buf.as_input(flat, dtype='f8')
+            dev = ybuf.device if ybuf.on_device else (device if device is not None else _buf.default_device())
+            stream = _buf.current_stream(dev) if ybuf.on_device else None
+            if ybuf.on_device:
+                xbuf = _buf.as_input(_buf._torch().as_tensor(x, device=ybuf.obj.device), dtype='f8')
+            else:
+                xbuf = _buf.as_input(x, dtype='f8')
+            # NaN columns simply propagate NaN through their own (independent) solve: no need to drop them
+            self._spline = _DeviceSpline(xbuf, ybuf, x.size, self._ncols, 1 if bc_type == 'clamped' else 0, self.interp_x == 'log',
+                                         self.interp_fun == 'log', self.extrap, dev, stream)
+            self._device = dev
+
+    def __call__(self, x, bounds_error=False, dx=0):
+        """Evaluate the spline (or its ``dx``-th derivative) at ``x``; result has shape ``x.shape + fun.shape[1:]``."""
+        dtype = _bcast_dtype(x)
+        q_on_device = _buf.is_device_array(x)
+        if q_on_device:
+            qbuf = _buf.as_input(x, dtype='f8')
+            q = qbuf.obj.reshape(-1)
+            qshape = tuple(qbuf.shape)
+        else:
+            q = np.asarray(x, dtype=dtype).astype('f8').ravel()
+            qshape = np.shape(x)
+        if bounds_error:
+            qh = q.cpu().numpy() if q_on_device else q
+            if qh.size and not ((qh >= self.xmin) & (qh <= self.xmax)).all():
+                raise ValueError('input outside of extrapolation range (min: {} vs. {}; max: {} vs. {})'.format(qh.min(), self.xmin, qh.max(), self.xmax))
+        out_shape = qshape + self.shape
+        nq = int(np.prod(qshape, dtype='i8'))
+        want_device = self._on_device or q_on_device
+        if self._spline is None or nq == 0 or self._ncols == 0:
+            if want_device:
+                torch = _buf._torch()
+                dev = q.device if q_on_device else 'cuda'
+                return torch.full(out_shape, float('nan'), dtype=torch.float32 if dtype == np.float32 else torch.float64, device=dev)
+            return np.full(out_shape, np.nan, dtype=dtype)
+        lib = _lib.load()
+        dev = self._spline.device
+        if want_device:
+            torch = _buf._torch()
+            if not q_on_device:
+                q = torch.as_tensor(q, device=torch.device('cuda', dev))
+            qbuf = _buf.as_input(q.contiguous(), dtype='f8')
+            out = _buf.empty_like_kind(qbuf, (nq, self._ncols), dtype='f8')
+            stream = _buf.current_stream(dev)
+        else:
+            qbuf = _buf.as_input(q, dtype='f8')
+            out = _buf.empty_like_kind(qbuf, (nq, self._ncols), dtype='f8')
+            stream = None
+        # evaluate in slabs of 65535 queries (grid.y limit of the kernel)
+        step = 65535
+        for start in range(0, nq, step):
+            cnt = min(step, nq - start)
+            rc = lib.cpf_spline_eval(self._spline.handle, qbuf.ptr + 8 * start, cnt, int(dx), out.ptr + 8 * start * self._ncols,
+                                     int(qbuf.on_device), stream)
+            _lib.check(rc)
+        res = out.obj
+        if want_device:
+            if dtype == np.float32:
+                res = res.to(_buf._torch().float32)
+            return res.reshape(out_shape)
+        return res.astype(dtype, copy=False).reshape(out_shape)

@@ -1,0 +1,160 @@
+"""GPU parity of the spline / interpolator / DST / Wallish2018 entry points (through the ctypes C ABI) against vectors
+produced by the unmodified reference and against the oracles on seeded inputs."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from cosmoprimo_b200 import _lib, synthetic as S
+from cosmoprimo_b200.interp import Interpolator1D
+from cosmoprimo_b200.interpolator import PowerSpectrumInterpolator1D, CorrelationFunctionInterpolator1D
+from cosmoprimo_b200.bao_filter import PowerSpectrumBAOFilter, Wallish2018PowerSpectrumBAOFilter
+from oracle import spline_oracle as SO
+from oracle import wallish_oracle as WO
+
+pytestmark = pytest.mark.gpu
+
+SPLINE_CASES = list(range(len(load_golden('spline_golden.npz').cases)))
+
+
+def close_with_nans(out, ref, rtol, atol=0.):
+    out, ref = np.asarray(out), np.asarray(ref)
+    assert out.shape == ref.shape and out.dtype == ref.dtype, (out.shape, ref.shape, out.dtype, ref.dtype)
+    assert np.array_equal(np.isnan(out), np.isnan(ref))
+    m = np.isfinite(ref)
+    assert np.array_equal(np.isinf(out), np.isinf(ref))
+    np.testing.assert_allclose(out[m], ref[m], rtol=rtol, atol=atol)
+
+
+@pytest.mark.parametrize('idx', SPLINE_CASES)
+def test_spline_golden(idx):
+    g = load_golden('spline_golden.npz')
+    case, d = g.cases[idx], g.data
+    ref = d['s{}'.format(idx)]
+    if case['kind'] == 'interp1d':
+        interp = Interpolator1D(d[case['x']], d[case['y']], interp_x=case['interp_x'], interp_fun=case['interp_fun'], extrap=case['extrap'],
+                                assume_sorted=case.get('assume_sorted', False))
+        out = interp(d[case['xq']], dx=case['dx'])
+        # values are O(1..1e3) with knot spacing down to 1e-3: derivatives amplify rounding by 1/dx
+        close_with_nans(out, ref, rtol=1e-10 if case['dx'] == 0 else 1e-7, atol=1e-12 * np.nanmax(np.abs(ref[np.isfinite(ref)])))
+    else:
+        interp = PowerSpectrumInterpolator1D(d[case['k']], d[case['pk']])
+        close_with_nans(interp(d[case['keval']]), ref, rtol=1e-10)
+        r = d['r']
+        close_with_nans(interp.sigma_r(r), d['s{}_sigma_r'.format(idx)], rtol=1e-10)
+        close_with_nans(np.asarray(interp.sigma8()), d['s{}_sigma8'.format(idx)], rtol=1e-10)
+        xi = interp.to_xi()
+        assert isinstance(xi, CorrelationFunctionInterpolator1D)
+        np.testing.assert_allclose(xi.s, d['s{}_xi_s'.format(idx)], rtol=1e-13)
+        xi_ref = d['s{}_xi'.format(idx)]
+        got = xi(d['s{}_seval'.format(idx)])
+        assert got.shape == xi_ref.shape
+        assert np.max(np.abs(got - xi_ref)) < 1e-10 * np.max(np.abs(xi_ref))
+        if 's{}_pk_back'.format(idx) in d.files:
+            back = xi.to_pk()(np.geomspace(1e-2, 10., 30))
+            np.testing.assert_allclose(back, d['s{}_pk_back'.format(idx)], rtol=1e-8)
+
+
+def test_spline_clamped_and_derivatives_vs_oracle():
+    rng = np.random.default_rng(3)
+    x = np.sort(rng.uniform(0., 50., 777))
+    y = np.cos(x)[:, None] * rng.uniform(0.5, 2., (777, 33))
+    xq = rng.uniform(0., 50., 500)
+    for bc in ['natural', 'clamped']:
+        s = SO.cubic_spline_slopes(x, y, bc)
+        interp = Interpolator1D(x, y, bc_type=bc, assume_sorted=True)
+        for nu in [0, 1, 2, 3]:
+            ref = SO.cubic_spline_eval(x, y, s, xq, nu=nu)
+            out = interp(xq, dx=nu)
+            assert np.max(np.abs(out - ref)) < 1e-9 * np.max(np.abs(ref)), (bc, nu)
+
+
+def test_spline_device_buffers_and_shapes():
+    torch = pytest.importorskip('torch')
+    g = load_golden('spline_golden.npz').data
+    x, y, xq = g['x'], g['y'], g['xq']
+    host = Interpolator1D(x, y)(xq)
+    dev = Interpolator1D(x, torch.from_numpy(y).cuda())
+    out = dev(xq)
+    assert isinstance(out, torch.Tensor) and out.is_cuda
+    assert np.array_equal(out.cpu().numpy(), host, equal_nan=True)
+    out = dev(torch.from_numpy(xq).cuda().reshape(8, 8))
+    assert tuple(out.shape) == (8, 8, 7)
+    # shape / dtype contract of the reference tests (tests/test_interpolator.py:8-32)
+    interp = Interpolator1D(x, y[:, 0])
+    assert interp(1.).shape == () and interp(np.array([])).shape == (0,) and interp(np.ones((2, 3))).shape == (2, 3)
+    assert interp(np.ones(4, dtype='f4')).dtype == np.float32 and interp(np.ones(4)).dtype == np.float64
+    with pytest.raises(ValueError):
+        interp(np.array([100.]), bounds_error=True)
+
+
+def fake_interpolator(klin, pklin, kout, pkout, extrap_kmin=1e-7, extrap_kmax=1e2):
+    """Object with the interpolator duck type that returns the reference's own evaluations (bit-identical inputs)."""
+    class Fake(object):
+        def __call__(self, k):
+            k = np.asarray(k)
+            if k.size == klin.size and np.array_equal(k, klin): return pklin
+            if k.size == kout.size and np.allclose(k, kout, rtol=1e-14): return pkout
+            raise AssertionError('unexpected grid')
+    f = Fake()
+    f.extrap_kmin, f.extrap_kmax = extrap_kmin, extrap_kmax
+    return f
+
+
+@pytest.mark.parametrize('idx', [0, 1])
+def test_wallish_golden(idx):
+    d = load_golden('wallish_golden.npz').data
+    klin, pklin, kout, pkout = (d['w%d_%s' % (idx, n)] for n in ['klin', 'pklin', 'kout', 'pkout'])
+    filt = PowerSpectrumBAOFilter(fake_interpolator(klin, pklin, kout, pkout), engine='wallish2018_cuda')
+    assert isinstance(filt, Wallish2018PowerSpectrumBAOFilter)
+    np.testing.assert_allclose(filt.k, kout, rtol=1e-14)
+    ref, dbg = WO.wallish2018(klin, pklin, kout, pkout, return_debug=True)
+    assert np.array_equal(filt._boxes, dbg['boxes'])                   # the four argmax boxes of every column
+    assert filt.pknow.shape == d['w%d_pknow' % idx].shape
+    assert np.max(np.abs(filt.pknow / d['w%d_pknow' % idx] - 1.)) < 1e-10
+    assert np.array_equal(filt.pk, pkout)
+    # a B-column run equals B single-column runs on the identical arrays
+    for col in [0, pklin.shape[1] - 1]:
+        one = PowerSpectrumBAOFilter(fake_interpolator(klin, pklin[:, col], kout, pkout[:, col]), engine='wallish2018_cuda')
+        assert one.pknow.shape == (kout.size,)
+        assert np.array_equal(one.pknow, filt.pknow[:, col])
+
+
+def test_wallish_seeded_batch_vs_oracle():
+    """End to end from tables: our PowerSpectrumInterpolator1D feeds the filter; 65 (odd) LHS cosmologies."""
+    ktab = np.geomspace(1e-5, 1e2, 512)
+    pk = S.eh_pk(ktab, S.lhs_cosmologies(65, seed=11)).T
+    interp = PowerSpectrumInterpolator1D(ktab, pk)
+    filt = PowerSpectrumBAOFilter(interp, engine='wallish2018')
+    klin = np.linspace(interp.extrap_kmin, 2., 4096)
+    ref, dbg = WO.wallish2018(klin, interp(klin), filt.k, interp(filt.k), return_debug=True)
+    same = np.all(filt._boxes == dbg['boxes'], axis=1)
+    assert same.mean() > 0.95, 'boxes differ in {} of {} columns'.format((~same).sum(), same.size)
+    assert np.max(np.abs(filt.pknow[:, same] / ref[:, same] - 1.)) < 1e-10
+    smooth = filt.smooth_pk_interpolator()
+    assert np.allclose(smooth(filt.k[10:-10]), filt.pknow[10:-10], rtol=1e-9)
+    # device-resident tables: same kernels, same bits
+    torch = pytest.importorskip('torch')
+    interp_d = PowerSpectrumInterpolator1D(ktab, torch.from_numpy(pk).cuda())
+    filt_d = PowerSpectrumBAOFilter(interp_d, engine='wallish2018')
+    assert isinstance(filt_d.pknow, torch.Tensor)
+    assert np.array_equal(filt_d.pknow.cpu().numpy(), filt.pknow)
+
+
+def test_dst_matches_scipy():
+    """cpf_dst == scipy.fftpack.dst / idst (type 2, ortho, axis 0) that the reference calls (bao_filter.py:372, 412)."""
+    from scipy import fftpack
+    lib = _lib.load()
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((4096, 7))
+    out = np.empty_like(x)
+    _lib.check(lib.cpf_dst(2, x.ctypes.data, 4096, 7, out.ctypes.data, 0, 0, None))
+    ref = fftpack.dst(x, type=2, axis=0, norm='ortho')
+    assert np.max(np.abs(out - ref)) < 1e-14 * np.max(np.abs(ref)) * 10
+    back = np.empty_like(x)
+    _lib.check(lib.cpf_dst(3, out.ctypes.data, 4096, 7, back.ctypes.data, 0, 0, None))
+    assert np.max(np.abs(back - fftpack.idst(ref, type=2, axis=0, norm='ortho'))) < 1e-13
+    assert np.max(np.abs(back - x)) < 1e-13
+    with pytest.raises(NotImplementedError):
+        _lib.check(lib.cpf_dst(2, x.ctypes.data, 2048, 7, out.ctypes.data, 0, 0, None))

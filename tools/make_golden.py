@@ -142,6 +142,105 @@ def make_fftlog():
     print('wrote {} ({} cases, {:.2f} MB)'.format(fn, len(cases), os.path.getsize(fn) / 1e6))
 
 
+def make_spline():
+    """Interpolator1D (jax.py:134-196) and the interpolator-level callers (interpolator.py) run by the reference."""
+    from cosmoprimo.jax import Interpolator1D
+    from cosmoprimo.interpolator import PowerSpectrumInterpolator1D
+    arrays, cases = {}, []
+    rng = np.random.default_rng(7)
+    x = np.sort(rng.uniform(0.1, 10., 200))
+    y = np.sin(x)[:, None] * rng.uniform(1., 2., (200, 7)) + 3.
+    xq = np.concatenate([[0.05, x[0], x[-1], 11.], rng.uniform(0.1, 10., 60)])
+    arrays.update(x=x, y=y, xq=xq)
+    for ix in ['lin', 'log']:
+        for ifun in ['lin', 'log']:
+            for ex in [False, True]:
+                interp = Interpolator1D(x, y, interp_x=ix, interp_fun=ifun, extrap=ex)
+                with np.errstate(all='ignore'):
+                    for dx in ([0, 1, 2] if (ix, ifun) == ('lin', 'lin') else [0]):
+                        arrays['s{}'.format(len(cases))] = interp(xq, dx=dx)
+                        cases.append(dict(kind='interp1d', x='x', y='y', xq='xq', interp_x=ix, interp_fun=ifun, extrap=ex, dx=dx))
+    # unsorted knots, N-D values, float32 queries, an all-NaN column
+    perm = rng.permutation(x.size)
+    y3 = y[:, :6].reshape(200, 2, 3).copy()
+    y3[:, 1, 2] = np.nan
+    arrays.update(x_perm=x[perm], y_perm=y3[perm], xq32=xq.astype('f4').reshape(8, 8))
+    interp = Interpolator1D(arrays['x_perm'], arrays['y_perm'])
+    arrays['s{}'.format(len(cases))] = interp(arrays['xq32'])
+    cases.append(dict(kind='interp1d', x='x_perm', y='y_perm', xq='xq32', interp_x='lin', interp_fun='lin', extrap=False, dx=0))
+    # the sigma(r) spline: linear abscissa on a log grid spanning 9 decades (interpolator.py:289)
+    s_ = np.geomspace(1e-2, 1e7, 2048)
+    var = (1. / (1. + s_)**1.5)[:, None] * np.array([1., 2., 0.5])
+    r = np.linspace(1., 20., 10)
+    arrays.update(s_ill=s_, var_ill=var, r=r)
+    arrays['s{}'.format(len(cases))] = Interpolator1D(s_, var, assume_sorted=True)(r)
+    cases.append(dict(kind='interp1d', x='s_ill', y='var_ill', xq='r', interp_x='lin', interp_fun='lin', extrap=False, dx=0, assume_sorted=True))
+    # interpolator-level callers
+    ktab = np.geomspace(1e-4, 50., 300)
+    pk1 = desi_pk(ktab)
+    pk3 = pk1[:, None] * np.array([1., 0.5, 2.])
+    keval = np.concatenate([[5e-8, 1e-7, 1e2, 2e2], np.geomspace(1e-7, 1e2, 200)])
+    arrays.update(ktab=ktab, pk1=pk1, pk3=pk3, keval=keval)
+    for name in ['pk1', 'pk3']:
+        interp = PowerSpectrumInterpolator1D(ktab, arrays[name])
+        idx = len(cases)
+        arrays['s{}'.format(idx)] = interp(keval)
+        arrays['s{}_sigma_r'.format(idx)] = interp.sigma_r(r)
+        arrays['s{}_sigma8'.format(idx)] = np.asarray(interp.sigma8())
+        xi = interp.to_xi()
+        seval = np.geomspace(xi.smin * 1.01, xi.smax * 0.99, 50)
+        arrays['s{}_seval'.format(idx)] = seval
+        arrays['s{}_xi'.format(idx)] = xi(seval)
+        arrays['s{}_xi_s'.format(idx)] = xi.s
+        if name == 'pk1':   # the reference's 1-D to_pk does not transpose multi-column xi (interpolator.py:1212): single column only
+            back = xi.to_pk()
+            arrays['s{}_pk_back'.format(idx)] = back(np.geomspace(1e-2, 10., 30))
+        cases.append(dict(kind='pk1d', k='ktab', pk=name, keval='keval'))
+    arrays['manifest'] = np.array(json.dumps(cases))
+    fn = os.path.join(GOLDEN, 'spline_golden.npz')
+    np.savez_compressed(fn, **arrays)
+    print('wrote {} ({} cases, {:.2f} MB)'.format(fn, len(cases), os.path.getsize(fn) / 1e6))
+
+
+def make_wallish():
+    """Wallish2018PowerSpectrumBAOFilter (bao_filter.py:345-431) run by the reference on EH (LHS) and CLASS spectra."""
+    from cosmoprimo.interpolator import PowerSpectrumInterpolator1D
+    from cosmoprimo.bao_filter import PowerSpectrumBAOFilter
+    from scipy import fftpack
+    sys.path.insert(0, ROOT)
+    from cosmoprimo_b200 import synthetic
+    arrays, cases = {}, []
+    ktab = np.geomspace(1e-5, 1e2, 512)
+    pk_eh = synthetic.eh_pk(ktab, synthetic.lhs_cosmologies(6, seed=42)).T             # (512, 6)
+    fid = '/root/reference/cosmoprimo/tests/fiducial'
+    kc, pc = np.loadtxt(os.path.join(fid, 'abacus_cosm000_CLASSv3.1.1.00_z1_pk.dat'), unpack=True)[:2]
+    pc3 = np.loadtxt(os.path.join(fid, 'abacus_cosm000_CLASSv3.1.1.00_z3_pk.dat'), unpack=True)[1]
+    sel = slice(None, None, 8)
+    arrays.update(ktab_eh=ktab, pk_eh=pk_eh, ktab_class=kc[sel], pk_class=np.array([pc[sel], pc3[sel]]).T)
+    for name in ['eh', 'class']:
+        interp = PowerSpectrumInterpolator1D(arrays['ktab_' + name], arrays['pk_' + name])
+        filt = PowerSpectrumBAOFilter(interp, engine='wallish2018')
+        klin = np.linspace(interp.extrap_kmin, 2., 4096)
+        pklin = interp(klin)
+        idx = len(cases)
+        arrays['w{}_klin'.format(idx)] = klin
+        arrays['w{}_pklin'.format(idx)] = pklin
+        arrays['w{}_kout'.format(idx)] = filt.k
+        arrays['w{}_pkout'.format(idx)] = filt.pk
+        arrays['w{}_pknow'.format(idx)] = filt.pknow
+        arrays['w{}_dd_even'.format(idx)] = filt._dd_even[:64]      # head of the second derivatives (where the boxes are)
+        arrays['w{}_dd_odd'.format(idx)] = filt._dd_odd[:64]
+        # the pre-cut DST coefficients must be recomputed: _even/_odd are views overwritten in place (SURVEY appendix B)
+        dst = fftpack.dst(np.log(klin[:, None] * pklin), type=2, axis=0, norm='ortho')
+        arrays['w{}_dst_head'.format(idx)] = dst[:256]
+        arrays['w{}_now_head'.format(idx)] = np.stack([filt._even_now[:128], filt._odd_now[:128]])
+        cases.append(dict(ktab='ktab_' + name, pk='pk_' + name, ncols=int(pklin.shape[1])))
+    arrays['manifest'] = np.array(json.dumps(cases))
+    fn = os.path.join(GOLDEN, 'wallish_golden.npz')
+    np.savez_compressed(fn, **arrays)
+    print('wrote {} ({} cases, {:.2f} MB)'.format(fn, len(cases), os.path.getsize(fn) / 1e6))
+
+
 if __name__ == '__main__':
     which = sys.argv[1:] or ['fftlog', 'spline', 'wallish']
     print('reference: cosmoprimo {} from {}; numpy {}'.format(cosmoprimo.__version__, os.path.dirname(cosmoprimo.__file__), np.__version__))
