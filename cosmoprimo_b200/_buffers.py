@@ -70,8 +70,25 @@ def empty_like_kind(ref, shape, dtype='f8'):
         tdtype = {'f8': torch.float64, 'c16': torch.complex128}[dtype]
         out = torch.empty(tuple(shape), dtype=tdtype, device=torch.device('cuda', ref.device))
         return Buffer(out, out.data_ptr(), shape, True, ref.device)
-    out = np.empty(tuple(shape), dtype=dtype)
+    out = _host_empty(tuple(shape), dtype)
     return Buffer(out, out.ctypes.data, shape, False, None)
+
+
+_PINNED_MIN_BYTES = 4 << 20
+
+
+def _host_empty(shape, dtype):
+    """Host result buffer.  Large results are page-locked (through torch's caching host allocator) so that the
+    device-to-host copy runs at full PCIe rate and overlaps with compute; small ones are plain numpy arrays."""
+    nbytes = int(np.prod(shape, dtype='i8')) * np.dtype(dtype).itemsize
+    if nbytes >= _PINNED_MIN_BYTES:
+        try:
+            torch = _torch()
+            tdtype = {'f8': torch.float64, 'c16': torch.complex128}[dtype]
+            return torch.empty(shape, dtype=tdtype, pin_memory=True).numpy()
+        except Exception:
+            pass
+    return np.empty(shape, dtype=dtype)
 
 
 def current_stream(device):

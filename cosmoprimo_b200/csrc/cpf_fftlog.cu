@@ -17,6 +17,7 @@
 // passes per FFT, two shared-memory exchanges per FFT); nothing but the input rows and the output rows touches HBM.
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <mutex>
 #include <vector>
 
@@ -167,6 +168,124 @@ __global__ void __launch_bounds__(16 * R1, 512 / (16 * R1)) fftlog_fast_kernel(c
       const double pi = CPOST ? post_im[j] : 0.;
       store_out(a, outA, o, v[r].x, pr, pi, CPOST);
       if (has1) store_out(a, outB, o, v[r].y, pr, pi, CPOST);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// persistent fast path (zero padding, cropped output, real post-factor): one 512-thread CTA per SM, split into
+// NG = 512/T independent groups that each process one pair of rows at a time.  Everything batch-invariant (FFT
+// twiddles, kernel spectrum, pre/post factors of the current plan row) is staged in shared memory once per CTA and plan
+// row, so the steady state touches L1/L2/HBM for the input and output rows only; the next pair's rows are prefetched
+// into L2 while the current pair is transformed.  (r01a profile: with per-CTA table loads through L1 the top stall
+// was long_scoreboard on those loads.)
+// ---------------------------------------------------------------------------------------------------------------
+template <int R1>
+struct PersistentSmem {
+  typedef Geo<R1> G;
+  static constexpr int NG = 512 / G::T;
+  static constexpr int EXCH = NG * G::SMEM_ELEMS;          // double2
+  static constexpr int TW1 = 6 * 256, TW2 = 6 * 16;
+  static constexpr int UH = G::N / 2 + 2;                  // N/2+1 rounded up to even
+  static constexpr int WIN = G::N / 4;                     // N/2 doubles = N/4 double2
+  static constexpr int TOTAL = EXCH + TW1 + TW2 + UH + 2 * WIN;
+  static constexpr size_t BYTES = (size_t)TOTAL * sizeof(double2);
+};
+
+__device__ __forceinline__ void group_barrier(const int g, const int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(nthreads) : "memory");
+}
+
+template <int R1>
+__global__ void __launch_bounds__(512, 1) fftlog_persistent_kernel(const FftlogArgs a) {
+  typedef Geo<R1> G;
+  typedef PersistentSmem<R1> L;
+  constexpr int T = G::T, N = G::N, NG = L::NG;
+  extern __shared__ double2 smem[];
+  const int g = threadIdx.x / T, t = threadIdx.x - g * T;
+  double2* S = smem + g * G::SMEM_ELEMS;
+  double2* s_tw1 = smem + L::EXCH;
+  double2* s_tw2 = s_tw1 + L::TW1;
+  double2* s_uh = s_tw2 + L::TW2;
+  double* s_pre = reinterpret_cast<double*>(s_uh + L::UH);
+  double* s_post = s_pre + N / 2;
+
+  for (int i = threadIdx.x; i < L::TW1; i += 512) s_tw1[i] = a.tw1[i];
+  for (int i = threadIdx.x; i < L::TW2; i += 512) s_tw2[i] = a.tw2[i];
+
+  for (int p = 0; p < a.P; ++p) {
+    __syncthreads();   // everybody is done with the previous plan row's tables
+    {
+      const double2* uh = a.ut + (size_t)p * (N / 2 + 1);
+      const double* pre = a.pre + (size_t)p * N + N / 4;
+      const double* post = a.post_re + (size_t)p * N + N / 4;
+      for (int i = threadIdx.x; i < N / 2 + 1; i += 512) s_uh[i] = uh[i];
+      for (int i = threadIdx.x; i < N / 2; i += 512) { s_pre[i] = pre[i]; s_post[i] = post[i]; }
+    }
+    __syncthreads();
+
+    const long long stride = (long long)gridDim.x * NG;
+    for (long long pair = (long long)blockIdx.x * NG + g; pair < a.pairs_per_p; pair += stride) {
+      const long long b0 = 2 * pair, b1 = b0 + 1;
+      const bool has1 = b1 < a.batch;
+      const double* rowA = a.in + (a.in_has_P ? (b0 * a.P + p) : b0) * (long long)a.n;
+      const double* rowB = has1 ? a.in + (a.in_has_P ? (b1 * a.P + p) : b1) * (long long)a.n : rowA;
+      // L2 prefetch of the rows this group transforms next
+      {
+        const long long nb0 = 2 * (pair + stride);
+        if (nb0 < a.batch) {
+          const int lines = (a.n * 8 + 127) / 128;
+          const double* nA = a.in + (a.in_has_P ? (nb0 * a.P + p) : nb0) * (long long)a.n;
+          const double* nB = nb0 + 1 < a.batch ? a.in + (a.in_has_P ? ((nb0 + 1) * a.P + p) : nb0 + 1) * (long long)a.n : nA;
+          for (int l = t; l < 2 * lines; l += T) {
+            const double* q = (l < lines ? nA : nB) + (size_t)(l < lines ? l : l - lines) * 16;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+          }
+        }
+      }
+      double2 v[16];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const int jw = t + T * r;                      // index inside the window [N/4, 3N/4)
+        const int i = jw + N / 4 - a.in_left;
+        const bool ok = (unsigned)i < (unsigned)a.n;
+        const double x = ok ? __ldcs(rowA + i) : 0.;
+        const double y = (ok && has1) ? __ldcs(rowB + i) : 0.;
+        const double pr = s_pre[jw];
+        v[r] = mk2(x * pr, y * pr);
+      }
+#pragma unroll
+      for (int r = 8; r < 16; ++r) v[r] = mk2(0., 0.);
+
+      fft_pass1<R1, true>(t, v, S, s_tw1);
+      group_barrier(g, T);
+      fft_pass2<R1>(t, S, s_tw2);
+      group_barrier(g, T);
+      fft_pass3<R1, false>(t, v, S);
+#pragma unroll
+      for (int r = 0; r < 8; ++r) v[r] = cmul(v[r], s_uh[t + T * r]);
+#pragma unroll
+      for (int r = 8; r < 16; ++r) v[r] = cmul_conj(v[r], s_uh[T * (16 - r) - t]);
+      group_barrier(g, T);
+      fft_pass1<R1, false>(t, v, S, s_tw1);
+      group_barrier(g, T);
+      fft_pass2<R1>(t, S, s_tw2);
+      group_barrier(g, T);
+      fft_pass3<R1, true>(t, v, S);
+
+      double* outA = a.out + (size_t)(b0 * a.P + p) * a.n_out;
+      double* outB = a.out + (size_t)(b1 * a.P + p) * a.n_out;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const int jw = t + T * r;
+        const int o = jw + N / 4 - a.out_left;
+        if ((unsigned)o < (unsigned)a.n_out) {
+          const double pr = s_post[jw];
+          __stcs(outA + o, v[r].x * pr);
+          if (has1) __stcs(outB + o, v[r].y * pr);
+        }
+      }
+      group_barrier(g, T);   // pass-3 reads of S are done before the next pair's pass 1 overwrites it
     }
   }
 }
@@ -523,6 +642,26 @@ static int launch_fast_r(const FftlogArgs& a, bool pruned, bool cpost, long long
   return cpost ? launch_fast<R1, false, true>(a, nblocks, stream) : launch_fast<R1, false, false>(a, nblocks, stream);
 }
 
+template <int R1>
+static int launch_persistent(const FftlogArgs& a, cudaStream_t stream) {
+  typedef PersistentSmem<R1> L;
+  auto kern = fftlog_persistent_kernel<R1>;
+  CPF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::BYTES));
+  int dev = 0, sms = 0;
+  CPF_CUDA(cudaGetDevice(&dev));
+  CPF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  long long grid = (a.pairs_per_p + L::NG - 1) / L::NG;
+  if (grid > sms) grid = sms;
+  kern<<<(unsigned)grid, 512, L::BYTES, stream>>>(a);
+  CPF_CUDA(cudaGetLastError());
+  return CPF_OK;
+}
+
+static bool persistent_enabled() {
+  const char* e = getenv("CPF_FFTLOG_PERSISTENT");
+  return !(e && e[0] == '0');
+}
+
 static int generic_threads(int N) {
   int t = N / 2;
   if (t < 32) t = 32;
@@ -540,6 +679,13 @@ static int launch_fftlog(const cpf_plan* pl, FftlogArgs a, bool pruned, cudaStre
     a.ut = pruned ? pl->d_uts : pl->d_ut;
     a.tw1 = pl->d_tw1;
     a.tw2 = pl->d_tw2;
+    if (pruned && !pl->post_complex && persistent_enabled()) {
+      switch (pl->fast_R1) {
+        case 16: return launch_persistent<16>(a, stream);
+        case 8: return launch_persistent<8>(a, stream);
+        default: return launch_persistent<4>(a, stream);
+      }
+    }
     switch (pl->fast_R1) {
       case 16: return launch_fast_r<16>(a, pruned, pl->post_complex, nblocks, stream);
       case 8: return launch_fast_r<8>(a, pruned, pl->post_complex, nblocks, stream);

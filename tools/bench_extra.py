@@ -1,0 +1,92 @@
+"""Secondary measurements on one GPU (the other BASELINE.json configs); the headline line is bench.py's.
+Prints one JSON object.  `--quick`: only a small Wallish2018 run (used under ncu)."""
+import os
+import sys
+import json
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch
+from cosmoprimo_b200 import synthetic as S, _lib
+from cosmoprimo_b200.fftlog import PowerToCorrelation, CorrelationToPower, TophatVariance
+from cosmoprimo_b200.interpolator import PowerSpectrumInterpolator1D
+from cosmoprimo_b200.bao_filter import PowerSpectrumBAOFilter
+
+
+def timed(fn, reps=20, warm=3):
+    for _ in range(warm): fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps): fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e-3 / reps
+
+
+def wallish(ncols, reps):
+    ktab = np.geomspace(1e-5, 1e2, 512)
+    base = S.eh_pk(ktab, S.lhs_cosmologies(256, seed=42)).T
+    pk = torch.from_numpy(np.tile(base, (1, ncols // 256)) * (1 + 1e-3 * np.arange(ncols) / ncols)).cuda()
+    interp = PowerSpectrumInterpolator1D(ktab, pk)
+    filt = PowerSpectrumBAOFilter(interp, engine='wallish2018')
+    t = timed(lambda: filt(interp), reps=reps, warm=1)
+    # kernel-only: the C entry point on pre-evaluated arrays
+    klin = np.linspace(interp.extrap_kmin, 2., 4096)
+    pklin, pkout = interp(klin), interp(filt.k)
+    lib = _lib.load()
+    kl, ko = torch.from_numpy(klin).cuda(), torch.from_numpy(filt.k).cuda()
+    out = torch.empty_like(pkout)
+    stream = torch.cuda.current_stream().cuda_stream
+    tk = timed(lambda: _lib.check(lib.cpf_wallish2018(kl.data_ptr(), pklin.data_ptr(), 4096, ko.data_ptr(), pkout.data_ptr(), filt.k.size, ncols,
+                                                      out.data_ptr(), None, 1, 0, stream)), reps=reps, warm=1)
+    return {'ncols': ncols, 'pk_per_s_with_spline_eval': ncols / t, 'pk_per_s_filter_only': ncols / tk, 'algorithmic_gb_s_filter_only': ncols * 40960 / tk / 1e9}
+
+
+def main():
+    quick = '--quick' in sys.argv
+    res = {}
+    if quick:
+        res['wallish2018'] = wallish(2048, 2)
+        print(json.dumps(res))
+        return
+    for n, B in [(2048, 100000), (1024, 100000)]:
+        k = np.geomspace(1e-5, 1e2, n)
+        base = S.eh_pk(k, S.lhs_cosmologies(1000, seed=42))
+        D2 = S.growth_factor(np.linspace(0., 3., B // 1000), 0.31)**2
+        fun = torch.from_numpy((base[:, None, :] * D2[None, :, None]).reshape(B, n)).cuda()
+        tv = TophatVariance(k)
+        t = timed(lambda: tv(fun))
+        res['tophat_variance_nk%d' % n] = {'rows': B, 'transforms_per_s': B / t}
+        p2x = PowerToCorrelation(k)
+        s, xi = p2x(fun)
+        x2p = CorrelationToPower(s)
+        t = timed(lambda: x2p(p2x(fun)[1]))
+        res['roundtrip_nk%d' % n] = {'rows': B, 'transforms_per_s': 2 * B / t}
+        # sigma(r,z): FFTLog + spline fit + evaluation at 10 radii (BASELINE config 3, reduced batch)
+        if n == 2048:
+            interp = PowerSpectrumInterpolator1D(k, fun[:20000].T.contiguous(), extrap_kmin=1e-5 * (1 - 1e-9), extrap_kmax=1e2 * (1 + 1e-9))
+            r = np.linspace(1., 20., 10)
+            t = timed(lambda: interp.sigma_r(r, nk=2048), reps=5, warm=1)
+            res['sigma_rz_nk2048'] = {'rows': 20000, 'rows_per_s': 20000 / t}
+    # config 1: latency of one host-array call, nk = 1024
+    k = np.geomspace(1e-5, 1e2, 1024)
+    pk = S.eh_pk(k)
+    f = PowerToCorrelation(k)
+    f(pk)
+    t0 = time.perf_counter()
+    for _ in range(200): f(pk)
+    res['single_call_latency_us_nk1024_host'] = (time.perf_counter() - t0) / 200 * 1e6
+    t0 = time.perf_counter()
+    for _ in range(50): PowerToCorrelation(k)(pk)
+    res['construct_plus_call_us_nk1024_host'] = (time.perf_counter() - t0) / 50 * 1e6
+    res['wallish2018'] = wallish(16384, 3)
+    print(json.dumps(res))
+
+
+if __name__ == '__main__':
+    main()
