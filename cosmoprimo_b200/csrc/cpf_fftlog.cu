@@ -657,9 +657,11 @@ static int launch_persistent(const FftlogArgs& a, cudaStream_t stream) {
   return CPF_OK;
 }
 
+// Opt-in (CPF_FFTLOG_PERSISTENT=1): measured 16 % slower than the per-pair kernel on B200 (profiles/r01b_summary.md):
+// the stall it was built to remove (long_scoreboard) turned out to be the latency of the input rows, not of the tables.
 static bool persistent_enabled() {
   const char* e = getenv("CPF_FFTLOG_PERSISTENT");
-  return !(e && e[0] == '0');
+  return e && e[0] == '1';
 }
 
 static int generic_threads(int N) {

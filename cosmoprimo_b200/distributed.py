@@ -1,0 +1,64 @@
+"""
+Multi-GPU plumbing for the FFTLog path: one process per GPU, rows (cosmology x redshift x multipole) split into
+contiguous blocks, no data-path collective (every row is independent).  The only optional collective is a
+gather of the result shards (``torch.distributed``: NCCL on GPUs, gloo in the CPU tests); it is never inside a throughput
+number.
+"""
+
+import numpy as np
+
+
+def shard_bounds(nrows, rank, world):
+    """[start, stop) of the contiguous block of ``nrows`` rows owned by ``rank`` (sizes differ by at most one)."""
+    if not 0 <= rank < world:
+        raise ValueError('rank {} not in [0, {})'.format(rank, world))
+    base, extra = divmod(int(nrows), int(world))
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+def _dist():
+    import torch.distributed as dist
+    if not dist.is_available() or not dist.is_initialized():
+        return None
+    return dist
+
+
+def rank_world():
+    dist = _dist()
+    if dist is None:
+        return 0, 1
+    return dist.get_rank(), dist.get_world_size()
+
+
+def shard(array, rank=None, world=None):
+    """Rows of ``array`` (leading axis) owned by this rank."""
+    if rank is None or world is None:
+        rank, world = rank_world()
+    start, stop = shard_bounds(array.shape[0], rank, world)
+    return array[start:stop]
+
+
+def gather_rows(local, nrows_total):
+    """
+    All-gather row shards produced by :func:`shard` back into the full array (same on every rank).  ``local`` is a
+    torch tensor (CUDA with NCCL, CPU with gloo) or a numpy array (converted through a CPU tensor).
+    """
+    import torch
+    dist = _dist()
+    is_numpy = isinstance(local, np.ndarray)
+    t = torch.from_numpy(np.ascontiguousarray(local)) if is_numpy else local.contiguous()
+    if dist is None:
+        return local
+    world = dist.get_world_size()
+    sizes = [shard_bounds(nrows_total, r, world) for r in range(world)]
+    if t.shape[0] != sizes[dist.get_rank()][1] - sizes[dist.get_rank()][0]:
+        raise ValueError('local shard has {} rows, expected {}'.format(t.shape[0], sizes[dist.get_rank()][1] - sizes[dist.get_rank()][0]))
+    # all_gather wants equal shapes: pad every shard to the largest one (they differ by at most one row), trim after
+    most = max(b - a for a, b in sizes)
+    if t.shape[0] < most:
+        t = torch.cat([t, t.new_zeros((most - t.shape[0],) + tuple(t.shape[1:]))], dim=0)
+    parts = [torch.empty_like(t) for _ in sizes]
+    dist.all_gather(parts, t)
+    out = torch.cat([part[:b - a] for part, (a, b) in zip(parts, sizes)], dim=0)
+    return out.numpy() if is_numpy else out

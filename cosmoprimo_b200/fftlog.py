@@ -461,7 +461,12 @@ class FFTlog(object):
         -------
         y, fftloged
         """
-        shape = tuple(fun.shape) if hasattr(fun, 'shape') else np.shape(fun)
+        if hasattr(fun, 'shape'):
+            shape = tuple(fun.shape)
+        elif hasattr(fun, '__cuda_array_interface__'):
+            shape = tuple(fun.__cuda_array_interface__['shape'])
+        else:
+            shape = np.shape(fun)
         n, P, N = self.size, self.nparallel, self.padded_size
         if len(shape) < 1 or shape[-1] != n:
             raise ValueError('last dimension of input is {}, expected len(x) = {}'.format(shape[-1] if shape else None, n))
