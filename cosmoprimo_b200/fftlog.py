@@ -423,27 +423,8 @@ class FFTlog(object):
         # copies: subclasses rescale the factors in place after construction (ref:280, 319, 405, 433)
         self.lnxy, self.y, self.padded_x, self.padded_y, self.padded_u, self.padded_prefactor, self.padded_postfactor = (t.copy() for t in tables)
 
-    # -- device plan, built lazily and re-validated against the (public, mutable) tables on every call ---------
     def _device_plan(self, device):
-        """
-        The tables are public attributes that subclasses rescale after the engine exists (ref:117 then 280, 319, 330,
-        369, 377, 405, 433) and that :meth:`inv` rewrites (ref:243-248), so the device copy is made at first use and
-        refreshed whenever the host arrays no longer match the snapshot it was built from.
-        """
-        pre, u, post = (np.asarray(t) for t in (self.padded_prefactor, self.padded_u, self.padded_postfactor))
-        entry = self._dev_plans.get(device, None)
-        if entry is not None:
-            snap, dplan = entry
-            if all(s.shape == t.shape and s.dtype == t.dtype and np.array_equal(s, t) for s, t in zip(snap, (pre, u, post))):
-                return dplan
-        P, N = self.nparallel, self.padded_size
-        if pre.shape != (P, N) or post.shape != (P, N) or u.shape != (P, N // 2 + 1):
-            raise ValueError('plan tables have shapes {}, {}, {}; expected {}, {}, {}'.format(pre.shape, u.shape, post.shape, (P, N), (P, N // 2 + 1), (P, N)))
-        if np.iscomplexobj(pre):
-            raise ValueError('complex padded_prefactor is not supported')
-        dplan = _DevicePlan(self.size, N, P, self.padded_size_in_left, self.padded_size_out_left, pre, u, post, device)
-        self._dev_plans[device] = ((pre.copy(), u.copy(), post.copy()), dplan)
-        return dplan
+        return _device_plan_for(self, device)
 
     def __call__(self, fun, extrap=0, keep_padding=False):
         """
@@ -461,32 +442,7 @@ class FFTlog(object):
         -------
         y, fftloged
         """
-        if hasattr(fun, 'shape'):
-            shape = tuple(fun.shape)
-        elif hasattr(fun, '__cuda_array_interface__'):
-            shape = tuple(fun.__cuda_array_interface__['shape'])
-        else:
-            shape = np.shape(fun)
-        n, P, N = self.size, self.nparallel, self.padded_size
-        if len(shape) < 1 or shape[-1] != n:
-            raise ValueError('last dimension of input is {}, expected len(x) = {}'.format(shape[-1] if shape else None, n))
-        lead = shape[:-1]
-        # numpy broadcasting of fun[..., n] against the (P, N) tables (ref:231): the output carries
-        # broadcast(lead, (P,)); an input whose second-to-last dimension is 1 (or absent) feeds every kernel
-        out_lead = tuple(np.broadcast_shapes(lead, (P,)))
-        if P == 1:
-            in_has_p, batch_shape = True, lead
-        else:
-            in_has_p = len(lead) > 0 and lead[-1] == P
-            batch_shape = lead[:-1]
-        batch = int(np.prod(batch_shape, dtype='i8')) if len(batch_shape) else 1
-        n_out = N if keep_padding else n
-        out = self._engine.fftlog(self._device_plan, fun, batch, in_has_p, extrap, keep_padding, out_lead + (n_out,))
-        y = self.padded_y if keep_padding else self.y
-        if not self.inparallel:
-            y = y[0]
-            out = out.reshape(lead + (n_out,))
-        return y, out
+        return fused_call(self, fun, extrap=extrap, keep_padding=keep_padding)
 
     def inv(self):
         """Inverse the transform, in place (ref:243-248, including the unpadded ``padded_x/padded_y`` of ref:246)."""
@@ -494,6 +450,68 @@ class FFTlog(object):
         self.padded_x, self.padded_y = self.y, self.x
         self.padded_prefactor, self.padded_postfactor = 1 / self.padded_postfactor, 1 / self.padded_prefactor
         self.padded_u = 1 / self.padded_u.conj()
+
+
+# -- device plan, built lazily and re-validated against the (public, mutable) tables on every call ------------------
+
+def _device_plan_for(self, device):
+    """
+    The tables are public attributes that subclasses rescale after the engine exists (ref:117 then 280, 319, 330,
+    369, 377, 405, 433) and that :meth:`inv` rewrites (ref:243-248), so the device copy is made at first use and
+    refreshed whenever the host arrays no longer match the snapshot it was built from.
+    """
+    pre, u, post = (np.asarray(t) for t in (self.padded_prefactor, self.padded_u, self.padded_postfactor))
+    if not hasattr(self, '_dev_plans'):
+        self._dev_plans = {}
+    entry = self._dev_plans.get(device, None)
+    if entry is not None:
+        snap, dplan = entry
+        if all(s.shape == t.shape and s.dtype == t.dtype and np.array_equal(s, t) for s, t in zip(snap, (pre, u, post))):
+            return dplan
+    P, N = self.x.shape[0], self.padded_size
+    if pre.shape != (P, N) or post.shape != (P, N) or u.shape != (P, N // 2 + 1):
+        raise ValueError('plan tables have shapes {}, {}, {}; expected {}, {}, {}'.format(pre.shape, u.shape, post.shape, (P, N), (P, N // 2 + 1), (P, N)))
+    if np.iscomplexobj(pre):
+        raise ValueError('complex padded_prefactor is not supported')
+    dplan = _DevicePlan(self.x.shape[-1], N, P, self.padded_size_in_left, self.padded_size_out_left, pre, u, post, device)
+    self._dev_plans[device] = ((pre.copy(), u.copy(), post.copy()), dplan)
+    return dplan
+
+
+
+def fused_call(self, fun, extrap=0, keep_padding=False):
+    """
+    ``FFTlog.__call__`` (ref:198-241) through the fused CUDA kernel, for any object carrying the reference's public
+    FFTlog attributes (``x``, ``y``, ``padded_*``, ``inparallel``) and a :class:`CudaFFTEngine` in ``_engine``: this
+    package's classes, or the reference's own ``cosmoprimo.fftlog.FFTlog`` built with ``engine=CudaFFTEngine(...)``.
+    """
+    if hasattr(fun, 'shape'):
+        shape = tuple(fun.shape)
+    elif hasattr(fun, '__cuda_array_interface__'):
+        shape = tuple(fun.__cuda_array_interface__['shape'])
+    else:
+        shape = np.shape(fun)
+    n, P, N = self.x.shape[-1], self.x.shape[0], self.padded_size
+    if len(shape) < 1 or shape[-1] != n:
+        raise ValueError('last dimension of input is {}, expected len(x) = {}'.format(shape[-1] if shape else None, n))
+    lead = shape[:-1]
+    # numpy broadcasting of fun[..., n] against the (P, N) tables (ref:231): the output carries
+    # broadcast(lead, (P,)); an input whose second-to-last dimension is 1 (or absent) feeds every kernel
+    out_lead = tuple(np.broadcast_shapes(lead, (P,)))
+    if P == 1:
+        in_has_p, batch_shape = True, lead
+    else:
+        in_has_p = len(lead) > 0 and lead[-1] == P
+        batch_shape = lead[:-1]
+    batch = int(np.prod(batch_shape, dtype='i8')) if len(batch_shape) else 1
+    n_out = N if keep_padding else n
+    out = self._engine.fftlog(lambda device: _device_plan_for(self, device), fun, batch, in_has_p, extrap, keep_padding, out_lead + (n_out,))
+    y = self.padded_y if keep_padding else self.y
+    if not self.inparallel:
+        y = y[0]
+        out = out.reshape(lead + (n_out,))
+    return y, out
+
 
 
 # ------------------------------------------------------------------------------------------------------------------
