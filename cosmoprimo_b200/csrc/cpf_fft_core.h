@@ -104,9 +104,10 @@ CPF_HDC int bitrev(int v, int bits) {
 //   on exit   w[k] = sum_j x[j] exp(-2 pi i jk/R)
 // HALF_IN : x[j] = 0 for j >= R/2 (odd slots are ignored and overwritten) — FFTLog's zero padding.
 // HALF_OUT: only w[k], k < R/2, are valid on exit — FFTLog's output crop.
-template <int R, bool HALF_IN, bool HALF_OUT>
-CPF_HD void dft_dit(double2 (&w)[R]) {
+template <int R, bool HALF_IN, bool HALF_OUT, int M>
+CPF_HD void dft_dit(double2 (&w)[M]) {   // only w[0..R) are touched
   static_assert(R == 4 || R == 8 || R == 16, "radix");
+  static_assert(M >= R, "array too short");
   // stage h = 1
 #pragma unroll
   for (int j = 0; j < R; j += 2) {

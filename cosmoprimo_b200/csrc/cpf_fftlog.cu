@@ -290,6 +290,12 @@ __global__ void __launch_bounds__(512, 1) fftlog_persistent_kernel(const FftlogA
   }
 }
 
+}  // namespace cpf
+
+#include "cpf_fftlog_pp.cuh"
+
+namespace cpf {
+
 // ---------------------------------------------------------------------------------------------------------------
 // generic path: any power-of-two N <= CPF_MAX_N, whole transform in shared memory, radix-2
 // ---------------------------------------------------------------------------------------------------------------
@@ -427,6 +433,58 @@ int upload(void** dptr, const void* src, size_t bytes) {
 
 static int fast_radix(int N) { return N == 4096 ? 16 : N == 2048 ? 8 : N == 1024 ? 4 : 0; }
 
+// per-thread table records of the ping-pong kernel (layout: cpf_fftlog_pp.cuh).  uhs = (-1)^k u/N, [P, N/2+1].
+static void build_pp_tables(int N, int R1, int P, const double* pre, const std::vector<double2>& uhs, const double* post_re,
+                            std::vector<double2>& tab) {
+  const int T = 16 * R1, C = 16 / R1, nb = N / 2 + 1;
+  double2 zero; zero.x = 0.; zero.y = 0.;
+  tab.assign((size_t)P * T * PP_REC, zero);
+  for (int p = 0; p < P; ++p)
+    for (int t = 0; t < T; ++t) {
+      double2* rec = &tab[((size_t)p * T + t) * PP_REC];
+      for (int c = 0; c < C; ++c)
+        for (int k1 = 0; k1 < R1; ++k1) rec[c * R1 + k1] = unit_root((long long)(t + T * c) * k1, N);
+      for (int l1 = 0; l1 < 16; ++l1) rec[16 + l1] = unit_root((long long)(t & 15) * l1, 256);
+      for (int r = 0; r < 16; ++r) {
+        const int k = t + T * r;
+        double2 v = uhs[(size_t)p * nb + (k <= N / 2 ? k : N - k)];
+        if (k > N / 2) v.y = -v.y;
+        rec[32 + r] = v;
+      }
+      double* dpre = reinterpret_cast<double*>(rec + 48);
+      double* dpost = reinterpret_cast<double*>(rec + 52);
+      for (int r = 0; r < 8; ++r) {
+        const size_t j = (size_t)p * N + N / 4 + t + T * r;
+        dpre[r] = pre[j];
+        dpost[r] = post_re[j];
+      }
+    }
+}
+
+// records of fftlog_pp16_kernel: thread 16 h + i holds bins h + 16 i + 256 r after FFT #1
+static void build_pp16_tables(int P, const std::vector<double2>& uhs, std::vector<double2>& tab, std::vector<double2>& m256) {
+  const int N = 4096, T = 256, nb = N / 2 + 1;
+  double2 zero; zero.x = 0.; zero.y = 0.;
+  tab.assign((size_t)P * T * PP_REC, zero);
+  m256.resize(256);
+  for (int hh = 0; hh < 16; ++hh)
+    for (int l = 0; l < 16; ++l) m256[16 * hh + l] = unit_root(hh * l, 256);
+  for (int p = 0; p < P; ++p)
+    for (int t = 0; t < T; ++t) {
+      const int hh = t >> 4, ii = t & 15;
+      double2* rec = &tab[((size_t)p * T + t) * PP_REC];
+      for (int k = 0; k < 16; ++k) {
+        rec[k] = unit_root((long long)t * k, N);                       // FFT #1 pass 1: n2 = t
+        rec[16 + k] = unit_root(ii * k, 256);                          // FFT #1 pass 2: m2 = i
+        rec[48 + k] = unit_root((long long)(hh + 16 * ii) * k, N);     // FFT #2 pass 1: n2' = h + 16 i
+        const int bin = hh + 16 * ii + 256 * k;
+        double2 v = uhs[(size_t)p * nb + (bin <= N / 2 ? bin : N - bin)];
+        if (bin > N / 2) v.y = -v.y;
+        rec[32 + k] = v;
+      }
+    }
+}
+
 // per-device twiddle cache for the unfused engine entry points
 struct GenericTw {
   int device, N;
@@ -499,6 +557,9 @@ struct cpf_plan {
   double2* d_tw = nullptr;    // generic [N/2]
   double2* d_tw1 = nullptr;   // fast [6,256]
   double2* d_tw2 = nullptr;   // fast [6,16]
+  double2* d_pp = nullptr;    // ping-pong kernel: per-thread table records [P, T, PP_REC] (cpf_fftlog_pp.cuh)
+  double2* d_pp16 = nullptr;  // N = 4096 variant with warp-local exchanges: records [P, 256, PP_REC]
+  double2* d_m256 = nullptr;  // its shared pass-2 twiddle table [16, 16]
 };
 
 extern "C" {
@@ -528,6 +589,9 @@ int cpf_plan_destroy(cpf_plan* plan) {
   cudaFree(plan->d_tw);
   cudaFree(plan->d_tw1);
   cudaFree(plan->d_tw2);
+  cudaFree(plan->d_pp);
+  cudaFree(plan->d_pp16);
+  cudaFree(plan->d_m256);
   delete plan;
   return CPF_OK;
 }
@@ -586,6 +650,17 @@ int cpf_plan_create(cpf_plan** out, int n, int N, int P, int in_left, int out_le
       }
       if ((rc = upload((void**)&pl->d_tw1, tw1.data(), tw1.size() * sizeof(double2)))) break;
       if ((rc = upload((void**)&pl->d_tw2, tw2.data(), tw2.size() * sizeof(double2)))) break;
+      if (pl->window_prunable && !post_im) {
+        std::vector<double2> tab;
+        build_pp_tables(N, pl->fast_R1, P, pre, uhs, post_re, tab);
+        if ((rc = upload((void**)&pl->d_pp, tab.data(), tab.size() * sizeof(double2)))) break;
+        if (pl->fast_R1 == 16) {
+          std::vector<double2> m256;
+          build_pp16_tables(P, uhs, tab, m256);
+          if ((rc = upload((void**)&pl->d_pp16, tab.data(), tab.size() * sizeof(double2)))) break;
+          if ((rc = upload((void**)&pl->d_m256, m256.data(), m256.size() * sizeof(double2)))) break;
+        }
+      }
     } else {
       std::vector<double2> ut(PN);
       for (int p = 0; p < P; ++p)
@@ -657,6 +732,54 @@ static int launch_persistent(const FftlogArgs& a, cudaStream_t stream) {
   return CPF_OK;
 }
 
+template <int R1, int MODE>
+static int launch_pp(const FftlogArgs& a, const double2* tab, cudaStream_t stream) {
+  typedef Geo<R1> G;
+  constexpr int NG = 512 / G::T;
+  const size_t smem = (size_t)NG * G::SMEM_ELEMS * sizeof(double2);
+  auto kern = fftlog_pp_kernel<R1, MODE>;
+  CPF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int dev = 0, sms = 0;
+  CPF_CUDA(cudaGetDevice(&dev));
+  CPF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  long long grid = (a.pairs_per_p + NG - 1) / NG;
+  if (grid > sms) grid = sms;
+  kern<<<(unsigned)grid, 512, smem, stream>>>(a, tab);
+  CPF_CUDA(cudaGetLastError());
+  return CPF_OK;
+}
+
+static int launch_pp16(const FftlogArgs& a, const double2* tab, const double2* m256, cudaStream_t stream) {
+  const size_t smem = (size_t)(2 * PP16_GROUP_ELEMS + 256) * sizeof(double2);
+  CPF_CUDA(cudaFuncSetAttribute(fftlog_pp16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int dev = 0, sms = 0;
+  CPF_CUDA(cudaGetDevice(&dev));
+  CPF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  long long grid = ((long long)a.P * a.pairs_per_p + 1) / 2;
+  if (grid > sms) grid = sms;
+  fftlog_pp16_kernel<<<(unsigned)grid, 512, smem, stream>>>(a, tab, m256);
+  CPF_CUDA(cudaGetLastError());
+  return CPF_OK;
+}
+
+template <int R1>
+static int launch_pp_mode(const FftlogArgs& a, const double2* tab, int mode, cudaStream_t stream) {
+  if (mode == 3) mode = 0;
+  if (mode == 2) {
+    if constexpr (R1 == 16) return launch_pp<R1, 2>(a, tab, stream);
+    else mode = 1;
+  }
+  return mode == 1 ? launch_pp<R1, 1>(a, tab, stream) : launch_pp<R1, 0>(a, tab, stream);
+}
+
+// kernel choice for the default call: CPF_FFTLOG_KERNEL = fast | persistent | pp0 | pp1 | pp2
+static int pp_mode() {
+  const char* e = getenv("CPF_FFTLOG_KERNEL");
+  if (!e) return -1;
+  if (e[0] == 'p' && e[1] == 'p' && e[2] >= '0' && e[2] <= '3') return e[2] - '0';   // pp3 = pp16 kernel
+  return -1;
+}
+
 // Opt-in (CPF_FFTLOG_PERSISTENT=1): measured 16 % slower than the per-pair kernel on B200 (profiles/r01b_summary.md):
 // the stall it was built to remove (long_scoreboard) turned out to be the latency of the input rows, not of the tables.
 static bool persistent_enabled() {
@@ -681,6 +804,15 @@ static int launch_fftlog(const cpf_plan* pl, FftlogArgs a, bool pruned, cudaStre
     a.ut = pruned ? pl->d_uts : pl->d_ut;
     a.tw1 = pl->d_tw1;
     a.tw2 = pl->d_tw2;
+    if (pruned && pl->d_pp && pp_mode() >= 0) {
+      const int mode = pp_mode();
+      if (mode == 3 && pl->d_pp16) return launch_pp16(a, pl->d_pp16, pl->d_m256, stream);
+      switch (pl->fast_R1) {
+        case 16: return launch_pp_mode<16>(a, pl->d_pp, mode, stream);
+        case 8: return launch_pp_mode<8>(a, pl->d_pp, mode, stream);
+        default: return launch_pp_mode<4>(a, pl->d_pp, mode, stream);
+      }
+    }
     if (pruned && !pl->post_complex && persistent_enabled()) {
       switch (pl->fast_R1) {
         case 16: return launch_persistent<16>(a, stream);
