@@ -249,8 +249,8 @@ def run_ours(args):
     # end to end through the public API with pinned host arrays (H2D + D2H inside the timed region)
     h_fun = torch.from_numpy(fun).pin_memory().numpy()
     e2e_steps = max(3, min(args.steps, 10))
-    for _ in range(2):
-        fftlog(h_fun)
+    for _ in range(3):   # results are kept alive across calls, as in the timed loop, so that the pinned-buffer cache is warm
+        h_out = fftlog(h_fun)[1]
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):

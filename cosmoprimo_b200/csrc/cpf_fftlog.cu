@@ -508,7 +508,7 @@ static int generic_twiddles(int device, int N, double2** out) {
 }
 
 // staging streams for host-pointer calls (H2D / kernel / D2H of successive chunks overlap)
-static const int kNumStage = 3;
+static const int kNumStage = 4;
 struct StagePool {
   int device;
   cudaStream_t s[kNumStage];
@@ -841,6 +841,46 @@ static int launch_fftlog(const cpf_plan* pl, FftlogArgs a, bool pruned, cudaStre
   return CPF_OK;
 }
 
+// How host-pointer calls move their data: CPF_HOST_PATH = staged (default) | zerocopy.
+//   staged   : chunks are copied in, processed and copied back on rotating streams (H2D / kernel / D2H overlap);
+//   zerocopy : when both buffers are page-locked, the kernel reads the input rows and writes the output rows straight
+//              over PCIe (unified addressing: one launch, both directions busy from the first to the last row).
+static bool host_zero_copy_enabled() {
+  const char* e = getenv("CPF_HOST_PATH");
+  return e && e[0] == 'z';
+}
+
+static bool pinned_device_pointer(const void* host, void** dev) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, host) != cudaSuccess) { cudaGetLastError(); return false; }
+  if (at.type != cudaMemoryTypeHost || !at.devicePointer) return false;
+  *dev = at.devicePointer;
+  return true;
+}
+
+// Chunk sizes (rows) of a staged host-pointer call: small chunks at both ends so that the pipeline fills and drains
+// quickly (the first H2D and the last D2H are not overlapped with anything), `cap`-sized chunks in the middle where
+// per-chunk overheads matter.  Every chunk but the last has an even number of rows.
+static std::vector<long long> chunk_schedule(long long rows, long long small, long long cap) {
+  // scheduled in row pairs; an odd row count shortens the last chunk by one row
+  const long long sp = small / 2 > 0 ? small / 2 : 1, cp = cap / 2 > sp ? cap / 2 : sp;
+  long long left = (rows + 1) / 2;
+  std::vector<long long> front, back;
+  for (long long c = sp; c < cp && left > 0; c *= 2) {
+    const long long f = c < left ? c : left;
+    front.push_back(f);
+    left -= f;
+    const long long b = c < left ? c : left;
+    if (b > 0) back.push_back(b);
+    left -= b;
+  }
+  for (; left > 0; left -= (cp < left ? cp : left)) front.push_back(cp < left ? cp : left);
+  for (size_t i = back.size(); i-- > 0;) front.push_back(back[i]);
+  for (auto& v : front) v *= 2;
+  if (rows & 1) front.back() -= 1;
+  return front;
+}
+
 // Runs `body(chunk_first_row, chunk_rows, d_in_chunk, d_out_chunk, stream)` over the batch.  Device-resident calls
 // are one chunk on the caller's stream.  Host-pointer calls are split into chunks that are copied in, processed and
 // copied back on rotating internal streams so that H2D, compute and D2H overlap; the call returns when all chunks
@@ -850,25 +890,36 @@ static int run_staged(int device, const double* in, size_t in_row_doubles, doubl
                       long long rows, bool in_dev, bool out_dev, cudaStream_t user_stream, Body body) {
   if (rows <= 0) return CPF_OK;
   if (in_dev && out_dev) return body(0LL, rows, in, out, user_stream);
+  if (!in_dev && !out_dev && host_zero_copy_enabled()) {
+    void *zin = nullptr, *zout = nullptr;
+    if (pinned_device_pointer(in, &zin) && pinned_device_pointer(out, &zout)) {
+      CPF_TRY(body(0LL, rows, (const double*)zin, (double*)zout, user_stream));
+      CPF_CUDA(cudaStreamSynchronize(user_stream));
+      return CPF_OK;
+    }
+  }
   StagePool* sp = nullptr;
   CPF_TRY(stage_pool(device, &sp));
   const size_t row_bytes = (in_row_doubles > out_row_doubles ? in_row_doubles : out_row_doubles) * sizeof(double);
-  long long chunk = (long long)((32u << 20) / (row_bytes ? row_bytes : 1));
-  chunk = chunk < 2 ? 2 : (chunk & ~1LL);           // even, so that row pairs never straddle chunks
-  if (chunk > rows) chunk = rows;
-  const int nbuf = rows > chunk ? kNumStage : 1;
+  long long cap = (long long)((16u << 20) / (row_bytes ? row_bytes : 1));
+  cap = cap < 2 ? 2 : (cap & ~1LL);                 // even, so that row pairs never straddle chunks
+  long long small = (long long)((1u << 20) / (row_bytes ? row_bytes : 1));
+  small = small < 2 ? 2 : (small & ~1LL);
+  const std::vector<long long> sched = chunk_schedule(rows, small, cap);
+  const int nbuf = sched.size() < (size_t)kNumStage ? (int)sched.size() : kNumStage;
+  const long long buf_rows = rows < cap ? rows : cap;
   ScratchBuf din[kNumStage], dout[kNumStage];
   CPF_CUDA(cudaEventRecord(sp->start, user_stream));
   for (int i = 0; i < nbuf; ++i) {
     CPF_CUDA(cudaStreamWaitEvent(sp->s[i], sp->start, 0));
-    if (!in_dev) CPF_CUDA(din[i].alloc((size_t)chunk * in_row_doubles * sizeof(double), sp->s[i]));
-    if (!out_dev) CPF_CUDA(dout[i].alloc((size_t)chunk * out_row_doubles * sizeof(double), sp->s[i]));
+    if (!in_dev) CPF_CUDA(din[i].alloc((size_t)buf_rows * in_row_doubles * sizeof(double), sp->s[i]));
+    if (!out_dev) CPF_CUDA(dout[i].alloc((size_t)buf_rows * out_row_doubles * sizeof(double), sp->s[i]));
   }
   int rc = CPF_OK;
-  long long c = 0;
-  for (long long first = 0; first < rows && rc == CPF_OK; first += chunk, ++c) {
+  long long first = 0;
+  for (size_t c = 0; c < sched.size() && rc == CPF_OK; ++c) {
     const int i = (int)(c % nbuf);
-    const long long cnt = rows - first < chunk ? rows - first : chunk;
+    const long long cnt = sched[c];
     const double* src = in + (size_t)first * in_row_doubles;
     double* dst = out + (size_t)first * out_row_doubles;
     const double* d_in = src;
@@ -885,6 +936,7 @@ static int run_staged(int device, const double* in, size_t in_row_doubles, doubl
       cudaError_t e = cudaMemcpyAsync(dst, d_out, (size_t)cnt * out_row_doubles * sizeof(double), cudaMemcpyDeviceToHost, sp->s[i]);
       if (e != cudaSuccess) { rc = fail(CPF_ECUDA, "D2H copy: %s", cudaGetErrorString(e)); break; }
     }
+    first += cnt;
   }
   for (int i = 0; i < nbuf; ++i) {
     cudaError_t e = cudaStreamSynchronize(sp->s[i]);
