@@ -293,6 +293,7 @@ __global__ void __launch_bounds__(512, 1) fftlog_persistent_kernel(const FftlogA
 }  // namespace cpf
 
 #include "cpf_fftlog_pp.cuh"
+#include "cpf_fftlog_stream.cuh"
 
 namespace cpf {
 
@@ -485,6 +486,28 @@ static void build_pp16_tables(int P, const std::vector<double2>& uhs, std::vecto
     }
 }
 
+// tables of fftlog_stream_kernel (cpf_fftlog_stream.cuh): thread tau = 16 H + L
+static void build_stream_tables(int P, const std::vector<double2>& uhs, std::vector<double2>& tw, std::vector<double2>& ut) {
+  const int N = 4096, T = 256, nb = N / 2 + 1;
+  tw.resize((size_t)T * 48);
+  ut.resize((size_t)P * T * 16);
+  for (int t = 0; t < T; ++t) {
+    const int H = t >> 4, L = t & 15;
+    for (int k = 0; k < 16; ++k) {
+      tw[(size_t)t * 48 + k] = unit_root((long long)t * k, N);                    // P1 : w_4096^{tau k1}
+      tw[(size_t)t * 48 + 16 + k] = unit_root(L * k, 256);                        // P2 : w_256^{L l1}
+      tw[(size_t)t * 48 + 32 + k] = unit_root((long long)(H + 16 * L) * k, N);    // P1': w_4096^{(H + 16 L) k1'}
+    }
+    for (int p = 0; p < P; ++p)
+      for (int k = 0; k < 16; ++k) {
+        const int bin = H + 16 * L + 256 * k;
+        double2 v = uhs[(size_t)p * nb + (bin <= N / 2 ? bin : N - bin)];
+        if (bin > N / 2) v.y = -v.y;
+        ut[((size_t)p * T + t) * 16 + k] = v;
+      }
+  }
+}
+
 // per-device twiddle cache for the unfused engine entry points
 struct GenericTw {
   int device, N;
@@ -560,6 +583,8 @@ struct cpf_plan {
   double2* d_pp = nullptr;    // ping-pong kernel: per-thread table records [P, T, PP_REC] (cpf_fftlog_pp.cuh)
   double2* d_pp16 = nullptr;  // N = 4096 variant with warp-local exchanges: records [P, 256, PP_REC]
   double2* d_m256 = nullptr;  // its shared pass-2 twiddle table [16, 16]
+  double2* d_st_tw = nullptr; // stream kernel: P1 / P2 / P1' twiddles [256, 3, 16]
+  double2* d_st_ut = nullptr; // stream kernel: kernel spectrum per thread [P, 256, 16]
 };
 
 extern "C" {
@@ -592,6 +617,8 @@ int cpf_plan_destroy(cpf_plan* plan) {
   cudaFree(plan->d_pp);
   cudaFree(plan->d_pp16);
   cudaFree(plan->d_m256);
+  cudaFree(plan->d_st_tw);
+  cudaFree(plan->d_st_ut);
   delete plan;
   return CPF_OK;
 }
@@ -659,6 +686,10 @@ int cpf_plan_create(cpf_plan** out, int n, int N, int P, int in_left, int out_le
           build_pp16_tables(P, uhs, tab, m256);
           if ((rc = upload((void**)&pl->d_pp16, tab.data(), tab.size() * sizeof(double2)))) break;
           if ((rc = upload((void**)&pl->d_m256, m256.data(), m256.size() * sizeof(double2)))) break;
+          std::vector<double2> stw, sut;
+          build_stream_tables(P, uhs, stw, sut);
+          if ((rc = upload((void**)&pl->d_st_tw, stw.data(), stw.size() * sizeof(double2)))) break;
+          if ((rc = upload((void**)&pl->d_st_ut, sut.data(), sut.size() * sizeof(double2)))) break;
         }
       }
     } else {
@@ -762,6 +793,31 @@ static int launch_pp16(const FftlogArgs& a, const double2* tab, const double2* m
   return CPF_OK;
 }
 
+static int launch_stream(const cpf_plan* pl, const FftlogArgs& a, cudaStream_t stream) {
+  if (a.pairs_per_p > 2147483000LL) return fail(CPF_EUNSUPPORTED, "cpf_fftlog: batch too large for one launch");
+  const bool fullwin = a.n == a.N / 2 && a.in_left == a.N / 4 && a.out_left == a.N / 4;
+  StreamArgs s;
+  s.in = a.in; s.out = a.out; s.pre = a.pre; s.post = a.post_re;
+  s.in_row = a.in_has_P ? (long long)a.P * a.n : (long long)a.n;
+  s.in_p = a.in_has_P ? a.n : 0;
+  s.out_row = (long long)a.P * a.n_out;
+  s.items = (long long)a.P * a.pairs_per_p;
+  s.n = a.n; s.n_out = a.n_out; s.P = a.P; s.pairs_per_p = (int)a.pairs_per_p;
+  s.odd_pair = (a.batch & 1) ? (int)(a.batch / 2) : -1;
+  s.off_in = a.N / 4 - a.in_left; s.off_out = a.N / 4 - a.out_left;
+  s.lines = (a.n * 8 + 127) / 128;
+  auto kern = fullwin ? fftlog_stream_kernel<true> : fftlog_stream_kernel<false>;
+  CPF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM_BYTES));
+  int dev = 0, sms = 0;
+  CPF_CUDA(cudaGetDevice(&dev));
+  CPF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  long long grid = (s.items + 1) / 2;
+  if (grid > sms) grid = sms;
+  kern<<<(unsigned)grid, 512, ST_SMEM_BYTES, stream>>>(s, pl->d_st_tw, pl->d_st_ut, pl->d_m256);
+  CPF_CUDA(cudaGetLastError());
+  return CPF_OK;
+}
+
 template <int R1>
 static int launch_pp_mode(const FftlogArgs& a, const double2* tab, int mode, cudaStream_t stream) {
   if (mode == 3) mode = 0;
@@ -776,6 +832,7 @@ static int launch_pp_mode(const FftlogArgs& a, const double2* tab, int mode, cud
 static int pp_mode() {
   const char* e = getenv("CPF_FFTLOG_KERNEL");
   if (!e) return -1;
+  if (e[0] == 's') return 4;   // stream kernel
   if (e[0] == 'p' && e[1] == 'p' && e[2] >= '0' && e[2] <= '3') return e[2] - '0';   // pp3 = pp16 kernel
   return -1;
 }
@@ -806,6 +863,9 @@ static int launch_fftlog(const cpf_plan* pl, FftlogArgs a, bool pruned, cudaStre
     a.tw2 = pl->d_tw2;
     if (pruned && pl->d_pp && pp_mode() >= 0) {
       const int mode = pp_mode();
+      if (mode == 4) {
+        if (pl->d_st_tw) return launch_stream(pl, a, stream);
+      } else
       if (mode == 3 && pl->d_pp16) return launch_pp16(a, pl->d_pp16, pl->d_m256, stream);
       switch (pl->fast_R1) {
         case 16: return launch_pp_mode<16>(a, pl->d_pp, mode, stream);

@@ -12,3 +12,14 @@ def test_three_pass_fft_emulation():
         res = subprocess.run([exe], capture_output=True, text=True)
     assert res.returncode == 0, res.stdout
     assert 'OK' in res.stdout
+
+
+def test_stream_kernel_flow_emulation():
+    """Data flow of the stream kernel (cpf_stream_core.h): slot ownership, warp-local exchanges, twiddle tables."""
+    here = os.path.dirname(os.path.abspath(__file__))
+    with tempfile.TemporaryDirectory() as tmp:
+        exe = os.path.join(tmp, 'emul_stream')
+        subprocess.run(['g++', '-O2', '-std=c++17', '-o', exe, os.path.join(here, 'emul', 'emul_stream.cpp')], check=True)
+        res = subprocess.run([exe], capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout
+    assert 'OK' in res.stdout
