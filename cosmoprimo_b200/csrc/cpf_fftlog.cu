@@ -531,12 +531,15 @@ static int generic_twiddles(int device, int N, double2** out) {
 }
 
 // staging streams for host-pointer calls (H2D / kernel / D2H of successive chunks overlap)
-static const int kNumStage = 4;
+static const int kNumStage = 8;
 struct StagePool {
   int device;
-  cudaStream_t s[kNumStage];
-  cudaEvent_t done[kNumStage];
+  cudaStream_t h2d, comp, d2h;      // one stream per engine: the two copy queues never wait behind a kernel
+  cudaEvent_t in_ready[kNumStage];  // H2D of the chunk in buffer i has landed
+  cudaEvent_t k_done[kNumStage];    // kernel on buffer i finished (input buffer i is free, output buffer i is full)
+  cudaEvent_t out_free[kNumStage];  // D2H of buffer i finished
   cudaEvent_t start;
+  std::mutex busy;                  // host-pointer calls on one device are serialised
 };
 static std::mutex g_stage_mutex;
 static std::vector<StagePool*> g_stage_pools;
@@ -547,9 +550,13 @@ static int stage_pool(int device, StagePool** out) {
     if (e->device == device) { *out = e; return CPF_OK; }
   StagePool* sp = new StagePool();
   sp->device = device;
+  CPF_CUDA(cudaStreamCreateWithFlags(&sp->h2d, cudaStreamNonBlocking));
+  CPF_CUDA(cudaStreamCreateWithFlags(&sp->comp, cudaStreamNonBlocking));
+  CPF_CUDA(cudaStreamCreateWithFlags(&sp->d2h, cudaStreamNonBlocking));
   for (int i = 0; i < kNumStage; ++i) {
-    CPF_CUDA(cudaStreamCreateWithFlags(&sp->s[i], cudaStreamNonBlocking));
-    CPF_CUDA(cudaEventCreateWithFlags(&sp->done[i], cudaEventDisableTiming));
+    CPF_CUDA(cudaEventCreateWithFlags(&sp->in_ready[i], cudaEventDisableTiming));
+    CPF_CUDA(cudaEventCreateWithFlags(&sp->k_done[i], cudaEventDisableTiming));
+    CPF_CUDA(cudaEventCreateWithFlags(&sp->out_free[i], cudaEventDisableTiming));
   }
   CPF_CUDA(cudaEventCreateWithFlags(&sp->start, cudaEventDisableTiming));
   // keep freed scratch in the pool instead of returning it to the OS after every call
@@ -793,7 +800,7 @@ static int launch_pp16(const FftlogArgs& a, const double2* tab, const double2* m
   return CPF_OK;
 }
 
-static int launch_stream(const cpf_plan* pl, const FftlogArgs& a, cudaStream_t stream) {
+static int launch_stream(const cpf_plan* pl, const FftlogArgs& a, cudaStream_t stream, int variant = 1) {
   if (a.pairs_per_p > 2147483000LL) return fail(CPF_EUNSUPPORTED, "cpf_fftlog: batch too large for one launch");
   const bool fullwin = a.n == a.N / 2 && a.in_left == a.N / 4 && a.out_left == a.N / 4;
   StreamArgs s;
@@ -806,13 +813,43 @@ static int launch_stream(const cpf_plan* pl, const FftlogArgs& a, cudaStream_t s
   s.odd_pair = (a.batch & 1) ? (int)(a.batch / 2) : -1;
   s.off_in = a.N / 4 - a.in_left; s.off_out = a.N / 4 - a.out_left;
   s.lines = (a.n * 8 + 127) / 128;
-  auto kern = fullwin ? fftlog_stream_kernel<true> : fftlog_stream_kernel<false>;
-  CPF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM_BYTES));
   int dev = 0, sms = 0;
   CPF_CUDA(cudaGetDevice(&dev));
   CPF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   long long grid = (s.items + 1) / 2;
   if (grid > sms) grid = sms;
+  if (variant >= 2) {   // 2: 2 groups interleaved, 3: 3 groups interleaved, 4: 3 groups sequential, 5: 2 groups sequential
+    const int ng = (variant == 3 || variant == 4) ? 3 : 2;
+    void (*kern)(const StreamArgs, const double2*, const double2*, const double2*) = nullptr;
+    if (variant == 2) kern = fullwin ? fftlog_stream2_kernel<true, 2, true> : fftlog_stream2_kernel<false, 2, true>;
+    else if (variant == 3) kern = fullwin ? fftlog_stream2_kernel<true, 3, true> : fftlog_stream2_kernel<false, 3, true>;
+    else if (variant == 4) kern = fullwin ? fftlog_stream2_kernel<true, 3, false> : fftlog_stream2_kernel<false, 3, false>;
+    else kern = fullwin ? fftlog_stream2_kernel<true, 2, false> : fftlog_stream2_kernel<false, 2, false>;
+    const int smem = ng == 3 ? st2_smem_bytes<3>() : st2_smem_bytes<2>();
+    CPF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    grid = (s.items + ng - 1) / ng;
+    if (grid > sms) grid = sms;
+    kern<<<(unsigned)grid, 128 * ng, smem, stream>>>(s, pl->d_st_tw, pl->d_st_ut, pl->d_m256);
+    CPF_CUDA(cudaGetLastError());
+    return CPF_OK;
+  }
+  auto kern = fullwin ? fftlog_stream_kernel<true> : fftlog_stream_kernel<false>;
+#ifdef CPF_LAB
+  if (const char* e = getenv("CPF_STREAM_ABL")) {
+    switch (atoi(e)) {
+      case 1: kern = fftlog_stream_kernel<true, 1>; break;
+      case 2: kern = fftlog_stream_kernel<true, 2>; break;
+      case 4: kern = fftlog_stream_kernel<true, 4>; break;
+      case 8: kern = fftlog_stream_kernel<true, 8>; break;
+      case 12: kern = fftlog_stream_kernel<true, 12>; break;
+      case 14: kern = fftlog_stream_kernel<true, 14>; break;
+      case 15: kern = fftlog_stream_kernel<true, 15>; break;
+      case 13: kern = fftlog_stream_kernel<true, 13>; break;
+      default: break;
+    }
+  }
+#endif
+  CPF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM_BYTES));
   kern<<<(unsigned)grid, 512, ST_SMEM_BYTES, stream>>>(s, pl->d_st_tw, pl->d_st_ut, pl->d_m256);
   CPF_CUDA(cudaGetLastError());
   return CPF_OK;
@@ -832,7 +869,7 @@ static int launch_pp_mode(const FftlogArgs& a, const double2* tab, int mode, cud
 static int pp_mode() {
   const char* e = getenv("CPF_FFTLOG_KERNEL");
   if (!e) return -1;
-  if (e[0] == 's') return 4;   // stream kernel
+  if (e[0] == 's') return (e[6] >= '2' && e[6] <= '5') ? 3 + (e[6] - '0') : 4;   // stream, stream2..stream5
   if (e[0] == 'p' && e[1] == 'p' && e[2] >= '0' && e[2] <= '3') return e[2] - '0';   // pp3 = pp16 kernel
   return -1;
 }
@@ -863,8 +900,8 @@ static int launch_fftlog(const cpf_plan* pl, FftlogArgs a, bool pruned, cudaStre
     a.tw2 = pl->d_tw2;
     if (pruned && pl->d_pp && pp_mode() >= 0) {
       const int mode = pp_mode();
-      if (mode == 4) {
-        if (pl->d_st_tw) return launch_stream(pl, a, stream);
+      if (mode >= 4) {
+        if (pl->d_st_tw) return launch_stream(pl, a, stream, mode - 3);
       } else
       if (mode == 3 && pl->d_pp16) return launch_pp16(a, pl->d_pp16, pl->d_m256, stream);
       switch (pl->fast_R1) {
@@ -960,46 +997,73 @@ static int run_staged(int device, const double* in, size_t in_row_doubles, doubl
   }
   StagePool* sp = nullptr;
   CPF_TRY(stage_pool(device, &sp));
+  std::lock_guard<std::mutex> lock(sp->busy);
   const size_t row_bytes = (in_row_doubles > out_row_doubles ? in_row_doubles : out_row_doubles) * sizeof(double);
-  long long cap = (long long)((16u << 20) / (row_bytes ? row_bytes : 1));
+  // tuning knobs (bytes / count): CPF_STAGE_CAP_KB (largest chunk), CPF_STAGE_SMALL_KB (first and last chunk), CPF_STAGE_NBUF
+  size_t cap_bytes = 16u << 20, small_bytes = 1u << 20;
+  int max_buf = 4;
+  if (const char* e = getenv("CPF_STAGE_CAP_KB")) cap_bytes = (size_t)atoll(e) << 10;
+  if (const char* e = getenv("CPF_STAGE_SMALL_KB")) small_bytes = (size_t)atoll(e) << 10;
+  if (const char* e = getenv("CPF_STAGE_NBUF")) max_buf = atoi(e);
+  if (max_buf < 1) max_buf = 1;
+  if (max_buf > kNumStage) max_buf = kNumStage;
+  long long cap = (long long)(cap_bytes / (row_bytes ? row_bytes : 1));
   cap = cap < 2 ? 2 : (cap & ~1LL);                 // even, so that row pairs never straddle chunks
-  long long small = (long long)((1u << 20) / (row_bytes ? row_bytes : 1));
+  long long small = (long long)(small_bytes / (row_bytes ? row_bytes : 1));
   small = small < 2 ? 2 : (small & ~1LL);
   const std::vector<long long> sched = chunk_schedule(rows, small, cap);
-  const int nbuf = sched.size() < (size_t)kNumStage ? (int)sched.size() : kNumStage;
+  const int nbuf = sched.size() < (size_t)max_buf ? (int)sched.size() : max_buf;
   const long long buf_rows = rows < cap ? rows : cap;
   ScratchBuf din[kNumStage], dout[kNumStage];
   CPF_CUDA(cudaEventRecord(sp->start, user_stream));
+  CPF_CUDA(cudaStreamWaitEvent(sp->h2d, sp->start, 0));
+  CPF_CUDA(cudaStreamWaitEvent(sp->comp, sp->start, 0));
+  CPF_CUDA(cudaStreamWaitEvent(sp->d2h, sp->start, 0));
   for (int i = 0; i < nbuf; ++i) {
-    CPF_CUDA(cudaStreamWaitEvent(sp->s[i], sp->start, 0));
-    if (!in_dev) CPF_CUDA(din[i].alloc((size_t)buf_rows * in_row_doubles * sizeof(double), sp->s[i]));
-    if (!out_dev) CPF_CUDA(dout[i].alloc((size_t)buf_rows * out_row_doubles * sizeof(double), sp->s[i]));
+    if (!in_dev) CPF_CUDA(din[i].alloc((size_t)buf_rows * in_row_doubles * sizeof(double), sp->comp));
+    if (!out_dev) CPF_CUDA(dout[i].alloc((size_t)buf_rows * out_row_doubles * sizeof(double), sp->comp));
   }
+  // the copy streams may touch the buffers only after the (stream-ordered) allocations on the compute stream
+  CPF_CUDA(cudaEventRecord(sp->start, sp->comp));
+  CPF_CUDA(cudaStreamWaitEvent(sp->h2d, sp->start, 0));
+  CPF_CUDA(cudaStreamWaitEvent(sp->d2h, sp->start, 0));
   int rc = CPF_OK;
   long long first = 0;
   for (size_t c = 0; c < sched.size() && rc == CPF_OK; ++c) {
     const int i = (int)(c % nbuf);
+    const bool reused = c >= (size_t)nbuf;
     const long long cnt = sched[c];
     const double* src = in + (size_t)first * in_row_doubles;
     double* dst = out + (size_t)first * out_row_doubles;
     const double* d_in = src;
     double* d_out = dst;
+    cudaError_t e = cudaSuccess;
     if (!in_dev) {
       d_in = (const double*)din[i].p;
-      cudaError_t e = cudaMemcpyAsync(din[i].p, src, (size_t)cnt * in_row_doubles * sizeof(double), cudaMemcpyHostToDevice, sp->s[i]);
+      if (reused) e = cudaStreamWaitEvent(sp->h2d, sp->k_done[i], 0);          // the kernel that read buffer i is done
+      if (e == cudaSuccess) e = cudaMemcpyAsync(din[i].p, src, (size_t)cnt * in_row_doubles * sizeof(double), cudaMemcpyHostToDevice, sp->h2d);
+      if (e == cudaSuccess) e = cudaEventRecord(sp->in_ready[i], sp->h2d);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(sp->comp, sp->in_ready[i], 0);
       if (e != cudaSuccess) { rc = fail(CPF_ECUDA, "H2D copy: %s", cudaGetErrorString(e)); break; }
     }
-    if (!out_dev) d_out = (double*)dout[i].p;
-    rc = body(first, cnt, d_in, d_out, sp->s[i]);
-    if (rc != CPF_OK) break;
     if (!out_dev) {
-      cudaError_t e = cudaMemcpyAsync(dst, d_out, (size_t)cnt * out_row_doubles * sizeof(double), cudaMemcpyDeviceToHost, sp->s[i]);
-      if (e != cudaSuccess) { rc = fail(CPF_ECUDA, "D2H copy: %s", cudaGetErrorString(e)); break; }
+      d_out = (double*)dout[i].p;
+      if (reused) e = cudaStreamWaitEvent(sp->comp, sp->out_free[i], 0);       // the D2H copy out of buffer i is done
+      if (e != cudaSuccess) { rc = fail(CPF_ECUDA, "stream wait: %s", cudaGetErrorString(e)); break; }
     }
+    rc = body(first, cnt, d_in, d_out, sp->comp);
+    if (rc != CPF_OK) break;
+    e = cudaEventRecord(sp->k_done[i], sp->comp);
+    if (e == cudaSuccess && !out_dev) {
+      e = cudaStreamWaitEvent(sp->d2h, sp->k_done[i], 0);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(dst, d_out, (size_t)cnt * out_row_doubles * sizeof(double), cudaMemcpyDeviceToHost, sp->d2h);
+      if (e == cudaSuccess) e = cudaEventRecord(sp->out_free[i], sp->d2h);
+    }
+    if (e != cudaSuccess) { rc = fail(CPF_ECUDA, "D2H copy: %s", cudaGetErrorString(e)); break; }
     first += cnt;
   }
-  for (int i = 0; i < nbuf; ++i) {
-    cudaError_t e = cudaStreamSynchronize(sp->s[i]);
+  for (cudaStream_t st : {sp->h2d, sp->comp, sp->d2h}) {
+    cudaError_t e = cudaStreamSynchronize(st);
     if (e != cudaSuccess && rc == CPF_OK) rc = fail(CPF_ECUDA, "stream sync: %s", cudaGetErrorString(e));
   }
   return rc;
