@@ -258,7 +258,9 @@ def run_ours(args):
     torch.cuda.synchronize()
     e2e_elapsed = max_over_ranks(time.perf_counter() - t0)
     e2e_value = world * per_step * e2e_steps / e2e_elapsed
-    assert np.array_equal(h_out, out.cpu().numpy())   # both paths ran the same kernel on the same data
+    # the host path runs the per-pair kernel on 16 MB chunks, the device path the persistent kernel: same transform, different rounding
+    d_out = out.cpu().numpy()
+    assert np.max(np.abs(h_out - d_out)) <= 1e-13 * np.max(np.abs(d_out))
 
     if rank != 0:
         return
@@ -276,7 +278,7 @@ def run_ours(args):
         roof = {'bound': 'fp64', 'achieved': ach_tflops, 'peak': f64_tflops, 'unit': 'TFLOP/s', 'frac': ach_tflops / f64_tflops}
     else:
         roof = {'bound': 'hbm', 'achieved': ach_gbs, 'peak': hbm_gbs, 'unit': 'GB/s', 'frac': ach_gbs / hbm_gbs}
-    roof.update({'traffic': None, 'kernel': 'fftlog_fast_kernel<16,pruned>', 'launch_ms': 1e3 * t_launch,
+    roof.update({'traffic': None, 'kernel': 'fftlog_stream_kernel<fullwin> (CPF_FFTLOG_KERNEL=%s)' % os.environ.get('CPF_FFTLOG_KERNEL', 'auto'), 'launch_ms': 1e3 * t_launch,
                  'algorithmic_flops_per_launch': per_step * FLOPS_PER_TRANSFORM, 'algorithmic_bytes_per_launch': per_step * BYTES_PER_TRANSFORM,
                  'peak_source': 'fp64: DFMA microbenchmark in this run (cpf_measure_fp64_peak); hbm: ' + hbm_src,
                  'hbm': {'achieved': ach_gbs, 'peak': hbm_gbs, 'unit': 'GB/s', 'frac': ach_gbs / hbm_gbs},

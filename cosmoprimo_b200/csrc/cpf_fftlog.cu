@@ -18,6 +18,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdlib.h>
+#include <string.h>
 #include <mutex>
 #include <vector>
 
@@ -172,124 +173,6 @@ __global__ void __launch_bounds__(16 * R1, 512 / (16 * R1)) fftlog_fast_kernel(c
   }
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// persistent fast path (zero padding, cropped output, real post-factor): one 512-thread CTA per SM, split into
-// NG = 512/T independent groups that each process one pair of rows at a time.  Everything batch-invariant (FFT
-// twiddles, kernel spectrum, pre/post factors of the current plan row) is staged in shared memory once per CTA and plan
-// row, so the steady state touches L1/L2/HBM for the input and output rows only; the next pair's rows are prefetched
-// into L2 while the current pair is transformed.  (r01a profile: with per-CTA table loads through L1 the top stall
-// was long_scoreboard on those loads.)
-// ---------------------------------------------------------------------------------------------------------------
-template <int R1>
-struct PersistentSmem {
-  typedef Geo<R1> G;
-  static constexpr int NG = 512 / G::T;
-  static constexpr int EXCH = NG * G::SMEM_ELEMS;          // double2
-  static constexpr int TW1 = 6 * 256, TW2 = 6 * 16;
-  static constexpr int UH = G::N / 2 + 2;                  // N/2+1 rounded up to even
-  static constexpr int WIN = G::N / 4;                     // N/2 doubles = N/4 double2
-  static constexpr int TOTAL = EXCH + TW1 + TW2 + UH + 2 * WIN;
-  static constexpr size_t BYTES = (size_t)TOTAL * sizeof(double2);
-};
-
-__device__ __forceinline__ void group_barrier(const int g, const int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(nthreads) : "memory");
-}
-
-template <int R1>
-__global__ void __launch_bounds__(512, 1) fftlog_persistent_kernel(const FftlogArgs a) {
-  typedef Geo<R1> G;
-  typedef PersistentSmem<R1> L;
-  constexpr int T = G::T, N = G::N, NG = L::NG;
-  extern __shared__ double2 smem[];
-  const int g = threadIdx.x / T, t = threadIdx.x - g * T;
-  double2* S = smem + g * G::SMEM_ELEMS;
-  double2* s_tw1 = smem + L::EXCH;
-  double2* s_tw2 = s_tw1 + L::TW1;
-  double2* s_uh = s_tw2 + L::TW2;
-  double* s_pre = reinterpret_cast<double*>(s_uh + L::UH);
-  double* s_post = s_pre + N / 2;
-
-  for (int i = threadIdx.x; i < L::TW1; i += 512) s_tw1[i] = a.tw1[i];
-  for (int i = threadIdx.x; i < L::TW2; i += 512) s_tw2[i] = a.tw2[i];
-
-  for (int p = 0; p < a.P; ++p) {
-    __syncthreads();   // everybody is done with the previous plan row's tables
-    {
-      const double2* uh = a.ut + (size_t)p * (N / 2 + 1);
-      const double* pre = a.pre + (size_t)p * N + N / 4;
-      const double* post = a.post_re + (size_t)p * N + N / 4;
-      for (int i = threadIdx.x; i < N / 2 + 1; i += 512) s_uh[i] = uh[i];
-      for (int i = threadIdx.x; i < N / 2; i += 512) { s_pre[i] = pre[i]; s_post[i] = post[i]; }
-    }
-    __syncthreads();
-
-    const long long stride = (long long)gridDim.x * NG;
-    for (long long pair = (long long)blockIdx.x * NG + g; pair < a.pairs_per_p; pair += stride) {
-      const long long b0 = 2 * pair, b1 = b0 + 1;
-      const bool has1 = b1 < a.batch;
-      const double* rowA = a.in + (a.in_has_P ? (b0 * a.P + p) : b0) * (long long)a.n;
-      const double* rowB = has1 ? a.in + (a.in_has_P ? (b1 * a.P + p) : b1) * (long long)a.n : rowA;
-      // L2 prefetch of the rows this group transforms next
-      {
-        const long long nb0 = 2 * (pair + stride);
-        if (nb0 < a.batch) {
-          const int lines = (a.n * 8 + 127) / 128;
-          const double* nA = a.in + (a.in_has_P ? (nb0 * a.P + p) : nb0) * (long long)a.n;
-          const double* nB = nb0 + 1 < a.batch ? a.in + (a.in_has_P ? ((nb0 + 1) * a.P + p) : nb0 + 1) * (long long)a.n : nA;
-          for (int l = t; l < 2 * lines; l += T) {
-            const double* q = (l < lines ? nA : nB) + (size_t)(l < lines ? l : l - lines) * 16;
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
-          }
-        }
-      }
-      double2 v[16];
-#pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        const int jw = t + T * r;                      // index inside the window [N/4, 3N/4)
-        const int i = jw + N / 4 - a.in_left;
-        const bool ok = (unsigned)i < (unsigned)a.n;
-        const double x = ok ? __ldcs(rowA + i) : 0.;
-        const double y = (ok && has1) ? __ldcs(rowB + i) : 0.;
-        const double pr = s_pre[jw];
-        v[r] = mk2(x * pr, y * pr);
-      }
-#pragma unroll
-      for (int r = 8; r < 16; ++r) v[r] = mk2(0., 0.);
-
-      fft_pass1<R1, true>(t, v, S, s_tw1);
-      group_barrier(g, T);
-      fft_pass2<R1>(t, S, s_tw2);
-      group_barrier(g, T);
-      fft_pass3<R1, false>(t, v, S);
-#pragma unroll
-      for (int r = 0; r < 8; ++r) v[r] = cmul(v[r], s_uh[t + T * r]);
-#pragma unroll
-      for (int r = 8; r < 16; ++r) v[r] = cmul_conj(v[r], s_uh[T * (16 - r) - t]);
-      group_barrier(g, T);
-      fft_pass1<R1, false>(t, v, S, s_tw1);
-      group_barrier(g, T);
-      fft_pass2<R1>(t, S, s_tw2);
-      group_barrier(g, T);
-      fft_pass3<R1, true>(t, v, S);
-
-      double* outA = a.out + (size_t)(b0 * a.P + p) * a.n_out;
-      double* outB = a.out + (size_t)(b1 * a.P + p) * a.n_out;
-#pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        const int jw = t + T * r;
-        const int o = jw + N / 4 - a.out_left;
-        if ((unsigned)o < (unsigned)a.n_out) {
-          const double pr = s_post[jw];
-          __stcs(outA + o, v[r].x * pr);
-          if (has1) __stcs(outB + o, v[r].y * pr);
-        }
-      }
-      group_barrier(g, T);   // pass-3 reads of S are done before the next pair's pass 1 overwrites it
-    }
-  }
-}
-
 }  // namespace cpf
 
 #include "cpf_fftlog_pp.cuh"
@@ -434,18 +317,17 @@ int upload(void** dptr, const void* src, size_t bytes) {
 
 static int fast_radix(int N) { return N == 4096 ? 16 : N == 2048 ? 8 : N == 1024 ? 4 : 0; }
 
-// per-thread table records of the ping-pong kernel (layout: cpf_fftlog_pp.cuh).  uhs = (-1)^k u/N, [P, N/2+1].
+// per-thread table records of the ping-pong kernel (layout: cpf_fftlog_pp.cuh).  uhs = (-1)^k u/N, [P, N/2+1];
+// tw = the batch-invariant part of a record ([T][32], see FastTw)
 static void build_pp_tables(int N, int R1, int P, const double* pre, const std::vector<double2>& uhs, const double* post_re,
-                            std::vector<double2>& tab) {
-  const int T = 16 * R1, C = 16 / R1, nb = N / 2 + 1;
+                            const std::vector<double2>& tw, std::vector<double2>& tab) {
+  const int T = 16 * R1, nb = N / 2 + 1;
   double2 zero; zero.x = 0.; zero.y = 0.;
   tab.assign((size_t)P * T * PP_REC, zero);
   for (int p = 0; p < P; ++p)
     for (int t = 0; t < T; ++t) {
       double2* rec = &tab[((size_t)p * T + t) * PP_REC];
-      for (int c = 0; c < C; ++c)
-        for (int k1 = 0; k1 < R1; ++k1) rec[c * R1 + k1] = unit_root((long long)(t + T * c) * k1, N);
-      for (int l1 = 0; l1 < 16; ++l1) rec[16 + l1] = unit_root((long long)(t & 15) * l1, 256);
+      for (int e = 0; e < 32; ++e) rec[e] = tw[(size_t)t * 32 + e];
       for (int r = 0; r < 16; ++r) {
         const int k = t + T * r;
         double2 v = uhs[(size_t)p * nb + (k <= N / 2 ? k : N - k)];
@@ -462,50 +344,77 @@ static void build_pp_tables(int N, int R1, int P, const double* pre, const std::
     }
 }
 
-// records of fftlog_pp16_kernel: thread 16 h + i holds bins h + 16 i + 256 r after FFT #1
-static void build_pp16_tables(int P, const std::vector<double2>& uhs, std::vector<double2>& tab, std::vector<double2>& m256) {
+// kernel spectrum in the order fftlog_stream_kernel reads it (cpf_fftlog_stream.cuh): [P][16][256], thread tau = 16 H + L
+// holds the bins H + 16 L + 256 l2
+static void build_stream_ut(int P, const std::vector<double2>& uhs, double2* ut) {
   const int N = 4096, T = 256, nb = N / 2 + 1;
-  double2 zero; zero.x = 0.; zero.y = 0.;
-  tab.assign((size_t)P * T * PP_REC, zero);
-  m256.resize(256);
-  for (int hh = 0; hh < 16; ++hh)
-    for (int l = 0; l < 16; ++l) m256[16 * hh + l] = unit_root(hh * l, 256);
   for (int p = 0; p < P; ++p)
-    for (int t = 0; t < T; ++t) {
-      const int hh = t >> 4, ii = t & 15;
-      double2* rec = &tab[((size_t)p * T + t) * PP_REC];
+    for (int t = 0; t < T; ++t)
       for (int k = 0; k < 16; ++k) {
-        rec[k] = unit_root((long long)t * k, N);                       // FFT #1 pass 1: n2 = t
-        rec[16 + k] = unit_root(ii * k, 256);                          // FFT #1 pass 2: m2 = i
-        rec[48 + k] = unit_root((long long)(hh + 16 * ii) * k, N);     // FFT #2 pass 1: n2' = h + 16 i
-        const int bin = hh + 16 * ii + 256 * k;
+        const int bin = (t >> 4) + 16 * (t & 15) + 256 * k;
         double2 v = uhs[(size_t)p * nb + (bin <= N / 2 ? bin : N - bin)];
         if (bin > N / 2) v.y = -v.y;
-        rec[32 + k] = v;
+        ut[((size_t)p * 16 + k) * T + t] = v;
       }
-    }
 }
 
-// tables of fftlog_stream_kernel (cpf_fftlog_stream.cuh): thread tau = 16 H + L
-static void build_stream_tables(int P, const std::vector<double2>& uhs, std::vector<double2>& tw, std::vector<double2>& ut) {
-  const int N = 4096, T = 256, nb = N / 2 + 1;
-  tw.resize((size_t)T * 48);
-  ut.resize((size_t)P * T * 16);
-  for (int t = 0; t < T; ++t) {
-    const int H = t >> 4, L = t & 15;
-    for (int k = 0; k < 16; ++k) {
-      tw[(size_t)t * 48 + k] = unit_root((long long)t * k, N);                    // P1 : w_4096^{tau k1}
-      tw[(size_t)t * 48 + 16 + k] = unit_root(L * k, 256);                        // P2 : w_256^{L l1}
-      tw[(size_t)t * 48 + 32 + k] = unit_root((long long)(H + 16 * L) * k, N);    // P1': w_4096^{(H + 16 L) k1'}
-    }
-    for (int p = 0; p < P; ++p)
-      for (int k = 0; k < 16; ++k) {
-        const int bin = H + 16 * L + 256 * k;
-        double2 v = uhs[(size_t)p * nb + (bin <= N / 2 ? bin : N - bin)];
-        if (bin > N / 2) v.y = -v.y;
-        ut[((size_t)p * T + t) * 16 + k] = v;
-      }
+// Batch- and plan-invariant twiddle tables of the register kernels, built once per (device, N) and never freed.
+struct FastTw {
+  int device, N;
+  double2* d_tw1;                 // per-pair kernel: [6, 256] factored pass-1 twiddles (cpf_fft_core.h)
+  double2* d_tw2;                 // per-pair kernel: [6, 16]
+  double2* d_st_tw;               // stream kernel (N = 4096): P1 / P2 / P1' twiddles [3, 16, 256]
+  double2* d_m256;                // stream kernel: P2' twiddles w_256^{h l}, [16, 16]
+  std::vector<double2> pp_tw;     // host: twiddle part of the ping-pong records, [T][32]
+};
+static std::mutex g_fast_mutex;
+static std::vector<FastTw*> g_fast_cache;
+
+static int fast_twiddles(int device, int N, const FastTw** out) {
+  std::lock_guard<std::mutex> lock(g_fast_mutex);
+  for (auto* e : g_fast_cache)
+    if (e->device == device && e->N == N) { *out = e; return CPF_OK; }
+  const int R1 = N / 256, T = 16 * R1, C = 16 / R1;
+  FastTw* f = new FastTw();
+  f->device = device; f->N = N;
+  f->d_tw1 = f->d_tw2 = f->d_st_tw = f->d_m256 = nullptr;
+  static const int expo[6] = {1, 2, 3, 4, 8, 12};
+  std::vector<double2> tw1(6 * 256), tw2(6 * 16);
+  for (int e = 0; e < 6; ++e) {
+    for (int n2 = 0; n2 < 256; ++n2) tw1[e * 256 + n2] = unit_root((long long)expo[e] * n2, N);
+    for (int m2 = 0; m2 < 16; ++m2) tw2[e * 16 + m2] = unit_root(expo[e] * m2, 256);
   }
+  f->pp_tw.resize((size_t)T * 32);
+  for (int t = 0; t < T; ++t) {
+    for (int c = 0; c < C; ++c)
+      for (int k1 = 0; k1 < R1; ++k1) f->pp_tw[(size_t)t * 32 + c * R1 + k1] = unit_root((long long)(t + T * c) * k1, N);
+    for (int l1 = 0; l1 < 16; ++l1) f->pp_tw[(size_t)t * 32 + 16 + l1] = unit_root((long long)(t & 15) * l1, 256);
+  }
+  int rc = upload((void**)&f->d_tw1, tw1.data(), tw1.size() * sizeof(double2));
+  if (rc == CPF_OK) rc = upload((void**)&f->d_tw2, tw2.data(), tw2.size() * sizeof(double2));
+  if (rc == CPF_OK && N == 4096) {
+    std::vector<double2> stw((size_t)48 * 256), m256(256);
+    for (int t = 0; t < 256; ++t) {
+      const int H = t >> 4, L = t & 15;
+      for (int k = 0; k < 16; ++k) {
+        stw[(size_t)k * 256 + t] = unit_root((long long)t * k, N);                        // P1 : w_4096^{tau k1}
+        stw[(size_t)(16 + k) * 256 + t] = unit_root(L * k, 256);                          // P2 : w_256^{L l1}
+        stw[(size_t)(32 + k) * 256 + t] = unit_root((long long)(H + 16 * L) * k, N);      // P1': w_4096^{(H + 16 L) k1'}
+      }
+    }
+    for (int hh = 0; hh < 16; ++hh)
+      for (int l = 0; l < 16; ++l) m256[16 * hh + l] = unit_root(hh * l, 256);
+    rc = upload((void**)&f->d_st_tw, stw.data(), stw.size() * sizeof(double2));
+    if (rc == CPF_OK) rc = upload((void**)&f->d_m256, m256.data(), m256.size() * sizeof(double2));
+  }
+  if (rc != CPF_OK) {
+    cudaFree(f->d_tw1); cudaFree(f->d_tw2); cudaFree(f->d_st_tw); cudaFree(f->d_m256);
+    delete f;
+    return rc;
+  }
+  g_fast_cache.push_back(f);
+  *out = f;
+  return CPF_OK;
 }
 
 // per-device twiddle cache for the unfused engine entry points
@@ -579,19 +488,21 @@ struct cpf_plan {
   bool post_complex;
   int fast_R1;
   bool window_prunable;
+  void* d_block = nullptr;    // one device allocation holds every per-plan table below
   double* d_pre = nullptr;
   double2* d_ut = nullptr;    // generic plans: [P,N] Hermitian-extended; fast plans: [P,N/2+1]
   double2* d_uts = nullptr;   // fast plans: (-1)^k u/N  (input and output windows rotated by N/4)
   double* d_post_re = nullptr;
   double* d_post_im = nullptr;
   double2* d_tw = nullptr;    // generic [N/2]
-  double2* d_tw1 = nullptr;   // fast [6,256]
-  double2* d_tw2 = nullptr;   // fast [6,16]
-  double2* d_pp = nullptr;    // ping-pong kernel: per-thread table records [P, T, PP_REC] (cpf_fftlog_pp.cuh)
-  double2* d_pp16 = nullptr;  // N = 4096 variant with warp-local exchanges: records [P, 256, PP_REC]
-  double2* d_m256 = nullptr;  // its shared pass-2 twiddle table [16, 16]
-  double2* d_st_tw = nullptr; // stream kernel: P1 / P2 / P1' twiddles [256, 3, 16]
-  double2* d_st_ut = nullptr; // stream kernel: kernel spectrum per thread [P, 256, 16]
+  double2* d_st_ut = nullptr; // stream kernel: kernel spectrum per thread [P, 16, 256]
+  const FastTw* fast = nullptr;   // batch-invariant twiddles of the register kernels (shared, not owned)
+  // ping-pong kernel: per-thread table records [P, T, PP_REC] (cpf_fftlog_pp.cuh); built at plan creation for
+  // N = 2048 / 1024, on first use for N = 4096 (where the stream kernel is the default)
+  mutable double2* d_pp = nullptr;
+  mutable std::mutex pp_mutex;
+  std::vector<double> h_pre_win, h_post_win;   // host copies kept for the lazy ping-pong tables (N = 4096 only)
+  std::vector<double2> h_uhs;
 };
 
 extern "C" {
@@ -613,19 +524,8 @@ int cpf_device_count(int* count) {
 int cpf_plan_destroy(cpf_plan* plan) {
   if (!plan) return CPF_OK;
   DeviceGuard guard(plan->device);
-  cudaFree(plan->d_pre);
-  cudaFree(plan->d_ut);
-  cudaFree(plan->d_uts);
-  cudaFree(plan->d_post_re);
-  cudaFree(plan->d_post_im);
-  cudaFree(plan->d_tw);
-  cudaFree(plan->d_tw1);
-  cudaFree(plan->d_tw2);
+  cudaFree(plan->d_block);
   cudaFree(plan->d_pp);
-  cudaFree(plan->d_pp16);
-  cudaFree(plan->d_m256);
-  cudaFree(plan->d_st_tw);
-  cudaFree(plan->d_st_ut);
   delete plan;
   return CPF_OK;
 }
@@ -665,38 +565,37 @@ int cpf_plan_create(cpf_plan** out, int n, int N, int P, int in_left, int out_le
       v.y = (m == 0 || m == N / 2) ? 0. : u_ri[2 * ((size_t)p * nb + m) + 1] * inv;
       uh[(size_t)p * nb + m] = v;
     }
+  // every per-plan table goes into one host staging buffer and one device allocation (one cudaMalloc + one copy)
+  std::vector<char> stage;
+  auto put = [&stage](const void* src, size_t bytes) {
+    const size_t off = (stage.size() + 255) & ~(size_t)255;
+    stage.resize(off + bytes);
+    if (src) memcpy(stage.data() + off, src, bytes);
+    return off;
+  };
+  const size_t NONE = ~(size_t)0;
+  size_t o_pre = put(pre, PN * sizeof(double)), o_post = put(post_re, PN * sizeof(double));
+  size_t o_post_im = post_im ? put(post_im, PN * sizeof(double)) : NONE;
+  size_t o_ut = NONE, o_uts = NONE, o_st_ut = NONE;
+  std::vector<double2> pp_tab;
   int rc = CPF_OK;
   do {
-    if ((rc = upload((void**)&pl->d_pre, pre, PN * sizeof(double)))) break;
-    if ((rc = upload((void**)&pl->d_post_re, post_re, PN * sizeof(double)))) break;
-    if (post_im && (rc = upload((void**)&pl->d_post_im, post_im, PN * sizeof(double)))) break;
     if (pl->fast_R1) {
+      if ((rc = fast_twiddles(device, N, &pl->fast))) break;
       std::vector<double2> uhs(uh);
       for (int p = 0; p < P; ++p)
         for (int m = 1; m < nb; m += 2) { uhs[(size_t)p * nb + m].x = -uhs[(size_t)p * nb + m].x; uhs[(size_t)p * nb + m].y = -uhs[(size_t)p * nb + m].y; }
-      if ((rc = upload((void**)&pl->d_ut, uh.data(), uh.size() * sizeof(double2)))) break;
-      if ((rc = upload((void**)&pl->d_uts, uhs.data(), uhs.size() * sizeof(double2)))) break;
-      static const int expo[6] = {1, 2, 3, 4, 8, 12};
-      std::vector<double2> tw1(6 * 256), tw2(6 * 16);
-      for (int e = 0; e < 6; ++e) {
-        for (int n2 = 0; n2 < 256; ++n2) tw1[e * 256 + n2] = unit_root((long long)expo[e] * n2, N);
-        for (int m2 = 0; m2 < 16; ++m2) tw2[e * 16 + m2] = unit_root(expo[e] * m2, 256);
-      }
-      if ((rc = upload((void**)&pl->d_tw1, tw1.data(), tw1.size() * sizeof(double2)))) break;
-      if ((rc = upload((void**)&pl->d_tw2, tw2.data(), tw2.size() * sizeof(double2)))) break;
+      o_ut = put(uh.data(), uh.size() * sizeof(double2));
+      o_uts = put(uhs.data(), uhs.size() * sizeof(double2));
       if (pl->window_prunable && !post_im) {
-        std::vector<double2> tab;
-        build_pp_tables(N, pl->fast_R1, P, pre, uhs, post_re, tab);
-        if ((rc = upload((void**)&pl->d_pp, tab.data(), tab.size() * sizeof(double2)))) break;
         if (pl->fast_R1 == 16) {
-          std::vector<double2> m256;
-          build_pp16_tables(P, uhs, tab, m256);
-          if ((rc = upload((void**)&pl->d_pp16, tab.data(), tab.size() * sizeof(double2)))) break;
-          if ((rc = upload((void**)&pl->d_m256, m256.data(), m256.size() * sizeof(double2)))) break;
-          std::vector<double2> stw, sut;
-          build_stream_tables(P, uhs, stw, sut);
-          if ((rc = upload((void**)&pl->d_st_tw, stw.data(), stw.size() * sizeof(double2)))) break;
-          if ((rc = upload((void**)&pl->d_st_ut, sut.data(), sut.size() * sizeof(double2)))) break;
+          o_st_ut = put(nullptr, (size_t)P * 16 * 256 * sizeof(double2));
+          build_stream_ut(P, uhs, reinterpret_cast<double2*>(stage.data() + o_st_ut));
+          pl->h_uhs.swap(uhs);                      // kept for the lazy ping-pong tables
+          pl->h_pre_win.assign(pre, pre + PN);
+          pl->h_post_win.assign(post_re, post_re + PN);
+        } else {
+          build_pp_tables(N, pl->fast_R1, P, pre, uhs, post_re, pl->fast->pp_tw, pp_tab);
         }
       }
     } else {
@@ -707,11 +606,20 @@ int cpf_plan_create(cpf_plan** out, int n, int N, int P, int in_left, int out_le
           if (k > N / 2) v.y = -v.y;
           ut[(size_t)p * N + k] = v;
         }
-      if ((rc = upload((void**)&pl->d_ut, ut.data(), ut.size() * sizeof(double2)))) break;
-      std::vector<double2> tw(N / 2);
-      for (int k = 0; k < N / 2; ++k) tw[k] = unit_root(k, N);
-      if ((rc = upload((void**)&pl->d_tw, tw.data(), tw.size() * sizeof(double2)))) break;
+      o_ut = put(ut.data(), ut.size() * sizeof(double2));
+      double2* tw = nullptr;
+      if ((rc = generic_twiddles(device, N, &tw))) break;
+      pl->d_tw = tw;
     }
+    if ((rc = upload(&pl->d_block, stage.data(), stage.size()))) break;
+    if (!pp_tab.empty() && (rc = upload((void**)&pl->d_pp, pp_tab.data(), pp_tab.size() * sizeof(double2)))) break;
+    char* base = static_cast<char*>(pl->d_block);
+    pl->d_pre = reinterpret_cast<double*>(base + o_pre);
+    pl->d_post_re = reinterpret_cast<double*>(base + o_post);
+    if (o_post_im != NONE) pl->d_post_im = reinterpret_cast<double*>(base + o_post_im);
+    if (o_ut != NONE) pl->d_ut = reinterpret_cast<double2*>(base + o_ut);
+    if (o_uts != NONE) pl->d_uts = reinterpret_cast<double2*>(base + o_uts);
+    if (o_st_ut != NONE) pl->d_st_ut = reinterpret_cast<double2*>(base + o_st_ut);
   } while (0);
   if (rc != CPF_OK) {
     std::string keep = g_last_error;
@@ -756,26 +664,11 @@ static int launch_fast_r(const FftlogArgs& a, bool pruned, bool cpost, long long
 }
 
 template <int R1>
-static int launch_persistent(const FftlogArgs& a, cudaStream_t stream) {
-  typedef PersistentSmem<R1> L;
-  auto kern = fftlog_persistent_kernel<R1>;
-  CPF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::BYTES));
-  int dev = 0, sms = 0;
-  CPF_CUDA(cudaGetDevice(&dev));
-  CPF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  long long grid = (a.pairs_per_p + L::NG - 1) / L::NG;
-  if (grid > sms) grid = sms;
-  kern<<<(unsigned)grid, 512, L::BYTES, stream>>>(a);
-  CPF_CUDA(cudaGetLastError());
-  return CPF_OK;
-}
-
-template <int R1, int MODE>
 static int launch_pp(const FftlogArgs& a, const double2* tab, cudaStream_t stream) {
   typedef Geo<R1> G;
   constexpr int NG = 512 / G::T;
   const size_t smem = (size_t)NG * G::SMEM_ELEMS * sizeof(double2);
-  auto kern = fftlog_pp_kernel<R1, MODE>;
+  auto kern = fftlog_pp_kernel<R1>;
   CPF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int dev = 0, sms = 0;
   CPF_CUDA(cudaGetDevice(&dev));
@@ -787,20 +680,7 @@ static int launch_pp(const FftlogArgs& a, const double2* tab, cudaStream_t strea
   return CPF_OK;
 }
 
-static int launch_pp16(const FftlogArgs& a, const double2* tab, const double2* m256, cudaStream_t stream) {
-  const size_t smem = (size_t)(2 * PP16_GROUP_ELEMS + 256) * sizeof(double2);
-  CPF_CUDA(cudaFuncSetAttribute(fftlog_pp16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int dev = 0, sms = 0;
-  CPF_CUDA(cudaGetDevice(&dev));
-  CPF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  long long grid = ((long long)a.P * a.pairs_per_p + 1) / 2;
-  if (grid > sms) grid = sms;
-  fftlog_pp16_kernel<<<(unsigned)grid, 512, smem, stream>>>(a, tab, m256);
-  CPF_CUDA(cudaGetLastError());
-  return CPF_OK;
-}
-
-static int launch_stream(const cpf_plan* pl, const FftlogArgs& a, cudaStream_t stream, int variant = 1) {
+static int launch_stream(const cpf_plan* pl, const FftlogArgs& a, cudaStream_t stream) {
   if (a.pairs_per_p > 2147483000LL) return fail(CPF_EUNSUPPORTED, "cpf_fftlog: batch too large for one launch");
   const bool fullwin = a.n == a.N / 2 && a.in_left == a.N / 4 && a.out_left == a.N / 4;
   StreamArgs s;
@@ -813,72 +693,85 @@ static int launch_stream(const cpf_plan* pl, const FftlogArgs& a, cudaStream_t s
   s.odd_pair = (a.batch & 1) ? (int)(a.batch / 2) : -1;
   s.off_in = a.N / 4 - a.in_left; s.off_out = a.N / 4 - a.out_left;
   s.lines = (a.n * 8 + 127) / 128;
+  s.dbg = nullptr;
   int dev = 0, sms = 0;
   CPF_CUDA(cudaGetDevice(&dev));
   CPF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   long long grid = (s.items + 1) / 2;
   if (grid > sms) grid = sms;
-  if (variant >= 2) {   // 2: 2 groups interleaved, 3: 3 groups interleaved, 4: 3 groups sequential, 5: 2 groups sequential
-    const int ng = (variant == 3 || variant == 4) ? 3 : 2;
-    void (*kern)(const StreamArgs, const double2*, const double2*, const double2*) = nullptr;
-    if (variant == 2) kern = fullwin ? fftlog_stream2_kernel<true, 2, true> : fftlog_stream2_kernel<false, 2, true>;
-    else if (variant == 3) kern = fullwin ? fftlog_stream2_kernel<true, 3, true> : fftlog_stream2_kernel<false, 3, true>;
-    else if (variant == 4) kern = fullwin ? fftlog_stream2_kernel<true, 3, false> : fftlog_stream2_kernel<false, 3, false>;
-    else kern = fullwin ? fftlog_stream2_kernel<true, 2, false> : fftlog_stream2_kernel<false, 2, false>;
-    const int smem = ng == 3 ? st2_smem_bytes<3>() : st2_smem_bytes<2>();
-    CPF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    grid = (s.items + ng - 1) / ng;
-    if (grid > sms) grid = sms;
-    kern<<<(unsigned)grid, 128 * ng, smem, stream>>>(s, pl->d_st_tw, pl->d_st_ut, pl->d_m256);
-    CPF_CUDA(cudaGetLastError());
-    return CPF_OK;
-  }
-  auto kern = fullwin ? fftlog_stream_kernel<true> : fftlog_stream_kernel<false>;
+  typedef void (*kern_t)(const StreamArgs, const double2*, const double2*, const double2*);
+  kern_t kern = fullwin ? (kern_t)fftlog_stream_kernel<true> : (kern_t)fftlog_stream_kernel<false>;
 #ifdef CPF_LAB
   if (const char* e = getenv("CPF_STREAM_ABL")) {
     switch (atoi(e)) {
       case 1: kern = fftlog_stream_kernel<true, 1>; break;
-      case 2: kern = fftlog_stream_kernel<true, 2>; break;
       case 4: kern = fftlog_stream_kernel<true, 4>; break;
-      case 8: kern = fftlog_stream_kernel<true, 8>; break;
-      case 12: kern = fftlog_stream_kernel<true, 12>; break;
-      case 14: kern = fftlog_stream_kernel<true, 14>; break;
-      case 15: kern = fftlog_stream_kernel<true, 15>; break;
+      case 5: kern = fftlog_stream_kernel<true, 5>; break;
       case 13: kern = fftlog_stream_kernel<true, 13>; break;
+      case 15: kern = fftlog_stream_kernel<true, 15>; break;
       default: break;
     }
   }
 #endif
   CPF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM_BYTES));
-  kern<<<(unsigned)grid, 512, ST_SMEM_BYTES, stream>>>(s, pl->d_st_tw, pl->d_st_ut, pl->d_m256);
+#ifdef CPF_LAB
+  static long long* d_dbg = nullptr;
+  if (getenv("CPF_STREAM_DBG")) {
+    if (!d_dbg) CPF_CUDA(cudaMalloc(&d_dbg, 8 * 256 * sizeof(long long)));
+    CPF_CUDA(cudaMemsetAsync(d_dbg, 0, 8 * 256 * sizeof(long long), stream));
+    s.dbg = d_dbg;
+  }
+#endif
+  kern<<<(unsigned)grid, 512, ST_SMEM_BYTES, stream>>>(s, pl->fast->d_st_tw, pl->d_st_ut, pl->fast->d_m256);
+#ifdef CPF_LAB
+  if (s.dbg && getenv("CPF_STREAM_DBG")[0] == '2') {     // print the time line of this launch (synchronises)
+    std::vector<long long> h(8 * 256);
+    CPF_CUDA(cudaStreamSynchronize(stream));
+    CPF_CUDA(cudaMemcpy(h.data(), d_dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    long long t0 = h[0], tend = 0;
+    for (long long b = 0; b < grid; ++b) { if (h[8 * b] < t0) t0 = h[8 * b]; if (h[8 * b + 6] > tend) tend = h[8 * b + 6]; }
+    printf("stream kernel time line (us after the first CTA start; grid %lld, span %.2f us)\n", grid, (tend - t0) * 1e-3);
+    printf("  cta   start  tw-done  p-tables  1st-pair  seg-end  loop-end  exit\n");
+    for (long long b = 0; b < grid; b += (grid > 16 ? grid / 12 : 1)) {
+      printf("  %3lld", b);
+      for (int k = 0; k < 7; ++k) printf(" %8.2f", (h[8 * b + k] - t0) * 1e-3);
+      printf("\n");
+    }
+    double mx[7] = {0}, mn[7];
+    for (int k = 0; k < 7; ++k) mn[k] = 1e30;
+    for (long long b = 0; b < grid; ++b)
+      for (int k = 0; k < 7; ++k) { const double v = (h[8 * b + k] - t0) * 1e-3; if (v > mx[k]) mx[k] = v; if (v < mn[k]) mn[k] = v; }
+    printf("  min"); for (int k = 0; k < 7; ++k) printf(" %8.2f", mn[k]); printf("\n  max"); for (int k = 0; k < 7; ++k) printf(" %8.2f", mx[k]); printf("\n");
+  }
+#endif
   CPF_CUDA(cudaGetLastError());
   return CPF_OK;
 }
 
-template <int R1>
-static int launch_pp_mode(const FftlogArgs& a, const double2* tab, int mode, cudaStream_t stream) {
-  if (mode == 3) mode = 0;
-  if (mode == 2) {
-    if constexpr (R1 == 16) return launch_pp<R1, 2>(a, tab, stream);
-    else mode = 1;
-  }
-  return mode == 1 ? launch_pp<R1, 1>(a, tab, stream) : launch_pp<R1, 0>(a, tab, stream);
+// ping-pong tables of an N = 4096 plan, built the first time that kernel is asked for
+static int ensure_pp_tables(const cpf_plan* pl) {
+  std::lock_guard<std::mutex> lock(pl->pp_mutex);
+  if (pl->d_pp) return CPF_OK;
+  if (pl->h_uhs.empty()) return fail(CPF_EUNSUPPORTED, "cpf_fftlog: this plan has no ping-pong tables");
+  std::vector<double2> tab;
+  build_pp_tables(pl->N, pl->fast_R1, pl->P, pl->h_pre_win.data(), pl->h_uhs, pl->h_post_win.data(), pl->fast->pp_tw, tab);
+  double2* d = nullptr;
+  CPF_TRY(upload((void**)&d, tab.data(), tab.size() * sizeof(double2)));
+  pl->d_pp = d;
+  return CPF_OK;
 }
 
-// kernel choice for the default call: CPF_FFTLOG_KERNEL = fast | persistent | pp0 | pp1 | pp2
-static int pp_mode() {
+// Kernel choice for the default call (zero padding, cropped output, real post-factor).  CPF_FFTLOG_KERNEL = fast | pp |
+// stream forces one family (where the plan has its tables); otherwise large launches go to the persistent kernels
+// (stream for N = 4096, ping-pong for N = 2048 / 1024) and small ones to the per-pair kernel, which has no start-up cost.
+enum { K_AUTO = -1, K_FAST = 0, K_PP = 1, K_STREAM = 2 };
+static int kernel_choice() {
   const char* e = getenv("CPF_FFTLOG_KERNEL");
-  if (!e) return -1;
-  if (e[0] == 's') return (e[6] >= '2' && e[6] <= '5') ? 3 + (e[6] - '0') : 4;   // stream, stream2..stream5
-  if (e[0] == 'p' && e[1] == 'p' && e[2] >= '0' && e[2] <= '3') return e[2] - '0';   // pp3 = pp16 kernel
-  return -1;
-}
-
-// Opt-in (CPF_FFTLOG_PERSISTENT=1): measured 16 % slower than the per-pair kernel on B200 (profiles/r01b_summary.md):
-// the stall it was built to remove (long_scoreboard) turned out to be the latency of the input rows, not of the tables.
-static bool persistent_enabled() {
-  const char* e = getenv("CPF_FFTLOG_PERSISTENT");
-  return e && e[0] == '1';
+  if (!e) return K_AUTO;
+  if (e[0] == 'f') return K_FAST;
+  if (e[0] == 'p') return K_PP;
+  if (e[0] == 's') return K_STREAM;
+  return K_AUTO;
 }
 
 static int generic_threads(int N) {
@@ -896,25 +789,22 @@ static int launch_fftlog(const cpf_plan* pl, FftlogArgs a, bool pruned, cudaStre
   if (nblocks > 2147483647LL) return fail(CPF_EUNSUPPORTED, "cpf_fftlog: batch too large for one launch");
   if (pl->fast_R1) {
     a.ut = pruned ? pl->d_uts : pl->d_ut;
-    a.tw1 = pl->d_tw1;
-    a.tw2 = pl->d_tw2;
-    if (pruned && pl->d_pp && pp_mode() >= 0) {
-      const int mode = pp_mode();
-      if (mode >= 4) {
-        if (pl->d_st_tw) return launch_stream(pl, a, stream, mode - 3);
-      } else
-      if (mode == 3 && pl->d_pp16) return launch_pp16(a, pl->d_pp16, pl->d_m256, stream);
-      switch (pl->fast_R1) {
-        case 16: return launch_pp_mode<16>(a, pl->d_pp, mode, stream);
-        case 8: return launch_pp_mode<8>(a, pl->d_pp, mode, stream);
-        default: return launch_pp_mode<4>(a, pl->d_pp, mode, stream);
-      }
-    }
-    if (pruned && !pl->post_complex && persistent_enabled()) {
-      switch (pl->fast_R1) {
-        case 16: return launch_persistent<16>(a, stream);
-        case 8: return launch_persistent<8>(a, stream);
-        default: return launch_persistent<4>(a, stream);
+    a.tw1 = pl->fast->d_tw1;
+    a.tw2 = pl->fast->d_tw2;
+    if (pruned && (pl->d_pp || pl->d_st_ut)) {     // (these tables exist only for prunable windows and a real post-factor)
+      const int choice = kernel_choice();
+      int dev = 0, sms = 0;
+      CPF_CUDA(cudaGetDevice(&dev));
+      CPF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+      const bool big = nblocks >= 16LL * sms;     // >= 8 pairs per 256-thread group: start-up and tail are amortised
+      if (pl->d_st_ut && (choice == K_STREAM || (choice == K_AUTO && big))) return launch_stream(pl, a, stream);
+      if (choice == K_PP || (choice == K_AUTO && big && !pl->d_st_ut)) {
+        if (!pl->d_pp) CPF_TRY(ensure_pp_tables(pl));
+        switch (pl->fast_R1) {
+          case 16: return launch_pp<16>(a, pl->d_pp, stream);
+          case 8: return launch_pp<8>(a, pl->d_pp, stream);
+          default: return launch_pp<4>(a, pl->d_pp, stream);
+        }
       }
     }
     switch (pl->fast_R1) {

@@ -14,9 +14,8 @@
 //     shape: one TMEM lane per thread).  TMEM reads do not go through the LSU, run beside LDS at full rate
 //     (tools/lab/mio_lab.cu) and cost no fp64 instructions, where the per-pair kernel spends 11 % of its fp64
 //     issue slots on rebuilding twiddles and 20 % of its LSU wavefronts on table loads;
-//   * with two groups (N = 4096) the groups alternate: one group runs a register FFT pass on the fp64 pipe while
-//     the other moves its data through shared memory (MODE 2 hands a "math token" back and forth with named
-//     barriers, MODE 1 only staggers the start, MODE 0 runs free);
+//   * the groups run free of each other (handing a "math token" back and forth, or staggering their start, was
+//     measured and is not faster: profiles/r01d_pp_driver_first.log);
 //   * the rows of the next pair are prefetched into L2 while the current pair is transformed.
 #pragma once
 
@@ -94,16 +93,11 @@ __device__ __forceinline__ void named_arrive(const int id, const int nthreads) {
 constexpr int PP_REC = 64, PP_REC_USED = 56;
 constexpr uint32_t PP_COL_TW1 = 0, PP_COL_TW2 = 64, PP_COL_UT = 128, PP_COL_PRE = 192, PP_COL_POST = 208;
 
-// barrier ids: 0 = __syncthreads, 1..8 = groups, 9/10 = math tokens, 11 = staggered start
-constexpr int PP_BAR_TOKEN = 9, PP_BAR_STAGGER = 11;
-
-// MODE 0: groups run free.  MODE 1: group g > 0 starts when group g-1 has finished its first pass (staggered
-// start, then free).  MODE 2 (two groups only): strict alternation of the fp64 phases through a token.
-template <int R1, int MODE>
+// barrier ids: 0 = __syncthreads, 1..8 = groups
+template <int R1>
 __global__ void __launch_bounds__(512, 1) fftlog_pp_kernel(const FftlogArgs a, const double2* __restrict__ tmtab) {
   typedef Geo<R1> G;
   constexpr int T = G::T, N = G::N, NG = 512 / T, RS = G::RS;
-  static_assert(MODE != 2 || NG == 2, "token mode needs exactly two groups");
   extern __shared__ double2 smem[];
   __shared__ uint32_t s_tmem_base;
   const int warp = threadIdx.x >> 5;
@@ -118,15 +112,10 @@ __global__ void __launch_bounds__(512, 1) fftlog_pp_kernel(const FftlogArgs a, c
   // group (t/32 < 4, >= 4) use different column halves, and both groups read the same copy
   const uint32_t tb = s_tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (T == 256 ? 256u * (uint32_t)(t >> 7) : 0u);
 
-  auto acquire = [&]() { if constexpr (MODE == 2) named_sync(PP_BAR_TOKEN + g, 512); };
-  auto release = [&]() { if constexpr (MODE == 2) named_arrive(PP_BAR_TOKEN + (g ^ 1), 512); };
   auto gbar = [&]() { named_sync(1 + g, T); };
-
-  if constexpr (MODE == 2) { if (g == 1) named_arrive(PP_BAR_TOKEN + 0, 512); }   // group 0 holds the token first
 
   const long long per_iter = (long long)gridDim.x * NG;
   const long long iters = (a.pairs_per_p + per_iter - 1) / per_iter;
-  bool first = true;
 
   for (int p = 0; p < a.P; ++p) {
     if (p > 0) { tmem_fence_before(); __syncthreads(); tmem_fence_after(); }   // all reads of the old tables are done
@@ -148,13 +137,11 @@ __global__ void __launch_bounds__(512, 1) fftlog_pp_kernel(const FftlogArgs a, c
     for (long long it = 0; it < iters; ++it) {
       const long long pair = (it * gridDim.x + blockIdx.x) * NG + g;
       const bool active = pair < a.pairs_per_p;
-      if (MODE != 2 && !active) break;
+      if (!active) break;
       const long long b0 = 2 * pair, b1 = b0 + 1;
       const bool has1 = active && b1 < a.batch;
       const double* rowA = a.in + (a.in_has_P ? (b0 * a.P + p) : b0) * (long long)a.n;
       const double* rowB = has1 ? a.in + (a.in_has_P ? (b1 * a.P + p) : b1) * (long long)a.n : rowA;
-
-      if (MODE == 1 && first && g > 0) named_sync(PP_BAR_STAGGER + g - 1, 2 * T);
 
       // L2 prefetch of the rows this group transforms next
       {
@@ -184,7 +171,6 @@ __global__ void __launch_bounds__(512, 1) fftlog_pp_kernel(const FftlogArgs a, c
           y[r] = (ok && has1) ? __ldcs(rowB + i) : 0.;
         }
         tmem_wait4(tq);
-        acquire();
 #pragma unroll
         for (int r = 0; r < 8; ++r) { const double pr = tq.getd(r); v[r] = mk2(x[r] * pr, y[r] * pr); }
 #pragma unroll
@@ -193,7 +179,7 @@ __global__ void __launch_bounds__(512, 1) fftlog_pp_kernel(const FftlogArgs a, c
 
       // a register pass followed by its twiddles (chunks of 4 from TMEM, next chunk in flight while this one is used)
       // and the scatter to shared memory
-      auto twiddle_store = [&](double2 (&w)[16], const int nw, const uint32_t col, double2* dst, const int stride, const bool rel) {
+      auto twiddle_store = [&](double2 (&w)[16], const int nw, const uint32_t col, double2* dst, const int stride) {
         // w[0..nw) are the DFT outputs; w[k] *= tw[k] for k >= 1; then dst[k * stride] = w[k]
         Tm4 tw[2];
         tmem_ld4(col, tw[0]);
@@ -210,7 +196,6 @@ __global__ void __launch_bounds__(512, 1) fftlog_pp_kernel(const FftlogArgs a, c
             if (4 * (ch + 1) < nw) tmem_wait4(tw[(ch + 1) & 1]);
           }
         }
-        if (rel) release();
 #pragma unroll
         for (int k = 0; k < 16; ++k)
           if (k < nw) dst[k * stride] = w[k];
@@ -225,7 +210,7 @@ __global__ void __launch_bounds__(512, 1) fftlog_pp_kernel(const FftlogArgs a, c
 #pragma unroll
           for (int n1 = 0; n1 < R1; ++n1) w[bitrev(n1, G::B1)] = v[n1 * G::C + c];
           dft_dit<R1, HALF_IN, false>(w);
-          twiddle_store(w, R1, tb + PP_COL_TW1 + 4 * (c * R1), S + n2, RS, c == G::C - 1);
+          twiddle_store(w, R1, tb + PP_COL_TW1 + 4 * (c * R1), S + n2, RS);
         }
       };
       auto pass2 = [&]() {
@@ -234,15 +219,12 @@ __global__ void __launch_bounds__(512, 1) fftlog_pp_kernel(const FftlogArgs a, c
         double2 w[16];
 #pragma unroll
         for (int m1 = 0; m1 < 16; ++m1) w[bitrev(m1, 4)] = row[16 * m1];
-        acquire();
         dft_dit<16, false, false>(w);
-        twiddle_store(w, 16, tb + PP_COL_TW2, row, 16, true);
+        twiddle_store(w, 16, tb + PP_COL_TW2, row, 16);
       };
 
       // ---- FFT #1 ----
       pass1(std::true_type());
-      if (MODE == 1 && first && g + 1 < NG) named_arrive(PP_BAR_STAGGER + g, 2 * T);
-      first = false;
       gbar();
       pass2();
       gbar();
@@ -253,7 +235,6 @@ __global__ void __launch_bounds__(512, 1) fftlog_pp_kernel(const FftlogArgs a, c
         for (int m2 = 0; m2 < 16; ++m2) v[bitrev(m2, 4)] = row[m2];
       }
       gbar();   // pass-3 reads of S are done before FFT #2 overwrites it (nothing below touches S before pass 1 stores)
-      acquire();
       dft_dit<16, false, false>(v);
       // ---- kernel multiply ----
       {
@@ -281,12 +262,10 @@ __global__ void __launch_bounds__(512, 1) fftlog_pp_kernel(const FftlogArgs a, c
       }
       gbar();   // S is free for the next pair
       tmem_ld4(tb + PP_COL_POST, tq);
-      acquire();
       dft_dit<16, false, true>(v);
       tmem_wait4(tq);
 #pragma unroll
       for (int r = 0; r < 8; ++r) { const double po = tq.getd(r); v[r].x *= po; v[r].y *= po; }
-      release();
       if (active) {
         double* outA = a.out + (size_t)(b0 * a.P + p) * a.n_out;
         double* outB = a.out + (size_t)(b1 * a.P + p) * a.n_out;
@@ -300,244 +279,6 @@ __global__ void __launch_bounds__(512, 1) fftlog_pp_kernel(const FftlogArgs a, c
         }
       }
     }
-    if (MODE == 1 && first) {   // a group that never ran must not leave its successor waiting
-      if (g + 1 < NG) named_arrive(PP_BAR_STAGGER + g, 2 * T);
-      if (g > 0) named_sync(PP_BAR_STAGGER + g - 1, 2 * T);
-      first = false;
-    }
-  }
-  if constexpr (MODE == 2) { if (g == 0) named_sync(PP_BAR_TOKEN + 0, 512); }   // absorb the last hand-over
-  tmem_fence_before();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc_all(s_tmem_base);
-}
-
-// ================================================================================================================
-// N = 4096 variant with warp-local inner exchanges ("pp16").
-//
-// The three-pass FFT (cpf_fft_core.h) exchanges data twice.  Writing n = 256 n1 + 16 m1 + m2 and
-// k = k1 + 16 l1 + 256 l2, pass 1 is run by thread (m1,m2), pass 2 by thread (k1,m2), pass 3 by thread (k1,l1):
-// exchange 1 only mixes threads with equal m2, exchange 2 only threads with equal k1.  Which 16 threads form a
-// half-warp is free to choose per pass, so in FFT #1 the SECOND exchange and in FFT #2 the FIRST exchange are made
-// half-warp local (thread = 16 k1 + m2 -> 16 k1 + l1, and 16 m2' + m1' -> 16 m2' + k1'): they need __syncwarp only
-// and their shared-memory rows belong to one half-warp.  The global loads (FFT #1 pass 1) and stores (FFT #2 pass 3)
-// keep the natural, coalesced thread order, so the remaining two exchanges cross warps and keep a group barrier.
-// Warps of a group therefore run unsynchronised through 3.5 of the 5 register passes; the two "buffer is free"
-// hand-overs are split arrive/wait mbarriers with a whole register pass of slack.  This matters because the fp64
-// pipe and the shared-memory pipe carry about the same load (4.7 k cycles each per pair of rows): with only two
-// lock-stepped groups per SM they idle a third of the time (profiles/r01e_summary.md).
-//
-// Tables: the FFT #1 bins end up permuted (thread 16 h + i holds bins h + 16 i + 256 r), which only changes the order
-// of the kernel-spectrum table; FFT #2 needs its own pass-1 twiddles (w_N^{(h+16i) k}) and pass-2 twiddles
-// (w_256^{h l}, uniform over a half-warp: read from a 4 KB shared table with broadcast loads).  TMEM per thread:
-// tw1, tw2, ut, tw1' = 64 complex = all 256 columns; pre/post come through L1.
-// ================================================================================================================
-constexpr int PP16_RS = 273;                       // row stride (complex): 16 x 17 + 1, odd
-constexpr int PP16_GROUP_ELEMS = 16 * PP16_RS;
-constexpr uint32_t PP16_COL_TW1 = 0, PP16_COL_TW2 = 64, PP16_COL_UT = 128, PP16_COL_TW1B = 192;
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, const int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(pp_smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(pp_smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, const uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE_%=;\n"
-      "bra WAIT_%=;\n"
-      "DONE_%=:\n"
-      "}\n" ::"r"(pp_smem_u32(bar)), "r"(parity)
-      : "memory");
-}
-
-__global__ void __launch_bounds__(512, 1) fftlog_pp16_kernel(const FftlogArgs a, const double2* __restrict__ tmtab,
-                                                             const double2* __restrict__ m256) {
-  constexpr int T = 256, N = 4096, NG = 2, RS = PP16_RS;
-  extern __shared__ double2 smem[];
-  __shared__ uint32_t s_tmem_base;
-  __shared__ __align__(8) uint64_t s_bar[NG][2];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g = threadIdx.x >> 8, t = threadIdx.x & 255;
-  const int h = t >> 4, i = t & 15;
-  double2* S = smem + g * PP16_GROUP_ELEMS;
-  double2* reg = S + h * RS;                       // the row this half-warp owns in the local exchanges
-  double2* M = smem + NG * PP16_GROUP_ELEMS;       // [16][16] w_256^{h l}
-
-  if (warp == 0) tmem_alloc_all(&s_tmem_base);
-  if (threadIdx.x < 256) M[threadIdx.x] = m256[threadIdx.x];
-  if (threadIdx.x == 0) {
-    for (int gg = 0; gg < NG; ++gg) { mbar_init(&s_bar[gg][0], T / 32); mbar_init(&s_bar[gg][1], T / 32); }
-  }
-  tmem_fence_before();
-  __syncthreads();
-  tmem_fence_after();
-  const uint32_t tb = s_tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + 256u * (uint32_t)(t >> 7);
-  uint64_t* bar_mid = &s_bar[g][0];    // "all pass-2' reads of this group are done"
-  uint64_t* bar_end = &s_bar[g][1];    // "all pass-3' reads of this group are done"
-
-  // work items = (plan row p, pair) in p-major order; each CTA takes one contiguous range
-  const long long items = (long long)a.P * a.pairs_per_p;
-  const long long lo = items * blockIdx.x / gridDim.x, hi = items * (blockIdx.x + 1) / gridDim.x;
-  unsigned cnt = 0;                     // pairs this group has processed (same in all its threads)
-  bool have_tables = false;
-
-  for (long long seg = lo; seg < hi;) {
-    const int p = (int)(seg / a.pairs_per_p);
-    const long long seg_hi = min(hi, (long long)(p + 1) * a.pairs_per_p);
-    if (have_tables) { tmem_fence_before(); __syncthreads(); tmem_fence_after(); }
-    if (g == 0) {
-      const double2* rec = tmtab + ((size_t)p * T + t) * PP_REC;
-#pragma unroll 2
-      for (int ch = 0; ch < PP_REC / 4; ++ch) {
-        double2 d[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) d[q] = rec[4 * ch + q];
-        tmem_st4(tb + 16 * ch, d);
-      }
-      tmem_wait_st();
-    }
-    tmem_fence_before();
-    __syncthreads();
-    tmem_fence_after();
-    have_tables = true;
-    const double* pre = a.pre + (size_t)p * N + N / 4;
-    const double* post = a.post_re + (size_t)p * N + N / 4;
-
-    for (long long item = seg + g; item < seg_hi; item += NG, ++cnt) {
-      const long long pair = item - (long long)p * a.pairs_per_p;
-      const long long b0 = 2 * pair, b1 = b0 + 1;
-      const bool has1 = b1 < a.batch;
-      const double* rowA = a.in + (a.in_has_P ? (b0 * a.P + p) : b0) * (long long)a.n;
-      const double* rowB = has1 ? a.in + (a.in_has_P ? (b1 * a.P + p) : b1) * (long long)a.n : rowA;
-      if (item + NG < seg_hi) {   // L2 prefetch of the rows this group transforms next (one 128 B line per thread)
-        const long long nb0 = b0 + 2 * NG;
-        const int lines = (a.n * 8 + 127) / 128;
-        const double* nA = a.in + (a.in_has_P ? (nb0 * a.P + p) : nb0) * (long long)a.n;
-        const double* nB = nb0 + 1 < a.batch ? a.in + (a.in_has_P ? ((nb0 + 1) * a.P + p) : nb0 + 1) * (long long)a.n : nA;
-        for (int l = t; l < 2 * lines; l += T) {
-          const double* q = (l < lines ? nA : nB) + (size_t)(l < lines ? l : l - lines) * 16;
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
-        }
-      }
-
-      double2 v[16];
-      double2 w[16];
-      // ---- rows -> registers (natural order, coalesced), times pre.  All 24 loads are issued before the first
-      // use, and out-of-window indices are clamped instead of branched around, so that one latency is exposed ----
-      {
-        double x[8], y[8], pr[8];
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-          const int jw = t + T * r;
-          const int idx = jw + N / 4 - a.in_left;
-          const int idc = min(max(idx, 0), a.n - 1);
-          x[r] = __ldcs(rowA + idc);
-          y[r] = __ldcs(rowB + idc);
-          pr[r] = ((unsigned)idx < (unsigned)a.n) ? __ldg(pre + jw) : 0.;
-        }
-#pragma unroll
-        for (int r = 0; r < 8; ++r) v[r] = mk2(x[r] * pr[r], has1 ? y[r] * pr[r] : 0.);
-      }
-#pragma unroll
-      for (int r = 8; r < 16; ++r) v[r] = mk2(0., 0.);
-
-      // w[k] *= tw[k] (k >= 1), twiddles in chunks of four from TMEM, next chunk in flight while this one is used
-      auto twiddle = [&](double2 (&ww)[16], const uint32_t col) {
-        Tm4 tw[2];
-        tmem_ld4(col, tw[0]);
-        tmem_wait4(tw[0]);
-#pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          if (ch < 3) tmem_ld4(col + 16 * (ch + 1), tw[(ch + 1) & 1]);
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            if (4 * ch + q > 0) ww[4 * ch + q] = cmul(ww[4 * ch + q], tw[ch & 1].get(q));
-          if (ch < 3) tmem_wait4(tw[(ch + 1) & 1]);
-        }
-      };
-
-      // ---- FFT #1, pass 1: thread (m1,m2) = (h,i); scatter A[k1][m1][m2] to S[k1][17 m1 + m2] (crosses warps) ----
-#pragma unroll
-      for (int n1 = 0; n1 < 16; ++n1) w[bitrev(n1, 4)] = v[n1];
-      dft_dit<16, true, false>(w);
-      twiddle(w, tb + PP16_COL_TW1);
-      if (cnt > 0) mbar_wait(bar_end, (cnt - 1) & 1);     // the previous pair's pass-3' reads of S are done
-#pragma unroll
-      for (int k1 = 0; k1 < 16; ++k1) S[k1 * RS + 17 * h + i] = w[k1];
-      named_sync(1 + g, T);
-      // ---- pass 2: thread (k1,m2) = (h,i), in place in the half-warp's row ----
-#pragma unroll
-      for (int m1 = 0; m1 < 16; ++m1) w[bitrev(m1, 4)] = reg[17 * m1 + i];
-      dft_dit<16, false, false>(w);
-      twiddle(w, tb + PP16_COL_TW2);
-#pragma unroll
-      for (int l1 = 0; l1 < 16; ++l1) reg[17 * l1 + i] = w[l1];
-      __syncwarp();
-      // ---- pass 3: thread (k1,l1) = (h,i); v[l2] = X[h + 16 i + 256 l2] ----
-#pragma unroll
-      for (int m2 = 0; m2 < 16; ++m2) v[bitrev(m2, 4)] = reg[17 * i + m2];
-      __syncwarp();                                       // the row is rewritten by pass 1 of FFT #2
-      dft_dit<16, false, false>(v);
-
-      {
-        Tm4 tu[2];
-        tmem_ld4(tb + PP16_COL_UT, tu[0]);
-        tmem_wait4(tu[0]);
-#pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          if (ch < 3) tmem_ld4(tb + PP16_COL_UT + 16 * (ch + 1), tu[(ch + 1) & 1]);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) v[4 * ch + q] = cmul(v[4 * ch + q], tu[ch & 1].get(q));
-          if (ch < 3) tmem_wait4(tu[(ch + 1) & 1]);
-        }
-      }
-      // ---- FFT #2, pass 1: thread holds n2' = h + 16 i, i.e. (m1',m2') = (i,h); A'[k1'][m1'] -> row[17 k1' + m1'] ----
-#pragma unroll
-      for (int n1 = 0; n1 < 16; ++n1) w[bitrev(n1, 4)] = v[n1];
-      dft_dit<16, false, false>(w);
-      twiddle(w, tb + PP16_COL_TW1B);
-#pragma unroll
-      for (int k1 = 0; k1 < 16; ++k1) reg[17 * k1 + i] = w[k1];
-      __syncwarp();
-      // ---- pass 2: thread (m2',k1') = (h,i); twiddles w_256^{h l1'} from the shared table (broadcast) ----
-#pragma unroll
-      for (int m1 = 0; m1 < 16; ++m1) w[bitrev(m1, 4)] = reg[17 * i + m1];
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_mid);
-      dft_dit<16, false, false>(w);
-#pragma unroll
-      for (int l1 = 1; l1 < 16; ++l1) w[l1] = cmul(w[l1], M[16 * h + l1]);
-      mbar_wait(bar_mid, cnt & 1);                        // every warp of the group has read its row
-#pragma unroll
-      for (int l1 = 0; l1 < 16; ++l1) S[i * RS + 17 * l1 + h] = w[l1];   // B'[k1'][l1'][m2'] (crosses warps)
-      named_sync(1 + g, T);
-      // ---- pass 3: thread (k1',l1') = (i,h) = natural order t = k1' + 16 l1' ----
-#pragma unroll
-      for (int m2 = 0; m2 < 16; ++m2) v[bitrev(m2, 4)] = S[i * RS + 17 * h + m2];
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_end);
-      double po[8];
-#pragma unroll
-      for (int r = 0; r < 8; ++r) po[r] = __ldg(post + t + T * r);
-      dft_dit<16, false, true>(v);
-      // ---- un-bias, crop, store ----
-      double* outA = a.out + (size_t)(b0 * a.P + p) * a.n_out;
-      double* outB = a.out + (size_t)(b1 * a.P + p) * a.n_out;
-#pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        const int o = t + T * r + N / 4 - a.out_left;
-        if ((unsigned)o < (unsigned)a.n_out) {
-          __stcs(outA + o, v[r].x * po[r]);
-          if (has1) __stcs(outB + o, v[r].y * po[r]);
-        }
-      }
-    }
-    seg = seg_hi;
   }
   tmem_fence_before();
   __syncthreads();

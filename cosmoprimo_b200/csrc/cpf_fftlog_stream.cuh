@@ -12,8 +12,9 @@
 //   * one 512-thread CTA per SM, two groups of 256 threads, each transforming one pair of rows at a time; a CTA owns
 //     a contiguous range of (plan row, pair) items so that it normally loads one plan row's tables once;
 //   * thread-private tables (P1, P2, P1' twiddles, kernel spectrum: 64 complex per thread) live in tensor memory;
-//     the P2' twiddles are uniform over a half-warp and come from a 4 KB shared table with broadcast reads; the
-//     pre/post factors of the window sit in shared memory (32 KB);
+//     threads tau and tau + 128 share a lane and the same P2 twiddles, which makes room for the 8 + 8 pre/post factors
+//     of a thread in tensor memory too; the P2' twiddles are uniform over a half-warp and come from a 4 KB shared
+//     table with broadcast reads;
 //   * the rows of the next pair are loaded into registers right after the last DFT of the current pair, before its
 //     post-factor multiply and stores, and the pair after that is prefetched into L2.
 #pragma once
@@ -22,13 +23,30 @@
 
 namespace cpf {
 
-constexpr int ST_SMEM_BYTES = (2 * ST_GROUP_ELEMS + 256) * (int)sizeof(double2) + 2 * 2048 * (int)sizeof(double);
+constexpr int ST_SMEM_BYTES = (2 * ST_GROUP_ELEMS + 256) * (int)sizeof(double2);
+
+// Tensor-memory layout of one lane (512 columns of 32 bits = 128 complex doubles).  Threads tau and tau + 128 of a
+// group share a lane (and have the same L = tau % 16, hence the same P2 twiddles); both groups read the same copy.
+//   [  0,  64)  P2 twiddles w_256^{L l1}                        (shared by the two halves)
+//   half h = tau / 128 at 64 + 224 h:
+//   [+  0,+ 64) P1 twiddles  w_4096^{tau k1}
+//   [+ 64,+128) kernel spectrum at the bins H + 16 L + 256 l2
+//   [+128,+192) P1' twiddles w_4096^{(H + 16 L) k1'}
+//   [+192,+208) pre-factor  at window elements tau + 256 r, r < 8   (8 doubles)
+//   [+208,+224) post-factor at window elements tau + 256 r, r < 8   (8 doubles)
+constexpr uint32_t ST_COL_HALF0 = 64, ST_COL_HALF = 224, ST_COL_PRE = 192, ST_COL_POST = 208;
+__host__ __device__ constexpr uint32_t st_table_col(const int table) {
+  return table == ST_TW1 ? 0u : table == ST_UT ? 64u : 128u;     // offset inside the half; ST_TW2 is the shared block
+}
 
 struct TmemTables {
-  uint32_t tb;
+  uint32_t lane;   // lane quarter of this warp, column 0
+  uint32_t half;   // this thread's half
   Tm4 buf[2];
   template <int TABLE, int SET>
-  __device__ __forceinline__ void issue(const int ch, const int b) { tmem_ld4(tb + 256u * SET + 64u * TABLE + 16u * ch, buf[b]); }
+  __device__ __forceinline__ void issue(const int ch, const int b) {
+    tmem_ld4((TABLE == ST_TW2 ? lane : half + st_table_col(TABLE)) + 16u * ch, buf[b]);
+  }
   __device__ __forceinline__ void wait(const int b) { tmem_wait4(buf[b]); }
   template <int SET>
   __device__ __forceinline__ double2 get(const int, const int, const int b, const int i) const { return buf[b].get(i); }
@@ -63,34 +81,101 @@ struct StreamArgs {
   int odd_pair;             // index of the pair whose second row does not exist (odd batch), or -1
   int off_in, off_out;      // N/4 - in_left, N/4 - out_left
   int lines;                // 128-byte lines per input row
+  long long* dbg;           // lab builds: per-CTA time stamps (globaltimer ns), else null
 };
 
-// twtab [256][3][16]: P1, P2, P1' twiddles of thread tau ; uttab [P][256][16]: kernel spectrum at the bins thread tau
-// holds after FFT #1 ((-1)^k and 1/N folded in) ; m256 [16][16] = w_256^{h l}
+// Work split: when there are at least as many CTAs as plan rows, every CTA works on ONE plan row (its tables are
+// loaded once) and the CTAs of a plan row share its pairs evenly; otherwise CTAs take contiguous item ranges.
+// (Drawing pairs from a per-plan-row atomic counter instead was measured and is not faster: r01n.)
+__device__ __forceinline__ void st_item_range(const StreamArgs& a, long long& lo, long long& hi) {
+  const int G = (int)gridDim.x, b = (int)blockIdx.x;
+  if (G >= a.P) {
+    const int base = G / a.P, rem = G % a.P;     // the first `rem` plan rows get base + 1 CTAs
+    int p, j, c;
+    if (b < rem * (base + 1)) { p = b / (base + 1); j = b - p * (base + 1); c = base + 1; }
+    else { const int bb = b - rem * (base + 1); p = rem + bb / base; j = bb - (p - rem) * base; c = base; }
+    lo = (long long)p * a.pairs_per_p + (long long)a.pairs_per_p * j / c;
+    hi = (long long)p * a.pairs_per_p + (long long)a.pairs_per_p * (j + 1) / c;
+  } else {
+    lo = a.items * b / G;
+    hi = a.items * (b + 1) / G;
+  }
+}
+
+#ifdef CPF_LAB
+#define ST_STAMP(slot)                                                                              \
+  do {                                                                                              \
+    if (a.dbg && threadIdx.x == 0) {                                                                \
+      long long t_;                                                                                 \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                        \
+      a.dbg[8 * blockIdx.x + (slot)] = t_;                                                          \
+    }                                                                                               \
+  } while (0)
+#else
+#define ST_STAMP(slot) do { } while (0)
+#endif
+
+// twtab [3][16][256]: P1, P2, P1' twiddles (entry-major: thread tau reads element [.][.][tau], coalesced) ;
+// uttab [P][16][256]: kernel spectrum at the bins thread tau holds after FFT #1 ((-1)^k and 1/N folded in) ;
+// m256 [16][16] = w_256^{h l}
 // ABL (lab builds only, -DCPF_LAB): ablation bits — 1: no group barriers (racy), 2: no P2' twiddle loads, 4: no global
-// loads/stores, 8: no pre/post-factor loads, 16: no fp64 DFT work is removed (reserved).  Results are wrong on purpose.
+// loads/stores, 8: no pre/post-factor loads.  Results are wrong on purpose.
 template <bool FULLWIN, int ABL = 0>
 __global__ void __launch_bounds__(512, 1) fftlog_stream_kernel(const StreamArgs a, const double2* __restrict__ twtab,
                                                                const double2* __restrict__ uttab, const double2* __restrict__ m256) {
-  constexpr int T = 256, N = 4096, NG = 2, W = N / 2;
+  constexpr int T = 256, N = 4096, NG = 2;
   extern __shared__ double2 smem[];
   __shared__ uint32_t s_tmem_base;
   const int warp = threadIdx.x >> 5;
   const int g = threadIdx.x >> 8, tau = threadIdx.x & 255;
   double2* S = smem + g * ST_GROUP_ELEMS;
   double2* M = smem + NG * ST_GROUP_ELEMS;
-  double* spre = reinterpret_cast<double*>(M + 256);
-  double* spost = spre + W;
 
+  ST_STAMP(0);
+  long long lo, hi;
+  st_item_range(a, lo, hi);
+
+  // L2 prefetch of the two rows of pair `pair` of plan row p (one 128-byte line per thread covers both rows)
+  auto prefetch_rows = [&](const int p, const int pair) {
+    if (tau < 2 * a.lines) {
+      const bool second = tau >= a.lines;
+      if (!second || pair != a.odd_pair) {
+        const double* q = a.in + (long long)p * a.in_p + (2LL * pair + (second ? 1 : 0)) * a.in_row + 16 * (second ? tau - a.lines : tau);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+      }
+    }
+  };
+
+  // batch-invariant twiddles: group 0 brings P1 and P2, group 1 brings P1' (the same lanes are visible to both);
+  // the loads are in flight while tensor memory is being allocated
+  double2 d[4][4];
+  const double2* rec = twtab + (g == 0 ? 0 : 32 * T) + tau;
+#pragma unroll
+  for (int ch = 0; ch < 4; ++ch)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) d[ch][q] = rec[(4 * ch + q) * T];
   if (warp == 0) tmem_alloc_all(&s_tmem_base);
   if (threadIdx.x < 256) M[threadIdx.x] = m256[threadIdx.x];
   tmem_fence_before();
   __syncthreads();
   tmem_fence_after();
   TmemTables tb;
-  // lane quarter of this warp; threads tau and tau + 128 share a lane and use different column halves; both groups
-  // read the same copy
-  tb.tb = s_tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + 256u * (uint32_t)(tau >> 7);
+  tb.lane = s_tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+  tb.half = tb.lane + ST_COL_HALF0 + ST_COL_HALF * (uint32_t)(tau >> 7);
+  {
+    const uint32_t col = tb.half + st_table_col(g == 1 ? ST_TW1B : ST_TW1);
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) tmem_st4(col + 16u * ch, d[ch]);
+    if (g == 0) {    // the shared P2 block (both halves write the same values)
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) d[ch][q] = rec[(16 + 4 * ch + q) * T];
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) tmem_st4(tb.lane + 16u * ch, d[ch]);
+    }
+  }
+  ST_STAMP(1);
 
   // which of this thread's 8 window elements exist in the unpadded rows
   unsigned m_in = 0xffu, m_out = 0xffu;
@@ -102,54 +187,51 @@ __global__ void __launch_bounds__(512, 1) fftlog_stream_kernel(const StreamArgs 
       if ((unsigned)(a.off_out + tau + T * r) < (unsigned)a.n_out) m_out |= 1u << r;
     }
   }
-
-  const long long lo = a.items * blockIdx.x / gridDim.x, hi = a.items * (blockIdx.x + 1) / gridDim.x;
-  bool have_tw = false;
+  bool first_seg = true, first_pair = true;
 
   for (long long seg = lo; seg < hi;) {
     const int p = (int)(seg / a.pairs_per_p);
     const long long seg_hi = min(hi, (long long)(p + 1) * a.pairs_per_p);
     const int pair_lo = (int)(seg - (long long)p * a.pairs_per_p), pair_hi = (int)(seg_hi - (long long)p * a.pairs_per_p);
     seg = seg_hi;
-    tmem_fence_before();
-    __syncthreads();           // nobody reads the previous plan row's tables any more
-    tmem_fence_after();
-    if (g == 0) {
-      double2 d[4];
-      if (!have_tw) {
-        const double2* rec = twtab + (size_t)tau * 48;
-#pragma unroll 2
-        for (int ch = 0; ch < 12; ++ch) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) d[q] = rec[4 * ch + q];
-          tmem_st4(tb.tb + 16u * ch + (ch >= 8 ? 64u : 0u), d);     // tables 0, 1 and 3
-        }
-      }
-      const double2* rec = uttab + ((size_t)p * T + tau) * 16;
-#pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) d[q] = rec[4 * ch + q];
-        tmem_st4(tb.tb + 64u * ST_UT + 16u * ch, d);
-      }
-      tmem_wait_st();
+    int pair = pair_lo + g;
+    if (pair < pair_hi) prefetch_rows(p, pair);
+    if (!first_seg) {
+      tmem_fence_before();
+      __syncthreads();           // nobody reads the previous plan row's tables any more
+      tmem_fence_after();
     }
-    have_tw = true;
-    {
-      const double* pre = a.pre + (size_t)p * N + N / 4;
-      const double* post = a.post + (size_t)p * N + N / 4;
-      for (int i = threadIdx.x; i < W; i += 512) { spre[i] = pre[i]; spost[i] = post[i]; }
+    first_seg = false;
+    if (g == 0) {              // plan-row tables: kernel spectrum, pre- and post-factor
+      const double2* ut = uttab + (size_t)p * 16 * T + tau;
+      const double* pre = a.pre + (size_t)p * N + N / 4 + tau;
+      const double* post = a.post + (size_t)p * N + N / 4 + tau;
+      double2 e[2][4];
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) d[ch][q] = ut[(4 * ch + q) * T];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        e[0][q] = mk2(pre[T * (2 * q)], pre[T * (2 * q + 1)]);
+        e[1][q] = mk2(post[T * (2 * q)], post[T * (2 * q + 1)]);
+      }
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) tmem_st4(tb.half + st_table_col(ST_UT) + 16u * ch, d[ch]);
+      tmem_st4(tb.half + ST_COL_PRE, e[0]);
+      tmem_st4(tb.half + ST_COL_POST, e[1]);
     }
+    tmem_wait_st();
     tmem_fence_before();
     __syncthreads();
     tmem_fence_after();
+    ST_STAMP(2);
 
-    // this thread's first window element of row 2*pair (input) / first output element
-    int pair = pair_lo + g;
-    const double* pa = a.in + (long long)p * a.in_p + 2LL * pair * a.in_row + (a.off_in + tau);
-    double* oa = a.out + 2LL * pair * a.out_row + (long long)p * a.n_out + (a.off_out + tau);
-    for (; pair < pair_hi; pair += NG, pa += 2 * NG * a.in_row, oa += 2 * NG * a.out_row) {
+    while (pair < pair_hi) {
       const bool has1 = pair != a.odd_pair;
+      // this thread's first window element of row 2*pair (input) / first output element
+      const double* pa = a.in + (long long)p * a.in_p + 2LL * pair * a.in_row + (a.off_in + tau);
+      double* oa = a.out + 2LL * pair * a.out_row + (long long)p * a.n_out + (a.off_out + tau);
       {
         double x[8], y[8];
         if (ABL & 4) {
@@ -157,18 +239,13 @@ __global__ void __launch_bounds__(512, 1) fftlog_stream_kernel(const StreamArgs 
           for (int r = 0; r < 8; ++r) { x[r] = 1. + tau; y[r] = 2. + r; }
         } else
         st_load_rows<FULLWIN>(pa, has1 ? pa + a.in_row : pa, m_in, x, y);
-        // the pair after next into L2 (one 128-byte line per thread covers both rows)
-        const int pf = pair + 2 * NG;
-        if (pf < pair_hi && tau < 2 * a.lines) {
-          const bool second = tau >= a.lines;
-          if (!second || pf != a.odd_pair) {
-            const double* q = pa - (a.off_in + tau) + 4 * NG * a.in_row + (second ? a.in_row + 16 * (tau - a.lines) : 16 * tau);
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
-          }
-        }
+        Tm4 tf;
+        tmem_ld4(tb.half + ST_COL_PRE, tf);
+        if (pair + 2 * NG < pair_hi) prefetch_rows(p, pair + 2 * NG);
+        tmem_wait4(tf);
         double2 v8[8];
 #pragma unroll
-        for (int r = 0; r < 8; ++r) { const double pr = (ABL & 8) ? 1.0000001 : spre[tau + T * r]; v8[r] = mk2(x[r] * pr, y[r] * pr); }   // odd tail: y = x, its output is not stored
+        for (int r = 0; r < 8; ++r) { const double pr = (ABL & 8) ? 1.0000001 : tf.getd(r); v8[r] = mk2(x[r] * pr, y[r] * pr); }   // odd tail: y = x, its output is not stored
         st_p1(tau, v8, S, tb);
       }
       if (!(ABL & 1)) named_sync(1 + g, T);
@@ -188,252 +265,33 @@ __global__ void __launch_bounds__(512, 1) fftlog_stream_kernel(const StreamArgs 
       st_p2b(tau, S, M);
       if (!(ABL & 1)) named_sync(1 + g, T);
       double2 v[16];
-      st_p3b(tau, v, S);
+      st_col_load(tau, S, v);
+      Tm4 tf;
+      tmem_ld4(tb.half + ST_COL_POST, tf);
+      st_p3b_compute(v);
+      tmem_wait4(tf);
       double* ob = oa + a.out_row;
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
         if (FULLWIN || ((m_out >> r) & 1u)) {
-          const double po = (ABL & 8) ? 0.9999999 : spost[tau + T * r];
+          const double po = (ABL & 8) ? 0.9999999 : tf.getd(r);
           if (ABL & 4) { if (v[r].x * po == 1.2345e-300) oa[0] = v[r].y; }
           else {
-          __stcs(oa + T * r, v[r].x * po);
-          if (has1) __stcs(ob + T * r, v[r].y * po);
+            __stcs(oa + T * r, v[r].x * po);
+            if (has1) __stcs(ob + T * r, v[r].y * po);
           }
         }
       }
+      if (first_pair) { ST_STAMP(3); first_pair = false; }
+      pair += NG;
     }
+    ST_STAMP(4);
   }
+  ST_STAMP(5);
   tmem_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc_all(s_tmem_base);
-}
-
-// ================================================================================================================
-// Two column sets per thread ("stream2"): 128 threads per pair of rows, thread t runs the phases of the virtual
-// threads tau = t and tau = t + 128 of cpf_stream_core.h.  NG groups (2 or 3) of 4 warps per CTA: every warp of a
-// group sits on a different SM sub-partition, so a sub-partition holds NG warps that belong to NG different pairs of
-// rows and never wait for each other.
-//
-// Why (profiles/r01f_summary.md, r01h ablations): with 256 threads per pair the two warps of a group that share a
-// sub-partition leave every barrier together and stay in step, so a sub-partition effectively holds two actors that
-// each alternate between fp64 work and shared-memory work, and the fp64 pipe idles whenever both are in a memory
-// phase (60 % busy; 83 % with the barriers removed).  Three groups need three exchange buffers (205 KB), which
-// leaves no room for the pre/post factors in shared memory: they are read through L1/L2 together with the rows.
-// ILV: the two column sets are interleaved by hand (the loads of one set are in flight while the other set's DFT
-// runs); otherwise they are processed one after the other.
-// ================================================================================================================
-template <int NG>
-constexpr int st2_smem_bytes() { return (NG * ST_GROUP_ELEMS + 256) * (int)sizeof(double2); }
-
-template <bool FULLWIN>
-__device__ __forceinline__ void st2_load_pre(const double* pre, const unsigned m, double (&f)[8]) {
-#pragma unroll
-  for (int r = 0; r < 8; ++r) f[r] = (FULLWIN || ((m >> r) & 1u)) ? __ldg(pre + 256 * r) : 0.;
-}
-
-template <bool FULLWIN, int NG, bool ILV>
-__global__ void __launch_bounds__(128 * NG, 1) fftlog_stream2_kernel(const StreamArgs a, const double2* __restrict__ twtab,
-                                                                     const double2* __restrict__ uttab, const double2* __restrict__ m256) {
-  constexpr int T = 128, N = 4096, NT = T * NG;
-  extern __shared__ double2 smem[];
-  __shared__ uint32_t s_tmem_base;
-  const int warp = threadIdx.x >> 5;
-  const int g = threadIdx.x >> 7, t = threadIdx.x & 127;
-  const int tau0 = t, tau1 = t + T;
-  double2* S = smem + g * ST_GROUP_ELEMS;
-  double2* M = smem + NG * ST_GROUP_ELEMS;
-
-  if (warp == 0) tmem_alloc_all(&s_tmem_base);
-  if (threadIdx.x < 256) M[threadIdx.x] = m256[threadIdx.x];
-  tmem_fence_before();
-  __syncthreads();
-  tmem_fence_after();
-  TmemTables tb;
-  // warps w, w + 4, w + 8 (one per group) share a lane quarter and read the same tables; set 0 in columns [0, 256),
-  // set 1 in [256, 512)
-  tb.tb = s_tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-  const double2* M0 = M + 16 * (tau0 >> 4);
-  const double2* M1 = M + 16 * (tau1 >> 4);
-
-  unsigned m_in = 0xffffu, m_out = 0xffffu;   // bit 8 s + r: window element tau_s + 256 r exists in the unpadded row
-  if (!FULLWIN) {
-    m_in = m_out = 0u;
-#pragma unroll
-    for (int s = 0; s < 2; ++s)
-#pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        if ((unsigned)(a.off_in + t + T * s + 256 * r) < (unsigned)a.n) m_in |= 1u << (8 * s + r);
-        if ((unsigned)(a.off_out + t + T * s + 256 * r) < (unsigned)a.n_out) m_out |= 1u << (8 * s + r);
-      }
-  }
-
-  const long long lo = a.items * blockIdx.x / gridDim.x, hi = a.items * (blockIdx.x + 1) / gridDim.x;
-  bool have_tw = false;
-
-  for (long long seg = lo; seg < hi;) {
-    const int p = (int)(seg / a.pairs_per_p);
-    const long long seg_hi = min(hi, (long long)(p + 1) * a.pairs_per_p);
-    const int pair_lo = (int)(seg - (long long)p * a.pairs_per_p), pair_hi = (int)(seg_hi - (long long)p * a.pairs_per_p);
-    seg = seg_hi;
-    tmem_fence_before();
-    __syncthreads();           // nobody reads the previous plan row's tables any more
-    tmem_fence_after();
-    if (g == 0) {
-      double2 d[4];
-#pragma unroll
-      for (int s = 0; s < 2; ++s) {
-        const int tau = t + T * s;
-        if (!have_tw) {
-          const double2* rec = twtab + (size_t)tau * 48;
-#pragma unroll 2
-          for (int ch = 0; ch < 12; ++ch) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) d[q] = rec[4 * ch + q];
-            tmem_st4(tb.tb + 256u * s + 16u * ch + (ch >= 8 ? 64u : 0u), d);     // tables 0, 1 and 3
-          }
-        }
-        const double2* rec = uttab + ((size_t)p * 256 + tau) * 16;
-#pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) d[q] = rec[4 * ch + q];
-          tmem_st4(tb.tb + 256u * s + 64u * ST_UT + 16u * ch, d);
-        }
-      }
-      tmem_wait_st();
-    }
-    have_tw = true;
-    tmem_fence_before();
-    __syncthreads();
-    tmem_fence_after();
-
-    int pair = pair_lo + g;
-    if (pair >= pair_hi) continue;
-    // this thread's first window element of row 2*pair (input) / first output element, and of the pre/post factors
-    const double* pa = a.in + (long long)p * a.in_p + 2LL * pair * a.in_row + (a.off_in + t);
-    double* oa = a.out + 2LL * pair * a.out_row + (long long)p * a.n_out + (a.off_out + t);
-    const double* pre = a.pre + (size_t)p * N + N / 4 + t;
-    const double* post = a.post + (size_t)p * N + N / 4 + t;
-
-    for (; pair < pair_hi; pair += NG, pa += 2 * NG * a.in_row, oa += 2 * NG * a.out_row) {
-      const bool has1 = pair != a.odd_pair;
-      const double* pb = has1 ? pa + a.in_row : pa;
-      double2 A[16], B[16];
-      // ---- rows -> registers, P1 of both sets (odd tail: y = x, its output is not stored) ----
-      {
-        double xa[8], ya[8], fa[8], xb[8], yb[8], fb[8];
-        st_load_rows<FULLWIN>(pa, pb, m_in, xa, ya);
-        st2_load_pre<FULLWIN>(pre, m_in, fa);
-        st_load_rows<FULLWIN>(pa + T, pb + T, m_in >> 8, xb, yb);
-        st2_load_pre<FULLWIN>(pre + T, m_in >> 8, fb);
-        const int pf = pair + 2 * NG;      // the pair after next into L2: two 128-byte lines per thread cover both rows
-        if (pf < pair_hi) {
-#pragma unroll
-          for (int s = 0; s < 2; ++s) {
-            const int l = t + T * s;
-            const bool second = l >= a.lines;
-            if (l < 2 * a.lines && (!second || pf != a.odd_pair)) {
-              const double* q = pa - (a.off_in + t) + 4 * NG * a.in_row + (second ? a.in_row + 16 * (l - a.lines) : 16 * l);
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
-            }
-          }
-        }
-        double2 v8[8];
-#pragma unroll
-        for (int r = 0; r < 8; ++r) v8[r] = mk2(xa[r] * fa[r], ya[r] * fa[r]);
-        st_p1_compute<TmemTables, 0>(v8, A, tb);
-        st_p1_store(tau0, A, S);
-#pragma unroll
-        for (int r = 0; r < 8; ++r) v8[r] = mk2(xb[r] * fb[r], yb[r] * fb[r]);
-        st_p1_compute<TmemTables, 1>(v8, B, tb);
-        st_p1_store(tau1, B, S);
-      }
-      named_sync(1 + g, T);
-      // ---- P2, P3, kernel multiply, P1', P2': warp-local ----
-      if (ILV) {
-        st_row_load(tau0, S, A);
-        st_row_load(tau1, S, B);
-        st_p2_compute<TmemTables, 0>(A, tb);
-        st_row_store(tau0, A, S);
-        __syncwarp();
-        st_own_load(tau0, S, A);
-        st_p2_compute<TmemTables, 1>(B, tb);
-        st_row_store(tau1, B, S);
-        __syncwarp();
-        st_own_load(tau1, S, B);
-        {
-          double2 A2[16];
-          st_p3_compute<TmemTables, 0>(A, A2, tb);
-          st_own_store(tau0, A2, S);
-        }
-        __syncwarp();
-        st_row_load(tau0, S, A);
-        {
-          double2 B2[16];
-          st_p3_compute<TmemTables, 1>(B, B2, tb);
-          st_own_store(tau1, B2, S);
-        }
-        __syncwarp();
-        st_row_load(tau1, S, B);
-        st_p2b_compute(A, M0);
-        st_row_store(tau0, A, S);
-        st_p2b_compute(B, M1);
-        st_row_store(tau1, B, S);
-      } else {
-        st_row_load(tau0, S, A);
-        st_p2_compute<TmemTables, 0>(A, tb);
-        st_row_store(tau0, A, S);
-        st_row_load(tau1, S, B);
-        st_p2_compute<TmemTables, 1>(B, tb);
-        st_row_store(tau1, B, S);
-        __syncwarp();
-        {
-          double2 A2[16];
-          st_own_load(tau0, S, A);
-          st_p3_compute<TmemTables, 0>(A, A2, tb);
-          st_own_store(tau0, A2, S);
-          st_own_load(tau1, S, B);
-          st_p3_compute<TmemTables, 1>(B, A2, tb);
-          st_own_store(tau1, A2, S);
-        }
-        __syncwarp();
-        st_row_load(tau0, S, A);
-        st_p2b_compute(A, M0);
-        st_row_store(tau0, A, S);
-        st_row_load(tau1, S, B);
-        st_p2b_compute(B, M1);
-        st_row_store(tau1, B, S);
-      }
-      named_sync(1 + g, T);
-      // ---- P3', post-factor, store ----
-      double fa[8], fb[8];
-      st2_load_pre<FULLWIN>(post, m_out, fa);
-      st2_load_pre<FULLWIN>(post + T, m_out >> 8, fb);
-      st_col_load(tau0, S, A);
-      if (ILV) st_col_load(tau1, S, B);
-      double* ob = oa + a.out_row;
-      st_p3b_compute(A);
-#pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        if (FULLWIN || ((m_out >> r) & 1u)) {
-          __stcs(oa + 256 * r, A[r].x * fa[r]);
-          if (has1) __stcs(ob + 256 * r, A[r].y * fa[r]);
-        }
-      }
-      if (!ILV) st_col_load(tau1, S, B);
-      st_p3b_compute(B);
-#pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        if (FULLWIN || ((m_out >> (8 + r)) & 1u)) {
-          __stcs(oa + T + 256 * r, B[r].x * fb[r]);
-          if (has1) __stcs(ob + T + 256 * r, B[r].y * fb[r]);
-        }
-      }
-    }
-  }
-  tmem_fence_before();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc_all(s_tmem_base);
+  ST_STAMP(6);
 }
 
 }  // namespace cpf

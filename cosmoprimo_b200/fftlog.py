@@ -323,6 +323,8 @@ def _cached_tables(key, builder):
 def clear_plan_cache():
     with _TABLE_LOCK:
         _TABLE_CACHE.clear()
+    with _DEVICE_PLANS_LOCK:
+        _DEVICE_PLANS.clear()
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -473,9 +475,33 @@ def _device_plan_for(self, device):
         raise ValueError('plan tables have shapes {}, {}, {}; expected {}, {}, {}'.format(pre.shape, u.shape, post.shape, (P, N), (P, N // 2 + 1), (P, N)))
     if np.iscomplexobj(pre):
         raise ValueError('complex padded_prefactor is not supported')
-    dplan = _DevicePlan(self.x.shape[-1], N, P, self.padded_size_in_left, self.padded_size_out_left, pre, u, post, device)
-    self._dev_plans[device] = ((pre.copy(), u.copy(), post.copy()), dplan)
+    snap, dplan = _shared_device_plan(self.x.shape[-1], N, P, self.padded_size_in_left, self.padded_size_out_left, pre, u, post, device)
+    self._dev_plans[device] = (snap, dplan)
     return dplan
+
+
+# Recently built device plans, shared between objects with identical tables: the reference (and this package's
+# interpolators) build a fresh FFTlog object on every sigma_r / to_xi call (interpolator.py:288, 602, 983).
+_DEVICE_PLANS = collections.OrderedDict()
+_DEVICE_PLANS_SIZE = 16
+_DEVICE_PLANS_LOCK = threading.Lock()
+
+
+def _shared_device_plan(n, N, P, in_left, out_left, pre, u, post, device):
+    key = (device, n, N, P, in_left, out_left, str(post.dtype))
+    tables = (pre, u, post)
+    with _DEVICE_PLANS_LOCK:
+        for full_key, (snap, dplan) in reversed(list(_DEVICE_PLANS.items())):
+            if full_key[:-1] == key and all(s.shape == t.shape and np.array_equal(s, t) for s, t in zip(snap, tables)):
+                _DEVICE_PLANS.move_to_end(full_key)
+                return snap, dplan
+    snap = tuple(t.copy() for t in tables)
+    dplan = _DevicePlan(n, N, P, in_left, out_left, pre, u, post, device)
+    with _DEVICE_PLANS_LOCK:
+        _DEVICE_PLANS[key + (id(dplan),)] = (snap, dplan)
+        while len(_DEVICE_PLANS) > _DEVICE_PLANS_SIZE:
+            _DEVICE_PLANS.popitem(last=False)
+    return snap, dplan
 
 
 

@@ -148,6 +148,38 @@ def test_multipoles_config2_shapes():
         assert scale_aware_error(one, xi[:, i], post[i]) < 1e-14
 
 
+@pytest.mark.parametrize('kernel,n,B,ells,per_ell', [
+    ('stream', 2048, 601, [0, 2, 4], True),     # full window, odd batch, one input row per ell
+    ('stream', 2048, 300, [0, 2], False),       # the same row for every ell (no P axis in the input)
+    ('stream', 2000, 77, [0, 2, 4], True),      # window narrower than N/2: masked loads and stores
+    ('stream', 1919, 40, [1], False),           # odd n, single plan row
+    ('stream', 2048, 2, [0, 2, 4], True),       # as many CTAs as plan rows
+    ('stream', 2048, 1, [0, 1, 2, 3, 4], True),  # fewer CTAs than plan rows: a CTA walks over several plan rows
+    ('pp', 1024, 333, [0, 2], True),            # N = 2048: ping-pong kernel, four groups per CTA
+    ('pp', 1000, 65, [2], False),
+    ('pp', 512, 129, [0, 2, 4], True),          # N = 1024: eight groups per CTA
+    ('pp', 2048, 67, [0, 2], True),             # N = 4096 through the ping-pong kernel
+])
+def test_persistent_kernels(monkeypatch, kernel, n, B, ells, per_ell):
+    """The persistent kernels (stream for N = 4096, ping-pong for N = 2048 / 1024) are chosen automatically for large
+    launches only; here they are forced on small odd batches and compared with the oracle and with the per-pair kernel."""
+    k, pk = lhs_pk(B, n)
+    fun = S.kaiser_multipoles(pk, np.full(B, 0.76))[:, :len(ells)] if per_ell else pk
+    if per_ell and len(ells) > 3:
+        fun = np.concatenate([fun, fun[:, :len(ells) - 3] * 0.5], axis=1)
+    obj = F.PowerToCorrelation(k, ell=ells)
+    monkeypatch.setenv('CPF_FFTLOG_KERNEL', 'fast')
+    ref_fast = obj(fun if per_ell else fun[:, None, :])[1]
+    monkeypatch.setenv('CPF_FFTLOG_KERNEL', kernel)
+    s, xi = obj(fun if per_ell else fun[:, None, :])
+    assert xi.shape == (B, len(ells), n) and np.isfinite(xi).all()
+    post = obj.padded_postfactor[:, obj.padded_size_out_left:obj.padded_size_out_left + n]
+    assert scale_aware_error(xi, ref_fast, post) < 1e-13
+    rows = sorted(set([0, B // 2, B - 1]))
+    ref = O.execute(O.plan_power_to_correlation(k, ell=ells), (fun if per_ell else fun[:, None, :])[rows])[1]
+    assert scale_aware_error(xi[rows], ref, post) < 1e-13
+
+
 def test_kernel_family_selection():
     lib = _lib.load()
     k = np.geomspace(1e-5, 1e2, 2048)

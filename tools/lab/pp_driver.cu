@@ -32,10 +32,10 @@ static int run_case(int n, int P, long long batch, int in_has_P, int reps) {
   CK(cudaMalloc(&d_in, in_elems * 8)); CK(cudaMalloc(&d_out, out_elems * 8));
   CK(cudaMemcpy(d_in, h_in.data(), in_elems * 8, cudaMemcpyHostToDevice));
   std::vector<double> ref(out_elems), got(out_elems);
-  const char* kernels[] = {"fast", "pp0", "pp1", "pp2", "persistent", "pp3", "stream", "stream2", "stream3", "stream4", "stream5"};
+  const char* kernels[] = {"fast", "pp0", "pp1", "pp2", "persistent", "pp3", "stream"};
   cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   int bad = 0;
-  for (int k = 0; k < 11; ++k) {
+  for (int k = 0; k < 7; ++k) {
     if (g_only && k > 0 && strcmp(g_only, kernels[k]) != 0) continue;
     setenv("CPF_FFTLOG_KERNEL", kernels[k], 1);
     setenv("CPF_FFTLOG_PERSISTENT", k == 4 ? "1" : "0", 1);
