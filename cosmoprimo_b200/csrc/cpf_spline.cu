@@ -97,6 +97,54 @@ __global__ void __launch_bounds__(128) spline_eval_kernel(const double* __restri
   out[(long long)q * ncols + col] = r;
 }
 
+// ---- row layout: splines along the LAST axis, windowed weights (cpf_spline_core.h) ------------------------------------
+// weights kernel: one thread per query; wq [nq, LW] weights, meta [3, nq] = (first knot, length or -1 for NaN), offset of the first kept weight
+__global__ void spline_row_weights_kernel(const double* __restrict__ x, const int nx, const int bc, const int W, const int LW,
+                                          const double* __restrict__ xq, const int nq, const int extrap,
+                                          double* __restrict__ wq, double* __restrict__ work, int* __restrict__ meta) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  const double xv = xq[q];
+  double* w = wq + (size_t)q * LW;
+  const bool inside = xv >= x[0] && xv <= x[nx - 1];
+  if ((!inside && !extrap) || !(xv == xv)) {
+    meta[2 * q] = 0;
+    meta[2 * q + 1] = -1;
+    meta[2 * nq + q] = 0;
+    return;
+  }
+  int first;
+  const int L = spline_window_weights(x, nx, bc, W, xv, w, work + (size_t)q * 2 * LW, &first);
+  int skip;
+  const int Lt = spline_trim_weights(w, L, &skip);
+  meta[2 * q] = first + skip;
+  meta[2 * q + 1] = Lt;
+  meta[2 * nq + q] = skip;
+}
+
+// dot kernel: one warp per row; out[q, row] = sum_j w[q, j] y[row, first_q + j].  Window loads are contiguous runs.
+__global__ void __launch_bounds__(256) spline_rows_dot_kernel(const double* __restrict__ y, const int nx, const long long rows,
+                                                              const double* __restrict__ wq, const int* __restrict__ meta,
+                                                              const int nq, const int LW, double* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const double* yr = y + row * nx;
+  for (int q = 0; q < nq; ++q) {
+    const int first = meta[2 * q], L = meta[2 * q + 1];
+    double acc = 0.;
+    if (L > 0) {
+      const double* w = wq + (size_t)q * LW + meta[2 * nq + q];
+      for (int j = lane; j < L; j += 32) acc = fma(w[j], yr[first + j], acc);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    } else {
+      acc = nan("");
+    }
+    if (lane == (q & 31)) out[(long long)q * rows + row] = acc;
+  }
+}
+
 // device-resident fit, shared with cpf_wallish.cu: slopes s[nx, ncols] of the splines through y[nx, ncols] on the
 // knots x[nx]; fac is scratch of 3*nx doubles
 int spline_fit_device(const double* d_x, const double* d_y, int nx, long long ncols, int bc, double* d_s, double* d_fac,
@@ -217,6 +265,52 @@ int cpf_spline_eval(const cpf_spline* sp, const double* xq, int nq, int nu, doub
   CPF_CUDA(cudaGetLastError());
   if (!on_device) {
     CPF_CUDA(cudaMemcpyAsync(out, d_out, cells * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    CPF_CUDA(cudaStreamSynchronize(stream));
+  }
+  return CPF_OK;
+}
+
+int cpf_spline_eval_rows(const double* x, const double* y, int nx, int64_t rows, const double* xq, int nq, int bc, int window,
+                         int extrap, double* out, int on_device, int device, void* stream_) {
+  if (nx < 2) return fail(CPF_EINVAL, "cpf_spline_eval_rows: need at least 2 knots, got %d", nx);
+  if (rows < 0 || nq < 0) return fail(CPF_EINVAL, "cpf_spline_eval_rows: negative size");
+  if (bc != 0 && bc != 1) return fail(CPF_EINVAL, "cpf_spline_eval_rows: bc must be 0 (natural) or 1 (clamped)");
+  if (window < 0) return fail(CPF_EINVAL, "cpf_spline_eval_rows: negative window");
+  if (rows == 0 || nq == 0) return CPF_OK;
+  if (!x || !y || !xq || !out) return fail(CPF_EINVAL, "cpf_spline_eval_rows: null buffer");
+  int ndev = 0;
+  CPF_TRY(cpf_device_count(&ndev));
+  if (device < 0 || device >= ndev) return fail(CPF_EINVAL, "cpf_spline_eval_rows: device %d out of range (%d visible)", device, ndev);
+  DeviceGuard guard(device);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int W = (window == 0 || window > nx) ? nx : window;   // the host default is 128 (cosmoprimo_b200/interp.py)
+  const int LW = (2 * W + 2 < nx) ? 2 * W + 2 : nx;
+  const size_t ycells = (size_t)rows * nx, ocells = (size_t)nq * rows;
+  ScratchBuf dx, dy, dq, dout, dw, dwork, dmeta;
+  const double *p_x = x, *p_y = y, *p_q = xq;
+  double* p_out = out;
+  if (!on_device) {
+    CPF_CUDA(dx.alloc(nx * sizeof(double), stream));
+    CPF_CUDA(dy.alloc(ycells * sizeof(double), stream));
+    CPF_CUDA(dq.alloc(nq * sizeof(double), stream));
+    CPF_CUDA(dout.alloc(ocells * sizeof(double), stream));
+    CPF_CUDA(cudaMemcpyAsync(dx.p, x, nx * sizeof(double), cudaMemcpyHostToDevice, stream));
+    CPF_CUDA(cudaMemcpyAsync(dy.p, y, ycells * sizeof(double), cudaMemcpyHostToDevice, stream));
+    CPF_CUDA(cudaMemcpyAsync(dq.p, xq, nq * sizeof(double), cudaMemcpyHostToDevice, stream));
+    p_x = (const double*)dx.p; p_y = (const double*)dy.p; p_q = (const double*)dq.p; p_out = (double*)dout.p;
+  }
+  CPF_CUDA(dw.alloc((size_t)nq * LW * sizeof(double), stream));
+  CPF_CUDA(dwork.alloc((size_t)nq * 2 * LW * sizeof(double), stream));
+  CPF_CUDA(dmeta.alloc((size_t)nq * 3 * sizeof(int), stream));
+  spline_row_weights_kernel<<<(nq + 63) / 64, 64, 0, stream>>>(p_x, nx, bc, W, LW, p_q, nq, extrap ? 1 : 0, (double*)dw.p,
+                                                              (double*)dwork.p, (int*)dmeta.p);
+  CPF_CUDA(cudaGetLastError());
+  const int wpb = 8;
+  spline_rows_dot_kernel<<<(unsigned)((rows + wpb - 1) / wpb), 32 * wpb, 0, stream>>>(p_y, nx, rows, (const double*)dw.p,
+                                                                                    (const int*)dmeta.p, nq, LW, p_out);
+  CPF_CUDA(cudaGetLastError());
+  if (!on_device) {
+    CPF_CUDA(cudaMemcpyAsync(out, p_out, ocells * sizeof(double), cudaMemcpyDeviceToHost, stream));
     CPF_CUDA(cudaStreamSynchronize(stream));
   }
   return CPF_OK;

@@ -64,4 +64,83 @@ CPF_SHD double spline_poly(const double x0, const double x1, const double y0, co
   return 6. * c0;
 }
 
+
+// ---- windowed evaluation weights -----------------------------------------------------------------------------------
+// The spline value at xv is linear in the ordinates: S(xv) = sum_j w_j y_j.  The slope system is strictly diagonally
+// dominant, so the influence of y_j on the slopes of the interval [x_i, x_{i+1}] holding xv decays like (2-sqrt 3)^|i-j|
+// ~ 0.27^|i-j|: restricting the solve to the knots a = max(0, i-W) .. b = min(nx-1, i+1+W) changes S(xv) by O(0.27^W)
+// (1e-23 for W = 40; W >= nx covers all knots and is the full solve).  The weights depend on the grid and on xv only,
+// so they are computed once per query and shared by all rows.
+//
+// Output: w[0..L-1] for the knots a..a+L-1 (L = b-a+1 <= 2W+2), *first = a.  `work` is scratch of 2*L doubles.
+// Truncated window ends use the natural end row (any consistent end row does: its effect is below the truncation).
+CPF_SHD int spline_window_weights(const double* x, const int nx, const int bc, const int W, const double xv, double* w,
+                                  double* work, int* first) {
+  const int i = spline_interval(x, nx, xv);
+  const int a = (i - W > 0) ? i - W : 0;
+  const int b = (i + 1 + W < nx - 1) ? i + 1 + W : nx - 1;
+  const int L = b - a + 1;
+  const double* xw = x + a;
+  const int bca = (a == 0) ? bc : 0, bcb = (b == nx - 1) ? bc : 0;   // end rows of the window system
+  const int p = i - a;
+  // Hermite form of the cubic on [x_i, x_{i+1}]: S = h00 y_i + h01 y_{i+1} + dx (h10 s_i + h11 s_{i+1})
+  const double dx = x[i + 1] - x[i];
+  const double u = (xv - x[i]) / dx;
+  const double h00 = (1. + 2. * u) * (1. - u) * (1. - u), h01 = u * u * (3. - 2. * u);
+  const double h10 = u * (1. - u) * (1. - u) * dx, h11 = -u * u * (1. - u) * dx;
+  // solve T^T z = h10 e_p + h11 e_{p+1}; row m of T^T: up_{m-1} z_{m-1} + di_m z_m + lo_{m+1} z_{m+1}
+  double* cp = work;        // modified super-diagonal
+  double* z = work + L;
+  auto row = [&](const int m, double& lo, double& di, double& up) {
+    if (m == 0) spline_row(xw, L, bca, 0, lo, di, up);
+    else if (m == L - 1) spline_row(xw, L, bcb, L - 1, lo, di, up);
+    else spline_row(xw, L, 0, m, lo, di, up);
+  };
+  double lo_m, di_m, up_m, lo_n, di_n, up_n;   // rows m and m+1 of T
+  double up_prev = 0., cprev = 0., zprev = 0.;
+  row(0, lo_m, di_m, up_m);
+  for (int m = 0; m < L; ++m) {
+    if (m + 1 < L) row(m + 1, lo_n, di_n, up_n); else { lo_n = 0.; di_n = 1.; up_n = 0.; }
+    const double rhs = (m == p ? h10 : 0.) + (m == p + 1 ? h11 : 0.);
+    const double piv = 1. / (di_m - up_prev * cprev);
+    cprev = lo_n * piv;            // super-diagonal of T^T in row m is lo_{m+1}
+    zprev = (rhs - up_prev * zprev) * piv;
+    cp[m] = cprev;
+    z[m] = zprev;
+    up_prev = up_m;                // sub-diagonal of T^T in row m+1 is up_m
+    lo_m = lo_n; di_m = di_n; up_m = up_n;
+  }
+  for (int m = L - 2; m >= 0; --m) z[m] -= cp[m] * z[m + 1];
+  // w_j = sum_m z_m d rhs_m / d y_j  (+ h00, h01)
+  for (int j = 0; j < L; ++j) w[j] = 0.;
+  for (int m = 0; m < L; ++m) {
+    const int bcm = (m == 0) ? bca : ((m == L - 1) ? bcb : 0);
+    if (m == 0) { if (bcm == 0) { w[0] -= 3. * z[0]; w[1] += 3. * z[0]; } }
+    else if (m == L - 1) { if (bcm == 0) { w[L - 1] += 3. * z[m]; w[L - 2] -= 3. * z[m]; } }
+    else {
+      const double dm = xw[m] - xw[m - 1], dp = xw[m + 1] - xw[m];
+      w[m - 1] -= 3. * z[m] * (dp / dm);
+      w[m] += 3. * z[m] * (dp / dm - dm / dp);
+      w[m + 1] += 3. * z[m] * (dm / dp);
+    }
+  }
+  w[p] += h00;
+  w[p + 1] += h01;
+  *first = a;
+  return L;
+}
+
+// Drop leading / trailing weights below 1e-40 of the largest one (they cannot reach the last bit of an fp64 sum unless
+// the ordinates span more than 24 decades): returns the trimmed length, *skip = number of leading weights dropped.
+CPF_SHD int spline_trim_weights(const double* w, const int L, int* skip) {
+  double wmax = 0.;
+  for (int j = 0; j < L; ++j) wmax = fmax(wmax, fabs(w[j]));
+  const double thr = 1e-40 * wmax;
+  int lo = 0, hi = L - 1;
+  while (lo < hi && !(fabs(w[lo]) > thr)) ++lo;
+  while (hi > lo && !(fabs(w[hi]) > thr)) --hi;
+  *skip = lo;
+  return hi - lo + 1;
+}
+
 }  // namespace cpf

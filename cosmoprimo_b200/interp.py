@@ -173,3 +173,37 @@ class Interpolator1D(object):
                 res = res.to(_buf._torch().float32)
             return res.reshape(out_shape)
         return res.astype(dtype, copy=False).reshape(out_shape)
+
+
+def spline_eval_rows(x, fun, xq, bc_type='natural', window=128, extrap=False, device=None):
+    """
+    Cubic splines along the LAST axis of ``fun`` (rows, nx) -- the layout FFTLog returns -- on the shared knots ``x``
+    (nx,), evaluated at ``xq`` (nq,): returns (nq, rows), i.e. what the reference obtains with
+    ``Interpolator1D(x, fun.T, assume_sorted=True)(xq)`` (``cosmoprimo/interpolator.py:289``) without the two transposes
+    and without a global fit (``cpf_spline_eval_rows``: the value is a weighted sum of the ordinates; the slope system is
+    solved on ``window`` knots either side of the bracketing interval, ``window=0``: all knots).
+    """
+    if bc_type not in ('natural', 'clamped'):
+        raise ValueError('bc_type must be "natural" or "clamped"')
+    lib = _lib.load()
+    _lib.require_device()
+    x = np.ascontiguousarray(x, dtype='f8').ravel()
+    q = np.ascontiguousarray(xq, dtype='f8').ravel()
+    ybuf = _buf.as_input(fun, dtype='f8')
+    if len(ybuf.shape) != 2 or ybuf.shape[1] != x.size:
+        raise ValueError('fun must have shape (rows, {}), got {}'.format(x.size, tuple(ybuf.shape)))
+    rows = int(ybuf.shape[0])
+    if ybuf.on_device:
+        torch = _buf._torch()
+        dev = ybuf.device
+        tdev = torch.device('cuda', dev)
+        xbuf = _buf.as_input(torch.as_tensor(x, device=tdev))
+        qbuf = _buf.as_input(torch.as_tensor(q, device=tdev))
+        stream = _buf.current_stream(dev)
+    else:
+        dev = device if device is not None else _buf.default_device()
+        xbuf, qbuf, stream = _buf.as_input(x), _buf.as_input(q), None
+    out = _buf.empty_like_kind(ybuf, (q.size, rows))
+    _lib.check(lib.cpf_spline_eval_rows(xbuf.ptr, ybuf.ptr, x.size, rows, qbuf.ptr, q.size, 1 if bc_type == 'clamped' else 0, int(window),
+                                        int(bool(extrap)), out.ptr, int(ybuf.on_device), dev, stream))
+    return out.obj

@@ -11,7 +11,7 @@ numpy tables in -> numpy results; CUDA tables in -> torch results (the spline li
 import numpy as np
 
 from . import _buffers as _buf
-from .interp import Interpolator1D, _bcast_dtype
+from .interp import Interpolator1D, _bcast_dtype, spline_eval_rows
 from .fftlog import PowerToCorrelation, CorrelationToPower, TophatVariance
 
 _default_extrap_kmin = 1e-7
@@ -118,10 +118,10 @@ class PowerSpectrumInterpolator1D(object):
         pk = self(k)
         lead = tuple(pk.shape[1:])
         s, var = TophatVariance(k, device=self._device)(_transpose(pk.reshape(nk, -1)))      # (B, nk)
-        interp = Interpolator1D(s, _transpose(var), assume_sorted=True, device=self._device)   # linear x on a log grid, ref:289
+        # natural spline of var in (linear) s evaluated at r, ref:289 -- on the (B, nk) rows as FFTLog wrote them
         dtype = _bcast_dtype(r, pk if pk.ndim > 1 else None)
         rr = np.asarray(r, dtype='f8')
-        tmp = (2. * np.pi**2) * interp(rr.ravel())
+        tmp = (2. * np.pi**2) * spline_eval_rows(s, var, rr.ravel(), device=self._device)
         sigma2 = 1. / (2. * np.pi**2) * tmp.reshape(rr.shape + lead)
         out = sigma2**0.5
         if _buf.is_device_array(out):

@@ -104,6 +104,17 @@ int cpf_spline_eval(const cpf_spline* spline, const double* xq, int nq, int nu, 
                     void* stream);
 int cpf_spline_destroy(cpf_spline* spline);
 
+/* Row layout, no handle: natural (bc=0) or clamped (bc=1) cubic splines along the LAST axis of y [rows, nx] (the layout
+ * cpf_fftlog writes) on shared knots x [nx], evaluated at xq [nq] -> out [nq, rows].  Replaces
+ * `Interpolator1D(s, var.T, assume_sorted=True)(r)` of integrate_sigma_r2(method='fftlog') (interpolator.py:288-289)
+ * without the two transposes and without a global fit: the value at xq is a weighted sum of the ordinates whose
+ * weights depend on (x, xq) only and decay like 0.27^distance, so the slope system is solved on `window` knots either
+ * side of the bracketing interval (truncation ~0.27^window; window = 0 or >= nx: all knots = the full solve).
+ *   extrap : 0 => NaN outside [x[0], x[nx-1]], 1 => extend the end polynomials
+ */
+int cpf_spline_eval_rows(const double* x, const double* y, int nx, int64_t rows, const double* xq, int nq, int bc,
+                         int window, int extrap, double* out, int on_device, int device, void* stream);
+
 /* ---- DST-II / DST-III (orthonormal) along axis 0: replaces scipy.fftpack.dst(type=2, norm='ortho', axis=0) and
  * idst(type=2, norm='ortho', axis=0) at bao_filter.py:372, 412.  data [nx, ncols] row-major, nx a power of two.
  */

@@ -23,3 +23,14 @@ def test_stream_kernel_flow_emulation():
         res = subprocess.run([exe], capture_output=True, text=True)
     assert res.returncode == 0, res.stdout
     assert 'OK' in res.stdout
+
+
+def test_spline_window_weights_emulation():
+    """Windowed spline weights behind cpf_spline_eval_rows (cpf_spline_core.h) against a long-double full solve."""
+    here = os.path.dirname(os.path.abspath(__file__))
+    with tempfile.TemporaryDirectory() as tmp:
+        exe = os.path.join(tmp, 'emul_spline_window')
+        subprocess.run(['g++', '-O2', '-std=c++17', '-o', exe, os.path.join(here, 'emul', 'emul_spline_window.cpp')], check=True)
+        res = subprocess.run([exe], capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout
+    assert 'OK' in res.stdout

@@ -7,7 +7,7 @@ import pytest
 
 from conftest import load_golden
 from cosmoprimo_b200 import _lib, synthetic as S
-from cosmoprimo_b200.interp import Interpolator1D
+from cosmoprimo_b200.interp import Interpolator1D, spline_eval_rows
 from cosmoprimo_b200.interpolator import PowerSpectrumInterpolator1D, CorrelationFunctionInterpolator1D
 from cosmoprimo_b200.bao_filter import PowerSpectrumBAOFilter, Wallish2018PowerSpectrumBAOFilter
 from oracle import spline_oracle as SO
@@ -87,6 +87,36 @@ def test_spline_device_buffers_and_shapes():
     assert interp(np.ones(4, dtype='f4')).dtype == np.float32 and interp(np.ones(4)).dtype == np.float64
     with pytest.raises(ValueError):
         interp(np.array([100.]), bounds_error=True)
+
+
+def test_spline_eval_rows_vs_oracle():
+    """cpf_spline_eval_rows (windowed weights, rows layout) == Interpolator1D(s, var.T)(r) of the reference (interpolator.py:289)."""
+    torch = pytest.importorskip('torch')
+    n, B = 2048, 37
+    k = np.geomspace(1e-5, 1e2, n)
+    pk = S.eh_pk(k, S.lhs_cosmologies(B, seed=5))
+    from oracle import fftlog_oracle as FO
+    s, var = FO.execute(FO.plan_tophat_variance(k), pk)
+    r = np.concatenate([np.linspace(1., 20., 10), [s[0], s[-1], 0.5 * (s[0] + s[1]), 8., s[0] * 0.5, s[-1] * 2, np.nan]])
+    ref = SO.interpolator1d(s, var.T, assume_sorted=True)(r)
+    for window in [0, 128, 40]:
+        out = spline_eval_rows(s, var, r, window=window)
+        assert out.shape == (r.size, B)
+        close_with_nans(out, ref, rtol=1e-11)
+    out = spline_eval_rows(s, torch.from_numpy(var).cuda(), r)
+    assert isinstance(out, torch.Tensor) and out.is_cuda
+    close_with_nans(out.cpu().numpy(), ref, rtol=1e-11)
+    # clamped ends, coarse random grid (full solve since nx < 2 * window + 2), extrapolation
+    rng = np.random.default_rng(11)
+    x = np.sort(rng.uniform(0., 10., 50))
+    y = rng.normal(size=(5, 50))
+    xq = np.concatenate([rng.uniform(x[0], x[-1], 40), [x[0] - 0.1, x[-1] + 0.2]])
+    for bc in ['natural', 'clamped']:
+        sl = SO.cubic_spline_slopes(x, y.T, bc)
+        ref = SO.cubic_spline_eval(x, y.T, sl, xq, extrapolate=True)
+        out = spline_eval_rows(x, y, xq, bc_type=bc, extrap=True)
+        assert np.max(np.abs(out - ref)) < 1e-12 * np.max(np.abs(ref)), bc
+    assert spline_eval_rows(x, y[:0], xq).shape == (xq.size, 0)
 
 
 def fake_interpolator(klin, pklin, kout, pkout, extrap_kmin=1e-7, extrap_kmax=1e2):
