@@ -20,21 +20,30 @@
 namespace cpf {
 
 // ---- factorisation: one thread, O(nx) ------------------------------------------------------------------------------
-// fac[0*nx + i] = lower_i (coefficient of s_{i-1}), fac[1*nx + i] = 1/pivot_i, fac[2*nx + i] = upper_i / pivot_i
+// fac[0*nx + i] = Lw_i, fac[1*nx + i] = cp_i, fac[2*nx + i] = P_i, fac[3*nx + i] = Q_i (spline_factor_step)
 __global__ void spline_factor_kernel(const double* __restrict__ x, const int nx, const int bc, double* __restrict__ fac) {
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
-  double* lower = fac;
-  double* winv = fac + nx;
-  double* cp = fac + 2 * nx;
   double cprev = 0.;
   for (int i = 0; i < nx; ++i) {
-    double lo, di, up;
-    spline_row(x, nx, bc, i, lo, di, up);
-    const double w = 1. / (di - lo * cprev);
-    lower[i] = lo;
-    winv[i] = w;
-    cprev = up * w;
-    cp[i] = cprev;
+    double Lw, P, Q;
+    spline_factor_step(x, nx, bc, i, cprev, Lw, P, Q);
+    fac[i] = Lw;
+    fac[nx + i] = cprev;
+    fac[2 * nx + i] = P;
+    fac[3 * nx + i] = Q;
+  }
+}
+
+// the same on the host, for callers that hold the knots there (cpf_wallish2018): 4*nx doubles
+void spline_factor_host(const double* x, const int nx, const int bc, double* fac) {
+  double cprev = 0.;
+  for (int i = 0; i < nx; ++i) {
+    double Lw, P, Q;
+    spline_factor_step(x, nx, bc, i, cprev, Lw, P, Q);
+    fac[i] = Lw;
+    fac[nx + i] = cprev;
+    fac[2 * nx + i] = P;
+    fac[3 * nx + i] = Q;
   }
 }
 
@@ -45,30 +54,90 @@ __global__ void log10_kernel(const double* __restrict__ in, double* __restrict__
 }
 
 // ---- per-column forward elimination + back substitution ------------------------------------------------------------
-__global__ void __launch_bounds__(128) spline_solve_kernel(const double* __restrict__ x, const double* __restrict__ y,
-                                                            const double* __restrict__ fac, const int nx, const long long ncols,
-                                                            const int bc, double* __restrict__ s) {
+// One thread per (column, chunk of SPLINE_CHUNK knots).  The recurrences are one FMA deep per knot; ordinates are loaded a
+// block of SPLINE_U knots ahead so that the HBM latency is paid once per block, not once per knot.  Chunks make enough
+// threads to hide that latency when there are few columns: the system is strictly diagonally dominant, a perturbation of
+// the recurrence decays by >= 2 (typically 3.7) per knot, so a chunk starts SPLINE_WARM knots early from zero (forward) /
+// from the reduced right-hand side (backward) and is exact to < 1e-19 where it starts storing.  nx <= SPLINE_SERIAL_MAX:
+// one chunk, i.e. the plain Thomas algorithm.
+#define SPLINE_U 16
+#define SPLINE_CHUNK 256
+#define SPLINE_WARM 64
+#define SPLINE_SERIAL_MAX 512
+
+// forward: dp_i = P_i (y_i - y_{i-1}) + Q_i (y_{i+1} - y_i) - Lw_i dp_{i-1}
+__global__ void __launch_bounds__(128) spline_forward_kernel(const double* __restrict__ y, const double* __restrict__ fac, const int nx,
+                                                              const long long ncols, const int chunk, double* __restrict__ dp) {
   const long long col = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (col >= ncols) return;
-  const double* lower = fac;
-  const double* winv = fac + nx;
-  const double* cp = fac + 2 * nx;
-  // forward: dp_i = (rhs_i - lower_i dp_{i-1}) / pivot_i, stored in s
-  double ym = 0., y0 = y[col], yp = nx > 1 ? y[ncols + col] : 0.;
-  double dprev = 0.;
-  for (int i = 0; i < nx; ++i) {
-    const double rhs = spline_rhs(x, nx, bc, i, ym, y0, yp);
-    dprev = (rhs - lower[i] * dprev) * winv[i];
-    s[(long long)i * ncols + col] = dprev;
-    ym = y0;
-    y0 = yp;
-    if (i + 2 < nx) yp = y[(long long)(i + 2) * ncols + col];
+  const int first = blockIdx.y * chunk, last = min(nx, first + chunk) - 1;
+  const int start = max(0, first - SPLINE_WARM);
+  const double* Lw = fac;
+  const double* P = fac + 2 * nx;
+  const double* Q = fac + 3 * nx;
+  const double* yc = y + col;
+  double* dc = dp + col;
+  double nxt[SPLINE_U];
+#pragma unroll
+  for (int u = 0; u < SPLINE_U; ++u) nxt[u] = (start + 1 + u < nx) ? yc[(long long)(start + 1 + u) * ncols] : 0.;
+  double ym = start > 0 ? yc[(long long)(start - 1) * ncols] : 0., y0 = yc[(long long)start * ncols], dprev = 0.;
+  for (int base = start; base <= last; base += SPLINE_U) {
+    double cur[SPLINE_U];
+#pragma unroll
+    for (int u = 0; u < SPLINE_U; ++u) cur[u] = nxt[u];
+#pragma unroll
+    for (int u = 0; u < SPLINE_U; ++u) {
+      const int j = base + SPLINE_U + 1 + u;
+      nxt[u] = (j < nx && j <= last + 1) ? yc[(long long)j * ncols] : 0.;
+    }
+#pragma unroll
+    for (int u = 0; u < SPLINE_U; ++u) {
+      const int i = base + u;
+      if (i <= last) {
+        const double yp = cur[u];
+        const double t = fma(__ldg(P + i), y0 - ym, __ldg(Q + i) * (yp - y0));
+        dprev = fma(-__ldg(Lw + i), dprev, t);
+        if (i >= first) dc[(long long)i * ncols] = dprev;
+        ym = y0;
+        y0 = yp;
+      }
+    }
   }
-  // backward: s_i = dp_i - cp_i s_{i+1}
-  double snext = dprev;
-  for (int i = nx - 2; i >= 0; --i) {
-    snext = s[(long long)i * ncols + col] - cp[i] * snext;
-    s[(long long)i * ncols + col] = snext;
+}
+
+// backward: s_i = dp_i - cp_i s_{i+1}
+__global__ void __launch_bounds__(128) spline_backward_kernel(const double* __restrict__ dp, const double* __restrict__ fac, const int nx,
+                                                               const long long ncols, const int chunk, double* __restrict__ s) {
+  const long long col = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (col >= ncols) return;
+  const int first = blockIdx.y * chunk, last = min(nx, first + chunk) - 1;
+  const int end = min(nx - 1, last + SPLINE_WARM);
+  const double* cp = fac + nx;
+  const double* dc = dp + col;
+  double* sc = s + col;
+  double snext = dc[(long long)end * ncols];
+  if (end == last) sc[(long long)end * ncols] = snext;      // last knot of the spline: s = dp
+  int top = end - 1;
+  double nxt[SPLINE_U];
+#pragma unroll
+  for (int u = 0; u < SPLINE_U; ++u) nxt[u] = (top - u >= first) ? dc[(long long)(top - u) * ncols] : 0.;
+  for (; top >= first; top -= SPLINE_U) {
+    double cur[SPLINE_U];
+#pragma unroll
+    for (int u = 0; u < SPLINE_U; ++u) cur[u] = nxt[u];
+#pragma unroll
+    for (int u = 0; u < SPLINE_U; ++u) {
+      const int j = top - SPLINE_U - u;
+      nxt[u] = j >= first ? dc[(long long)j * ncols] : 0.;
+    }
+#pragma unroll
+    for (int u = 0; u < SPLINE_U; ++u) {
+      const int i = top - u;
+      if (i >= first) {
+        snext = fma(-__ldg(cp + i), snext, cur[u]);
+        if (i <= last) sc[(long long)i * ncols] = snext;
+      }
+    }
   }
 }
 
@@ -98,28 +167,52 @@ __global__ void __launch_bounds__(128) spline_eval_kernel(const double* __restri
 }
 
 // ---- row layout: splines along the LAST axis, windowed weights (cpf_spline_core.h) ------------------------------------
-// weights kernel: one thread per query; wq [nq, LW] weights, meta [3, nq] = (first knot, length or -1 for NaN), offset of the first kept weight
-__global__ void spline_row_weights_kernel(const double* __restrict__ x, const int nx, const int bc, const int W, const int LW,
-                                          const double* __restrict__ xq, const int nq, const int extrap,
-                                          double* __restrict__ wq, double* __restrict__ work, int* __restrict__ meta) {
-  const int q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= nq) return;
+// weights kernel: one warp per query (the Thomas sweep is serial on lane 0, in shared memory when the window fits; the
+// weights and their trimming use the whole warp).  wq [nq, LW] weights, meta [3, nq] = (first knot, length or -1 for NaN),
+// offset of the first kept weight
+__global__ void __launch_bounds__(32) spline_row_weights_kernel(const double* __restrict__ x, const int nx, const int bc, const int W,
+                                                               const int LW, const double* __restrict__ xq, const int nq,
+                                                               const int extrap, const int use_smem, double* __restrict__ wq,
+                                                               double* __restrict__ work, int* __restrict__ meta) {
+  extern __shared__ double sw_smem[];
+  const int q = blockIdx.x, lane = threadIdx.x;
   const double xv = xq[q];
   double* w = wq + (size_t)q * LW;
   const bool inside = xv >= x[0] && xv <= x[nx - 1];
   if ((!inside && !extrap) || !(xv == xv)) {
-    meta[2 * q] = 0;
-    meta[2 * q + 1] = -1;
-    meta[2 * nq + q] = 0;
+    if (lane == 0) { meta[2 * q] = 0; meta[2 * q + 1] = -1; meta[2 * nq + q] = 0; }
     return;
   }
-  int first;
-  const int L = spline_window_weights(x, nx, bc, W, xv, w, work + (size_t)q * 2 * LW, &first);
-  int skip;
-  const int Lt = spline_trim_weights(w, L, &skip);
-  meta[2 * q] = first + skip;
-  meta[2 * q + 1] = Lt;
-  meta[2 * nq + q] = skip;
+  const SplineWindow sw = spline_window_setup(x, nx, bc, W, xv);
+  double* cp = use_smem ? sw_smem : work + (size_t)q * 2 * LW;
+  double* z = cp + LW;
+  if (lane == 0) spline_window_solve(x + sw.a, sw, cp, z);
+  __syncwarp();
+  double wmax = 0.;
+  for (int j = lane; j < sw.L; j += 32) {
+    const double wj = spline_window_weight(x + sw.a, sw, z, j);
+    w[j] = wj;
+    wmax = fmax(wmax, fabs(wj));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) wmax = fmax(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+  __syncwarp();
+  // trimmed range (spline_trim_weights): first / last weight above 1e-40 of the largest
+  const double thr = 1e-40 * wmax;
+  int lo = sw.L, hi = -1;
+  for (int j = lane; j < sw.L; j += 32)
+    if (fabs(w[j]) > thr) { lo = min(lo, j); hi = max(hi, j); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if (hi < lo) { lo = 0; hi = 0; }
+  if (lane == 0) {
+    meta[2 * q] = sw.a + lo;
+    meta[2 * q + 1] = hi - lo + 1;
+    meta[2 * nq + q] = lo;
+  }
 }
 
 // dot kernel: one warp per row; out[q, row] = sum_j w[q, j] y[row, first_q + j].  Window loads are contiguous runs.
@@ -146,11 +239,18 @@ __global__ void __launch_bounds__(256) spline_rows_dot_kernel(const double* __re
 }
 
 // device-resident fit, shared with cpf_wallish.cu: slopes s[nx, ncols] of the splines through y[nx, ncols] on the
-// knots x[nx]; fac is scratch of 3*nx doubles
+// knots x[nx]; fac is scratch of 4*nx doubles (already filled by spline_factor_host when fac_ready)
 int spline_fit_device(const double* d_x, const double* d_y, int nx, long long ncols, int bc, double* d_s, double* d_fac,
-                      cudaStream_t stream) {
-  spline_factor_kernel<<<1, 32, 0, stream>>>(d_x, nx, bc, d_fac);
-  if (ncols > 0) spline_solve_kernel<<<(unsigned)((ncols + 127) / 128), 128, 0, stream>>>(d_x, d_y, d_fac, nx, ncols, bc, d_s);
+                      cudaStream_t stream, bool fac_ready) {
+  if (!fac_ready) spline_factor_kernel<<<1, 32, 0, stream>>>(d_x, nx, bc, d_fac);
+  if (ncols > 0) {
+    ScratchBuf dp;
+    CPF_CUDA(dp.alloc((size_t)nx * (size_t)ncols * sizeof(double), stream));
+    const int chunk = nx <= SPLINE_SERIAL_MAX ? nx : SPLINE_CHUNK;
+    const dim3 grid((unsigned)((ncols + 127) / 128), (unsigned)((nx + chunk - 1) / chunk));
+    spline_forward_kernel<<<grid, 128, 0, stream>>>(d_y, d_fac, nx, ncols, chunk, (double*)dp.p);
+    spline_backward_kernel<<<grid, 128, 0, stream>>>((const double*)dp.p, d_fac, nx, ncols, chunk, d_s);
+  }
   CPF_CUDA(cudaGetLastError());
   return CPF_OK;
 }
@@ -226,8 +326,8 @@ int cpf_spline_create(cpf_spline** out, const double* x, const double* y, int nx
     sp->xmin_raw = ends[0]; sp->xmax_raw = ends[1];
     log10_kernel<<<(nx + 255) / 256, 256, 0, stream>>>(src_x, sp->d_x, nx, sp->log_x);
     if (cells) log10_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, stream>>>(src_y, sp->d_y, (long long)cells, sp->log_y);
-    SP_CUDA(fac.alloc(3 * (size_t)nx * sizeof(double), stream));
-    if ((rc = spline_fit_device(sp->d_x, sp->d_y, nx, ncols, bc, sp->d_s, (double*)fac.p, stream)) != CPF_OK) break;
+    SP_CUDA(fac.alloc(4 * (size_t)nx * sizeof(double), stream));
+    if ((rc = spline_fit_device(sp->d_x, sp->d_y, nx, ncols, bc, sp->d_s, (double*)fac.p, stream, false)) != CPF_OK) break;
     if (!on_device) SP_CUDA(cudaStreamSynchronize(stream));   // staging buffers of the caller may go away
 #undef SP_CUDA
   } while (0);
@@ -283,7 +383,7 @@ int cpf_spline_eval_rows(const double* x, const double* y, int nx, int64_t rows,
   if (device < 0 || device >= ndev) return fail(CPF_EINVAL, "cpf_spline_eval_rows: device %d out of range (%d visible)", device, ndev);
   DeviceGuard guard(device);
   cudaStream_t stream = (cudaStream_t)stream_;
-  const int W = (window == 0 || window > nx) ? nx : window;   // the host default is 128 (cosmoprimo_b200/interp.py)
+  const int W = (window == 0 || window > nx) ? nx : window;   // the host default is 64 (cosmoprimo_b200/interp.py)
   const int LW = (2 * W + 2 < nx) ? 2 * W + 2 : nx;
   const size_t ycells = (size_t)rows * nx, ocells = (size_t)nq * rows;
   ScratchBuf dx, dy, dq, dout, dw, dwork, dmeta;
@@ -302,8 +402,10 @@ int cpf_spline_eval_rows(const double* x, const double* y, int nx, int64_t rows,
   CPF_CUDA(dw.alloc((size_t)nq * LW * sizeof(double), stream));
   CPF_CUDA(dwork.alloc((size_t)nq * 2 * LW * sizeof(double), stream));
   CPF_CUDA(dmeta.alloc((size_t)nq * 3 * sizeof(int), stream));
-  spline_row_weights_kernel<<<(nq + 63) / 64, 64, 0, stream>>>(p_x, nx, bc, W, LW, p_q, nq, extrap ? 1 : 0, (double*)dw.p,
-                                                              (double*)dwork.p, (int*)dmeta.p);
+  const size_t wsmem = 2 * (size_t)LW * sizeof(double);
+  const int use_smem = wsmem <= 48 * 1024;
+  spline_row_weights_kernel<<<nq, 32, use_smem ? wsmem : 0, stream>>>(p_x, nx, bc, W, LW, p_q, nq, extrap ? 1 : 0, use_smem,
+                                                                     (double*)dw.p, (double*)dwork.p, (int*)dmeta.p);
   CPF_CUDA(cudaGetLastError());
   const int wpb = 8;
   spline_rows_dot_kernel<<<(unsigned)((rows + wpb - 1) / wpb), 32 * wpb, 0, stream>>>(p_y, nx, rows, (const double*)dw.p,

@@ -38,6 +38,25 @@ CPF_SHD double spline_rhs(const double* x, const int nx, const int bc, const int
   return 3. * (dp * ((y0 - ym) / dm) + dm * ((yp - y0) / dp));
 }
 
+// One step of the factorisation shared by all columns: given c'_{i-1} (cprev) returns the four per-knot factors
+//   Lw_i = lo_i / piv_i, cp_i = up_i / piv_i, P_i, Q_i with  rhs_i / piv_i = P_i (y_i - y_{i-1}) + Q_i (y_{i+1} - y_i)
+// (differences of neighbouring ordinates are taken first, as scipy does, so smooth data keep their accuracy).
+CPF_SHD void spline_factor_step(const double* x, const int nx, const int bc, const int i, double& cprev, double& Lw, double& P,
+                                double& Q) {
+  double lo, di, up;
+  spline_row(x, nx, bc, i, lo, di, up);
+  const double w = 1. / (di - lo * cprev);
+  Lw = lo * w;
+  cprev = up * w;
+  if (i == 0) { P = 0.; Q = bc == 1 ? 0. : 3. * w; }
+  else if (i == nx - 1) { Q = 0.; P = bc == 1 ? 0. : 3. * w; }
+  else {
+    const double dm = x[i] - x[i - 1], dp = x[i + 1] - x[i];
+    P = 3. * (dp / dm) * w;
+    Q = 3. * (dm / dp) * w;
+  }
+}
+
 // Interval index i with x_i <= xv < x_{i+1}, clamped to [0, nx-2] (so xv == x_{nx-1} and extrapolated points use the
 // end polynomials, as scipy's PPoly does).
 CPF_SHD int spline_interval(const double* x, const int nx, const double xv) {
@@ -72,36 +91,50 @@ CPF_SHD double spline_poly(const double x0, const double x1, const double y0, co
 // (1e-23 for W = 40; W >= nx covers all knots and is the full solve).  The weights depend on the grid and on xv only,
 // so they are computed once per query and shared by all rows.
 //
-// Output: w[0..L-1] for the knots a..a+L-1 (L = b-a+1 <= 2W+2), *first = a.  `work` is scratch of 2*L doubles.
+// Split in three steps so that the kernel can run the last one (and the trimming) with a whole warp:
+//   spline_window_setup  : window [a, b], Hermite factors of the bracketing interval
+//   spline_window_solve  : z = T^-T (h10 e_p + h11 e_{p+1}) by Thomas elimination on the transposed window system (serial)
+//   spline_window_weight : w_j = sum_m z_m d rhs_m / d y_j (+ h00, h01), independent for every j
 // Truncated window ends use the natural end row (any consistent end row does: its effect is below the truncation).
-CPF_SHD int spline_window_weights(const double* x, const int nx, const int bc, const int W, const double xv, double* w,
-                                  double* work, int* first) {
+struct SplineWindow {
+  int a, L, p, bca, bcb;
+  double h00, h01, h10, h11;
+};
+
+CPF_SHD SplineWindow spline_window_setup(const double* x, const int nx, const int bc, const int W, const double xv) {
+  SplineWindow sw;
   const int i = spline_interval(x, nx, xv);
-  const int a = (i - W > 0) ? i - W : 0;
+  sw.a = (i - W > 0) ? i - W : 0;
   const int b = (i + 1 + W < nx - 1) ? i + 1 + W : nx - 1;
-  const int L = b - a + 1;
-  const double* xw = x + a;
-  const int bca = (a == 0) ? bc : 0, bcb = (b == nx - 1) ? bc : 0;   // end rows of the window system
-  const int p = i - a;
+  sw.L = b - sw.a + 1;
+  sw.bca = (sw.a == 0) ? bc : 0;
+  sw.bcb = (b == nx - 1) ? bc : 0;
+  sw.p = i - sw.a;
   // Hermite form of the cubic on [x_i, x_{i+1}]: S = h00 y_i + h01 y_{i+1} + dx (h10 s_i + h11 s_{i+1})
   const double dx = x[i + 1] - x[i];
   const double u = (xv - x[i]) / dx;
-  const double h00 = (1. + 2. * u) * (1. - u) * (1. - u), h01 = u * u * (3. - 2. * u);
-  const double h10 = u * (1. - u) * (1. - u) * dx, h11 = -u * u * (1. - u) * dx;
-  // solve T^T z = h10 e_p + h11 e_{p+1}; row m of T^T: up_{m-1} z_{m-1} + di_m z_m + lo_{m+1} z_{m+1}
-  double* cp = work;        // modified super-diagonal
-  double* z = work + L;
-  auto row = [&](const int m, double& lo, double& di, double& up) {
-    if (m == 0) spline_row(xw, L, bca, 0, lo, di, up);
-    else if (m == L - 1) spline_row(xw, L, bcb, L - 1, lo, di, up);
-    else spline_row(xw, L, 0, m, lo, di, up);
-  };
+  sw.h00 = (1. + 2. * u) * (1. - u) * (1. - u);
+  sw.h01 = u * u * (3. - 2. * u);
+  sw.h10 = u * (1. - u) * (1. - u) * dx;
+  sw.h11 = -u * u * (1. - u) * dx;
+  return sw;
+}
+
+CPF_SHD void spline_window_row(const double* xw, const SplineWindow& sw, const int m, double& lo, double& di, double& up) {
+  if (m == 0) spline_row(xw, sw.L, sw.bca, 0, lo, di, up);
+  else if (m == sw.L - 1) spline_row(xw, sw.L, sw.bcb, sw.L - 1, lo, di, up);
+  else spline_row(xw, sw.L, 0, m, lo, di, up);
+}
+
+// cp, z: scratch / result of L doubles each.  Row m of T^T: up_{m-1} z_{m-1} + di_m z_m + lo_{m+1} z_{m+1} = rhs_m.
+CPF_SHD void spline_window_solve(const double* xw, const SplineWindow& sw, double* cp, double* z) {
+  const int L = sw.L;
   double lo_m, di_m, up_m, lo_n, di_n, up_n;   // rows m and m+1 of T
   double up_prev = 0., cprev = 0., zprev = 0.;
-  row(0, lo_m, di_m, up_m);
+  spline_window_row(xw, sw, 0, lo_m, di_m, up_m);
   for (int m = 0; m < L; ++m) {
-    if (m + 1 < L) row(m + 1, lo_n, di_n, up_n); else { lo_n = 0.; di_n = 1.; up_n = 0.; }
-    const double rhs = (m == p ? h10 : 0.) + (m == p + 1 ? h11 : 0.);
+    if (m + 1 < L) spline_window_row(xw, sw, m + 1, lo_n, di_n, up_n); else { lo_n = 0.; di_n = 1.; up_n = 0.; }
+    const double rhs = (m == sw.p ? sw.h10 : 0.) + (m == sw.p + 1 ? sw.h11 : 0.);
     const double piv = 1. / (di_m - up_prev * cprev);
     cprev = lo_n * piv;            // super-diagonal of T^T in row m is lo_{m+1}
     zprev = (rhs - up_prev * zprev) * piv;
@@ -110,24 +143,44 @@ CPF_SHD int spline_window_weights(const double* x, const int nx, const int bc, c
     up_prev = up_m;                // sub-diagonal of T^T in row m+1 is up_m
     lo_m = lo_n; di_m = di_n; up_m = up_n;
   }
-  for (int m = L - 2; m >= 0; --m) z[m] -= cp[m] * z[m + 1];
-  // w_j = sum_m z_m d rhs_m / d y_j  (+ h00, h01)
-  for (int j = 0; j < L; ++j) w[j] = 0.;
-  for (int m = 0; m < L; ++m) {
-    const int bcm = (m == 0) ? bca : ((m == L - 1) ? bcb : 0);
-    if (m == 0) { if (bcm == 0) { w[0] -= 3. * z[0]; w[1] += 3. * z[0]; } }
-    else if (m == L - 1) { if (bcm == 0) { w[L - 1] += 3. * z[m]; w[L - 2] -= 3. * z[m]; } }
-    else {
-      const double dm = xw[m] - xw[m - 1], dp = xw[m + 1] - xw[m];
-      w[m - 1] -= 3. * z[m] * (dp / dm);
-      w[m] += 3. * z[m] * (dp / dm - dm / dp);
-      w[m + 1] += 3. * z[m] * (dm / dp);
-    }
+  double zn = z[L - 1];
+  for (int m = L - 2; m >= 0; --m) {
+    zn = z[m] - cp[m] * zn;
+    z[m] = zn;
   }
-  w[p] += h00;
-  w[p + 1] += h01;
-  *first = a;
-  return L;
+}
+
+// rhs_m = 3 (dp (y_m - y_{m-1}) / dm + dm (y_{m+1} - y_m) / dp) inside, 3 (y_1 - y_0) / 3 (y_{L-1} - y_{L-2}) on natural
+// end rows, 0 on clamped ones: collect the three rows that see y_j.
+CPF_SHD double spline_window_weight(const double* xw, const SplineWindow& sw, const double* z, const int j) {
+  const int L = sw.L;
+  double w = 0.;
+  if (j >= 1) {                                   // row m = j-1 sees y_j as y_{m+1}
+    const int m = j - 1;
+    if (m == 0) { if (sw.bca == 0) w += 3. * z[0]; }
+    else { const double dm = xw[m] - xw[m - 1], dp = xw[m + 1] - xw[m]; w += 3. * z[m] * (dm / dp); }
+  }
+  if (j == 0) { if (sw.bca == 0) w -= 3. * z[0]; }
+  else if (j == L - 1) { if (sw.bcb == 0) w += 3. * z[j]; }
+  else { const double dm = xw[j] - xw[j - 1], dp = xw[j + 1] - xw[j]; w += 3. * z[j] * (dp / dm - dm / dp); }
+  if (j + 1 <= L - 1) {                           // row m = j+1 sees y_j as y_{m-1}
+    const int m = j + 1;
+    if (m == L - 1) { if (sw.bcb == 0) w -= 3. * z[m]; }
+    else { const double dm = xw[m] - xw[m - 1], dp = xw[m + 1] - xw[m]; w -= 3. * z[m] * (dp / dm); }
+  }
+  if (j == sw.p) w += sw.h00;
+  if (j == sw.p + 1) w += sw.h01;
+  return w;
+}
+
+// serial driver (CPU emulation): w[0..L-1] for the knots a..a+L-1, *first = a; `work` is scratch of 2*L doubles
+CPF_SHD int spline_window_weights(const double* x, const int nx, const int bc, const int W, const double xv, double* w,
+                                  double* work, int* first) {
+  const SplineWindow sw = spline_window_setup(x, nx, bc, W, xv);
+  spline_window_solve(x + sw.a, sw, work, work + sw.L);
+  for (int j = 0; j < sw.L; ++j) w[j] = spline_window_weight(x + sw.a, sw, work + sw.L, j);
+  *first = sw.a;
+  return sw.L;
 }
 
 // Drop leading / trailing weights below 1e-40 of the largest one (they cannot reach the last bit of an fp64 sum unless

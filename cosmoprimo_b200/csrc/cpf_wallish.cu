@@ -22,7 +22,8 @@ namespace cpf {
 
 // defined in cpf_spline.cu
 int spline_fit_device(const double* d_x, const double* d_y, int nx, long long ncols, int bc, double* d_s, double* d_fac,
-                      cudaStream_t stream);
+                      cudaStream_t stream, bool fac_ready);
+void spline_factor_host(const double* x, int nx, int bc, double* fac);
 
 struct WallishTables {
   int device;
@@ -35,6 +36,8 @@ struct WallishTables {
 struct WallishArgs {
   const double* klin;     // [4096]
   const double* pklin;    // [4096, ncols]
+  double2* packed;        // [npairs, 4096]: in  = sign * log(k P) of both columns of a pair in Makhoul order (wallish_pack_kernel),
+                          //                 out = raw FFT bins of the DST-III (consumed by wallish_unpack_kernel)
   long long ncols;
   int i0, i1;             // rows of klin kept (1e-2 < k < 1.5)
   int nl;                 // rows of the knot matrix before them
@@ -90,6 +93,33 @@ __device__ __forceinline__ int makhoul_src(const int n, double& sign) {
   return 2 * (WallishGeo::N - 1 - n) + 1;
 }
 
+// warp-level argmax of the chunk candidates of both columns; lane 0 of warp w (sequence parity h = w / 4) leaves the
+// warp's best of column col in red / redi [2 w + col]
+__device__ __forceinline__ void wallish_best_reduce(const int t, WallishBest b, double* red, int* redi) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ovx = __shfl_xor_sync(0xffffffffu, b.vx, o), ovy = __shfl_xor_sync(0xffffffffu, b.vy, o);
+    const int oix = __shfl_xor_sync(0xffffffffu, b.ix, o), oiy = __shfl_xor_sync(0xffffffffu, b.iy, o);
+    wallish_best_merge(b.vx, b.ix, ovx, oix);
+    wallish_best_merge(b.vy, b.iy, ovy, oiy);
+  }
+  if ((t & 31) == 0) {
+    const int w = t >> 5;
+    red[2 * w] = b.vx; redi[2 * w] = b.ix;
+    red[2 * w + 1] = b.vy; redi[2 * w + 1] = b.iy;
+  }
+}
+
+// sequence q = 2 h + col: merge the four warps of parity h
+__device__ __forceinline__ int wallish_best_final(const int q, const double* red, const int* redi) {
+  const int h = q >> 1, col = q & 1;
+  double v = 0.;
+  int i = -1;
+#pragma unroll
+  for (int w = 4 * h; w < 4 * h + 4; ++w) wallish_best_merge(v, i, red[2 * w + col], redi[2 * w + col]);
+  return i;
+}
+
 __global__ void __launch_bounds__(256, 1) wallish_fused_kernel(const WallishArgs a) {
   typedef WallishGeo G;
   extern __shared__ double2 smem_raw[];
@@ -98,34 +128,34 @@ __global__ void __launch_bounds__(256, 1) wallish_fused_kernel(const WallishArgs
   const long long col0 = 2LL * blockIdx.x;
   const bool has1 = col0 + 1 < a.ncols;
   double2 v[16];
-  // log(k P), Makhoul order                                                                   (bao_filter.py:371)
+  // sign * log(k P) in Makhoul order, packed per pair by wallish_pack_kernel                  (bao_filter.py:371)
+  double2* zrow = a.packed + (long long)blockIdx.x * G::N;
 #pragma unroll
-  for (int r = 0; r < 16; ++r) {
-    double sign;
-    const int j = makhoul_src(t + 256 * r, sign);
-    const double k = a.klin[j];
-    const double* row = a.pklin + (long long)j * a.ncols + col0;
-    const double pa = __ldcs(row), pb = has1 ? __ldcs(row + 1) : pa;
-    v[r] = mk2(sign * log(k * pa), sign * log(k * pb));
-  }
+  for (int r = 0; r < 16; ++r) v[r] = __ldcs(zrow + t + 256 * r);
   dst2_in_smem(t, v, sm, a.tw1, a.tw2, a.twd);                                              // :372
   // second derivatives of the clamped splines through the even / odd coefficients           (:377-382)
   wallish_forward(t, sm.X, sm.S, a.wtab);
   __syncthreads();
-  wallish_backward_dd(t, sm.X, sm.S, sm.DD, a.wtab);
+  WallishBest chunk;
+  wallish_backward_dd(t, sm.X, sm.S, sm.DD, a.wtab, &chunk);
+  // boxes (:392-395): argmax over [20, H-20), then over [first + 5, H-20); per-chunk maxima come out of the backward pass,
+  // warps reduce them with shuffles, thread q < 4 merges the four warps of its sequence
+  wallish_best_reduce(t, chunk, sm.red, sm.redi);
   __syncthreads();
-  // boxes                                                                                   (:392-395)
-  wallish_argmax_local(t, sm.DD, G::MARGIN_FIRST, G::H - G::MARGIN_FIRST, sm.red, sm.redi);
+  if (t < 4) sm.box[2 * t] = wallish_best_final(t, sm.red, sm.redi);
   __syncthreads();
-  if (t < 4) sm.box[2 * t] = wallish_argmax_final(t, sm.red, sm.redi);
-  __syncthreads();
-  wallish_argmax_local(t, sm.DD, sm.box[2 * (t >> 6)] + G::MARGIN_SECOND, G::H - G::MARGIN_FIRST, sm.red, sm.redi);
+  {
+    const int h = t >> 7;
+    const WallishBest cand = wallish_chunk_candidate(t, sm.DD, sm.box[4 * h] + G::MARGIN_SECOND, sm.box[4 * h + 2] + G::MARGIN_SECOND, chunk);
+    wallish_best_reduce(t, cand, sm.red, sm.redi);     // red / redi were consumed before the previous barrier
+  }
   __syncthreads();
   if (t < 4) {
-    const int h = t >> 1, col = t & 1;
-    const int amax = sm.box[2 * t], bmax = wallish_argmax_final(t, sm.red, sm.redi);
+    const int col = t & 1, h = t >> 1;
+    const int amax = sm.box[2 * t], bmax = wallish_best_final(t, sm.red, sm.redi);
     const int b0 = amax + G::OFF_LO, b1 = (bmax < 0 ? G::H : bmax + G::OFF_HI);   // empty second range: treated as "to the end"
-    sm.gaps[t] = wallish_gap_solve(sm.X, h, col, b0, b1, a.wtab);                 // (:396-401)
+    sm.box[2 * t] = b0;
+    sm.box[2 * t + 1] = b1;
     if (a.boxes && (col == 0 || has1)) {
       int* dst = a.boxes + (col0 + col) * 4 + 2 * h;
       dst[0] = b0;
@@ -133,26 +163,107 @@ __global__ void __launch_bounds__(256, 1) wallish_fused_kernel(const WallishArgs
     }
   }
   __syncthreads();
-  for (int e = t; e < G::N; e += 256) {                                                     // :402
-    const int h = e >> 11, i = e & (G::H - 1);
-    const double2 y = sm.X[wpos(h, i)];
-    sm.X[wpos(h, i)] = mk2(wallish_fill(y.x, i, sm.gaps[2 * h]), wallish_fill(y.y, i, sm.gaps[2 * h + 1]));
+  // cut + re-spline (:396-401): right-hand sides of the 8 one-sided eliminations by all threads (DD is free now), the 8
+  // chains on 8 threads, the 2x2 solves on 4
+  double* gr = reinterpret_cast<double*>(sm.DD);
+  {
+    const int e = t >> 5, q = e >> 1;                  // warp e runs elimination e: sequence q, side e & 1
+    const int b0 = sm.box[2 * q], b1 = sm.box[2 * q + 1];
+    const bool ok = wallish_gap_ok(b0, b1);
+    for (int step = t & 31; step < G::WARM; step += 32)
+      gr[e * G::WARM + step] = ok ? wallish_gap_rhs(sm.X, q >> 1, q & 1, wallish_gap_row(b0, b1, e & 1, step)) : 0.;
+  }
+  __syncthreads();
+  if (t < 8) {
+    const int q = t >> 1;
+    const int b0 = sm.box[2 * q], b1 = sm.box[2 * q + 1];
+    sm.red[t] = wallish_gap_ok(b0, b1) ? wallish_gap_chain(gr + t * G::WARM, b0, b1, t & 1, a.wtab) : 0.;
+  }
+  __syncthreads();
+  if (t < 4) sm.gaps[t] = wallish_gap_finish(sm.X, t >> 1, t & 1, sm.box[2 * t], sm.box[2 * t + 1], sm.red[2 * t], sm.red[2 * t + 1], a.wtab);
+  __syncthreads();
+  {                                                                                         // :402
+    // only the knots of the removed box change (64 threads per sequence); a box that reaches the end of the array
+    // leaves NaN from b0 on, as the reference's spline does beyond its last knot
+    const int q = t >> 6, h = q >> 1, col = q & 1;
+    const WallishGap g = sm.gaps[q];
+    const int iend = g.ok ? g.b1 : G::H - 1;
+    for (int i = g.b0 + (t & 63); i <= iend; i += 64) {
+      double* y = reinterpret_cast<double*>(sm.X + wpos(h, i)) + col;
+      *y = wallish_fill(*y, i, g);
+    }
   }
   __syncthreads();
   // DST-III and exp(.)/k on the kept rows                                                   (:409-416)
   wallish_dst3_pre(t, sm.X, v, a.twd);
   fft4096(t, v, sm.S, a.tw1, a.tw2);
+  // FFT bins of the DST-III, bin order (coalesced); exp(.)/k and the transposition happen in wallish_unpack_kernel
+#pragma unroll
+  for (int r = 0; r < 16; ++r) __stcs(zrow + t + 256 * r, v[r]);
+}
+
+// ---- layout changes around the fused kernel: both are 64-row x 32-column tile transpositions through shared memory ----
+// pack: pklin [4096, ncols] -> packed [npairs, 4096] double2 = sign * log(k P), Makhoul order (n < N/2: j = 2n, else j = 2(N-1-n)+1).
+// 64 consecutive rows j0 .. j0+63 hold 32 ascending samples n = j0/2 + i (even j) and 32 descending n = N-1-j0/2-i (odd j).
+__global__ void __launch_bounds__(256) wallish_pack_kernel(const double* __restrict__ klin, const double* __restrict__ pklin,
+                                                           const long long ncols, double2* __restrict__ packed) {
+  typedef WallishGeo G;
+  __shared__ double tile[64][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int j0 = blockIdx.y * 64;
+  const long long c0 = (long long)blockIdx.x * 32;
+  const long long col = c0 + tx < ncols ? c0 + tx : ncols - 1;      // odd column count: the last pair repeats its column
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int j = j0 + ty + 8 * i;
+    const double v = log(klin[j] * __ldcs(pklin + (long long)j * ncols + col));
+    tile[ty + 8 * i][tx] = (j & 1) ? -v : v;
+  }
+  __syncthreads();
+  // unit u = (pair p, parity): 32 lanes write 32 consecutive samples
+  for (int u = ty; u < 32; u += 8) {
+    const int p = u >> 1, odd = u & 1;
+    const long long pair = (c0 >> 1) + p;
+    if (2 * pair >= ncols) continue;
+    int jj, n;
+    if (!odd) { jj = 2 * tx; n = (j0 >> 1) + tx; }
+    else { jj = 2 * (31 - tx) + 1; n = G::N - 1 - (j0 >> 1) - (31 - tx); }
+    packed[pair * G::N + n] = mk2(tile[jj][2 * p], tile[jj][2 * p + 1]);
+  }
+}
+
+// unpack: packed [npairs, 4096] FFT bins m of the DST-III -> vals [nl + (j - i0), col] = exp(sign * bin / N) / k_j for rows
+// i0 <= j < i1 (bao_filter.py:412-416); j odd <-> m = (j+1)/2, j even <-> m = N - j/2 (m = 0 for j = 0), sign as in
+// wallish_dst3_out_index.
+__global__ void __launch_bounds__(256) wallish_unpack_kernel(const double* __restrict__ klin, const double2* __restrict__ packed,
+                                                             const long long ncols, const int i0, const int i1, const int nl,
+                                                             double* __restrict__ vals) {
+  typedef WallishGeo G;
+  __shared__ double tile[64][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int j0 = blockIdx.y * 64;
+  const long long c0 = (long long)blockIdx.x * 32;
+  for (int u = ty; u < 32; u += 8) {
+    const int p = u >> 1, odd = u & 1;
+    const long long pair = (c0 >> 1) + p;
+    if (2 * pair >= ncols) continue;
+    int jj, m;
+    if (odd) { jj = 2 * tx + 1; m = ((j0 + jj) + 1) >> 1; }
+    else { jj = 2 * (31 - tx); m = (G::N - ((j0 + jj) >> 1)) & (G::N - 1); }
+    const double2 z = __ldcs(packed + pair * G::N + m);
+    tile[jj][2 * p] = z.x;
+    tile[jj][2 * p + 1] = z.y;
+  }
+  __syncthreads();
+  const long long col = c0 + tx;
+  if (col >= ncols) return;
   const double inv = 1. / G::N;
 #pragma unroll
-  for (int r = 0; r < 16; ++r) {
-    double sign;
-    const int j = wallish_dst3_out_index(t + 256 * r, sign);
-    if (j > a.i0 - 1 && j < a.i1) {
-      const double k = a.klin[j];
-      double* dst = a.vals + (long long)(a.nl + j - a.i0) * a.ncols + col0;
-      dst[0] = exp(sign * inv * v[r].x) / k;
-      if (has1) dst[1] = exp(sign * inv * v[r].y) / k;
-    }
+  for (int i = 0; i < 8; ++i) {
+    const int j = j0 + ty + 8 * i;
+    if (j < i0 || j >= i1) continue;
+    const double sign = (j & 1) ? -1. : 1.;           // j = 0 (m = 0) and even j: +1; odd j: -1
+    vals[(long long)(nl + j - i0) * ncols + col] = exp(sign * inv * tile[ty + 8 * i][tx]) / klin[j];
   }
 }
 
@@ -367,7 +478,7 @@ int cpf_wallish2018(const double* klin, const double* pklin, int nlin, const dou
 
   const size_t lin_bytes = (size_t)nlin * ncols * sizeof(double), out_bytes = (size_t)nk * ncols * sizeof(double);
   const size_t knot_bytes = (size_t)nknots * ncols * sizeof(double);
-  ScratchBuf d_klin, d_pklin, d_kout, d_pkout, d_pknow, d_boxes, d_knots, d_idx, d_vals, d_slopes, d_fac;
+  ScratchBuf d_klin, d_pklin, d_kout, d_pkout, d_pknow, d_boxes, d_knots, d_idx, d_vals, d_slopes, d_fac, d_packed;
   const double *p_klin = klin, *p_pklin = pklin, *p_kout = kout, *p_pkout = pkout;
   double* p_pknow = pknow;
   int* p_boxes = boxes;
@@ -392,23 +503,32 @@ int cpf_wallish2018(const double* klin, const double* pklin, int nlin, const dou
   CPF_CUDA(d_idx.alloc(nk * sizeof(int), stream));
   CPF_CUDA(d_vals.alloc(knot_bytes, stream));
   CPF_CUDA(d_slopes.alloc(knot_bytes, stream));
-  CPF_CUDA(d_fac.alloc(3 * (size_t)nknots * sizeof(double), stream));
+  CPF_CUDA(d_fac.alloc(4 * (size_t)nknots * sizeof(double), stream));
+  const long long npairs = (ncols + 1) / 2;
+  CPF_CUDA(d_packed.alloc((size_t)npairs * WallishGeo::N * sizeof(double2), stream));
+  // the factors of the final clamped spline depend on the spliced knots only: computed here, on the host copy
+  std::vector<double> h_fac(4 * (size_t)nknots);
+  spline_factor_host(h_knots.data(), nknots, 1, h_fac.data());
+  CPF_CUDA(cudaMemcpyAsync(d_fac.p, h_fac.data(), h_fac.size() * sizeof(double), cudaMemcpyHostToDevice, stream));
   CPF_CUDA(cudaMemcpyAsync(d_knots.p, h_knots.data(), nknots * sizeof(double), cudaMemcpyHostToDevice, stream));
   CPF_CUDA(cudaMemcpyAsync(d_idx.p, h_idx.data(), nk * sizeof(int), cudaMemcpyHostToDevice, stream));
 
   WallishArgs a;
-  a.klin = p_klin; a.pklin = p_pklin; a.ncols = ncols; a.i0 = i0; a.i1 = i1; a.nl = nl;
+  a.klin = p_klin; a.pklin = p_pklin; a.packed = (double2*)d_packed.p; a.ncols = ncols; a.i0 = i0; a.i1 = i1; a.nl = nl;
   a.vals = (double*)d_vals.p; a.boxes = p_boxes;
   a.tw1 = wt.tw1; a.tw2 = wt.tw2; a.twd = wt.twd; a.wtab = wt.wtab;
   CPF_CUDA(cudaFuncSetAttribute(wallish_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWallishSmemBytes));
-  wallish_fused_kernel<<<(unsigned)((ncols + 1) / 2), 256, kWallishSmemBytes, stream>>>(a);
+  const dim3 tgrid((unsigned)((ncols + 31) / 32), WallishGeo::N / 64);
+  wallish_pack_kernel<<<tgrid, 256, 0, stream>>>(p_klin, p_pklin, ncols, a.packed);
+  wallish_fused_kernel<<<(unsigned)npairs, 256, kWallishSmemBytes, stream>>>(a);
+  wallish_unpack_kernel<<<tgrid, 256, 0, stream>>>(p_klin, a.packed, ncols, i0, i1, nl, a.vals);
   CPF_CUDA(cudaGetLastError());
   const unsigned ctile = (unsigned)((ncols + 127) / 128);
   if (nl + nr > 0) {
     wallish_edges_kernel<<<dim3(ctile, (unsigned)(nl + nr)), 128, 0, stream>>>(p_pkout, nk, ncols, nl, nmid, nr, (double*)d_vals.p);
     CPF_CUDA(cudaGetLastError());
   }
-  CPF_TRY(spline_fit_device((const double*)d_knots.p, (const double*)d_vals.p, nknots, ncols, 1, (double*)d_slopes.p, (double*)d_fac.p, stream));
+  CPF_TRY(spline_fit_device((const double*)d_knots.p, (const double*)d_vals.p, nknots, ncols, 1, (double*)d_slopes.p, (double*)d_fac.p, stream, true));
   wallish_final_kernel<<<dim3(ctile, (unsigned)nk), 128, 0, stream>>>((const double*)d_knots.p, (const double*)d_vals.p, (const double*)d_slopes.p,
                                                                         ncols, p_kout, (const int*)d_idx.p, p_pkout, p_pknow);
   CPF_CUDA(cudaGetLastError());

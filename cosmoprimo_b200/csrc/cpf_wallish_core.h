@@ -98,14 +98,29 @@ CPF_HD void wallish_forward(const int t, const double2* X, double2* D, const dou
 
 // ---- back substitution of one chunk, fused with the second derivative at the knots (bao_filter.py:379, 382) ----
 // dd_i = 2 c1 = 2 (3 m_i - 2 s_i - s_{i+1}), m_i = y_{i+1} - y_i; last knot: -6 m_{n-2} + 2 s_{n-2} + 4 s_{n-1}
-CPF_HD void wallish_backward_dd(const int t, const double2* X, const double2* D, double2* DD, const double* wtab) {
+// best second derivative of a thread's 16-knot chunk inside the search range [MARGIN_FIRST, H - MARGIN_FIRST) of both
+// columns (index -1: no knot of the chunk is in range); ties keep the lowest index (numpy argmax)
+struct WallishBest {
+  double vx, vy;
+  int ix, iy;
+};
+
+CPF_HD void wallish_best_update(WallishBest& b, const double x, const double y, const int i, const int lox, const int loy) {
+  const int hi = WallishGeo::H - WallishGeo::MARGIN_FIRST;
+  if (i >= lox && i < hi && (b.ix < 0 || x > b.vx || (x == b.vx && i < b.ix))) { b.vx = x; b.ix = i; }
+  if (i >= loy && i < hi && (b.iy < 0 || y > b.vy || (y == b.vy && i < b.iy))) { b.vy = y; b.iy = i; }
+}
+
+CPF_HD void wallish_backward_dd(const int t, const double2* X, const double2* D, double2* DD, const double* wtab,
+                                WallishBest* best = nullptr) {
   typedef WallishGeo G;
   const int h = t >> 7, c = t & 127;
   const int first = c * G::CH, last = first + G::CH - 1;
   const int end = last + G::WARM < G::H - 1 ? last + G::WARM : G::H - 1;
   double2 s = D[wpos(h, end)];          // exact when end = n-1, otherwise forgotten after WARM steps
   double2 yn = X[wpos(h, end)];
-  double2 s_last = s;
+  WallishBest b;
+  b.vx = b.vy = 0.; b.ix = b.iy = -1;
   for (int i = end - 1; i >= first; --i) {
     const double cp = wcp(wtab, i, G::H);
     const double2 di = D[wpos(h, i)], yi = X[wpos(h, i)];
@@ -113,39 +128,38 @@ CPF_HD void wallish_backward_dd(const int t, const double2* X, const double2* D,
     s = mk2(di.x - cp * sn.x, di.y - cp * sn.y);
     if (i <= last) {
       const double mx = yn.x - yi.x, my = yn.y - yi.y;
-      DD[wpos(h, i)] = mk2(2. * (3. * mx - 2. * s.x - sn.x), 2. * (3. * my - 2. * s.y - sn.y));
+      const double2 dd = mk2(2. * (3. * mx - 2. * s.x - sn.x), 2. * (3. * my - 2. * s.y - sn.y));
+      DD[wpos(h, i)] = dd;
+      wallish_best_update(b, dd.x, dd.y, i, G::MARGIN_FIRST, G::MARGIN_FIRST);
       if (i == G::H - 2) DD[wpos(h, G::H - 1)] = mk2(-6. * mx + 2. * s.x + 4. * sn.x, -6. * my + 2. * s.y + 4. * sn.y);
     }
     yn = yi;
   }
-  (void)s_last;
+  if (best) *best = b;
 }
 
-// ---- argmax over [lo, hi) of one (parity, column) sequence, numpy semantics (first maximum) ------------------------
-// 64 threads per sequence; sequence q = t / 64 = 2*h + col.  Partial results go to red (val) / redi (idx).
-CPF_HD void wallish_argmax_local(const int t, const double2* DD, const int lo, const int hi, double* red, int* redi) {
-  const int q = t >> 6, l = t & 63, h = q >> 1, col = q & 1;
-  double best = 0.;
-  int bi = -1;
-  for (int i = lo + l; i < hi; i += 64) {
-    const double2 v = DD[wpos(h, i)];
-    const double x = col ? v.y : v.x;
-    if (bi < 0 || x > best) { best = x; bi = i; }
+// candidate of a thread's chunk for the second search range [lb, H - MARGIN_FIRST) (lb per column): the chunk best when
+// the whole chunk lies above lb, a re-scan of the chunk's knots >= lb when lb falls inside it, nothing below
+CPF_HD WallishBest wallish_chunk_candidate(const int t, const double2* DD, const int lbx, const int lby, const WallishBest& chunk) {
+  typedef WallishGeo G;
+  const int h = t >> 7, first = (t & 127) * G::CH, last = first + G::CH - 1;
+  WallishBest b;
+  b.vx = b.vy = 0.; b.ix = b.iy = -1;
+  if (first >= lbx) { b.vx = chunk.vx; b.ix = chunk.ix; }
+  if (first >= lby) { b.vy = chunk.vy; b.iy = chunk.iy; }
+  if ((first < lbx && last >= lbx) || (first < lby && last >= lby)) {
+    const int lox = first < lbx ? lbx : G::H, loy = first < lby ? lby : G::H;     // columns already settled are skipped
+    for (int i = first; i <= last; ++i) {
+      const double2 dd = DD[wpos(h, i)];
+      wallish_best_update(b, dd.x, dd.y, i, lox, loy);
+    }
   }
-  red[t] = best;
-  redi[t] = bi;
+  return b;
 }
 
-CPF_HD int wallish_argmax_final(const int q, const double* red, const int* redi) {
-  double best = 0.;
-  int bi = -1;
-  for (int l = 0; l < 64; ++l) {
-    const int i = redi[q * 64 + l];
-    if (i < 0) continue;
-    const double x = red[q * 64 + l];
-    if (bi < 0 || x > best || (x == best && i < bi)) { best = x; bi = i; }
-  }
-  return bi;
+// merge rule of the reductions: keep the larger value, the lower index on ties, ignore empty candidates
+CPF_HD void wallish_best_merge(double& v, int& i, const double ov, const int oi) {
+  if (oi >= 0 && (i < 0 || ov > v || (ov == v && oi < i))) { v = ov; i = oi; }
 }
 
 // ---- cut + re-spline: slopes at the knots L = b0-1 and R = b1+1 bounding the removed box (values y x^2) ------------
@@ -156,35 +170,61 @@ struct WallishGap {
   int ok;              // 0: box reaches the end of the array (reference yields NaN there)
 };
 
-CPF_HD WallishGap wallish_gap_solve(const double2* X, const int h, const int col, const int b0, const int b1, const double* wtab) {
+// The two one-sided eliminations of a sequence run over at most WARM rows each: left over rows < L ascending (unaffected by
+// the cut), right over rows > R descending (mirrored system: the pivots are those of row n-1-i).  Split into pieces so that
+// the kernel computes the right-hand sides with all threads, runs the 8 short chains (4 sequences x 2 sides) on 8 threads
+// and finishes with the 2x2 solves; wallish_gap_solve chains the same pieces serially (CPU emulation, reference flow).
+CPF_HD int wallish_gap_row(const int b0, const int b1, const int side, const int step) {
+  typedef WallishGeo Gm;
+  const int n = Gm::H, L = b0 - 1, R = b1 + 1;
+  if (side == 0) {
+    const int i = (L - Gm::WARM > 0 ? L - Gm::WARM : 0) + step;
+    return i < L ? i : -1;
+  }
+  const int i = (R + Gm::WARM < n - 1 ? R + Gm::WARM : n - 1) - step;
+  return i > R ? i : -1;
+}
+
+CPF_HD double wallish_gap_y(const double2* X, const int h, const int col, const int i) {
+  const double2 y = wallish_y(X, h, i, 1);
+  return col ? y.y : y.x;
+}
+
+CPF_HD bool wallish_gap_ok(const int b0, const int b1) { return b0 - 1 >= 1 && b1 + 1 <= WallishGeo::H - 2; }
+
+// right-hand side of row i of the y x^2 system (0 on the clamped end rows and for padding steps, i < 0)
+CPF_HD double wallish_gap_rhs(const double2* X, const int h, const int col, const int i) {
+  if (i <= 0 || i >= WallishGeo::H - 1) return 0.;
+  return 3. * (wallish_gap_y(X, h, col, i + 1) - wallish_gap_y(X, h, col, i - 1));
+}
+
+// reduced right-hand side at the last eliminated row; r[step] = wallish_gap_rhs of row wallish_gap_row(.., step)
+CPF_HD double wallish_gap_chain(const double* r, const int b0, const int b1, const int side, const double* wtab) {
+  typedef WallishGeo Gm;
+  const int n = Gm::H;
+  double d = 0.;
+  for (int step = 0; step < Gm::WARM; ++step) {
+    const int i = wallish_gap_row(b0, b1, side, step);
+    if (i < 0) break;
+    const bool edge = (i == 0 || i == n - 1);
+    d = (r[step] - (edge ? 0. : 1.) * d) * wpivot(wtab, side ? n - 1 - i : i, n);
+  }
+  return d;
+}
+
+CPF_HD WallishGap wallish_gap_finish(const double2* X, const int h, const int col, const int b0, const int b1, const double dpL,
+                                     const double dqR, const double* wtab) {
   typedef WallishGeo Gm;
   WallishGap g;
   g.b0 = b0; g.b1 = b1;
   const int n = Gm::H, L = b0 - 1, R = b1 + 1;
-  g.ok = (L >= 1 && R <= n - 2) ? 1 : 0;
+  g.ok = wallish_gap_ok(b0, b1) ? 1 : 0;
   g.sL = g.sR = g.yL = g.m = 0.; g.G = 1.;
   if (!g.ok) return g;
-#define WY(i) (col ? wallish_y(X, h, (i), 1).y : wallish_y(X, h, (i), 1).x)
-  // left elimination over rows < L (unaffected by the cut)
-  double d = 0.;
-  for (int i = (L - Gm::WARM > 0 ? L - Gm::WARM : 0); i < L; ++i) {
-    const bool edge = i == 0;
-    const double r = edge ? 0. : 3. * (WY(i + 1) - WY(i - 1));
-    d = (r - (edge ? 0. : 1.) * d) * wpivot(wtab, i, n);
-  }
-  const double cpL = wcp(wtab, L - 1, n), dpL = d;
-  // right elimination over rows > R, mirrored (pivots of the mirrored system are those of row n-1-i)
-  d = 0.;
-  for (int i = (R + Gm::WARM < n - 1 ? R + Gm::WARM : n - 1); i > R; --i) {
-    const bool edge = i == n - 1;
-    const double r = edge ? 0. : 3. * (WY(i + 1) - WY(i - 1));
-    d = (r - (edge ? 0. : 1.) * d) * wpivot(wtab, n - 1 - i, n);
-  }
-  const double cqR = wcp(wtab, n - 1 - (R + 1), n), dqR = d;
+  const double cpL = wcp(wtab, L - 1, n), cqR = wcp(wtab, n - 1 - (R + 1), n);
   const double G = (double)(R - L);
-  const double yL = WY(L), yR = WY(R);
-  const double mleft = yL - WY(L - 1), mgap = (yR - yL) / G, mright = WY(R + 1) - yR;
-#undef WY
+  const double yL = wallish_gap_y(X, h, col, L), yR = wallish_gap_y(X, h, col, R);
+  const double mleft = yL - wallish_gap_y(X, h, col, L - 1), mgap = (yR - yL) / G, mright = wallish_gap_y(X, h, col, R + 1) - yR;
   const double rhsL = 3. * (G * mleft + mgap), rhsR = 3. * (mgap + G * mright);
   const double a11 = 2. * (1. + G) - G * cpL, a22 = 2. * (G + 1.) - G * cqR;
   const double b1_ = rhsL - G * dpL, b2_ = rhsR - G * dqR;
@@ -195,14 +235,27 @@ CPF_HD WallishGap wallish_gap_solve(const double2* X, const int h, const int col
   return g;
 }
 
+CPF_HD WallishGap wallish_gap_solve(const double2* X, const int h, const int col, const int b0, const int b1, const double* wtab) {
+  typedef WallishGeo Gm;
+  double d[2] = {0., 0.};
+  if (wallish_gap_ok(b0, b1)) {
+    double r[Gm::WARM];
+    for (int side = 0; side < 2; ++side) {
+      for (int step = 0; step < Gm::WARM; ++step) r[step] = wallish_gap_rhs(X, h, col, wallish_gap_row(b0, b1, side, step));
+      d[side] = wallish_gap_chain(r, b0, b1, side, wtab);
+    }
+  }
+  return wallish_gap_finish(X, h, col, b0, b1, d[0], d[1], wtab);
+}
+
 // new value of knot i of a sequence after cut + re-spline: spline(x_i)/x_i^2 (bao_filter.py:402)
 CPF_HD double wallish_fill(const double y, const int i, const WallishGap& g) {
   const double x = (double)(i + 1), x2 = x * x;
   if (!g.ok) {
     // box reaches the array end: the reference's spline is not defined beyond its last knot (extrapolate=False)
-    return i >= g.b0 ? nan("") : (y * x2) / x2;
+    return i >= g.b0 ? nan("") : y;
   }
-  if (i < g.b0 || i > g.b1) return (y * x2) / x2;
+  if (i < g.b0 || i > g.b1) return y;   // the reference's (y x^2) / x^2 differs from y by at most one ulp
   const double t = (g.sL + g.sR - 2. * g.m) / g.G;
   const double c0 = t / g.G, c1 = (g.m - g.sL) / g.G - t;
   const double d = (double)(i - (g.b0 - 1));

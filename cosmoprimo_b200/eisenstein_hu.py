@@ -1,0 +1,104 @@
+"""
+On-device Eisenstein & Hu (1998) linear matter power spectra for batches of flat LCDM cosmologies without massive
+neutrinos: what the reference computes, one cosmology at a time, with
+``Cosmology(..., m_ncdm=None, engine='eisenstein_hu').get_fourier().pk_interpolator()(k, z)``
+(``cosmoprimo/eisenstein_hu.py`` — coefficients :34-92, transfer function :241-283, primordial spectrum :189-214, P(k)
+:321-324, growth factor with ``znorm=0`` / growth rate :115-153 on the background of ``cosmoprimo/cosmology.py:1675-1760``).
+
+The kernel (``csrc/cpf_eh.cu`` behind ``cpf_eh_pk``) writes rows in the (rows, nk) layout FFTLog reads, so a sweep over
+cosmologies x redshifts runs generator -> FFTLog without any host-to-device copy of spectra.
+"""
+
+import numpy as np
+
+from . import _lib
+from . import _buffers as _buf
+
+T_CMB = 2.7255
+N_UR = 3.044
+K_PIVOT = 0.05     # 1/Mpc
+
+
+def omega_radiation(T_cmb=T_CMB, N_ur=N_UR):
+    """``Omega0_r h^2``: photons + ``N_ur`` massless neutrinos, with the reference's constants (cosmology.py:355-367,
+    constants.py:12-14; scipy.constants for c, G, sigma_SB and the parsec)."""
+    from scipy import constants
+    megaparsec_over_m = 1e6 * constants.parsec
+    rho_crit = 3.0 * (100. * 1e3 / megaparsec_over_m)**2 / (8 * constants.pi * constants.gravitational_constant)   # h^2 kg/m^3
+    T_ur = T_cmb * (4. / 11.)**(1. / 3.)
+    rho = (T_cmb**4 + N_ur * 7. / 8. * T_ur**4) * 4. / constants.c**3 * constants.Stefan_Boltzmann
+    return rho / rho_crit
+
+
+class EisensteinHu(object):
+    """
+    Batch of B cosmologies; parameters are scalars or (B,) arrays (broadcast against each other).
+
+    Parameters
+    ----------
+    h, omega_b, omega_cdm, n_s : array_like
+    A_s or logA : array_like
+        Scalar amplitude, or ``ln(1e10 A_s)`` (the reference's ``logA``, cosmology.py:949-950).
+    T_cmb, N_ur, k_pivot : float
+        Reference defaults (constants.py:17-19, cosmology.py defaults); ``k_pivot`` in 1/Mpc.
+    device : int, default=None
+        CUDA device.
+    """
+
+    def __init__(self, h, omega_b, omega_cdm, n_s, A_s=None, logA=None, T_cmb=T_CMB, N_ur=N_UR, k_pivot=K_PIVOT, device=None):
+        if (A_s is None) == (logA is None):
+            raise ValueError('provide either A_s or logA')
+        if A_s is None:
+            A_s = 1e-10 * np.exp(np.asarray(logA, dtype='f8'))
+        cols = np.broadcast_arrays(*[np.asarray(v, dtype='f8') for v in (h, omega_b, omega_cdm, n_s, A_s)])
+        self.shape = cols[0].shape
+        self.params = np.ascontiguousarray(np.stack([c.ravel() for c in cols], axis=-1))      # (B, 5)
+        self.T_cmb, self.N_ur, self.k_pivot = float(T_cmb), float(N_ur), float(k_pivot)
+        self.omega_r = omega_radiation(self.T_cmb, self.N_ur)
+        self.device = device
+
+    @property
+    def size(self):
+        return self.params.shape[0]
+
+    def _run(self, k, z, kaiser, on_device, want_pk=True):
+        lib = _lib.load()
+        _lib.require_device()
+        k = np.ascontiguousarray(k, dtype='f8').ravel()
+        B = self.size
+        zz = None
+        if z is not None:
+            zz = np.ascontiguousarray(np.broadcast_to(np.asarray(z, dtype='f8').ravel() if np.ndim(z) else np.asarray(z, dtype='f8'), (B,)))
+        dev = self.device if self.device is not None else _buf.default_device()
+        P = 3 if kaiser else 1
+        nk = k.size if want_pk else 1
+        kk = k if want_pk else np.ones(1)
+        if on_device:
+            torch = _buf._torch()
+            tdev = torch.device('cuda', dev)
+            params = torch.as_tensor(self.params, device=tdev)
+            kd = torch.as_tensor(kk, device=tdev)
+            zd = torch.as_tensor(zz, device=tdev) if zz is not None else None
+            out = torch.empty((B, P, nk) if kaiser else (B, nk), dtype=torch.float64, device=tdev)
+            derived = torch.empty((B, 4), dtype=torch.float64, device=tdev)
+            rc = lib.cpf_eh_pk(params.data_ptr(), zd.data_ptr() if zd is not None else None, B, kd.data_ptr(), nk, self.T_cmb, self.omega_r,
+                               self.k_pivot, int(kaiser), out.data_ptr(), derived.data_ptr(), 1, dev, _buf.current_stream(dev))
+        else:
+            out = np.empty((B, P, nk) if kaiser else (B, nk), dtype='f8')
+            derived = np.empty((B, 4), dtype='f8')
+            rc = lib.cpf_eh_pk(self.params.ctypes.data, zz.ctypes.data if zz is not None else None, B, kk.ctypes.data, nk, self.T_cmb,
+                               self.omega_r, self.k_pivot, int(kaiser), out.ctypes.data, derived.ctypes.data, 0, dev, None)
+        _lib.check(rc)
+        return out, derived
+
+    def pk(self, k, z=None, kaiser=False, on_device=True):
+        """
+        Linear P(k, z) in (Mpc/h)^3 on ``k`` [h/Mpc]: (B, nk), or the Kaiser multipoles ell = 0, 2, 4 with
+        f = growth_rate(z), (B, 3, nk), if ``kaiser``.  ``z``: scalar or (B,) (one redshift per cosmology; repeat the
+        parameters to sweep redshifts).  Returns a torch CUDA tensor (``on_device``) or a numpy array.
+        """
+        return self._run(k, z, kaiser, on_device)[0]
+
+    def derived(self, z=None, on_device=False):
+        """(B, 4): rs_drag [Mpc/h], z_drag, growth_factor(z, znorm=0)**2, growth_rate(z)."""
+        return self._run(None, z, False, on_device, want_pk=False)[1]

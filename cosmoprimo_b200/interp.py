@@ -175,7 +175,7 @@ class Interpolator1D(object):
         return res.astype(dtype, copy=False).reshape(out_shape)
 
 
-def spline_eval_rows(x, fun, xq, bc_type='natural', window=128, extrap=False, device=None):
+def spline_eval_rows(x, fun, xq, bc_type='natural', window=64, extrap=False, device=None):
     """
     Cubic splines along the LAST axis of ``fun`` (rows, nx) -- the layout FFTLog returns -- on the shared knots ``x``
     (nx,), evaluated at ``xq`` (nq,): returns (nq, rows), i.e. what the reference obtains with

@@ -69,12 +69,35 @@ def eh_transfer(k, h, omega_b, omega_m):
     return fb * Tb + (1 - fb) * Tc
 
 
-def growth_factor(z, Omega0_m):
+def omega_radiation():
+    """Omega0_r h^2 of the reference's default background (photons at T_cmb + N_ur = 3.044 massless neutrinos)."""
+    from .eisenstein_hu import omega_radiation as _omega_r
+    return _omega_r(T_CMB, 3.044)
+
+
+def background(z, Omega0_m, h):
+    """Omega_m(z), Omega_de(z) of flat LCDM with radiation, as the reference's background (cosmology.py:1675-1760)."""
+    Omega0_r = omega_radiation() / h**2
+    Omega0_de = 1. - Omega0_m - Omega0_r
+    crit = Omega0_m + Omega0_r * (1 + z) + Omega0_de / (1 + z)**3
+    return Omega0_m / crit, Omega0_de / (1 + z)**3 / crit
+
+
+def growth_factor(z, Omega0_m, h=None):
     """Carroll-Press-Turner growth factor, flat LCDM, normalised to 1/(1+z) in matter domination — the ``znorm=0``
-    convention the reference's Fourier.pk_interpolator applies (eisenstein_hu.py:319)."""
-    E2 = Omega0_m * (1 + z)**3 + 1. - Omega0_m
-    Om, Ode = Omega0_m * (1 + z)**3 / E2, (1. - Omega0_m) / E2
+    convention the reference's Fourier.pk_interpolator applies (eisenstein_hu.py:115-140, 319).  With ``h`` the
+    background includes radiation exactly as the reference's does; without, matter + Lambda only."""
+    if h is None:
+        E2 = Omega0_m * (1 + z)**3 + 1. - Omega0_m
+        Om, Ode = Omega0_m * (1 + z)**3 / E2, (1. - Omega0_m) / E2
+    else:
+        Om, Ode = background(z, Omega0_m, h)
     return 1. / (1 + z) * 5 * Om / 2. / (Om**(4. / 7.) - Ode + (1. + Om / 2.) * (1 + Ode / 70.))
+
+
+def growth_rate(z, Omega0_m, h):
+    """f(z) = Omega_m(z)^0.55 (eisenstein_hu.py:141-153 for w = -1)."""
+    return background(z, Omega0_m, h)[0]**0.55
 
 
 def eh_pk(k, params=None, z=0.):
@@ -95,7 +118,7 @@ def eh_pk(k, params=None, z=0.):
     curvature_to_potential = 9. / 25. * 2. * np.pi**2 / k**3 / h**3
     primordial = h**3 * A_s * (k / (K_PIVOT / h))**(p['n_s'] - 1.)
     pk = T**2 * potential_to_density * curvature_to_potential * primordial
-    D = growth_factor(np.atleast_1d(np.asarray(z, dtype='f8'))[:, None] if np.ndim(z) else z, Omega0_m)
+    D = growth_factor(np.atleast_1d(np.asarray(z, dtype='f8'))[:, None] if np.ndim(z) else z, Omega0_m, h)
     pk = pk * D**2
     return pk[0] if scalar else pk
 

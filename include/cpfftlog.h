@@ -132,6 +132,20 @@ int cpf_wallish2018(const double* klin, const double* pklin, int nlin, const dou
                     int nk, int64_t ncols, double* pknow, int32_t* boxes,
                     int on_device, int device, void* stream);
 
+/* ---- on-device Eisenstein & Hu linear P(k, z): replaces, for B flat LCDM cosmologies without massive neutrinos,
+ * `Cosmology(..., engine='eisenstein_hu').get_fourier().pk_interpolator()(k, z)` (eisenstein_hu.py:34-92 coefficients,
+ * 241-283 transfer function, 189-214 primordial spectrum, 321-324 P(k), 115-153 growth factor (znorm=0) / growth rate on
+ * the background of cosmology.py:1675-1760) and writes rows in the layout cpf_fftlog reads.
+ *   params  [B, 5]  (h, omega_b, omega_cdm, n_s, A_s) per cosmology
+ *   z       [B] or NULL (= 0): one redshift per row
+ *   k       [nk]    wavenumbers, h/Mpc
+ *   T_cmb, omega_r (= Omega0_r h^2: photons + massless neutrinos, cosmology.py:355-367), k_pivot [1/Mpc]
+ *   kaiser  0: out [B, nk] = P(k, z);  1: out [B, 3, nk] = Kaiser multipoles ell = 0, 2, 4 with f = growth_rate(z)
+ *   derived [B, 4] or NULL: rs_drag [Mpc/h], z_drag, growth_factor(z, znorm=0)^2, growth_rate(z)
+ */
+int cpf_eh_pk(const double* params, const double* z, int64_t B, const double* k, int nk, double T_cmb, double omega_r,
+              double k_pivot, int kaiser, double* out, double* derived, int on_device, int device, void* stream);
+
 /* ---- measurement helper: peak fp64 FMA rate of the device (DFMA chains), in FLOP/s; used by bench.py for the
  * fp64 roofline denominator that MEASURED_PEAKS.json lacks. */
 int cpf_measure_fp64_peak(int device, double* flops_per_s);

@@ -43,7 +43,7 @@ static ld full_eval(const std::vector<double>& x, const std::vector<double>& y, 
 int main() {
   int bad = 0;
   double worst = 0.;
-  for (int nx : {2, 3, 5, 60, 100, 2048}) {
+  for (int nx : {2, 3, 5, 60, 100, 300, 2048}) {
     std::vector<double> x(nx), y(nx);
     for (int i = 0; i < nx; ++i) {
       x[i] = 1e-2 * pow(1e7, nx > 1 ? (double)i / (nx - 1) : 0.);        // s grid of TophatVariance on k in [1e-5, 1e2]
@@ -51,7 +51,7 @@ int main() {
     }
     for (int bc = 0; bc < 2; ++bc) {
       const std::vector<ld> s = full_slopes(x, y, bc);
-      for (int W : {40, 128, 4096}) {
+      for (int W : {40, 64, 4096}) {
         if (W == 40 && nx != 2048) continue;   // a 40-knot window needs the fine grid (ordinates within ~3 % per knot)
         const int LW = 2 * W + 2 < nx ? 2 * W + 2 : nx;
         std::vector<double> w(LW), work(2 * LW);

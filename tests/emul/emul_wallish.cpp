@@ -61,12 +61,19 @@ int main(int argc, char** argv) {
   for (int t = 0; t < 256; ++t) wallish_forward(t, X.data(), S.data(), wtab);
   for (int t = 0; t < 256; ++t) wallish_backward_dd(t, X.data(), S.data(), DD.data(), wtab);
   for (int h = 0; h < 2; ++h) for (int i = 0; i < G::H; ++i) { out.push_back(DD[wpos(h, i)].x); out.push_back(DD[wpos(h, i)].y); }
-  for (int t = 0; t < 256; ++t) wallish_argmax_local(t, DD.data(), G::MARGIN_FIRST, G::H - G::MARGIN_FIRST, red.data(), redi.data());
-  for (int t = 0; t < 4; ++t) box[2 * t] = wallish_argmax_final(t, red.data(), redi.data());
-  for (int t = 0; t < 256; ++t) wallish_argmax_local(t, DD.data(), box[2 * (t >> 6)] + G::MARGIN_SECOND, G::H - G::MARGIN_FIRST, red.data(), redi.data());
+  // argmax boxes: per-chunk maxima from the backward pass, merged in thread order (the kernel merges with warp shuffles)
+  std::vector<WallishBest> chunk(256), cand(256);
+  for (int t = 0; t < 256; ++t) wallish_backward_dd(t, X.data(), S.data(), DD.data(), wtab, &chunk[t]);
+  auto merge = [&](const std::vector<WallishBest>& b, int q) {
+    double v = 0.; int i = -1;
+    for (int t = 128 * (q >> 1); t < 128 * (q >> 1) + 128; ++t) wallish_best_merge(v, i, (q & 1) ? b[t].vy : b[t].vx, (q & 1) ? b[t].iy : b[t].ix);
+    return i;
+  };
+  for (int q = 0; q < 4; ++q) box[2 * q] = merge(chunk, q);
+  for (int t = 0; t < 256; ++t) cand[t] = wallish_chunk_candidate(t, DD.data(), box[4 * (t >> 7)] + G::MARGIN_SECOND, box[4 * (t >> 7) + 2] + G::MARGIN_SECOND, chunk[t]);
   for (int t = 0; t < 4; ++t) {
     const int h = t >> 1, col = t & 1;
-    const int amax = box[2 * t], bmax = wallish_argmax_final(t, red.data(), redi.data());
+    const int amax = box[2 * t], bmax = merge(cand, t);
     const int b0 = amax + G::OFF_LO, b1 = bmax < 0 ? G::H : bmax + G::OFF_HI;
     gaps[t] = wallish_gap_solve(X.data(), h, col, b0, b1, wtab);
     out.push_back((double)b0); out.push_back((double)b1);

@@ -99,7 +99,7 @@ def test_spline_eval_rows_vs_oracle():
     s, var = FO.execute(FO.plan_tophat_variance(k), pk)
     r = np.concatenate([np.linspace(1., 20., 10), [s[0], s[-1], 0.5 * (s[0] + s[1]), 8., s[0] * 0.5, s[-1] * 2, np.nan]])
     ref = SO.interpolator1d(s, var.T, assume_sorted=True)(r)
-    for window in [0, 128, 40]:
+    for window in [0, 128, 64, 40]:
         out = spline_eval_rows(s, var, r, window=window)
         assert out.shape == (r.size, B)
         close_with_nans(out, ref, rtol=1e-11)

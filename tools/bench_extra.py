@@ -15,6 +15,8 @@ from cosmoprimo_b200 import synthetic as S, _lib
 from cosmoprimo_b200.fftlog import PowerToCorrelation, CorrelationToPower, TophatVariance
 from cosmoprimo_b200.interpolator import PowerSpectrumInterpolator1D
 from cosmoprimo_b200.bao_filter import PowerSpectrumBAOFilter
+from cosmoprimo_b200.eisenstein_hu import EisensteinHu
+from cosmoprimo_b200.interp import spline_eval_rows
 
 
 def timed(fn, reps=20, warm=3):
@@ -73,6 +75,29 @@ def main():
             r = np.linspace(1., 20., 10)
             t = timed(lambda: interp.sigma_r(r, nk=2048), reps=5, warm=1)
             res['sigma_rz_nk2048'] = {'rows': 20000, 'rows_per_s': 20000 / t}
+    # on-device Eisenstein-Hu generator: rows/s alone, and generator -> FFTLog -> sigma(r) (config 3 shape:
+    # cosmologies x redshifts, nk = 2048, 10 radii) without any host copy of spectra
+    n, ncosmo, nz = 2048, 1000, 100
+    k = np.geomspace(1e-5, 1e2, n)
+    par = S.lhs_cosmologies(ncosmo, seed=42)
+    rep = lambda a: np.repeat(a, nz)
+    eh = EisensteinHu(rep(par['h']), rep(par['omega_b']), rep(par['omega_cdm']), rep(par['n_s']), logA=rep(par['logA']))
+    zz = np.tile(np.linspace(0., 3., nz), ncosmo)
+    t = timed(lambda: eh.pk(k, z=zz), reps=5, warm=1)
+    res['eh_generator_nk2048'] = {'rows': ncosmo * nz, 'rows_per_s': ncosmo * nz / t, 'points_per_s': ncosmo * nz * n / t}
+    tv = TophatVariance(k)
+    r = np.linspace(1., 20., 10)
+    s_grid = tv.y if tv.y.ndim == 1 else tv.y[0]
+
+    def sigma_rows():
+        var = tv(eh.pk(k, z=zz))[1]
+        return (spline_eval_rows(s_grid, var, r))**0.5
+    t = timed(sigma_rows, reps=5, warm=1)
+    res['eh_to_sigma_rz_nk2048'] = {'rows': ncosmo * nz, 'rows_per_s': ncosmo * nz / t}
+    fun = eh.pk(k, z=zz)
+    t = timed(lambda: spline_eval_rows(s_grid, tv(fun)[1], r), reps=5, warm=1)
+    res['sigma_rz_rows_nk2048'] = {'rows': ncosmo * nz, 'rows_per_s': ncosmo * nz / t, 'note': 'TophatVariance + windowed row splines at 10 radii, device rows in'}
+    del fun
     # config 1: latency of one host-array call, nk = 1024
     k = np.geomspace(1e-5, 1e2, 1024)
     pk = S.eh_pk(k)

@@ -241,8 +241,41 @@ def make_wallish():
     print('wrote {} ({} cases, {:.2f} MB)'.format(fn, len(cases), os.path.getsize(fn) / 1e6))
 
 
+def make_eh():
+    """Eisenstein & Hu P(k, z), rs_drag, z_drag, growth factor / rate and sigma8 from the reference's engine
+    (Cosmology(..., engine='eisenstein_hu'), flat LCDM without massive neutrinos) for Latin-hypercube cosmologies."""
+    from cosmoprimo import Cosmology
+    sys.path.insert(0, ROOT)
+    from cosmoprimo_b200 import synthetic
+    B = 8
+    par = synthetic.lhs_cosmologies(B, seed=42)
+    par = {name: np.concatenate([val, [synthetic.DESI_FIDUCIAL[name]]]) for name, val in par.items()}      # + DESI-like fiducial
+    k = np.geomspace(1e-5, 1e2, 256)
+    zs = np.array([0., 0.5, 3.])
+    rs = np.array([1., 8., 20.])
+    pk, derived, sigma8, sigma_rz, growth_rate_rz = [], [], [], [], []
+    for i in range(B + 1):
+        cosmo = Cosmology(h=par['h'][i], omega_b=par['omega_b'][i], omega_cdm=par['omega_cdm'][i], n_s=par['n_s'][i],
+                          A_s=1e-10 * np.exp(par['logA'][i]), m_ncdm=None, engine='eisenstein_hu')
+        fo, ba, th = cosmo.get_fourier(), cosmo.get_background(), cosmo.get_thermodynamics()
+        interp = fo.pk_interpolator()
+        pk.append(interp(k, z=zs).T)                                                                        # (nz, nk)
+        derived.append([[th.rs_drag, th.z_drag, float(ba.growth_factor(z, znorm=0.))**2, float(ba.growth_rate(z))] for z in zs])
+        sigma8.append(float(interp.sigma8_z(0.)))                     # integrate_sigma_r2(method='fftlog', nk=1024), interpolator.py:200, 285
+        sigma_rz.append(interp.sigma_rz(rs, zs))                      # (nr, nz)
+        growth_rate_rz.append(interp.growth_rate_rz(rs, zs))
+        if i == 0:
+            T_cmb, N_ur, k_pivot = float(cosmo['T_cmb']), float(cosmo['N_ur']), float(cosmo['k_pivot'])
+            omega_r = float(ba.Omega0_r * cosmo['h']**2)
+    arrays = dict(k=k, z=zs, pk=np.array(pk), derived=np.array(derived), sigma8=np.array(sigma8), r=rs, sigma_rz=np.array(sigma_rz), growth_rate_rz=np.array(growth_rate_rz), T_cmb=T_cmb, N_ur=N_ur, k_pivot=k_pivot,
+                  omega_r=omega_r, **{'par_' + name: val for name, val in par.items()})
+    fn = os.path.join(GOLDEN, 'eh_golden.npz')
+    np.savez_compressed(fn, **arrays)
+    print('wrote {} ({} cosmologies x {} redshifts x {} k, {:.2f} MB)'.format(fn, B + 1, zs.size, k.size, os.path.getsize(fn) / 1e6))
+
+
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['fftlog', 'spline', 'wallish']
+    which = sys.argv[1:] or ['fftlog', 'spline', 'wallish', 'eh']
     print('reference: cosmoprimo {} from {}; numpy {}'.format(cosmoprimo.__version__, os.path.dirname(cosmoprimo.__file__), np.__version__))
     for name in which:
         fn = globals().get('make_' + name, None)
