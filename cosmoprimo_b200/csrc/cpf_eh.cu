@@ -1,44 +1,59 @@
 // cpf_eh.cu — on-device Eisenstein & Hu linear P(k, z) rows: the input generator of every FFTLog workload
 // (cosmoprimo/eisenstein_hu.py, see cpf_eh_core.h), written directly in the (rows, nk) layout cpf_fftlog reads, optionally
 // as Kaiser multipoles ell = 0, 2, 4.  One CTA per cosmology: thread 0 derives the ~20 fitting coefficients, all threads
-// then evaluate the transfer function on the shared k grid (2 log, 5 exp, 1 cbrt, 1 sin per point).
+// then evaluate the transfer function on the shared k grid once and write one row per redshift of that cosmology (the
+// z dependence is the growth factor only).
 #include "cpf_common.h"
 #include "cpf_eh_core.h"
 
 namespace cpf {
 
+#define EH_MAX_NZ 1024
+
 __global__ void __launch_bounds__(256) eh_pk_kernel(const double* __restrict__ params, const double* __restrict__ z, const long long B,
-                                                    const double* __restrict__ k, const int nk, const double T_cmb, const double omega_r,
-                                                    const double k_pivot, const int kaiser, double* __restrict__ out,
-                                                    double* __restrict__ derived) {
+                                                    const int nz, const double* __restrict__ k, const int nk, const double T_cmb,
+                                                    const double omega_r, const double k_pivot, const int kaiser,
+                                                    double* __restrict__ out, double* __restrict__ derived) {
   __shared__ EHCoeffs sc;
+  __shared__ double g2[EH_MAX_NZ], gf[EH_MAX_NZ];
+  const int P = kaiser ? 3 : 1;
   for (long long b = blockIdx.x; b < B; b += gridDim.x) {
     __syncthreads();
     if (threadIdx.x == 0) {
       const double* p = params + 5 * b;
-      sc = eh_coeffs(p[0], p[1], p[2], p[3], p[4], z ? z[b] : 0., T_cmb, omega_r, k_pivot);
-      if (derived) {
-        double* d = derived + 4 * b;
-        d[0] = sc.rs_drag * sc.h;     // Thermodynamics.rs_drag, Mpc/h (:163)
-        d[1] = sc.z_drag;
-        d[2] = sc.growth_sq;
-        d[3] = sc.growth_rate;
-      }
+      sc = eh_coeffs(p[0], p[1], p[2], p[3], p[4], 0., T_cmb, omega_r, k_pivot);
     }
     __syncthreads();
     const EHCoeffs c = sc;
-    const double f = c.growth_rate;
-    const double m0 = 1. + 2. * f / 3. + f * f / 5., m2 = 4. * f / 3. + 4. * f * f / 7., m4 = 8. * f * f / 35.;
+    for (int iz = threadIdx.x; iz < nz; iz += blockDim.x) {
+      double gs, fr;
+      eh_growth(c, z ? z[b * nz + iz] : 0., gs, fr);
+      g2[iz] = gs;
+      gf[iz] = fr;
+      if (derived) {
+        double* d = derived + 4 * (b * nz + iz);
+        d[0] = c.rs_drag * c.h;       // Thermodynamics.rs_drag, Mpc/h (:163)
+        d[1] = c.z_drag;
+        d[2] = gs;
+        d[3] = fr;
+      }
+    }
+    __syncthreads();
+    // the transfer function does not depend on z: one evaluation per k feeds all nz rows of the cosmology
     for (int j = threadIdx.x; j < nk; j += blockDim.x) {
       const double kj = k[j];
-      const double pk = eh_pk_point(c, kj, log(kj));
-      if (kaiser) {
-        double* o = out + (b * 3) * nk + j;
-        __stcs(o, m0 * pk);
-        __stcs(o + nk, m2 * pk);
-        __stcs(o + 2 * (long long)nk, m4 * pk);
-      } else {
-        __stcs(out + b * nk + j, pk);
+      const double pk0 = eh_pk0_point(c, kj, log(kj));
+      for (int iz = 0; iz < nz; ++iz) {
+        const double pk = pk0 * g2[iz];
+        double* o = out + ((b * nz + iz) * P) * nk + j;
+        if (kaiser) {
+          const double f = gf[iz];
+          __stcs(o, (1. + 2. * f / 3. + f * f / 5.) * pk);
+          __stcs(o + nk, (4. * f / 3. + 4. * f * f / 7.) * pk);
+          __stcs(o + 2 * (long long)nk, (8. * f * f / 35.) * pk);
+        } else {
+          __stcs(o, pk);
+        }
       }
     }
   }
@@ -50,9 +65,11 @@ using namespace cpf;
 
 extern "C" {
 
-int cpf_eh_pk(const double* params, const double* z, int64_t B, const double* k, int nk, double T_cmb, double omega_r,
+int cpf_eh_pk(const double* params, const double* z, int64_t B, int nz, const double* k, int nk, double T_cmb, double omega_r,
               double k_pivot, int kaiser, double* out, double* derived, int on_device, int device, void* stream_) {
   if (B < 0 || nk < 0) return fail(CPF_EINVAL, "cpf_eh_pk: negative size");
+  if (nz < 1 || nz > EH_MAX_NZ) return fail(CPF_EINVAL, "cpf_eh_pk: nz = %d must be in 1..%d", nz, EH_MAX_NZ);
+  if (!z && nz != 1) return fail(CPF_EINVAL, "cpf_eh_pk: z = NULL (redshift 0) needs nz = 1");
   if (B == 0 || nk == 0) return CPF_OK;
   if (!params || !k || !out) return fail(CPF_EINVAL, "cpf_eh_pk: null buffer");
   if (!(T_cmb > 0.) || !(omega_r >= 0.) || !(k_pivot > 0.)) return fail(CPF_EINVAL, "cpf_eh_pk: T_cmb, k_pivot must be > 0 and omega_r >= 0");
@@ -62,7 +79,7 @@ int cpf_eh_pk(const double* params, const double* z, int64_t B, const double* k,
   DeviceGuard guard(device);
   cudaStream_t stream = (cudaStream_t)stream_;
   const int P = kaiser ? 3 : 1;
-  const size_t ocells = (size_t)B * P * nk;
+  const size_t ocells = (size_t)B * nz * P * nk;
   ScratchBuf dp, dz, dk, dout, dder;
   const double *p_params = params, *p_z = z, *p_k = k;
   double *p_out = out, *p_der = derived;
@@ -74,21 +91,21 @@ int cpf_eh_pk(const double* params, const double* z, int64_t B, const double* k,
     CPF_CUDA(cudaMemcpyAsync(dk.p, k, (size_t)nk * sizeof(double), cudaMemcpyHostToDevice, stream));
     p_params = (const double*)dp.p; p_k = (const double*)dk.p; p_out = (double*)dout.p;
     if (z) {
-      CPF_CUDA(dz.alloc((size_t)B * sizeof(double), stream));
-      CPF_CUDA(cudaMemcpyAsync(dz.p, z, (size_t)B * sizeof(double), cudaMemcpyHostToDevice, stream));
+      CPF_CUDA(dz.alloc((size_t)B * nz * sizeof(double), stream));
+      CPF_CUDA(cudaMemcpyAsync(dz.p, z, (size_t)B * nz * sizeof(double), cudaMemcpyHostToDevice, stream));
       p_z = (const double*)dz.p;
     }
     if (derived) {
-      CPF_CUDA(dder.alloc((size_t)B * 4 * sizeof(double), stream));
+      CPF_CUDA(dder.alloc((size_t)B * nz * 4 * sizeof(double), stream));
       p_der = (double*)dder.p;
     }
   }
   const unsigned grid = (unsigned)(B < 148LL * 64 ? B : 148LL * 64);
-  eh_pk_kernel<<<grid, 256, 0, stream>>>(p_params, p_z, B, p_k, nk, T_cmb, omega_r, k_pivot, kaiser ? 1 : 0, p_out, p_der);
+  eh_pk_kernel<<<grid, 256, 0, stream>>>(p_params, p_z, B, nz, p_k, nk, T_cmb, omega_r, k_pivot, kaiser ? 1 : 0, p_out, p_der);
   CPF_CUDA(cudaGetLastError());
   if (!on_device) {
     CPF_CUDA(cudaMemcpyAsync(out, p_out, ocells * sizeof(double), cudaMemcpyDeviceToHost, stream));
-    if (derived) CPF_CUDA(cudaMemcpyAsync(derived, p_der, (size_t)B * 4 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    if (derived) CPF_CUDA(cudaMemcpyAsync(derived, p_der, (size_t)B * nz * 4 * sizeof(double), cudaMemcpyDeviceToHost, stream));
     CPF_CUDA(cudaStreamSynchronize(stream));
   }
   return CPF_OK;

@@ -67,7 +67,8 @@ __global__ void log10_kernel(const double* __restrict__ in, double* __restrict__
 
 // forward: dp_i = P_i (y_i - y_{i-1}) + Q_i (y_{i+1} - y_i) - Lw_i dp_{i-1}
 __global__ void __launch_bounds__(128) spline_forward_kernel(const double* __restrict__ y, const double* __restrict__ fac, const int nx,
-                                                              const long long ncols, const int chunk, double* __restrict__ dp) {
+                                                              const long long ncols, const int chunk, const int nak,
+                                                              double* __restrict__ dp) {
   const long long col = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (col >= ncols) return;
   const int first = blockIdx.y * chunk, last = min(nx, first + chunk) - 1;
@@ -81,6 +82,7 @@ __global__ void __launch_bounds__(128) spline_forward_kernel(const double* __res
 #pragma unroll
   for (int u = 0; u < SPLINE_U; ++u) nxt[u] = (start + 1 + u < nx) ? yc[(long long)(start + 1 + u) * ncols] : 0.;
   double ym = start > 0 ? yc[(long long)(start - 1) * ncols] : 0., y0 = yc[(long long)start * ncols], dprev = 0.;
+  double ymm = start > 1 ? yc[(long long)(start - 2) * ncols] : 0.;     // only the not-a-knot end row looks two knots back
   for (int base = start; base <= last; base += SPLINE_U) {
     double cur[SPLINE_U];
 #pragma unroll
@@ -95,9 +97,15 @@ __global__ void __launch_bounds__(128) spline_forward_kernel(const double* __res
       const int i = base + u;
       if (i <= last) {
         const double yp = cur[u];
-        const double t = fma(__ldg(P + i), y0 - ym, __ldg(Q + i) * (yp - y0));
+        double a = y0 - ym, b = yp - y0;
+        if (nak) {                                          // not-a-knot end rows use the two intervals next to the end
+          if (i == 0) { a = yp - y0; b = cur[u + 1 < SPLINE_U ? u + 1 : u] - yp; }      // i = 0 is always u = 0 of the first block
+          else if (i == nx - 1) { a = ym - ymm; b = y0 - ym; }
+        }
+        const double t = fma(__ldg(P + i), a, __ldg(Q + i) * b);
         dprev = fma(-__ldg(Lw + i), dprev, t);
         if (i >= first) dc[(long long)i * ncols] = dprev;
+        ymm = ym;
         ym = y0;
         y0 = yp;
       }
@@ -248,7 +256,7 @@ int spline_fit_device(const double* d_x, const double* d_y, int nx, long long nc
     CPF_CUDA(dp.alloc((size_t)nx * (size_t)ncols * sizeof(double), stream));
     const int chunk = nx <= SPLINE_SERIAL_MAX ? nx : SPLINE_CHUNK;
     const dim3 grid((unsigned)((ncols + 127) / 128), (unsigned)((nx + chunk - 1) / chunk));
-    spline_forward_kernel<<<grid, 128, 0, stream>>>(d_y, d_fac, nx, ncols, chunk, (double*)dp.p);
+    spline_forward_kernel<<<grid, 128, 0, stream>>>(d_y, d_fac, nx, ncols, chunk, bc == 2 ? 1 : 0, (double*)dp.p);
     spline_backward_kernel<<<grid, 128, 0, stream>>>((const double*)dp.p, d_fac, nx, ncols, chunk, d_s);
   }
   CPF_CUDA(cudaGetLastError());
@@ -287,7 +295,8 @@ int cpf_spline_create(cpf_spline** out, const double* x, const double* y, int nx
   if (!x || (!y && ncols > 0)) return fail(CPF_EINVAL, "cpf_spline_create: null buffer");
   if (nx < 2) return fail(CPF_EINVAL, "cpf_spline_create: need at least 2 knots, got %d", nx);
   if (ncols < 0) return fail(CPF_EINVAL, "cpf_spline_create: negative column count");
-  if (bc != 0 && bc != 1) return fail(CPF_EINVAL, "cpf_spline_create: bc must be 0 (natural) or 1 (clamped)");
+  if (bc < 0 || bc > 2) return fail(CPF_EINVAL, "cpf_spline_create: bc must be 0 (natural), 1 (clamped) or 2 (not-a-knot)");
+  if (bc == 2 && nx < 4) return fail(CPF_EUNSUPPORTED, "cpf_spline_create: not-a-knot ends need at least 4 knots, got %d", nx);
   int ndev = 0;
   CPF_TRY(cpf_device_count(&ndev));
   if (device < 0 || device >= ndev) return fail(CPF_EINVAL, "cpf_spline_create: device %d out of range (%d visible)", device, ndev);

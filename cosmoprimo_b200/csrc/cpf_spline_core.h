@@ -12,15 +12,18 @@
 
 namespace cpf {
 
-// Row i of the slope system: lo * s_{i-1} + di * s_i + up * s_{i+1} = rhs_i.   bc: 0 natural, 1 clamped (zero slope).
+// Row i of the slope system: lo * s_{i-1} + di * s_i + up * s_{i+1} = rhs_i.   bc: 0 natural, 1 clamped (zero slope),
+// 2 not-a-knot (third derivative continuous at x_1 and x_{nx-2}; scipy/interpolate/_cubic.py, nx >= 4 required).
 CPF_SHD void spline_row(const double* x, const int nx, const int bc, const int i, double& lo, double& di, double& up) {
   if (i == 0) {
     lo = 0.;
     if (bc == 1) { di = 1.; up = 0.; }
+    else if (bc == 2) { di = x[2] - x[1]; up = x[2] - x[0]; }
     else { const double d0 = x[1] - x[0]; di = 2. * d0; up = d0; }
   } else if (i == nx - 1) {
     up = 0.;
     if (bc == 1) { di = 1.; lo = 0.; }
+    else if (bc == 2) { di = x[nx - 2] - x[nx - 3]; lo = x[nx - 1] - x[nx - 3]; }
     else { const double dl = x[nx - 1] - x[nx - 2]; di = 2. * dl; lo = dl; }
   } else {
     const double dm = x[i] - x[i - 1], dp = x[i + 1] - x[i];
@@ -40,6 +43,7 @@ CPF_SHD double spline_rhs(const double* x, const int nx, const int bc, const int
 
 // One step of the factorisation shared by all columns: given c'_{i-1} (cprev) returns the four per-knot factors
 //   Lw_i = lo_i / piv_i, cp_i = up_i / piv_i, P_i, Q_i with  rhs_i / piv_i = P_i (y_i - y_{i-1}) + Q_i (y_{i+1} - y_i)
+// (not-a-knot end rows: P_0 (y_1 - y_0) + Q_0 (y_2 - y_1) and P_{n-1} (y_{n-2} - y_{n-3}) + Q_{n-1} (y_{n-1} - y_{n-2}))
 // (differences of neighbouring ordinates are taken first, as scipy does, so smooth data keep their accuracy).
 CPF_SHD void spline_factor_step(const double* x, const int nx, const int bc, const int i, double& cprev, double& Lw, double& P,
                                 double& Q) {
@@ -48,7 +52,18 @@ CPF_SHD void spline_factor_step(const double* x, const int nx, const int bc, con
   const double w = 1. / (di - lo * cprev);
   Lw = lo * w;
   cprev = up * w;
-  if (i == 0) { P = 0.; Q = bc == 1 ? 0. : 3. * w; }
+  if (bc == 2 && i == 0) {
+    // rhs_0 = ((dx0 + 2 d) dx1 m_0 + dx0^2 m_1) / d, d = x_2 - x_0: applied to (y_1 - y_0) and (y_2 - y_1)
+    const double dx0 = x[1] - x[0], dx1 = x[2] - x[1], d = x[2] - x[0];
+    P = (dx0 + 2. * d) * dx1 / (d * dx0) * w;
+    Q = dx0 * dx0 / (d * dx1) * w;
+  } else if (bc == 2 && i == nx - 1) {
+    // rhs_{n-1} = (dxl^2 m_{n-3} + (2 d + dxl) dxm m_{n-2}) / d, d = x_{n-1} - x_{n-3}: applied to (y_{n-2} - y_{n-3}) and (y_{n-1} - y_{n-2})
+    const double dxl = x[nx - 1] - x[nx - 2], dxm = x[nx - 2] - x[nx - 3], d = x[nx - 1] - x[nx - 3];
+    P = dxl * dxl / (d * dxm) * w;
+    Q = (2. * d + dxl) * dxm / (d * dxl) * w;
+  }
+  else if (i == 0) { P = 0.; Q = bc == 1 ? 0. : 3. * w; }
   else if (i == nx - 1) { Q = 0.; P = bc == 1 ? 0. : 3. * w; }
   else {
     const double dm = x[i] - x[i - 1], dp = x[i + 1] - x[i];

@@ -11,8 +11,8 @@
 //    sqrt(1/2N), last coefficient sqrt(1/4N) (scipy norm='ortho').  DST-III is the exact inverse of these steps.
 //  * clamped cubic spline on the uniform knots 1..n: slopes solve s_{i-1} + 4 s_i + s_{i+1} = 3 (y_{i+1} - y_{i-1}),
 //    s_0 = s_{n-1} = 0.  The Thomas pivots depend on i only (and converge to 2 - sqrt 3 within 20 rows); influence of a
-//    right-hand side decays by 0.27 per knot, so each thread eliminates its own 16-knot chunk after a 48-knot warm-up
-//    (error < 1e-27): fully parallel, no scratch beyond one array.
+//    right-hand side decays by 0.27 per knot, so each thread eliminates its own 16-knot chunk after a 32-knot warm-up
+//    (error 5e-19): fully parallel, no scratch beyond one array.
 //  * cut + re-spline: the second spline (bao_filter.py:400-402) differs from the first only by the removed box, so
 //    only the two slopes at the knots bounding the box are needed: two short one-sided eliminations + a 2x2 solve.
 #pragma once
@@ -26,7 +26,7 @@ struct WallishGeo {
   static constexpr int H = 2048;            // even / odd sequence length
   static constexpr int T = 256;             // threads per CTA
   static constexpr int CH = 16;             // knots per thread in the chunked eliminations
-  static constexpr int WARM = 48;           // warm-up knots
+  static constexpr int WARM = 32;           // warm-up knots: (2 - sqrt 3)^32 = 5e-19, below the rounding of the exact solve
   static constexpr int HP = H + H / CH;     // padded half length (one pad element per 16: conflict-free chunk access)
   static constexpr int BUF = 2 * HP;        // elements of one shared-memory array (>= 16*257 exchange elements)
   static constexpr int MARGIN_FIRST = 20, MARGIN_SECOND = 5, OFF_LO = -10, OFF_HI = 20;   // bao_filter.py:387-389

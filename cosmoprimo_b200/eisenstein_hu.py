@@ -64,41 +64,52 @@ class EisensteinHu(object):
     def _run(self, k, z, kaiser, on_device, want_pk=True):
         lib = _lib.load()
         _lib.require_device()
-        k = np.ascontiguousarray(k, dtype='f8').ravel()
         B = self.size
-        zz = None
+        zz, nz, zshape = None, 1, ()
         if z is not None:
-            zz = np.ascontiguousarray(np.broadcast_to(np.asarray(z, dtype='f8').ravel() if np.ndim(z) else np.asarray(z, dtype='f8'), (B,)))
+            zz = np.asarray(z, dtype='f8')
+            if zz.ndim == 2:                                   # (B, nz): a redshift grid per cosmology
+                if zz.shape[0] not in (1, B):
+                    raise ValueError('z must have shape (), ({0},), (1, nz) or ({0}, nz)'.format(B))
+                nz = zz.shape[1]
+                zshape = (nz,)
+                zz = np.broadcast_to(zz, (B, nz))
+            else:                                              # scalar or (B,): one redshift per cosmology
+                zz = np.broadcast_to(zz, (B,))
+            zz = np.array(zz, dtype='f8', order='C')
         dev = self.device if self.device is not None else _buf.default_device()
-        P = 3 if kaiser else 1
-        nk = k.size if want_pk else 1
-        kk = k if want_pk else np.ones(1)
+        pshape = (3,) if kaiser else ()
+        kk = np.ascontiguousarray(k, dtype='f8').ravel() if want_pk else np.ones(1)
+        nk = kk.size
+        oshape = (B,) + zshape + pshape + (nk,)
+        dshape = (B,) + zshape + (4,)
         if on_device:
             torch = _buf._torch()
             tdev = torch.device('cuda', dev)
             params = torch.as_tensor(self.params, device=tdev)
             kd = torch.as_tensor(kk, device=tdev)
             zd = torch.as_tensor(zz, device=tdev) if zz is not None else None
-            out = torch.empty((B, P, nk) if kaiser else (B, nk), dtype=torch.float64, device=tdev)
-            derived = torch.empty((B, 4), dtype=torch.float64, device=tdev)
-            rc = lib.cpf_eh_pk(params.data_ptr(), zd.data_ptr() if zd is not None else None, B, kd.data_ptr(), nk, self.T_cmb, self.omega_r,
-                               self.k_pivot, int(kaiser), out.data_ptr(), derived.data_ptr(), 1, dev, _buf.current_stream(dev))
+            out = torch.empty(oshape, dtype=torch.float64, device=tdev)
+            derived = torch.empty(dshape, dtype=torch.float64, device=tdev)
+            rc = lib.cpf_eh_pk(params.data_ptr(), zd.data_ptr() if zd is not None else None, B, nz, kd.data_ptr(), nk, self.T_cmb,
+                               self.omega_r, self.k_pivot, int(kaiser), out.data_ptr(), derived.data_ptr(), 1, dev, _buf.current_stream(dev))
         else:
-            out = np.empty((B, P, nk) if kaiser else (B, nk), dtype='f8')
-            derived = np.empty((B, 4), dtype='f8')
-            rc = lib.cpf_eh_pk(self.params.ctypes.data, zz.ctypes.data if zz is not None else None, B, kk.ctypes.data, nk, self.T_cmb,
+            out = np.empty(oshape, dtype='f8')
+            derived = np.empty(dshape, dtype='f8')
+            rc = lib.cpf_eh_pk(self.params.ctypes.data, zz.ctypes.data if zz is not None else None, B, nz, kk.ctypes.data, nk, self.T_cmb,
                                self.omega_r, self.k_pivot, int(kaiser), out.ctypes.data, derived.ctypes.data, 0, dev, None)
         _lib.check(rc)
         return out, derived
 
     def pk(self, k, z=None, kaiser=False, on_device=True):
         """
-        Linear P(k, z) in (Mpc/h)^3 on ``k`` [h/Mpc]: (B, nk), or the Kaiser multipoles ell = 0, 2, 4 with
-        f = growth_rate(z), (B, 3, nk), if ``kaiser``.  ``z``: scalar or (B,) (one redshift per cosmology; repeat the
-        parameters to sweep redshifts).  Returns a torch CUDA tensor (``on_device``) or a numpy array.
+        Linear P(k, z) in (Mpc/h)^3 on ``k`` [h/Mpc].  ``z``: scalar or (B,) -- one redshift per cosmology, result
+        (B, nk) -- or (B, nz) / (1, nz) -- a redshift grid per cosmology, result (B, nz, nk); the transfer function is
+        evaluated once per cosmology.  ``kaiser``: the Kaiser multipoles ell = 0, 2, 4 with f = growth_rate(z) instead,
+        (..., 3, nk).  Returns a torch CUDA tensor (``on_device``) or a numpy array.
         """
         return self._run(k, z, kaiser, on_device)[0]
 
     def derived(self, z=None, on_device=False):
-        """(B, 4): rs_drag [Mpc/h], z_drag, growth_factor(z, znorm=0)**2, growth_rate(z)."""
+        """(..., 4): rs_drag [Mpc/h], z_drag, growth_factor(z, znorm=0)**2, growth_rate(z); leading shape as :meth:`pk`."""
         return self._run(None, z, False, on_device, want_pk=False)[1]

@@ -26,6 +26,9 @@ def _bcast_dtype(*args):
     return out if np.issubdtype(out, np.floating) else np.dtype('f8')
 
 
+_BC_CODES = {'natural': 0, 'clamped': 1, 'not-a-knot': 2}
+
+
 class _DeviceSpline(object):
     """Owner of a ``cpf_spline*``."""
 
@@ -61,7 +64,8 @@ class Interpolator1D(object):
         Interpolate in log10 of the abscissa / ordinate (ref:152-153, 189-191).
     extrap : bool, default=False
         If False, NaN outside ``[x.min(), x.max()]``.
-    bc_type : 'natural' (the reference's choice, ref:172) or 'clamped' (used by the Wallish2018 filter).
+    bc_type : 'natural' (the reference's choice, ref:172), 'clamped' (used by the Wallish2018 filter) or 'not-a-knot'
+        (the ends of FITPACK's interpolating splines: building block of :class:`Interpolator2D`).
     device : int, default=None
         CUDA device for host input.
     """
@@ -69,8 +73,8 @@ class Interpolator1D(object):
     def __init__(self, x, fun, k=3, interp_x='lin', interp_fun='lin', extrap=False, assume_sorted=False, bc_type='natural', device=None):
         if k != 3:
             raise NotImplementedError('cosmoprimo_b200.Interpolator1D implements the cubic spline (k=3) only')
-        if bc_type not in ('natural', 'clamped'):
-            raise ValueError('bc_type must be "natural" or "clamped"')
+        if bc_type not in _BC_CODES:
+            raise ValueError('bc_type must be one of {}'.format(sorted(_BC_CODES)))
         _lib.load()
         self.interp_x, self.interp_fun = str(interp_x), str(interp_fun)
         self.extrap = bool(extrap)
@@ -119,7 +123,7 @@ class Interpolator1D(object):
             else:
                 xbuf = _buf.as_input(x, dtype='f8')
             # NaN columns simply propagate NaN through their own (independent) solve: no need to drop them
-            self._spline = _DeviceSpline(xbuf, ybuf, x.size, self._ncols, 1 if bc_type == 'clamped' else 0, self.interp_x == 'log',
+            self._spline = _DeviceSpline(xbuf, ybuf, x.size, self._ncols, _BC_CODES[bc_type], self.interp_x == 'log',
                                          self.interp_fun == 'log', self.extrap, dev, stream)
             self._device = dev
 
@@ -173,6 +177,87 @@ class Interpolator1D(object):
                 res = res.to(_buf._torch().float32)
             return res.reshape(out_shape)
         return res.astype(dtype, copy=False).reshape(out_shape)
+
+
+class Interpolator2D(object):
+    """
+    Bicubic interpolation on a rectangular grid, drop-in for the numpy path of ``cosmoprimo.jax.Interpolator2D``
+    (ref:213-277), which wraps ``scipy.interpolate.RectBivariateSpline(x, y, fun, kx=3, ky=3, s=0)``: FITPACK's interpolating
+    tensor-product spline has not-a-knot ends in both directions, and tensor-product interpolation factorises, so the value
+    at (xq, yq) is obtained by 1-D not-a-knot splines along y for every x knot (fitted once, here), then a 1-D not-a-knot
+    spline along x through the values at yq (fitted per call: nx knots x nyq columns).  Both steps are the batched spline
+    kernels of ``csrc/cpf_spline.cu``.  ``fun`` has shape (nx, ny); numpy or CUDA array.
+    """
+
+    def __init__(self, x, y, fun, kx=3, ky=3, interp_x='lin', interp_y='lin', interp_fun='lin', extrap=False, assume_sorted=False, device=None):
+        if kx != 3 or ky != 3:
+            raise NotImplementedError('cosmoprimo_b200.Interpolator2D implements bicubic splines (kx = ky = 3) only')
+        self.interp_x, self.interp_y, self.interp_fun = str(interp_x), str(interp_y), str(interp_fun)
+        self.extrap = bool(extrap)
+        x, y = (np.array(xx, dtype='f8').ravel() for xx in (x, y))
+        on_device = _buf.is_device_array(fun)
+        fun = _buf.as_input(fun, dtype='f8').obj if on_device else np.array(fun, dtype='f8')
+        if tuple(fun.shape) != (x.size, y.size):
+            raise ValueError('fun must have shape ({}, {}), got {}'.format(x.size, y.size, tuple(fun.shape)))
+        if x.size < 4 or y.size < 4:
+            raise NotImplementedError('bicubic interpolation needs at least 4 knots in each direction')
+        if not assume_sorted:
+            ix, iy = np.argsort(x), np.argsort(y)
+            x, y = x[ix], y[iy]
+            if on_device:
+                torch = _buf._torch()
+                fun = fun[torch.as_tensor(ix, device=fun.device)][:, torch.as_tensor(iy, device=fun.device)]
+            else:
+                fun = fun[np.ix_(ix, iy)]
+        self.xmin, self.xmax, self.ymin, self.ymax = x[0], x[-1], y[0], y[-1]
+        self._on_device = on_device
+        self._device = device
+        self._xt = np.log10(x) if self.interp_x == 'log' else x
+        yt = np.log10(y) if self.interp_y == 'log' else y
+        if self.interp_fun == 'log':
+            fun = _buf._torch().log10(fun) if on_device else np.log10(fun)
+        funT = fun.T.contiguous() if on_device else np.ascontiguousarray(fun.T)       # (ny, nx): knots of the y splines along axis 0
+        self._along_y = Interpolator1D(yt, funT, bc_type='not-a-knot', extrap=True, assume_sorted=True, device=device)
+
+    def __call__(self, x, y, grid=True, bounds_error=False):
+        dtype = _bcast_dtype(x, y)
+        x, y = (np.asarray(xx, dtype=dtype).astype('f8') for xx in (x, y))
+        shape = x.shape + y.shape if grid else x.shape
+        x, y = x.ravel(), y.ravel()
+        masks = []
+        for q, lo, hi in ((x, self.xmin, self.xmax), (y, self.ymin, self.ymax)):
+            m = (q >= lo) & (q <= hi)
+            if bounds_error and not m.all():
+                raise ValueError('input outside of extrapolation range (min: {} vs. {}; max: {} vs. {})'.format(q.min(), lo, q.max(), hi))
+            masks.append(m)
+        mask = masks[0][:, None] & masks[1] if grid else masks[0] & masks[1]
+        xt = np.log10(x) if self.interp_x == 'log' else x
+        yt = np.log10(y) if self.interp_y == 'log' else y
+        if x.size == 0 or y.size == 0:
+            out = np.zeros(shape, dtype=dtype)
+            return _buf._torch().as_tensor(out, device='cuda') if self._on_device else out
+        vals = self._along_y(yt)                                              # (nyq, nx)
+        valsT = vals.T.contiguous() if self._on_device else np.ascontiguousarray(vals.T)      # (nx, nyq)
+        if grid:
+            tmp = Interpolator1D(self._xt, valsT, bc_type='not-a-knot', extrap=True, assume_sorted=True, device=self._device)(xt)   # (nxq, nyq)
+        else:
+            # pairs (x_i, y_i): column i of the x splines evaluated at x_i only
+            step, parts = 2048, []
+            for start in range(0, x.size, step):
+                sl = slice(start, start + step)
+                full = Interpolator1D(self._xt, valsT[:, sl], bc_type='not-a-knot', extrap=True, assume_sorted=True, device=self._device)(xt[sl])
+                parts.append(full.diagonal() if self._on_device else np.diagonal(full))
+            tmp = (_buf._torch().cat(parts) if self._on_device else np.concatenate(parts))
+        if self.interp_fun == 'log':
+            tmp = 10**tmp
+        if self._on_device:
+            torch = _buf._torch()
+            if not self.extrap:
+                tmp = torch.where(torch.as_tensor(mask, device=tmp.device), tmp, torch.full_like(tmp, float('nan')))
+            return tmp.to(torch.float32 if dtype == np.float32 else torch.float64).reshape(shape)
+        if not self.extrap:
+            tmp = np.where(mask, tmp, np.nan)
+        return tmp.astype(dtype).reshape(shape)
 
 
 def spline_eval_rows(x, fun, xq, bc_type='natural', window=64, extrap=False, device=None):

@@ -91,7 +91,8 @@ int cpf_irfft_conj(int size, const double* in, int64_t rows, double* out, int in
  * scipy.interpolate.CubicSpline(x, fun, axis=0, bc_type='natural') + PPoly evaluation, and the clamped splines of the
  * Wallish2018 filter (bao_filter.py:377-382, 400-402, 420).
  * Column layout as in the reference (axis 0 = knots): y [nx, ncols] row-major, shared strictly increasing x [nx].
- *   bc            : 0 = natural (y''=0 at both ends), 1 = clamped (y'=0 at both ends)
+ *   bc            : 0 = natural (y''=0 at both ends), 1 = clamped (y'=0 at both ends), 2 = not-a-knot (nx >= 4; the ends of
+ *                   FITPACK's interpolating splines, i.e. of RectBivariateSpline(s=0) behind Interpolator2D, jax.py:213-243)
  *   log_x, log_y  : fit in log10(x) / log10(y) and return 10**spline (interp_x='log' / interp_fun='log', jax.py:152-153,189-191)
  *   extrap        : 0 => NaN outside [x[0], x[nx-1]] (jax.py:188-192), 1 => extend the end polynomials
  * The handle owns device copies of the (transformed) knots and the fitted slopes.
@@ -137,13 +138,14 @@ int cpf_wallish2018(const double* klin, const double* pklin, int nlin, const dou
  * 241-283 transfer function, 189-214 primordial spectrum, 321-324 P(k), 115-153 growth factor (znorm=0) / growth rate on
  * the background of cosmology.py:1675-1760) and writes rows in the layout cpf_fftlog reads.
  *   params  [B, 5]  (h, omega_b, omega_cdm, n_s, A_s) per cosmology
- *   z       [B] or NULL (= 0): one redshift per row
+ *   z       [B, nz] redshifts of every cosmology, 1 <= nz <= 1024 (the transfer function is evaluated once per
+ *           cosmology); NULL with nz = 1: redshift 0
  *   k       [nk]    wavenumbers, h/Mpc
  *   T_cmb, omega_r (= Omega0_r h^2: photons + massless neutrinos, cosmology.py:355-367), k_pivot [1/Mpc]
- *   kaiser  0: out [B, nk] = P(k, z);  1: out [B, 3, nk] = Kaiser multipoles ell = 0, 2, 4 with f = growth_rate(z)
- *   derived [B, 4] or NULL: rs_drag [Mpc/h], z_drag, growth_factor(z, znorm=0)^2, growth_rate(z)
+ *   kaiser  0: out [B, nz, nk] = P(k, z);  1: out [B, nz, 3, nk] = Kaiser multipoles ell = 0, 2, 4 with f = growth_rate(z)
+ *   derived [B, nz, 4] or NULL: rs_drag [Mpc/h], z_drag, growth_factor(z, znorm=0)^2, growth_rate(z)
  */
-int cpf_eh_pk(const double* params, const double* z, int64_t B, const double* k, int nk, double T_cmb, double omega_r,
+int cpf_eh_pk(const double* params, const double* z, int64_t B, int nz, const double* k, int nk, double T_cmb, double omega_r,
               double k_pivot, int kaiser, double* out, double* derived, int on_device, int device, void* stream);
 
 /* ---- measurement helper: peak fp64 FMA rate of the device (DFMA chains), in FLOP/s; used by bench.py for the

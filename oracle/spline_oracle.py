@@ -106,3 +106,44 @@ def interpolator1d(x, fun, interp_x='lin', interp_fun='lin', extrap=False, assum
         return toret.astype(dtype).reshape(toret_shape)
 
     return call
+
+
+def interpolator2d(x, y, fun, interp_x='lin', interp_y='lin', interp_fun='lin', extrap=False):
+    """Restatement of Interpolator2D (jax.py:213-277), kx = ky = 3, numpy path: the same third-party call,
+    ``scipy.interpolate.RectBivariateSpline(x, y, fun, s=0)`` (FITPACK).  Returns ``(xq, yq, grid=True) -> values``."""
+    from scipy.interpolate import RectBivariateSpline
+    x, y, fun = (np.array(a, dtype='f8') for a in (x, y, fun))
+    ix, iy = np.argsort(x), np.argsort(y)                                       # :224-226
+    x, y, fun = x[ix], y[iy], fun[np.ix_(ix, iy)]
+    xmin, xmax, ymin, ymax = x[0], x[-1], y[0], y[-1]
+    if interp_x == 'log': x = np.log10(x)
+    if interp_y == 'log': y = np.log10(y)
+    if interp_fun == 'log': fun = np.log10(fun)
+    spline = RectBivariateSpline(x, y, fun, kx=3, ky=3, s=0)                    # :242-243
+
+    def call(xq, yq, grid=True):
+        xq, yq = np.asarray(xq, dtype='f8'), np.asarray(yq, dtype='f8')
+        shape = xq.shape + yq.shape if grid else xq.shape
+        xq, yq = xq.ravel(), yq.ravel()
+        mx, my = (xq >= xmin) & (xq <= xmax), (yq >= ymin) & (yq <= ymax)       # :254-256
+        mask = mx[:, None] & my if grid else mx & my
+        if interp_x == 'log': xq = np.log10(xq)
+        if interp_y == 'log': yq = np.log10(yq)
+        if grid:
+            i_x, i_y = np.argsort(xq), np.argsort(yq)                           # :268-270
+            tmp = spline(xq[i_x], yq[i_y], grid=True)[np.ix_(np.argsort(i_x), np.argsort(i_y))]
+        else:
+            tmp = spline(xq, yq, grid=False)
+        if interp_fun == 'log': tmp = 10**tmp
+        return (tmp if extrap else np.where(mask, tmp, np.nan)).reshape(shape)
+
+    return call
+
+
+def interpolator2d_factorised(x, y, fun, xq, yq):
+    """The formulation the CUDA path uses (cosmoprimo_b200/interp.py::Interpolator2D): FITPACK's interpolating bicubic
+    spline has not-a-knot ends, and tensor-product interpolation factorises into 1-D not-a-knot splines along y for every
+    x knot followed by 1-D not-a-knot splines along x.  Library-free of FITPACK; checked against :func:`interpolator2d`."""
+    from scipy.interpolate import CubicSpline
+    vals = CubicSpline(y, np.asarray(fun, dtype='f8').T, axis=0, bc_type='not-a-knot')(yq)       # (nyq, nx)
+    return CubicSpline(x, vals.T, axis=0, bc_type='not-a-knot')(xq)                               # (nxq, nyq)

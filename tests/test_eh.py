@@ -80,6 +80,13 @@ def test_cuda_generator_matches_reference():
     k = np.geomspace(1e-5, 1e2, 2048)
     eh2 = EisensteinHu(par2['h'], par2['omega_b'], par2['omega_cdm'], par2['n_s'], logA=par2['logA'])
     np.testing.assert_allclose(eh2.pk(k, z=zz).cpu().numpy(), S.eh_pk(k, par2, z=zz), rtol=RTOL)
+    # redshift grid per cosmology: (B, nz, nk), one transfer-function evaluation per cosmology
+    eh9 = EisensteinHu(par['h'], par['omega_b'], par['omega_cdm'], par['n_s'], logA=par['logA'])
+    grid = eh9.pk(d['k'], z=d['z'][None, :])
+    assert tuple(grid.shape) == (par['h'].size, d['z'].size, d['k'].size)
+    np.testing.assert_allclose(grid.cpu().numpy(), d['pk'], rtol=RTOL)
+    np.testing.assert_allclose(eh9.derived(z=d['z'][None, :]), d['derived'], rtol=RTOL)
+    assert tuple(eh9.pk(d['k'], z=d['z'][None, :], kaiser=True).shape) == (par['h'].size, d['z'].size, 3, d['k'].size)
 
 
 @pytest.mark.gpu

@@ -1,0 +1,93 @@
+"""2-D (k, z) interpolators: golden vectors from the reference's PowerSpectrumInterpolator2D /
+CorrelationFunctionInterpolator2D / Interpolator2D (tools/make_golden.py::make_interp2d)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_DIR
+from oracle import spline_oracle as SO
+
+
+def golden():
+    return np.load(os.path.join(GOLDEN_DIR, 'interp2d_golden.npz'))
+
+
+def close_with_nans(out, ref, rtol, atol=0.):
+    out, ref = np.asarray(out), np.asarray(ref)
+    assert out.shape == ref.shape, (out.shape, ref.shape)
+    assert np.array_equal(np.isnan(out), np.isnan(ref))
+    m = np.isfinite(ref)
+    np.testing.assert_allclose(out[m], ref[m], rtol=rtol, atol=atol)
+
+
+def test_oracle_2d_and_factorisation_vs_reference():
+    d = golden()
+    i2 = SO.interpolator2d(d['k'], d['z'], d['pk'], interp_x='log', interp_fun='log')
+    close_with_nans(i2(d['kq'], d['zq']), d['i2_grid'], rtol=1e-13)
+    close_with_nans(i2(d['kp'], d['zp'], grid=False), d['i2_pairs'], rtol=1e-13)
+    # not-a-knot factorisation == FITPACK's bicubic interpolant (inside the table)
+    inside_k, inside_z = (d['kq'] >= d['k'][0]) & (d['kq'] <= d['k'][-1]), (d['zq'] >= 0.) & (d['zq'] <= 3.)
+    kq, zq = d['kq'][inside_k], d['zq'][inside_z]
+    fact = 10**SO.interpolator2d_factorised(np.log10(d['k']), d['z'], np.log10(d['pk']), np.log10(kq), zq)
+    np.testing.assert_allclose(fact, d['i2_grid'][np.ix_(inside_k, inside_z)], rtol=1e-11)
+
+
+@pytest.mark.gpu
+def test_interpolator2d_golden():
+    torch = pytest.importorskip('torch')
+    from cosmoprimo_b200.interp import Interpolator2D
+    d = golden()
+    i2 = Interpolator2D(d['k'], d['z'], d['pk'], interp_x='log', interp_fun='log')
+    close_with_nans(i2(d['kq'], d['zq']), d['i2_grid'], rtol=1e-10)
+    close_with_nans(i2(d['kp'], d['zp'], grid=False), d['i2_pairs'], rtol=1e-10)
+    lin = Interpolator2D(np.log(d['k']), d['z'], np.log(d['pk']), extrap=True)
+    got, ref = lin(np.log(d['kq']), d['zq']), d['i2_lin_extrap']
+    assert np.max(np.abs(got - ref)) < 1e-9 * np.max(np.abs(ref))          # includes extrapolated end polynomials
+    dev = Interpolator2D(d['k'], d['z'], torch.from_numpy(d['pk']).cuda(), interp_x='log', interp_fun='log')
+    out = dev(d['kq'], d['zq'])
+    assert isinstance(out, torch.Tensor) and out.is_cuda
+    close_with_nans(out.cpu().numpy(), d['i2_grid'], rtol=1e-10)
+    # unsorted input, shapes, dtype
+    perm_k, perm_z = np.random.default_rng(0).permutation(d['k'].size), np.random.default_rng(1).permutation(d['z'].size)
+    shuffled = Interpolator2D(d['k'][perm_k], d['z'][perm_z], d['pk'][np.ix_(perm_k, perm_z)], interp_x='log', interp_fun='log')
+    close_with_nans(shuffled(d['kq'], d['zq']), d['i2_grid'], rtol=1e-10)
+    assert i2(0.1, 0.5).shape == () and i2(np.ones((2, 3)), np.ones(4)).shape == (2, 3, 4)
+    assert i2(np.ones(3, dtype='f4'), np.ones(2, dtype='f4')).dtype == np.float32
+
+
+@pytest.mark.gpu
+def test_power_spectrum_interpolator2d_golden():
+    from cosmoprimo_b200.interpolator import PowerSpectrumInterpolator2D, CorrelationFunctionInterpolator2D, PowerSpectrumInterpolator1D
+    d = golden()
+    interp = PowerSpectrumInterpolator2D(d['k'], d['z'], d['pk'])
+    close_with_nans(interp(d['kq'], d['zq']), d['p2_grid'], rtol=1e-10)
+    close_with_nans(interp(d['kp'], d['zp'], grid=False), d['p2_pairs'], rtol=1e-10)
+    np.testing.assert_allclose(interp.sigma_rz(d['r'], d['zs']), d['p2_sigma_rz'], rtol=1e-10)
+    np.testing.assert_allclose(interp.sigma8_z(d['zs']), d['p2_sigma8_z'], rtol=1e-10)
+    # finite differences with dz = 1e-3 amplify the 1e-13 agreement of sigma by 1/dz
+    np.testing.assert_allclose(interp.growth_rate_rz(d['r'], d['zs']), d['p2_growth_rate_rz'], rtol=1e-8)
+    one = interp.to_1d(0.55)
+    assert isinstance(one, PowerSpectrumInterpolator1D)
+    close_with_nans(one(d['kq']), d['p2_to_1d'], rtol=1e-10)
+    xi = interp.to_xi()
+    assert isinstance(xi, CorrelationFunctionInterpolator2D)
+    np.testing.assert_allclose(xi.s, d['xi_s'], rtol=1e-13)
+    got = xi(d['sq'], d['zq'][:5])
+    assert np.max(np.abs(got - d['p2_xi'])) < 1e-10 * np.max(np.abs(d['p2_xi']))
+    back = xi.to_pk(extrap_pk='lin')(np.geomspace(1e-3, 10., 30), d['zs'])
+    np.testing.assert_allclose(back, d['p2_xi_back'], rtol=1e-8)
+    interp.rescale_sigma8(0.8)
+    np.testing.assert_allclose(interp(d['kq'][:20], d['zs']), d['p2_rescaled'], rtol=1e-10)
+    assert abs(float(interp.sigma8_z(0.)) - 0.8) < 1e-12
+    # single column + growth_factor_sq callable
+    z, D2 = d['z'], None
+    from cosmoprimo_b200 import synthetic as S
+    D2 = S.growth_factor(z, 0.3137721026737606, 0.6736)**2
+    gf = lambda zz: np.interp(zz, z, D2 / D2[0])
+    interp = PowerSpectrumInterpolator2D(d['k'], 0., S.eh_pk(d['k']), growth_factor_sq=gf)
+    close_with_nans(interp(d['kq'], d['zq']), d['g_grid'], rtol=1e-10)
+    np.testing.assert_allclose(interp.sigma_rz(d['r'], d['zs']), d['g_sigma_rz'], rtol=1e-10)
+    np.testing.assert_allclose(interp.growth_rate_rz(d['r'], d['zs']), d['g_growth_rate_rz'], rtol=1e-8)
+    got = interp.to_xi()(d['sq'], d['zs'])
+    assert np.max(np.abs(got - d['g_xi'])) < 1e-10 * np.max(np.abs(d['g_xi']))

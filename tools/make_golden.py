@@ -274,8 +274,60 @@ def make_eh():
     print('wrote {} ({} cosmologies x {} redshifts x {} k, {:.2f} MB)'.format(fn, B + 1, zs.size, k.size, os.path.getsize(fn) / 1e6))
 
 
+def make_interp2d():
+    """PowerSpectrumInterpolator2D / CorrelationFunctionInterpolator2D of the reference (interpolator.py:608-987, 1219-1498;
+    jax.py:213-277 = RectBivariateSpline) on a tabulated EH P(k, z): evaluation on grids and pairs, sigma_rz, sigma8_z,
+    growth_rate_rz, to_1d, to_xi, to_pk, rescale_sigma8; with and without a growth_factor_sq callable."""
+    from cosmoprimo.interpolator import PowerSpectrumInterpolator2D
+    from cosmoprimo.jax import Interpolator2D
+    sys.path.insert(0, ROOT)
+    from cosmoprimo_b200 import synthetic
+    arrays = {}
+    k = np.geomspace(1e-4, 50., 300)
+    z = np.array([0., 0.2, 0.5, 0.9, 1.4, 2., 3.])
+    Om0, h = 0.3137721026737606, 0.6736
+    D2 = synthetic.growth_factor(z, Om0, h)**2
+    pk0 = synthetic.eh_pk(k)                                       # z = 0, DESI-like fiducial
+    pk = pk0[:, None] * (D2 / D2[0]) * (1. + 0.05 * z * np.log10(k / 0.1)[:, None]**2 / 9.)     # mildly scale-dependent growth
+    rng = np.random.default_rng(2)
+    kq = np.concatenate([np.geomspace(2e-7, 90., 60), [1e-8, 200.]])
+    zq = np.array([0., 0.1, 0.55, 1.7, 3., 3.5, -0.1])
+    kp, zp = np.exp(rng.uniform(np.log(1e-6), np.log(80.), 50)), rng.uniform(0., 3., 50)
+    r = np.array([1., 8., 20.])
+    zs = np.array([0., 0.5, 1.1, 3.])
+    arrays.update(k=k, z=z, pk=pk, kq=kq, zq=zq, kp=kp, zp=zp, r=r, zs=zs)
+    # raw Interpolator2D (lin / log axes)
+    i2 = Interpolator2D(k, z, pk, interp_x='log', interp_fun='log')
+    arrays['i2_grid'] = i2(kq, zq)
+    arrays['i2_pairs'] = i2(kp, zp, grid=False)
+    i2 = Interpolator2D(np.log(k), z, np.log(pk), extrap=True)
+    arrays['i2_lin_extrap'] = i2(np.log(kq), zq)
+    interp = PowerSpectrumInterpolator2D(k, z, pk)
+    arrays['p2_grid'] = interp(kq, zq)
+    arrays['p2_pairs'] = interp(kp, zp, grid=False)
+    arrays['p2_sigma_rz'] = interp.sigma_rz(r, zs)
+    arrays['p2_sigma8_z'] = interp.sigma8_z(zs)
+    arrays['p2_growth_rate_rz'] = interp.growth_rate_rz(r, zs)
+    arrays['p2_to_1d'] = interp.to_1d(0.55)(kq)
+    xi = interp.to_xi()
+    sq = np.geomspace(xi.s[0] * 1.01, xi.s[-1] * 0.99, 40)
+    arrays.update(sq=sq, xi_s=xi.s, p2_xi=xi(sq, zq[:5]), p2_xi_back=xi.to_pk(extrap_pk='lin')(np.geomspace(1e-3, 10., 30), zs))   # default extrap_pk='log' yields NaN: negative P(k) at the edges
+    interp.rescale_sigma8(0.8)
+    arrays['p2_rescaled'] = interp(kq[:20], zs)
+    # single column + growth_factor_sq callable
+    gf = lambda zz: np.interp(zz, z, D2 / D2[0])
+    interp = PowerSpectrumInterpolator2D(k, 0., pk0, growth_factor_sq=gf)
+    arrays['g_grid'] = interp(kq, zq)
+    arrays['g_sigma_rz'] = interp.sigma_rz(r, zs)
+    arrays['g_growth_rate_rz'] = interp.growth_rate_rz(r, zs)
+    arrays['g_xi'] = interp.to_xi()(sq, zs)
+    fn = os.path.join(GOLDEN, 'interp2d_golden.npz')
+    np.savez_compressed(fn, **arrays)
+    print('wrote {} ({:.2f} MB)'.format(fn, os.path.getsize(fn) / 1e6))
+
+
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['fftlog', 'spline', 'wallish', 'eh']
+    which = sys.argv[1:] or ['fftlog', 'spline', 'wallish', 'eh', 'interp2d']
     print('reference: cosmoprimo {} from {}; numpy {}'.format(cosmoprimo.__version__, os.path.dirname(cosmoprimo.__file__), np.__version__))
     for name in which:
         fn = globals().get('make_' + name, None)
