@@ -51,7 +51,22 @@ struct ScratchBuf {
   cudaStream_t s = nullptr;
   cudaError_t alloc(size_t bytes, cudaStream_t stream) {
     s = stream;
+    keep_pool_warm();
     return cudaMallocAsync(&p, bytes ? bytes : 1, stream);
+  }
+  // The default memory pool hands its free blocks back to the driver at every synchronisation (release threshold 0), which
+  // makes each cudaMallocAsync after a sync a fresh driver allocation (~100 us, milliseconds for GB-sized scratch).  Raise
+  // the threshold once per device so that scratch memory is recycled inside the pool.
+  static void keep_pool_warm() {
+    static bool done[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || done[dev]) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      uint64_t threshold = UINT64_MAX;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+    }
+    done[dev] = true;
   }
   ~ScratchBuf() {
     if (p) cudaFreeAsync(p, s);

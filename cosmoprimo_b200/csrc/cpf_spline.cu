@@ -246,6 +246,44 @@ __global__ void __launch_bounds__(256) spline_rows_dot_kernel(const double* __re
   }
 }
 
+// transposed evaluation: out[col, q] (rows = splines: the layout cpf_fftlog reads), 32 x 32 tiles through shared memory so
+// that both the knot-matrix reads (contiguous in col) and the stores (contiguous in q) are coalesced
+__global__ void __launch_bounds__(256) spline_eval_t_kernel(const double* __restrict__ x, const double* __restrict__ y,
+                                                            const double* __restrict__ s, const int nx, const long long ncols,
+                                                            const double* __restrict__ xq, const int nq, const int nu,
+                                                            const int extrap, const int log_x, const int log_y,
+                                                            const double xmin_raw, const double xmax_raw, double* __restrict__ out) {
+  __shared__ double tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const long long c0 = (long long)blockIdx.x * 32;
+  const int q0 = blockIdx.y * 32;
+  const long long col = c0 + tx;
+  for (int qq = ty; qq < 32; qq += 8) {
+    const int q = q0 + qq;
+    double r = 0.;
+    if (q < nq && col < ncols) {
+      const double raw = xq[q];
+      const bool inside = raw >= xmin_raw && raw <= xmax_raw;
+      const double xv = log_x ? log10(raw) : raw;
+      if ((!inside && !extrap) || !(xv == xv)) {
+        r = nan("");
+      } else {
+        const int i = spline_interval(x, nx, xv);
+        const long long o = (long long)i * ncols + col;
+        r = spline_poly(x[i], x[i + 1], y[o], y[o + ncols], s[o], s[o + ncols], xv, nu);
+        if (log_y) r = pow(10., r);
+      }
+    }
+    tile[qq][tx] = r;
+  }
+  __syncthreads();
+  for (int cc = ty; cc < 32; cc += 8) {
+    const long long c = c0 + cc;
+    const int q = q0 + tx;
+    if (c < ncols && q < nq) out[c * nq + q] = tile[tx][cc];
+  }
+}
+
 // device-resident fit, shared with cpf_wallish.cu: slopes s[nx, ncols] of the splines through y[nx, ncols] on the
 // knots x[nx]; fac is scratch of 4*nx doubles (already filled by spline_factor_host when fac_ready)
 int spline_fit_device(const double* d_x, const double* d_y, int nx, long long ncols, int bc, double* d_s, double* d_fac,
@@ -348,13 +386,15 @@ int cpf_spline_create(cpf_spline** out, const double* x, const double* y, int nx
   return CPF_OK;
 }
 
-int cpf_spline_eval(const cpf_spline* sp, const double* xq, int nq, int nu, double* out, int on_device, void* stream_) {
+static int spline_eval_impl(const cpf_spline* sp, const double* xq, int nq, int nu, double* out, int on_device, int transposed,
+                            void* stream_) {
   if (!sp) return fail(CPF_EINVAL, "cpf_spline_eval: null spline");
   if (nq < 0) return fail(CPF_EINVAL, "cpf_spline_eval: negative query count");
   if (nu < 0 || nu > 3) return fail(CPF_EINVAL, "cpf_spline_eval: derivative order %d not in 0..3", nu);
   if (nq == 0 || sp->ncols == 0) return CPF_OK;
   if (!xq || !out) return fail(CPF_EINVAL, "cpf_spline_eval: null buffer");
-  if (nq > 65535) return fail(CPF_EUNSUPPORTED, "cpf_spline_eval: more than 65535 query points in one call");
+  if (!transposed && nq > 65535) return fail(CPF_EUNSUPPORTED, "cpf_spline_eval: more than 65535 query points in one call");
+  if (transposed && (nq + 31) / 32 > 65535) return fail(CPF_EUNSUPPORTED, "cpf_spline_eval_t: more than 2 M query points in one call");
   DeviceGuard guard(sp->device);
   cudaStream_t stream = (cudaStream_t)stream_;
   const size_t cells = (size_t)nq * (size_t)sp->ncols;
@@ -368,15 +408,29 @@ int cpf_spline_eval(const cpf_spline* sp, const double* xq, int nq, int nu, doub
     d_xq = (const double*)dq.p;
     d_out = (double*)dout.p;
   }
-  dim3 grid((unsigned)((sp->ncols + 127) / 128), (unsigned)nq);
-  spline_eval_kernel<<<grid, 128, 0, stream>>>(sp->d_x, sp->d_y, sp->d_s, sp->nx, sp->ncols, d_xq, nq, nu, sp->extrap, sp->log_x,
-                                               sp->log_y, sp->xmin_raw, sp->xmax_raw, d_out);
+  if (transposed) {
+    dim3 grid((unsigned)((sp->ncols + 31) / 32), (unsigned)((nq + 31) / 32));
+    spline_eval_t_kernel<<<grid, 256, 0, stream>>>(sp->d_x, sp->d_y, sp->d_s, sp->nx, sp->ncols, d_xq, nq, nu, sp->extrap, sp->log_x,
+                                                   sp->log_y, sp->xmin_raw, sp->xmax_raw, d_out);
+  } else {
+    dim3 grid((unsigned)((sp->ncols + 127) / 128), (unsigned)nq);
+    spline_eval_kernel<<<grid, 128, 0, stream>>>(sp->d_x, sp->d_y, sp->d_s, sp->nx, sp->ncols, d_xq, nq, nu, sp->extrap, sp->log_x,
+                                                 sp->log_y, sp->xmin_raw, sp->xmax_raw, d_out);
+  }
   CPF_CUDA(cudaGetLastError());
   if (!on_device) {
     CPF_CUDA(cudaMemcpyAsync(out, d_out, cells * sizeof(double), cudaMemcpyDeviceToHost, stream));
     CPF_CUDA(cudaStreamSynchronize(stream));
   }
   return CPF_OK;
+}
+
+int cpf_spline_eval(const cpf_spline* sp, const double* xq, int nq, int nu, double* out, int on_device, void* stream_) {
+  return spline_eval_impl(sp, xq, nq, nu, out, on_device, 0, stream_);
+}
+
+int cpf_spline_eval_t(const cpf_spline* sp, const double* xq, int nq, int nu, double* out, int on_device, void* stream_) {
+  return spline_eval_impl(sp, xq, nq, nu, out, on_device, 1, stream_);
 }
 
 int cpf_spline_eval_rows(const double* x, const double* y, int nx, int64_t rows, const double* xq, int nq, int bc, int window,

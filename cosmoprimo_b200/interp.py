@@ -178,6 +178,30 @@ class Interpolator1D(object):
             return res.reshape(out_shape)
         return res.astype(dtype, copy=False).reshape(out_shape)
 
+    def eval_rows(self, x, dx=0):
+        """
+        Same values as ``self(x)`` for 1-D ``x``, transposed: (ncols, nq) float64 with one row per spline -- the layout the
+        FFTLog entry points read -- written directly by the kernel (``cpf_spline_eval_t``), no transposition pass.
+        Result kind (numpy / torch) follows the fitted table.
+        """
+        q = np.asarray(x, dtype='f8').ravel()
+        nq = q.size
+        if self._spline is None or nq == 0 or self._ncols == 0:
+            out = np.full((self._ncols, nq), np.nan)
+            return _buf._torch().as_tensor(out, device='cuda') if self._on_device else out
+        lib = _lib.load()
+        dev = self._spline.device
+        if self._on_device:
+            torch = _buf._torch()
+            qbuf = _buf.as_input(torch.as_tensor(q, device=torch.device('cuda', dev)), dtype='f8')
+            stream = _buf.current_stream(dev)
+        else:
+            qbuf = _buf.as_input(q, dtype='f8')
+            stream = None
+        out = _buf.empty_like_kind(qbuf, (self._ncols, nq), dtype='f8')
+        _lib.check(lib.cpf_spline_eval_t(self._spline.handle, qbuf.ptr, nq, int(dx), out.ptr, int(qbuf.on_device), stream))
+        return out.obj
+
 
 class Interpolator2D(object):
     """
@@ -219,7 +243,8 @@ class Interpolator2D(object):
         funT = fun.T.contiguous() if on_device else np.ascontiguousarray(fun.T)       # (ny, nx): knots of the y splines along axis 0
         self._along_y = Interpolator1D(yt, funT, bc_type='not-a-knot', extrap=True, assume_sorted=True, device=device)
 
-    def __call__(self, x, y, grid=True, bounds_error=False):
+    def __call__(self, x, y, grid=True, bounds_error=False, rows=False):
+        """``rows=True`` (grid only, 1-D queries): the float64 result transposed, (ny, nx), one row per y query."""
         dtype = _bcast_dtype(x, y)
         x, y = (np.asarray(xx, dtype=dtype).astype('f8') for xx in (x, y))
         shape = x.shape + y.shape if grid else x.shape
@@ -231,14 +256,19 @@ class Interpolator2D(object):
                 raise ValueError('input outside of extrapolation range (min: {} vs. {}; max: {} vs. {})'.format(q.min(), lo, q.max(), hi))
             masks.append(m)
         mask = masks[0][:, None] & masks[1] if grid else masks[0] & masks[1]
-        xt = np.log10(x) if self.interp_x == 'log' else x
-        yt = np.log10(y) if self.interp_y == 'log' else y
+        # FITPACK evaluates queries outside the table at the nearest edge (bispev clamps its arguments): with ``extrap`` the
+        # reference therefore returns edge values, not extended polynomials
+        xt = np.log10(np.clip(x, self.xmin, self.xmax)) if self.interp_x == 'log' else np.clip(x, self.xmin, self.xmax)
+        yt = np.log10(np.clip(y, self.ymin, self.ymax)) if self.interp_y == 'log' else np.clip(y, self.ymin, self.ymax)
         if x.size == 0 or y.size == 0:
             out = np.zeros(shape, dtype=dtype)
             return _buf._torch().as_tensor(out, device='cuda') if self._on_device else out
         vals = self._along_y(yt)                                              # (nyq, nx)
         valsT = vals.T.contiguous() if self._on_device else np.ascontiguousarray(vals.T)      # (nx, nyq)
-        if grid:
+        if grid and rows:
+            tmp = Interpolator1D(self._xt, valsT, bc_type='not-a-knot', extrap=True, assume_sorted=True, device=self._device).eval_rows(xt)   # (nyq, nxq)
+            mask, shape, dtype = mask.T, (y.size, x.size), np.dtype('f8')
+        elif grid:
             tmp = Interpolator1D(self._xt, valsT, bc_type='not-a-knot', extrap=True, assume_sorted=True, device=self._device)(xt)   # (nxq, nyq)
         else:
             # pairs (x_i, y_i): column i of the x splines evaluated at x_i only
@@ -260,6 +290,22 @@ class Interpolator2D(object):
         return tmp.astype(dtype).reshape(shape)
 
 
+_DEVICE_COPIES = {}
+
+
+def _device_copy(a, dev):
+    """Device copy of a small host grid, cached by content: the same knots / radii come back on every sigma(r) call and a
+    pageable host-to-device copy synchronises the stream."""
+    key = (dev, a.size, a.tobytes())
+    hit = _DEVICE_COPIES.get(key)
+    if hit is None:
+        if len(_DEVICE_COPIES) >= 16:
+            _DEVICE_COPIES.pop(next(iter(_DEVICE_COPIES)))
+        torch = _buf._torch()
+        hit = _DEVICE_COPIES[key] = torch.as_tensor(a, device=torch.device('cuda', dev))
+    return hit
+
+
 def spline_eval_rows(x, fun, xq, bc_type='natural', window=64, extrap=False, device=None):
     """
     Cubic splines along the LAST axis of ``fun`` (rows, nx) -- the layout FFTLog returns -- on the shared knots ``x``
@@ -279,11 +325,9 @@ def spline_eval_rows(x, fun, xq, bc_type='natural', window=64, extrap=False, dev
         raise ValueError('fun must have shape (rows, {}), got {}'.format(x.size, tuple(ybuf.shape)))
     rows = int(ybuf.shape[0])
     if ybuf.on_device:
-        torch = _buf._torch()
         dev = ybuf.device
-        tdev = torch.device('cuda', dev)
-        xbuf = _buf.as_input(torch.as_tensor(x, device=tdev))
-        qbuf = _buf.as_input(torch.as_tensor(q, device=tdev))
+        xbuf = _buf.as_input(_device_copy(x, dev))
+        qbuf = _buf.as_input(_device_copy(q, dev))
         stream = _buf.current_stream(dev)
     else:
         dev = device if device is not None else _buf.default_device()

@@ -116,7 +116,8 @@ class PowerSpectrumInterpolator1D(object):
         R.m.s. of perturbations in spheres of radius ``r``: FFTLog top-hat variance on ``nk`` log-spaced wavenumbers, then
         a natural cubic spline in (linear) s evaluated at ``r`` — ``integrate_sigma_r2(method='fftlog')``, ref:285-291.
         """
-        out = integrate_sigma_r2(r, self, kmin=self.extrap_kmin, kmax=self.extrap_kmax, nk=nk, device=self._device)**0.5
+        rows = lambda k: (self._interp.eval_rows(k) * self._rsigma8sq, self._interp.shape)
+        out = integrate_sigma_r2(r, self, kmin=self.extrap_kmin, kmax=self.extrap_kmax, nk=nk, device=self._device, pk_rows=rows)**0.5
         if _buf.is_device_array(out):
             return out
         return out.astype(_bcast_dtype(r))
@@ -195,20 +196,27 @@ class CorrelationFunctionInterpolator1D(object):
         return self.sigma_r(8., **kwargs)
 
 
-def integrate_sigma_r2(r, pk, kmin=1e-7, kmax=1e2, nk=None, device=None):
+def integrate_sigma_r2(r, pk, kmin=1e-7, kmax=1e2, nk=None, device=None, pk_rows=None):
     r"""
     Variance of perturbations in spheres of radius ``r``, :math:`\sigma_r^2 = \frac{1}{2\pi^2}\int dk\,k^2 P(k) W^2(kr)`, by
     the reference's default method (``integrate_sigma_r2(method='fftlog')``, ref:200, 285-291): FFTLog top-hat variance on
     ``nk`` (default 1024) log-spaced wavenumbers, then a natural cubic spline in (linear) s evaluated at ``r``.
     ``pk`` is a callable returning (nk,) or (nk, ...) for an array of wavenumbers; result ``r.shape + pk.shape[1:]``.
+    ``pk_rows`` (optional, used by the interpolators of this module): callable returning the same values as (B, nk) rows
+    and the trailing shape, so that nothing is transposed between the spline evaluation and FFTLog.
     """
     if nk is None: nk = 1024
     k = np.geomspace(kmin, kmax, nk)
-    p = pk(k)
-    lead = tuple(p.shape[1:])
-    dtype = _bcast_dtype(r, p if p.ndim > 1 else None)
+    if pk_rows is not None:
+        rows, lead = pk_rows(k)
+        dtype = _bcast_dtype(r) if not lead else np.dtype('f8')
+    else:
+        p = pk(k)
+        lead = tuple(p.shape[1:])
+        dtype = _bcast_dtype(r, p if p.ndim > 1 else None)
+        rows = _transpose(p.reshape(nk, -1))
     rr = np.asarray(r, dtype='f8')
-    s, var = TophatVariance(k, device=device)(_transpose(p.reshape(nk, -1)))               # (B, nk)
+    s, var = TophatVariance(k, device=device)(rows)                                        # (B, nk)
     tmp = (2. * np.pi**2) * spline_eval_rows(s, var, rr.ravel(), device=device)            # ref:289, rows layout
     sigma2 = 1. / (2. * np.pi**2) * tmp.reshape(rr.shape + lead)
     if _buf.is_device_array(sigma2):
@@ -285,12 +293,14 @@ class PowerSpectrumInterpolator2D(object):
         state.update(kwargs)
         return self.__class__(**state)
 
-    def __call__(self, k, z, grid=True, ignore_growth=False, bounds_error=False):
-        """P(k, z): shape ``k.shape + z.shape`` if ``grid`` else ``k.shape``; NaN outside the (extrapolated) ranges (ref:720-800)."""
+    def __call__(self, k, z, grid=True, ignore_growth=False, bounds_error=False, rows=False):
+        """P(k, z): shape ``k.shape + z.shape`` if ``grid`` else ``k.shape``; NaN outside the (extrapolated) ranges (ref:720-800).
+        ``rows=True`` (grid, 1-D arguments): the float64 result transposed, (nz, nk), one row per redshift (FFTLog's layout)."""
         dtype = _bcast_dtype(k, z)
         k, z = (np.asarray(xx, dtype=dtype) for xx in (k, z))
         shape = k.shape + z.shape if grid else k.shape
         k, z = k.ravel(), z.ravel()
+        rows = bool(rows and grid)
         mask_k = (k >= self.extrap_kmin) & (k <= self.extrap_kmax)
         mask_z = (z >= self.zmin) & (z <= self.zmax)
         if bounds_error and not (mask_k.all() and (mask_z.all() or not self._is2d)):
@@ -298,14 +308,20 @@ class PowerSpectrumInterpolator2D(object):
         if not self._is2d: mask_z = np.ones_like(mask_z)                    # ignore input z (ref:784)
         mask = mask_k[:, None] & mask_z if grid else mask_k & mask_z
         if self._is2d:
-            # queries outside [zmin, zmax] are masked below; clip them so that the bicubic table is not asked to extrapolate
-            tmp = self._interp(k, np.clip(z, self.zmin, self.zmax), grid=grid)
+            # queries outside [zmin, zmax] are masked below; the bicubic table clamps them to its edge meanwhile
+            tmp = self._interp(k, z, grid=grid, rows=rows)
         else:
             tmp = self._interp(k)
             if grid:
-                tmp = tmp[:, None].expand(-1, z.size) if _buf.is_device_array(tmp) else np.repeat(tmp[:, None], z.size, axis=-1)
+                if rows:
+                    tmp = tmp[None, :].expand(z.size, -1) if _buf.is_device_array(tmp) else np.repeat(tmp[None, :], z.size, axis=0)
+                else:
+                    tmp = tmp[:, None].expand(-1, z.size) if _buf.is_device_array(tmp) else np.repeat(tmp[:, None], z.size, axis=-1)
+        if rows:
+            mask, shape, dtype = mask.T, (z.size, k.size), np.dtype('f8')
         if self.growth_factor_sq is not None and not ignore_growth:
-            tmp = _times(tmp, np.asarray(self.growth_factor_sq(z)).astype(dtype))
+            growth = np.asarray(self.growth_factor_sq(z)).astype(dtype)
+            tmp = _times(tmp, growth[:, None] if rows else growth)
         if _buf.is_device_array(tmp):
             torch = _buf._torch()
             tmp = torch.where(torch.as_tensor(mask, device=tmp.device), tmp, torch.full_like(tmp, float('nan')))
@@ -314,7 +330,16 @@ class PowerSpectrumInterpolator2D(object):
 
     def sigma_rz(self, r, z, nk=None):
         """R.m.s. of perturbations in spheres of radius ``r`` at redshifts ``z``: (r.size, z.size) (ref:846-876)."""
-        toret = integrate_sigma_r2(r, lambda k: self(k, z), kmin=self.extrap_kmin, kmax=self.extrap_kmax, nk=nk, device=self._device)**0.5
+        # redshifts outside the table give NaN columns in the reference (ref:781-795).  The FFTLog kernels transform rows in
+        # pairs (two real rows = one complex FFT), so a NaN row would also spoil its partner: evaluate those rows at the
+        # clipped redshift and blank the result afterwards instead.
+        zz = np.asarray(z, dtype='f8')
+        bad = ~((zz >= self.zmin) & (zz <= self.zmax)) if self._is2d else np.zeros(zz.shape, dtype='?')
+        zc = np.clip(zz, self.zmin, self.zmax) if self._is2d else zz
+        rows = lambda k: (self(k, zc.ravel(), rows=True), zz.shape)
+        toret = integrate_sigma_r2(r, lambda k: self(k, zc), kmin=self.extrap_kmin, kmax=self.extrap_kmax, nk=nk, device=self._device, pk_rows=rows)**0.5
+        if bad.any():
+            toret[..., _buf._torch().as_tensor(bad, device=toret.device) if _buf.is_device_array(toret) else bad] = float('nan')
         dtype = _bcast_dtype(r, z)
         if _buf.is_device_array(toret):
             return toret.to(_buf._torch().float32) if dtype == np.float32 else toret

@@ -103,6 +103,10 @@ int cpf_spline_create(cpf_spline** spline, const double* x, const double* y, int
                       int log_x, int log_y, int extrap, int on_device, int device, void* stream);
 int cpf_spline_eval(const cpf_spline* spline, const double* xq, int nq, int nu, double* out, int on_device,
                     void* stream);
+/* same values, transposed: out [ncols, nq] -- one row per spline, the layout cpf_fftlog reads (saves the `.T` copy of
+ * `TophatVariance(k)(pk(k).T)`, interpolator.py:288, 602, 983) */
+int cpf_spline_eval_t(const cpf_spline* spline, const double* xq, int nq, int nu, double* out, int on_device,
+                      void* stream);
 int cpf_spline_destroy(cpf_spline* spline);
 
 /* Row layout, no handle: natural (bc=0) or clamped (bc=1) cubic splines along the LAST axis of y [rows, nx] (the layout

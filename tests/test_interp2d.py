@@ -43,7 +43,7 @@ def test_interpolator2d_golden():
     close_with_nans(i2(d['kp'], d['zp'], grid=False), d['i2_pairs'], rtol=1e-10)
     lin = Interpolator2D(np.log(d['k']), d['z'], np.log(d['pk']), extrap=True)
     got, ref = lin(np.log(d['kq']), d['zq']), d['i2_lin_extrap']
-    assert np.max(np.abs(got - ref)) < 1e-9 * np.max(np.abs(ref))          # includes extrapolated end polynomials
+    assert np.max(np.abs(got - ref)) < 1e-10 * np.max(np.abs(ref))         # outside the table: FITPACK clamps to the edge
     dev = Interpolator2D(d['k'], d['z'], torch.from_numpy(d['pk']).cuda(), interp_x='log', interp_fun='log')
     out = dev(d['kq'], d['zq'])
     assert isinstance(out, torch.Tensor) and out.is_cuda

@@ -81,6 +81,11 @@ def test_spline_device_buffers_and_shapes():
     assert np.array_equal(out.cpu().numpy(), host, equal_nan=True)
     out = dev(torch.from_numpy(xq).cuda().reshape(8, 8))
     assert tuple(out.shape) == (8, 8, 7)
+    # transposed evaluation (rows = splines) is the same numbers, on host and device tables, odd sizes
+    assert np.array_equal(Interpolator1D(x, y).eval_rows(xq), host.T, equal_nan=True)
+    rows = dev.eval_rows(xq[:37])
+    assert isinstance(rows, torch.Tensor) and tuple(rows.shape) == (7, 37)
+    assert np.array_equal(rows.cpu().numpy(), host[:37].T, equal_nan=True)
     # shape / dtype contract of the reference tests (tests/test_interpolator.py:8-32)
     interp = Interpolator1D(x, y[:, 0])
     assert interp(1.).shape == () and interp(np.array([])).shape == (0,) and interp(np.ones((2, 3))).shape == (2, 3)
