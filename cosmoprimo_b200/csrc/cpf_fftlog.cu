@@ -64,6 +64,17 @@ struct FftlogArgs {
   double ex_l_val, ex_r_val;
 };
 
+// Two real rows ride one complex FFT, so a NaN / Inf in one row would spoil its partner, which the reference's row-wise
+// numpy FFTs do not do.  Every kernel therefore replaces non-finite samples by zero on load, ORs "row a is bad" / "row b is
+// bad" over the threads of the pair through two barriers it executes anyway (barrier.red), and writes NaN to the whole
+// output row of a bad input row -- what numpy.fft returns for a row holding a NaN.
+// (exponent field all ones, tested on the integer pipe: the fp64 pipe is the bottleneck of these kernels)
+__device__ __forceinline__ bool nonfinite(const double v) { return (__double2hiint(v) & 0x7ff00000) == 0x7ff00000; }
+__device__ __forceinline__ double scrub(const double v, bool& bad) {
+  if (nonfinite(v)) { bad = true; return 0.; }
+  return v;
+}
+
 // value of the padded input at unpadded index i (i < 0 or i >= n is the extrapolated part) — fftlog.py:466-505
 __device__ __forceinline__ double padded_value(const double* __restrict__ row, const int i, const FftlogArgs& a) {
   if ((unsigned)i < (unsigned)a.n) return __ldcs(row + i);
@@ -79,8 +90,9 @@ __device__ __forceinline__ double padded_value(const double* __restrict__ row, c
   return fl / pow(__ldg(row + a.n - 2) / fl, (double)(i - (a.n - 1)));   // :497-501
 }
 
-__device__ __forceinline__ void store_out(const FftlogArgs& a, double* __restrict__ orow, const int o, const double g,
-                                          const double pr, const double pi, const bool cpost) {
+__device__ __forceinline__ void store_out(const FftlogArgs& a, double* __restrict__ orow, const int o, double g,
+                                          const double pr, const double pi, const bool cpost, const bool bad) {
+  if (bad) g = nan("");
   if (cpost) {
     double2 r;
     r.x = g * pr;
@@ -112,6 +124,7 @@ __global__ void __launch_bounds__(16 * R1, 512 / (16 * R1)) fftlog_fast_kernel(c
   const double* pre = a.pre + (size_t)p * N;
 
   double2 v[16];
+  bool bad_a = false, bad_b = false;
 #pragma unroll
   for (int r = 0; r < NR; ++r) {
     const int j = t + T * r + SHIFT;
@@ -125,6 +138,8 @@ __global__ void __launch_bounds__(16 * R1, 512 / (16 * R1)) fftlog_fast_kernel(c
       x = padded_value(rowA, i, a);
       y = has1 ? padded_value(rowB, i, a) : 0.;
     }
+    x = scrub(x, bad_a);
+    y = scrub(y, bad_b);
     const double pr = pre[j];
     v[r] = mk2(x * pr, y * pr);
   }
@@ -133,9 +148,9 @@ __global__ void __launch_bounds__(16 * R1, 512 / (16 * R1)) fftlog_fast_kernel(c
 
   // FFT #1
   fft_pass1<R1, PRUNED>(t, v, S, a.tw1);
-  __syncthreads();
+  const bool row_a_bad = __syncthreads_or(bad_a);
   fft_pass2<R1>(t, S, a.tw2);
-  __syncthreads();
+  const bool row_b_bad = __syncthreads_or(bad_b);
   fft_pass3<R1, false>(t, v, S);
 
   // kernel multiply: thread t holds bins k = t + T*r.  Only bins 0..N/2 are stored; k > N/2 uses conj(u[N-k]).
@@ -167,8 +182,8 @@ __global__ void __launch_bounds__(16 * R1, 512 / (16 * R1)) fftlog_fast_kernel(c
     if ((unsigned)o < (unsigned)a.n_out) {
       const double pr = post_re[j];
       const double pi = CPOST ? post_im[j] : 0.;
-      store_out(a, outA, o, v[r].x, pr, pi, CPOST);
-      if (has1) store_out(a, outB, o, v[r].y, pr, pi, CPOST);
+      store_out(a, outA, o, v[r].x, pr, pi, CPOST, row_a_bad);
+      if (has1) store_out(a, outB, o, v[r].y, pr, pi, CPOST, row_b_bad);
     }
   }
 }
@@ -219,16 +234,18 @@ __global__ void fftlog_generic_kernel(const FftlogArgs a) {
   const double* rowA = a.in + (a.in_has_P ? (b0 * a.P + p) : b0) * (long long)a.n;
   const double* rowB = has1 ? a.in + (a.in_has_P ? (b1 * a.P + p) : b1) * (long long)a.n : rowA;
   const double* pre = a.pre + (size_t)p * N;
+  bool bad_a = false, bad_b = false;
   for (int j = threadIdx.x; j < N; j += blockDim.x) {
     const int i = j - a.in_left;
     const double pr = pre[j];
-    S[j] = mk2(padded_value(rowA, i, a) * pr, has1 ? padded_value(rowB, i, a) * pr : 0.);
+    const double x = scrub(padded_value(rowA, i, a), bad_a), y = has1 ? scrub(padded_value(rowB, i, a), bad_b) : 0.;
+    S[j] = mk2(x * pr, y * pr);
   }
-  __syncthreads();
+  const bool row_a_bad = __syncthreads_or(bad_a);
   block_fft_forward(S, N, a.log2N, a.tw1);
   const double2* ut = a.ut + (size_t)p * N;
   for (int j = threadIdx.x; j < N; j += blockDim.x) S[j] = cmul(S[j], __ldg(ut + j));
-  __syncthreads();
+  const bool row_b_bad = __syncthreads_or(bad_b);
   block_fft_forward(S, N, a.log2N, a.tw1);
   const size_t osz = (size_t)a.n_out * (CPOST ? 2 : 1);
   double* outA = a.out + (size_t)(b0 * a.P + p) * osz;
@@ -240,8 +257,8 @@ __global__ void fftlog_generic_kernel(const FftlogArgs a) {
     const int j = o + off;
     const double pr = __ldg(post_re + j);
     const double pi = CPOST ? __ldg(post_im + j) : 0.;
-    store_out(a, outA, o, S[j].x, pr, pi, CPOST);
-    if (has1) store_out(a, outB, o, S[j].y, pr, pi, CPOST);
+    store_out(a, outA, o, S[j].x, pr, pi, CPOST, row_a_bad);
+    if (has1) store_out(a, outB, o, S[j].y, pr, pi, CPOST, row_b_bad);
   }
 }
 

@@ -78,6 +78,16 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 __device__ __forceinline__ void named_sync(const int id, const int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+// barrier with an OR reduction of `pred` over its threads (barrier.red): returns the OR
+__device__ __forceinline__ bool named_sync_or(const int id, const int nthreads, const bool pred) {
+  unsigned ret;
+  asm volatile(
+      "{\n\t.reg .pred pin, pout;\n\tsetp.ne.u32 pin, %3, 0;\n\tbar.red.or.pred pout, %1, %2, pin;\n\tselp.u32 %0, 1, 0, pout;\n\t}"
+      : "=r"(ret)
+      : "r"(id), "r"(nthreads), "r"((unsigned)pred)
+      : "memory");
+  return ret != 0;
+}
 __device__ __forceinline__ void named_arrive(const int id, const int nthreads) {
   asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -159,6 +169,7 @@ __global__ void __launch_bounds__(512, 1) fftlog_pp_kernel(const FftlogArgs a, c
 
       double2 v[16];
       Tm4 tq;
+      bool bad_a = false, bad_b = false;     // non-finite samples are zeroed; their row is written as NaN (see scrub)
       // ---- load the two rows (window [N/4, 3N/4) of the padded row), times pre ----
       {
         tmem_ld4(tb + PP_COL_PRE, tq);
@@ -167,8 +178,8 @@ __global__ void __launch_bounds__(512, 1) fftlog_pp_kernel(const FftlogArgs a, c
         for (int r = 0; r < 8; ++r) {
           const int i = t + T * r + N / 4 - a.in_left;
           const bool ok = active && (unsigned)i < (unsigned)a.n;
-          x[r] = ok ? __ldcs(rowA + i) : 0.;
-          y[r] = (ok && has1) ? __ldcs(rowB + i) : 0.;
+          x[r] = scrub(ok ? __ldcs(rowA + i) : 0., bad_a);
+          y[r] = scrub((ok && has1) ? __ldcs(rowB + i) : 0., bad_b);
         }
         tmem_wait4(tq);
 #pragma unroll
@@ -225,9 +236,9 @@ __global__ void __launch_bounds__(512, 1) fftlog_pp_kernel(const FftlogArgs a, c
 
       // ---- FFT #1 ----
       pass1(std::true_type());
-      gbar();
+      const bool row_a_bad = named_sync_or(1 + g, T, bad_a);
       pass2();
-      gbar();
+      const bool row_b_bad = named_sync_or(1 + g, T, bad_b);
       {
         const int k1 = t & (R1 - 1), l1 = t >> G::B1;
         const double2* row = S + k1 * RS + 16 * l1;
@@ -273,8 +284,8 @@ __global__ void __launch_bounds__(512, 1) fftlog_pp_kernel(const FftlogArgs a, c
         for (int r = 0; r < 8; ++r) {
           const int o = t + T * r + N / 4 - a.out_left;
           if ((unsigned)o < (unsigned)a.n_out) {
-            __stcs(outA + o, v[r].x);
-            if (has1) __stcs(outB + o, v[r].y);
+            __stcs(outA + o, row_a_bad ? nan("") : v[r].x);
+            if (has1) __stcs(outB + o, row_b_bad ? nan("") : v[r].y);
           }
         }
       }

@@ -53,7 +53,8 @@ struct TmemTables {
 };
 
 template <bool FULLWIN>
-__device__ __forceinline__ void st_load_rows(const double* pa, const double* pb, const unsigned m_in, double (&x)[8], double (&y)[8]) {
+__device__ __forceinline__ void st_load_rows(const double* pa, const double* pb, const unsigned m_in, double (&x)[8], double (&y)[8],
+                                             bool& bad_a, bool& bad_b) {
 #pragma unroll
   for (int r = 0; r < 8; ++r) {
     if (FULLWIN) {
@@ -64,6 +65,12 @@ __device__ __forceinline__ void st_load_rows(const double* pa, const double* pb,
       x[r] = ok ? __ldcs(pa + 256 * r) : 0.;
       y[r] = ok ? __ldcs(pb + 256 * r) : 0.;
     }
+  }
+  // non-finite samples are zeroed here and their row is written as NaN at the end (see scrub in cpf_fftlog.cu)
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    x[r] = scrub(x[r], bad_a);
+    y[r] = scrub(y[r], bad_b);
   }
 }
 
@@ -232,13 +239,14 @@ __global__ void __launch_bounds__(512, 1) fftlog_stream_kernel(const StreamArgs 
       // this thread's first window element of row 2*pair (input) / first output element
       const double* pa = a.in + (long long)p * a.in_p + 2LL * pair * a.in_row + (a.off_in + tau);
       double* oa = a.out + 2LL * pair * a.out_row + (long long)p * a.n_out + (a.off_out + tau);
+      bool bad_a = false, bad_b = false, row_a_bad = false, row_b_bad = false;
       {
         double x[8], y[8];
         if (ABL & 4) {
 #pragma unroll
           for (int r = 0; r < 8; ++r) { x[r] = 1. + tau; y[r] = 2. + r; }
         } else
-        st_load_rows<FULLWIN>(pa, has1 ? pa + a.in_row : pa, m_in, x, y);
+        st_load_rows<FULLWIN>(pa, has1 ? pa + a.in_row : pa, m_in, x, y, bad_a, bad_b);
         Tm4 tf;
         tmem_ld4(tb.half + ST_COL_PRE, tf);
         if (pair + 2 * NG < pair_hi) prefetch_rows(p, pair + 2 * NG);
@@ -248,7 +256,7 @@ __global__ void __launch_bounds__(512, 1) fftlog_stream_kernel(const StreamArgs 
         for (int r = 0; r < 8; ++r) { const double pr = (ABL & 8) ? 1.0000001 : tf.getd(r); v8[r] = mk2(x[r] * pr, y[r] * pr); }   // odd tail: y = x, its output is not stored
         st_p1(tau, v8, S, tb);
       }
-      if (!(ABL & 1)) named_sync(1 + g, T);
+      if (!(ABL & 1)) row_a_bad = named_sync_or(1 + g, T, bad_a);
       st_p2(tau, S, tb);
       __syncwarp();
       st_p3_mul_p1(tau, S, tb);
@@ -263,7 +271,7 @@ __global__ void __launch_bounds__(512, 1) fftlog_stream_kernel(const StreamArgs 
         st_row_store(tau, w, S);
       } else
       st_p2b(tau, S, M);
-      if (!(ABL & 1)) named_sync(1 + g, T);
+      if (!(ABL & 1)) row_b_bad = named_sync_or(1 + g, T, bad_b);
       double2 v[16];
       st_col_load(tau, S, v);
       Tm4 tf;
@@ -277,8 +285,8 @@ __global__ void __launch_bounds__(512, 1) fftlog_stream_kernel(const StreamArgs 
           const double po = (ABL & 8) ? 0.9999999 : tf.getd(r);
           if (ABL & 4) { if (v[r].x * po == 1.2345e-300) oa[0] = v[r].y; }
           else {
-            __stcs(oa + T * r, v[r].x * po);
-            if (has1) __stcs(ob + T * r, v[r].y * po);
+            __stcs(oa + T * r, row_a_bad ? nan("") : v[r].x * po);
+            if (has1) __stcs(ob + T * r, row_b_bad ? nan("") : v[r].y * po);
           }
         }
       }

@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(128) spline_eval_kernel(const double* __restri
     const int i = spline_interval(x, nx, xv);
     const long long o = (long long)i * ncols + col;
     r = spline_poly(x[i], x[i + 1], y[o], y[o + ncols], s[o], s[o + ncols], xv, nu);
-    if (log_y) r = pow(10., r);   // jax.py:191
+    if (log_y) r = exp10(r);   // 10**tmp, jax.py:191
   }
   out[(long long)q * ncols + col] = r;
 }
@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(256) spline_eval_t_kernel(const double* __rest
         const int i = spline_interval(x, nx, xv);
         const long long o = (long long)i * ncols + col;
         r = spline_poly(x[i], x[i + 1], y[o], y[o + ncols], s[o], s[o + ncols], xv, nu);
-        if (log_y) r = pow(10., r);
+        if (log_y) r = exp10(r);
       }
     }
     tile[qq][tx] = r;

@@ -180,6 +180,43 @@ def test_persistent_kernels(monkeypatch, kernel, n, B, ells, per_ell):
     assert scale_aware_error(xi[rows], ref, post) < 1e-13
 
 
+@pytest.mark.parametrize('kernel,n,B,ells', [
+    ('stream', 2048, 37, [0, 2, 4]),      # persistent stream kernel, odd batch (the last pair has one row)
+    ('pp', 1024, 20, [0, 2]),             # ping-pong kernel
+    ('fast', 2048, 9, [0]),               # per-pair kernel
+    ('fast', 1000, 6, [0, 2]),
+    ('auto', 60, 7, [0]),                 # generic shared-memory kernel (N = 128)
+])
+def test_non_finite_rows_stay_in_their_row(monkeypatch, kernel, n, B, ells):
+    """The reference transforms rows independently (numpy.fft along the last axis): a NaN / Inf sample turns ITS row into NaN
+    and leaves every other row untouched.  The kernels pack two rows into one complex FFT, so this has to be enforced."""
+    torch = pytest.importorskip('torch')
+    k, pk = lhs_pk(B, n)
+    fun = np.repeat(pk[:, None, :], len(ells), axis=1) * (1. + np.arange(len(ells)))[None, :, None]
+    obj = F.PowerToCorrelation(k, ell=ells)
+    monkeypatch.setenv('CPF_FFTLOG_KERNEL', kernel)
+    clean = obj(fun)[1]
+    dirty = fun.copy()
+    bad = [(0, 0, 0, np.nan), (3, len(ells) - 1, n // 2, np.inf), (B - 1, 0, n - 1, -np.inf)]       # rows a, b of pairs, odd tail
+    if B > 5:
+        bad += [(4, 0, 5, np.nan), (5, 0, 7, np.nan)]                                                # both rows of one pair
+    for b, p, i, val in bad:
+        dirty[b, p, i] = val
+    for arr in (dirty, torch.from_numpy(dirty).cuda()):
+        out = obj(arr)[1]
+        out = out.cpu().numpy() if isinstance(out, torch.Tensor) else out
+        hit = np.zeros((B, len(ells)), dtype='?')
+        for b, p, i, val in bad:
+            hit[b, p] = True
+        assert np.isnan(out[hit]).all()
+        assert np.array_equal(out[~hit], clean[~hit])
+    # with extrapolated padding the pads of a poisoned row are poisoned too, and stay in that row
+    if kernel in ('fast', 'auto'):
+        clean = obj(fun, extrap='log')[1]
+        out = obj(dirty, extrap='log')[1]
+        assert np.isnan(out[hit]).all() and np.array_equal(out[~hit], clean[~hit])
+
+
 def test_kernel_family_selection():
     lib = _lib.load()
     k = np.geomspace(1e-5, 1e2, 2048)
