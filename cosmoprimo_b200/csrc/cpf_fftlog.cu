@@ -74,6 +74,26 @@ __device__ __forceinline__ double scrub(const double v, bool& bad) {
   if (nonfinite(v)) { bad = true; return 0.; }
   return v;
 }
+// The same for a thread's 8 + 8 samples of a pair in the persistent kernels: two integer instructions per sample on the
+// common path (the minimum of ~hi & 0x7ff00000 is 0 iff some exponent field is all ones), the scrubbing itself in a branch
+// that is almost never taken.
+__device__ __forceinline__ void scrub_rows(double (&x)[8], double (&y)[8], bool& bad_a, bool& bad_b) {
+  unsigned ma = 0x7ff00000u, mb = 0x7ff00000u;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    ma = min(ma, ~(unsigned)__double2hiint(x[r]) & 0x7ff00000u);
+    mb = min(mb, ~(unsigned)__double2hiint(y[r]) & 0x7ff00000u);
+  }
+  bad_a = ma == 0u;
+  bad_b = mb == 0u;
+  if (bad_a | bad_b) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      if (nonfinite(x[r])) x[r] = 0.;
+      if (nonfinite(y[r])) y[r] = 0.;
+    }
+  }
+}
 
 // value of the padded input at unpadded index i (i < 0 or i >= n is the extrapolated part) — fftlog.py:466-505
 __device__ __forceinline__ double padded_value(const double* __restrict__ row, const int i, const FftlogArgs& a) {

@@ -178,9 +178,10 @@ __global__ void __launch_bounds__(512, 1) fftlog_pp_kernel(const FftlogArgs a, c
         for (int r = 0; r < 8; ++r) {
           const int i = t + T * r + N / 4 - a.in_left;
           const bool ok = active && (unsigned)i < (unsigned)a.n;
-          x[r] = scrub(ok ? __ldcs(rowA + i) : 0., bad_a);
-          y[r] = scrub((ok && has1) ? __ldcs(rowB + i) : 0., bad_b);
+          x[r] = ok ? __ldcs(rowA + i) : 0.;
+          y[r] = (ok && has1) ? __ldcs(rowB + i) : 0.;
         }
+        scrub_rows(x, y, bad_a, bad_b);
         tmem_wait4(tq);
 #pragma unroll
         for (int r = 0; r < 8; ++r) { const double pr = tq.getd(r); v[r] = mk2(x[r] * pr, y[r] * pr); }

@@ -67,11 +67,7 @@ __device__ __forceinline__ void st_load_rows(const double* pa, const double* pb,
     }
   }
   // non-finite samples are zeroed here and their row is written as NaN at the end (see scrub in cpf_fftlog.cu)
-#pragma unroll
-  for (int r = 0; r < 8; ++r) {
-    x[r] = scrub(x[r], bad_a);
-    y[r] = scrub(y[r], bad_b);
-  }
+  scrub_rows(x, y, bad_a, bad_b);
 }
 
 // everything the loop needs, precomputed on the host so that it sits in the constant bank instead of registers

@@ -196,6 +196,7 @@ def test_non_finite_rows_stay_in_their_row(monkeypatch, kernel, n, B, ells):
     obj = F.PowerToCorrelation(k, ell=ells)
     monkeypatch.setenv('CPF_FFTLOG_KERNEL', kernel)
     clean = obj(fun)[1]
+    post = obj.padded_postfactor[:, obj.padded_size_out_left:obj.padded_size_out_left + n]
     dirty = fun.copy()
     bad = [(0, 0, 0, np.nan), (3, len(ells) - 1, n // 2, np.inf), (B - 1, 0, n - 1, -np.inf)]       # rows a, b of pairs, odd tail
     if B > 5:
@@ -209,12 +210,14 @@ def test_non_finite_rows_stay_in_their_row(monkeypatch, kernel, n, B, ells):
         for b, p, i, val in bad:
             hit[b, p] = True
         assert np.isnan(out[hit]).all()
-        assert np.array_equal(out[~hit], clean[~hit])
+        # the partner of a poisoned row is now transformed next to zeros instead of next to its neighbour: same numbers up
+        # to the rounding of the complex arithmetic
+        assert np.isfinite(out[~hit]).all() and scale_aware_error(out[~hit], clean[~hit], post[np.nonzero(~hit)[1]]) < 1e-13
     # with extrapolated padding the pads of a poisoned row are poisoned too, and stay in that row
     if kernel in ('fast', 'auto'):
         clean = obj(fun, extrap='log')[1]
         out = obj(dirty, extrap='log')[1]
-        assert np.isnan(out[hit]).all() and np.array_equal(out[~hit], clean[~hit])
+        assert np.isnan(out[hit]).all() and scale_aware_error(out[~hit], clean[~hit], post[np.nonzero(~hit)[1]]) < 1e-13
 
 
 def test_kernel_family_selection():
