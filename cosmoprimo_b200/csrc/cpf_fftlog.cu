@@ -865,13 +865,19 @@ static int launch_fftlog(const cpf_plan* pl, FftlogArgs a, bool pruned, cudaStre
   return CPF_OK;
 }
 
-// How host-pointer calls move their data: CPF_HOST_PATH = staged (default) | zerocopy.
+// How host-pointer calls move their data: CPF_HOST_PATH = staged (default) | zerocopy | mixed.
 //   staged   : chunks are copied in, processed and copied back on rotating streams (H2D / kernel / D2H overlap);
 //   zerocopy : when both buffers are page-locked, the kernel reads the input rows and writes the output rows straight
 //              over PCIe (unified addressing: one launch, both directions busy from the first to the last row).
 static bool host_zero_copy_enabled() {
   const char* e = getenv("CPF_HOST_PATH");
   return e && e[0] == 'z';
+}
+//   mixed    : inputs are staged as above, results are written by the kernels straight into the (page-locked) host buffer:
+//              posted PCIe writes from the SMs, no device-to-host copies (and no dependency chain between the two copy engines).
+static bool host_direct_out_enabled() {
+  const char* e = getenv("CPF_HOST_PATH");
+  return e && e[0] == 'm';
 }
 
 static bool pinned_device_pointer(const void* host, void** dev) {
@@ -939,6 +945,10 @@ static int run_staged(int device, const double* in, size_t in_row_doubles, doubl
   long long small = (long long)(small_bytes / (row_bytes ? row_bytes : 1));
   small = small < 2 ? 2 : (small & ~1LL);
   const std::vector<long long> sched = chunk_schedule(rows, small, cap);
+  void* zout = nullptr;
+  const bool direct_out = !out_dev && host_direct_out_enabled() && pinned_device_pointer(out, &zout);
+  if (direct_out) out_dev = true;          // from here on the output is "a device pointer": the mapped host buffer
+  double* const out_base = direct_out ? (double*)zout : out;
   const int nbuf = sched.size() < (size_t)max_buf ? (int)sched.size() : max_buf;
   const long long buf_rows = rows < cap ? rows : cap;
   ScratchBuf din[kNumStage], dout[kNumStage];
@@ -961,7 +971,7 @@ static int run_staged(int device, const double* in, size_t in_row_doubles, doubl
     const bool reused = c >= (size_t)nbuf;
     const long long cnt = sched[c];
     const double* src = in + (size_t)first * in_row_doubles;
-    double* dst = out + (size_t)first * out_row_doubles;
+    double* dst = out_base + (size_t)first * out_row_doubles;
     const double* d_in = src;
     double* d_out = dst;
     cudaError_t e = cudaSuccess;

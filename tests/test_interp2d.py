@@ -91,3 +91,34 @@ def test_power_spectrum_interpolator2d_golden():
     np.testing.assert_allclose(interp.growth_rate_rz(d['r'], d['zs']), d['g_growth_rate_rz'], rtol=1e-8, atol=1e-9)   # exactly 0 at z = 0 in the reference (flat growth callable below the table)
     got = interp.to_xi()(d['sq'], d['zs'])
     assert np.max(np.abs(got - d['g_xi'])) < 1e-10 * np.max(np.abs(d['g_xi']))
+
+
+@pytest.mark.gpu
+def test_wallish2018_on_2d_interpolator():
+    """BAO filter fed by a 2-D (k, z) interpolator (ref bao_filter.py:92-102, 115-145): one column per redshift of the table,
+    no growth factor; smooth interpolators come back 2-D.  Checked against the oracle on the arrays our interpolator returns
+    (the filter's argmax boxes need bit-identical inputs)."""
+    from cosmoprimo_b200.interpolator import PowerSpectrumInterpolator2D, CorrelationFunctionInterpolator2D
+    from cosmoprimo_b200.bao_filter import PowerSpectrumBAOFilter
+    from oracle import wallish_oracle as WO
+    d = golden()
+    interp = PowerSpectrumInterpolator2D(d['k'], d['z'], d['pk'])
+    filt = PowerSpectrumBAOFilter(interp, engine='wallish2018')
+    assert filt.pknow.shape == (1024, d['z'].size) and filt.pk.shape == filt.pknow.shape
+    klin = np.linspace(interp.extrap_kmin, 2., 4096)
+    ref, dbg = WO.wallish2018(klin, interp(klin, interp.z, ignore_growth=True), filt.k, interp(filt.k, interp.z, ignore_growth=True), return_debug=True)
+    assert np.array_equal(filt._boxes, dbg['boxes'])
+    assert np.max(np.abs(filt.pknow / ref - 1.)) < 1e-10
+    smooth = filt.smooth_pk_interpolator()
+    assert isinstance(smooth, PowerSpectrumInterpolator2D)
+    inner = slice(10, -10)
+    np.testing.assert_allclose(smooth(filt.k[inner], d['z']), filt.pknow[inner], rtol=1e-9)
+    xi = filt.smooth_xi_interpolator()
+    assert isinstance(xi, CorrelationFunctionInterpolator2D)
+    sq = np.geomspace(1., 150., 20)
+    assert np.isfinite(xi(sq, d['z'])).all()
+    # no BAO peak left: the smooth correlation function at z = 0 has no local maximum between 80 and 130 Mpc/h, the input does
+    sfine = np.linspace(80., 130., 200)
+    peak = lambda v: np.any((v[1:-1] > v[:-2]) & (v[1:-1] > v[2:]))
+    z0 = np.zeros(1)
+    assert peak(interp.to_xi()(sfine, z0)[:, 0] * sfine**2) and not peak(xi(sfine, z0)[:, 0] * sfine**2)

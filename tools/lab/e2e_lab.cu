@@ -31,7 +31,9 @@ int main() {
   struct Cfg { const char* cap; const char* small; const char* nbuf; const char* path; };
   const Cfg cfgs[] = {{"16384", "1024", "4", "staged"}, {"32768", "32768", "3", "staged"}, {"8192", "1024", "4", "staged"},
                       {"8192", "8192", "4", "staged"},  {"4096", "1024", "8", "staged"},   {"16384", "2048", "8", "staged"},
-                      {"16384", "16384", "2", "staged"}, {"65536", "65536", "4", "staged"}, {"16384", "1024", "4", "zerocopy"}};
+                      {"16384", "16384", "2", "staged"}, {"65536", "65536", "4", "staged"}, {"16384", "1024", "4", "zerocopy"},
+                      {"16384", "1024", "4", "mixed"},  {"4096", "1024", "4", "mixed"},   {"32768", "2048", "4", "mixed"},
+                      {"8192", "1024", "8", "mixed"},   {"65536", "4096", "3", "mixed"}};
   for (const Cfg& c : cfgs) {
     setenv("CPF_STAGE_CAP_KB", c.cap, 1); setenv("CPF_STAGE_SMALL_KB", c.small, 1); setenv("CPF_STAGE_NBUF", c.nbuf, 1);
     setenv("CPF_HOST_PATH", c.path, 1);
