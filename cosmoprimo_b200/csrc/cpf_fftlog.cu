@@ -746,6 +746,9 @@ static int launch_stream(const cpf_plan* pl, const FftlogArgs& a, cudaStream_t s
       case 5: kern = fftlog_stream_kernel<true, 5>; break;
       case 13: kern = fftlog_stream_kernel<true, 13>; break;
       case 15: kern = fftlog_stream_kernel<true, 15>; break;
+      case 16: kern = fftlog_stream_kernel<true, 16>; break;
+      case 32: kern = fftlog_stream_kernel<true, 32>; break;
+      case 48: kern = fftlog_stream_kernel<true, 48>; break;
       default: break;
     }
   }

@@ -122,7 +122,8 @@ __device__ __forceinline__ void st_item_range(const StreamArgs& a, long long& lo
 // uttab [P][16][256]: kernel spectrum at the bins thread tau holds after FFT #1 ((-1)^k and 1/N folded in) ;
 // m256 [16][16] = w_256^{h l}
 // ABL (lab builds only, -DCPF_LAB): ablation bits — 1: no group barriers (racy), 2: no P2' twiddle loads, 4: no global
-// loads/stores, 8: no pre/post-factor loads.  Results are wrong on purpose.
+// loads/stores, 8: no pre/post-factor loads (results are wrong on purpose); 16: L1 prefetch of the group's next pair,
+// 32: L2 prefetch three pairs ahead instead of two (results unchanged).
 template <bool FULLWIN, int ABL = 0>
 __global__ void __launch_bounds__(512, 1) fftlog_stream_kernel(const StreamArgs a, const double2* __restrict__ twtab,
                                                                const double2* __restrict__ uttab, const double2* __restrict__ m256) {
@@ -139,12 +140,13 @@ __global__ void __launch_bounds__(512, 1) fftlog_stream_kernel(const StreamArgs 
   st_item_range(a, lo, hi);
 
   // L2 prefetch of the two rows of pair `pair` of plan row p (one 128-byte line per thread covers both rows)
-  auto prefetch_rows = [&](const int p, const int pair) {
+  auto prefetch_rows = [&](const int p, const int pair, const bool l1 = false) {
     if (tau < 2 * a.lines) {
       const bool second = tau >= a.lines;
       if (!second || pair != a.odd_pair) {
         const double* q = a.in + (long long)p * a.in_p + (2LL * pair + (second ? 1 : 0)) * a.in_row + 16 * (second ? tau - a.lines : tau);
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+        if (l1) asm volatile("prefetch.global.L1 [%0];" ::"l"(q));
+        else asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
       }
     }
   };
@@ -245,7 +247,8 @@ __global__ void __launch_bounds__(512, 1) fftlog_stream_kernel(const StreamArgs 
         st_load_rows<FULLWIN>(pa, has1 ? pa + a.in_row : pa, m_in, x, y, bad_a, bad_b);
         Tm4 tf;
         tmem_ld4(tb.half + ST_COL_PRE, tf);
-        if (pair + 2 * NG < pair_hi) prefetch_rows(p, pair + 2 * NG);
+        if (pair + ((ABL & 32) ? 3 : 2) * NG < pair_hi) prefetch_rows(p, pair + ((ABL & 32) ? 3 : 2) * NG);
+        if ((ABL & 16) && pair + NG < pair_hi) prefetch_rows(p, pair + NG, true);      // lab: the group's next pair into L1
         tmem_wait4(tf);
         double2 v8[8];
 #pragma unroll
