@@ -738,6 +738,14 @@ static int launch_stream(const cpf_plan* pl, const FftlogArgs& a, cudaStream_t s
   if (grid > sms) grid = sms;
   typedef void (*kern_t)(const StreamArgs, const double2*, const double2*, const double2*);
   kern_t kern = fullwin ? (kern_t)fftlog_stream_kernel<true> : (kern_t)fftlog_stream_kernel<false>;
+  // staged variant: bulk copies need 16-byte aligned rows; CPF_STREAM_TMA=0 selects the direct-load kernel (A/B runs)
+  int smem_bytes = ST_SMEM_BYTES;
+  const char* tma_env = getenv("CPF_STREAM_TMA");
+  const bool want_tma = !tma_env || tma_env[0] != '0';
+  if (fullwin && want_tma && ((uintptr_t)a.in % 16 == 0) && (s.in_row % 2 == 0) && (s.in_p % 2 == 0)) {
+    kern = (kern_t)fftlog_stream_kernel<true, 0, true>;
+    smem_bytes = ST_SMEM_BYTES_TMA;
+  }
 #ifdef CPF_LAB
   if (const char* e = getenv("CPF_STREAM_ABL")) {
     switch (atoi(e)) {
@@ -753,7 +761,7 @@ static int launch_stream(const cpf_plan* pl, const FftlogArgs& a, cudaStream_t s
     }
   }
 #endif
-  CPF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM_BYTES));
+  CPF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
 #ifdef CPF_LAB
   static long long* d_dbg = nullptr;
   if (getenv("CPF_STREAM_DBG")) {
@@ -762,7 +770,7 @@ static int launch_stream(const cpf_plan* pl, const FftlogArgs& a, cudaStream_t s
     s.dbg = d_dbg;
   }
 #endif
-  kern<<<(unsigned)grid, 512, ST_SMEM_BYTES, stream>>>(s, pl->fast->d_st_tw, pl->d_st_ut, pl->fast->d_m256);
+  kern<<<(unsigned)grid, 512, smem_bytes, stream>>>(s, pl->fast->d_st_tw, pl->d_st_ut, pl->fast->d_m256);
 #ifdef CPF_LAB
   if (s.dbg && getenv("CPF_STREAM_DBG")[0] == '2') {     // print the time line of this launch (synchronises)
     std::vector<long long> h(8 * 256);

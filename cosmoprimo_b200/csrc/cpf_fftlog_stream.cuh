@@ -24,6 +24,30 @@
 namespace cpf {
 
 constexpr int ST_SMEM_BYTES = (2 * ST_GROUP_ELEMS + 256) * (int)sizeof(double2);
+// TMA variant (full window, n = 2048): + one staging buffer of two input rows per group, filled by bulk copies one pair ahead
+constexpr int ST_STAGE_DOUBLES = 2 * 2048;
+constexpr int ST_SMEM_BYTES_TMA = ST_SMEM_BYTES + 2 * ST_STAGE_DOUBLES * (int)sizeof(double);
+
+// ---- mbarrier + bulk copy (TMA, non-tensor form) ------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, const unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(pp_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, const unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pp_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, const unsigned parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
+      ::"r"(pp_smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+// global -> shared bulk copy of `bytes` (multiple of 16, both addresses 16-byte aligned), completion counted on `bar`
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, const unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(pp_smem_u32(dst)), "l"(src), "r"(bytes), "r"(pp_smem_u32(bar))
+               : "memory");
+}
 
 // Tensor-memory layout of one lane (512 columns of 32 bits = 128 complex doubles).  Threads tau and tau + 128 of a
 // group share a lane (and have the same L = tau % 16, hence the same P2 twiddles); both groups read the same copy.
@@ -124,16 +148,33 @@ __device__ __forceinline__ void st_item_range(const StreamArgs& a, long long& lo
 // ABL (lab builds only, -DCPF_LAB): ablation bits — 1: no group barriers (racy), 2: no P2' twiddle loads, 4: no global
 // loads/stores, 8: no pre/post-factor loads (results are wrong on purpose); 16: L1 prefetch of the group's next pair,
 // 32: L2 prefetch three pairs ahead instead of two (results unchanged).
-template <bool FULLWIN, int ABL = 0>
+// TMA (full window only): the two rows of a group's next pair are brought into a shared-memory staging buffer by bulk copies
+// issued by one thread right after the first group barrier of the current pair (every thread has consumed the staged rows by
+// then), a whole pair ahead of their use; threads then read their 8 + 8 samples with conflict-free 64-bit shared loads instead
+// of waiting for global loads.
+template <bool FULLWIN, int ABL = 0, bool TMA = false>
 __global__ void __launch_bounds__(512, 1) fftlog_stream_kernel(const StreamArgs a, const double2* __restrict__ twtab,
                                                                const double2* __restrict__ uttab, const double2* __restrict__ m256) {
+  static_assert(!TMA || FULLWIN, "the staged variant covers the full window only");
   constexpr int T = 256, N = 4096, NG = 2;
   extern __shared__ double2 smem[];
   __shared__ uint32_t s_tmem_base;
+  __shared__ __align__(8) uint64_t s_mbar[NG];
   const int warp = threadIdx.x >> 5;
   const int g = threadIdx.x >> 8, tau = threadIdx.x & 255;
   double2* S = smem + g * ST_GROUP_ELEMS;
   double2* M = smem + NG * ST_GROUP_ELEMS;
+  double* stage = reinterpret_cast<double*>(M + 256) + g * ST_STAGE_DOUBLES;     // TMA only
+  unsigned stage_parity = 0;
+  if (TMA && tau == 0) { mbar_init(&s_mbar[g], 1); mbar_fence_init(); }
+  // bulk copies of the rows of pair `pair` of plan row p into this group's staging buffer (one thread)
+  auto stage_rows = [&](const int p, const int pair) {
+    const double* ra = a.in + (long long)p * a.in_p + 2LL * pair * a.in_row;
+    const bool two = pair != a.odd_pair;
+    mbar_expect_tx(&s_mbar[g], two ? 2u * N * 4u : N * 4u);          // a row is N/2 doubles = 4 N bytes
+    bulk_g2s(stage, ra, N * 4u, &s_mbar[g]);
+    if (two) bulk_g2s(stage + N / 2, ra + a.in_row, N * 4u, &s_mbar[g]);
+  };
 
   ST_STAMP(0);
   long long lo, hi;
@@ -200,7 +241,7 @@ __global__ void __launch_bounds__(512, 1) fftlog_stream_kernel(const StreamArgs 
     const int pair_lo = (int)(seg - (long long)p * a.pairs_per_p), pair_hi = (int)(seg_hi - (long long)p * a.pairs_per_p);
     seg = seg_hi;
     int pair = pair_lo + g;
-    if (pair < pair_hi) prefetch_rows(p, pair);
+    if (!TMA && pair < pair_hi) prefetch_rows(p, pair);
     if (!first_seg) {
       tmem_fence_before();
       __syncthreads();           // nobody reads the previous plan row's tables any more
@@ -231,6 +272,7 @@ __global__ void __launch_bounds__(512, 1) fftlog_stream_kernel(const StreamArgs 
     __syncthreads();
     tmem_fence_after();
     ST_STAMP(2);
+    if (TMA && tau == 0 && pair < pair_hi) stage_rows(p, pair);     // nobody reads the staging buffer any more (barrier above)
 
     while (pair < pair_hi) {
       const bool has1 = pair != a.odd_pair;
@@ -243,11 +285,20 @@ __global__ void __launch_bounds__(512, 1) fftlog_stream_kernel(const StreamArgs 
         if (ABL & 4) {
 #pragma unroll
           for (int r = 0; r < 8; ++r) { x[r] = 1. + tau; y[r] = 2. + r; }
+        } else if (TMA) {
+          mbar_wait(&s_mbar[g], stage_parity);
+          stage_parity ^= 1u;
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            x[r] = stage[tau + 256 * r];
+            y[r] = has1 ? stage[N / 2 + tau + 256 * r] : x[r];
+          }
+          scrub_rows(x, y, bad_a, bad_b);
         } else
         st_load_rows<FULLWIN>(pa, has1 ? pa + a.in_row : pa, m_in, x, y, bad_a, bad_b);
         Tm4 tf;
         tmem_ld4(tb.half + ST_COL_PRE, tf);
-        if (pair + ((ABL & 32) ? 3 : 2) * NG < pair_hi) prefetch_rows(p, pair + ((ABL & 32) ? 3 : 2) * NG);
+        if (!TMA && pair + ((ABL & 32) ? 3 : 2) * NG < pair_hi) prefetch_rows(p, pair + ((ABL & 32) ? 3 : 2) * NG);
         if ((ABL & 16) && pair + NG < pair_hi) prefetch_rows(p, pair + NG, true);      // lab: the group's next pair into L1
         tmem_wait4(tf);
         double2 v8[8];
@@ -256,6 +307,7 @@ __global__ void __launch_bounds__(512, 1) fftlog_stream_kernel(const StreamArgs 
         st_p1(tau, v8, S, tb);
       }
       if (!(ABL & 1)) row_a_bad = named_sync_or(1 + g, T, bad_a);
+      if (TMA && tau == 0 && pair + NG < pair_hi) stage_rows(p, pair + NG);   // every thread of the group has its samples in registers
       st_p2(tau, S, tb);
       __syncwarp();
       st_p3_mul_p1(tau, S, tb);
