@@ -712,8 +712,18 @@ static int launch_pp(const FftlogArgs& a, const double2* tab, cudaStream_t strea
   CPF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   long long grid = (a.pairs_per_p + NG - 1) / NG;
   if (grid > sms) grid = sms;
-  kern<<<(unsigned)grid, 512, smem, stream>>>(a, tab);
-  CPF_CUDA(cudaGetLastError());
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(512);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  const char* pdl_env = getenv("CPF_STREAM_PDL");
+  cfg.attrs = attr;
+  cfg.numAttrs = (pdl_env && pdl_env[0] == '0') ? 0 : 1;
+  CPF_CUDA(cudaLaunchKernelEx(&cfg, kern, a, tab));
   return CPF_OK;
 }
 
@@ -731,6 +741,10 @@ static int launch_stream(const cpf_plan* pl, const FftlogArgs& a, cudaStream_t s
   s.off_in = a.N / 4 - a.in_left; s.off_out = a.N / 4 - a.out_left;
   s.lines = (a.n * 8 + 127) / 128;
   s.dbg = nullptr;
+  s.skew_ns = 0;
+#ifdef CPF_LAB
+  if (const char* e = getenv("CPF_STREAM_SKEW_NS")) s.skew_ns = atoi(e);
+#endif
   int dev = 0, sms = 0;
   CPF_CUDA(cudaGetDevice(&dev));
   CPF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -770,7 +784,20 @@ static int launch_stream(const cpf_plan* pl, const FftlogArgs& a, cudaStream_t s
     s.dbg = d_dbg;
   }
 #endif
-  kern<<<(unsigned)grid, 512, smem_bytes, stream>>>(s, pl->fast->d_st_tw, pl->d_st_ut, pl->fast->d_m256);
+  // launched with programmatic stream serialisation: back-to-back calls on a stream overlap this kernel's prologue with the
+  // tail of the previous one (the kernel executes griddepcontrol.wait before it touches rows); CPF_STREAM_PDL=0 turns it off
+  const char* pdl_env = getenv("CPF_STREAM_PDL");
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(512);
+  cfg.dynamicSmemBytes = (size_t)smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (pdl_env && pdl_env[0] == '0') ? 0 : 1;
+  CPF_CUDA(cudaLaunchKernelEx(&cfg, kern, s, (const double2*)pl->fast->d_st_tw, (const double2*)pl->d_st_ut, (const double2*)pl->fast->d_m256));
 #ifdef CPF_LAB
   if (s.dbg && getenv("CPF_STREAM_DBG")[0] == '2') {     // print the time line of this launch (synchronises)
     std::vector<long long> h(8 * 256);

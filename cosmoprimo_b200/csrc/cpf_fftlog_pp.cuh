@@ -114,6 +114,8 @@ __global__ void __launch_bounds__(512, 1) fftlog_pp_kernel(const FftlogArgs a, c
   const int g = threadIdx.x / T, t = threadIdx.x - g * T;
   double2* S = smem + g * G::SMEM_ELEMS;
 
+  // programmatic dependent launch (see fftlog_stream_kernel): the next kernel of the stream may start its prologue early
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (warp == 0) tmem_alloc_all(&s_tmem_base);
   tmem_fence_before();
   __syncthreads();
@@ -144,6 +146,7 @@ __global__ void __launch_bounds__(512, 1) fftlog_pp_kernel(const FftlogArgs a, c
     __syncthreads();
     tmem_fence_after();
 
+    if (p == 0) asm volatile("griddepcontrol.wait;" ::: "memory");      // plan tables only so far; rows may come from the previous kernel
     for (long long it = 0; it < iters; ++it) {
       const long long pair = (it * gridDim.x + blockIdx.x) * NG + g;
       const bool active = pair < a.pairs_per_p;

@@ -109,6 +109,7 @@ struct StreamArgs {
   int off_in, off_out;      // N/4 - in_left, N/4 - out_left
   int lines;                // 128-byte lines per input row
   long long* dbg;           // lab builds: per-CTA time stamps (globaltimer ns), else null
+  int skew_ns;              // lab builds: group 1 starts its first pair this much later (phase offset between the groups)
 };
 
 // Work split: when there are at least as many CTAs as plan rows, every CTA works on ONE plan row (its tables are
@@ -177,6 +178,9 @@ __global__ void __launch_bounds__(512, 1) fftlog_stream_kernel(const StreamArgs 
   };
 
   ST_STAMP(0);
+  // programmatic dependent launch: let the next kernel of the stream start its CTAs as SMs become free (its prologue -- TMEM
+  // allocation, plan tables -- then overlaps the tail of this grid); it waits below, before touching caller data
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   long long lo, hi;
   st_item_range(a, lo, hi);
 
@@ -234,6 +238,9 @@ __global__ void __launch_bounds__(512, 1) fftlog_stream_kernel(const StreamArgs 
     }
   }
   bool first_seg = true, first_pair = true;
+#ifdef CPF_LAB
+  if (a.skew_ns > 0 && g == 1) __nanosleep((unsigned)a.skew_ns);
+#endif
 
   for (long long seg = lo; seg < hi;) {
     const int p = (int)(seg / a.pairs_per_p);
@@ -272,6 +279,8 @@ __global__ void __launch_bounds__(512, 1) fftlog_stream_kernel(const StreamArgs 
     __syncthreads();
     tmem_fence_after();
     ST_STAMP(2);
+    // everything above read plan tables only; rows may have been written by the previous kernel of the stream
+    if (first_pair) asm volatile("griddepcontrol.wait;" ::: "memory");
     if (TMA && tau == 0 && pair < pair_hi) stage_rows(p, pair);     // nobody reads the staging buffer any more (barrier above)
 
     while (pair < pair_hi) {
