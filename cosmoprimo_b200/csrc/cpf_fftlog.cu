@@ -19,6 +19,7 @@
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
+#include <atomic>
 #include <mutex>
 #include <vector>
 
@@ -704,8 +705,16 @@ template <int R1>
 static int launch_pp(const FftlogArgs& a, const double2* tab, cudaStream_t stream) {
   typedef Geo<R1> G;
   constexpr int NG = 512 / G::T;
-  const size_t smem = (size_t)NG * G::SMEM_ELEMS * sizeof(double2);
-  auto kern = fftlog_pp_kernel<R1>;
+  size_t smem = (size_t)NG * G::SMEM_ELEMS * sizeof(double2);
+  typedef void (*kern_t)(const FftlogArgs, const double2*);
+  kern_t kern = fftlog_pp_kernel<R1, false>;
+  // full window + 16-byte aligned rows: input rows staged by bulk copies (CPF_STREAM_TMA=0: direct loads)
+  const char* tma_env = getenv("CPF_STREAM_TMA");
+  const bool fullwin = a.n == G::N / 2 && a.in_left == G::N / 4 && !a.keep_padding;
+  if (fullwin && R1 < 16 && !(tma_env && tma_env[0] == '0') && ((uintptr_t)a.in % 16 == 0)) {
+    kern = fftlog_pp_kernel<R1, true>;
+    smem += (size_t)NG * G::N * sizeof(double);
+  }
   CPF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int dev = 0, sms = 0;
   CPF_CUDA(cudaGetDevice(&dev));
@@ -724,6 +733,26 @@ static int launch_pp(const FftlogArgs& a, const double2* tab, cudaStream_t strea
   cfg.attrs = attr;
   cfg.numAttrs = (pdl_env && pdl_env[0] == '0') ? 0 : 1;
   CPF_CUDA(cudaLaunchKernelEx(&cfg, kern, a, tab));
+  return CPF_OK;
+}
+
+// Ticket counters of the dynamically scheduled stream kernel: a per-device ring of kTicketSlots slots of kTicketSlotWords
+// counters.  A launch takes the next slot; its counters are back at zero when it completes (st_draw_ticket), and launches that
+// overlap (programmatic dependent launch, other streams) are on different slots unless more than kTicketSlots are in flight.
+constexpr int kTicketSlots = 64, kTicketSlotWords = 64;
+static std::atomic<unsigned> g_ticket_seq{0};
+static std::mutex g_ticket_mutex;
+static std::vector<std::pair<int, unsigned*>> g_ticket_rings;
+
+static int ticket_ring(int device, unsigned** out) {
+  std::lock_guard<std::mutex> lock(g_ticket_mutex);
+  for (auto& e : g_ticket_rings)
+    if (e.first == device) { *out = e.second; return CPF_OK; }
+  unsigned* p = nullptr;
+  CPF_CUDA(cudaMalloc(&p, (size_t)kTicketSlots * kTicketSlotWords * sizeof(unsigned)));
+  CPF_CUDA(cudaMemset(p, 0, (size_t)kTicketSlots * kTicketSlotWords * sizeof(unsigned)));
+  g_ticket_rings.emplace_back(device, p);
+  *out = p;
   return CPF_OK;
 }
 
@@ -756,9 +785,18 @@ static int launch_stream(const cpf_plan* pl, const FftlogArgs& a, cudaStream_t s
   int smem_bytes = ST_SMEM_BYTES;
   const char* tma_env = getenv("CPF_STREAM_TMA");
   const bool want_tma = !tma_env || tma_env[0] != '0';
+  s.tickets = nullptr;
   if (fullwin && want_tma && ((uintptr_t)a.in % 16 == 0) && (s.in_row % 2 == 0) && (s.in_p % 2 == 0)) {
     kern = (kern_t)fftlog_stream_kernel<true, 0, true>;
     smem_bytes = ST_SMEM_BYTES_TMA;
+    // dynamic scheduling when every CTA owns one plan row and has a queue worth drawing from (opt-in until measured: CPF_STREAM_DYNAMIC=1)
+    const char* dyn_env = getenv("CPF_STREAM_DYNAMIC");
+    const long long ctas_per_row = (grid + a.P - 1) / a.P;
+    if ((dyn_env && dyn_env[0] == '1') && grid >= a.P && a.P <= kTicketSlotWords && a.pairs_per_p >= 8 * ctas_per_row) {
+      unsigned* ring = nullptr;
+      CPF_TRY(ticket_ring(dev, &ring));
+      s.tickets = ring + (size_t)(g_ticket_seq.fetch_add(1u) % kTicketSlots) * kTicketSlotWords;
+    }
   }
 #ifdef CPF_LAB
   if (const char* e = getenv("CPF_STREAM_ABL")) {

@@ -92,6 +92,27 @@ __device__ __forceinline__ void named_arrive(const int id, const int nthreads) {
   asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// ---- mbarrier + bulk copy (TMA, non-tensor form) ------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, const unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(pp_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, const unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pp_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, const unsigned parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
+      ::"r"(pp_smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+// global -> shared bulk copy of `bytes` (multiple of 16, both addresses 16-byte aligned), completion counted on `bar`
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, const unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(pp_smem_u32(dst)), "l"(src), "r"(bytes), "r"(pp_smem_u32(bar))
+               : "memory");
+}
+
 // ---- per-thread table record (host builds it, see build_pp_tables in cpf_fftlog.cu) ---------------------------
 // 64 complex doubles per (plan row p, thread slot t); the first PP_REC_USED are copied to the thread's TMEM lane.
 //   [ 0,16)  tw1: pass-1 twiddles  w_N^{n2 k1},  index c*R1 + k1 (n2 = t + T c)
@@ -104,15 +125,29 @@ constexpr int PP_REC = 64, PP_REC_USED = 56;
 constexpr uint32_t PP_COL_TW1 = 0, PP_COL_TW2 = 64, PP_COL_UT = 128, PP_COL_PRE = 192, PP_COL_POST = 208;
 
 // barrier ids: 0 = __syncthreads, 1..8 = groups
-template <int R1>
+// TMA (full window: n = N/2, in_left = N/4, 16-byte aligned rows): the rows of a group's next pair are staged in shared memory by
+// bulk copies issued after the first group barrier of the current pair, as in fftlog_stream_kernel.
+template <int R1, bool TMA = false>
 __global__ void __launch_bounds__(512, 1) fftlog_pp_kernel(const FftlogArgs a, const double2* __restrict__ tmtab) {
   typedef Geo<R1> G;
   constexpr int T = G::T, N = G::N, NG = 512 / T, RS = G::RS;
   extern __shared__ double2 smem[];
   __shared__ uint32_t s_tmem_base;
+  __shared__ __align__(8) uint64_t s_mbar[NG];
   const int warp = threadIdx.x >> 5;
   const int g = threadIdx.x / T, t = threadIdx.x - g * T;
   double2* S = smem + g * G::SMEM_ELEMS;
+  double* stage = reinterpret_cast<double*>(smem + NG * G::SMEM_ELEMS) + g * N;      // TMA only: two rows of N/2 doubles
+  unsigned stage_parity = 0;
+  if (TMA && t == 0) { mbar_init(&s_mbar[g], 1); mbar_fence_init(); }
+  auto stage_rows = [&](const int p, const long long pair) {                        // one thread per group
+    const long long b0 = 2 * pair;
+    const double* ra = a.in + (a.in_has_P ? (b0 * a.P + p) : b0) * (long long)a.n;
+    const bool two = b0 + 1 < a.batch;
+    mbar_expect_tx(&s_mbar[g], two ? 2u * N * 4u : N * 4u);
+    bulk_g2s(stage, ra, N * 4u, &s_mbar[g]);
+    if (two) bulk_g2s(stage + N / 2, a.in + (a.in_has_P ? ((b0 + 1) * a.P + p) : b0 + 1) * (long long)a.n, N * 4u, &s_mbar[g]);
+  };
 
   // programmatic dependent launch (see fftlog_stream_kernel): the next kernel of the stream may start its prologue early
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -147,6 +182,7 @@ __global__ void __launch_bounds__(512, 1) fftlog_pp_kernel(const FftlogArgs a, c
     tmem_fence_after();
 
     if (p == 0) asm volatile("griddepcontrol.wait;" ::: "memory");      // plan tables only so far; rows may come from the previous kernel
+    if (TMA && t == 0 && (long long)blockIdx.x * NG + g < a.pairs_per_p) stage_rows(p, (long long)blockIdx.x * NG + g);
     for (long long it = 0; it < iters; ++it) {
       const long long pair = (it * gridDim.x + blockIdx.x) * NG + g;
       const bool active = pair < a.pairs_per_p;
@@ -157,7 +193,7 @@ __global__ void __launch_bounds__(512, 1) fftlog_pp_kernel(const FftlogArgs a, c
       const double* rowB = has1 ? a.in + (a.in_has_P ? (b1 * a.P + p) : b1) * (long long)a.n : rowA;
 
       // L2 prefetch of the rows this group transforms next
-      {
+      if (!TMA) {
         const long long nb0 = 2 * (pair + per_iter);
         if (nb0 < a.batch) {
           const int lines = (a.n * 8 + 127) / 128;
@@ -177,12 +213,22 @@ __global__ void __launch_bounds__(512, 1) fftlog_pp_kernel(const FftlogArgs a, c
       {
         tmem_ld4(tb + PP_COL_PRE, tq);
         double x[8], y[8];
+        if (TMA) {
+          mbar_wait(&s_mbar[g], stage_parity);
+          stage_parity ^= 1u;
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-          const int i = t + T * r + N / 4 - a.in_left;
-          const bool ok = active && (unsigned)i < (unsigned)a.n;
-          x[r] = ok ? __ldcs(rowA + i) : 0.;
-          y[r] = (ok && has1) ? __ldcs(rowB + i) : 0.;
+          for (int r = 0; r < 8; ++r) {
+            x[r] = stage[t + T * r];
+            y[r] = has1 ? stage[N / 2 + t + T * r] : 0.;
+          }
+        } else {
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            const int i = t + T * r + N / 4 - a.in_left;
+            const bool ok = active && (unsigned)i < (unsigned)a.n;
+            x[r] = ok ? __ldcs(rowA + i) : 0.;
+            y[r] = (ok && has1) ? __ldcs(rowB + i) : 0.;
+          }
         }
         scrub_rows(x, y, bad_a, bad_b);
         tmem_wait4(tq);
@@ -241,6 +287,7 @@ __global__ void __launch_bounds__(512, 1) fftlog_pp_kernel(const FftlogArgs a, c
       // ---- FFT #1 ----
       pass1(std::true_type());
       const bool row_a_bad = named_sync_or(1 + g, T, bad_a);
+      if (TMA && t == 0 && pair + per_iter < a.pairs_per_p) stage_rows(p, pair + per_iter);   // the staged rows are in registers everywhere
       pass2();
       const bool row_b_bad = named_sync_or(1 + g, T, bad_b);
       {

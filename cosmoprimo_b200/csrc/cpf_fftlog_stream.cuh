@@ -28,27 +28,6 @@ constexpr int ST_SMEM_BYTES = (2 * ST_GROUP_ELEMS + 256) * (int)sizeof(double2);
 constexpr int ST_STAGE_DOUBLES = 2 * 2048;
 constexpr int ST_SMEM_BYTES_TMA = ST_SMEM_BYTES + 2 * ST_STAGE_DOUBLES * (int)sizeof(double);
 
-// ---- mbarrier + bulk copy (TMA, non-tensor form) ------------------------------------------------------------------
-__device__ __forceinline__ void mbar_init(uint64_t* bar, const unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(pp_smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, const unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pp_smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, const unsigned parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
-      ::"r"(pp_smem_u32(bar)), "r"(parity)
-      : "memory");
-}
-// global -> shared bulk copy of `bytes` (multiple of 16, both addresses 16-byte aligned), completion counted on `bar`
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, const unsigned bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(pp_smem_u32(dst)), "l"(src), "r"(bytes), "r"(pp_smem_u32(bar))
-               : "memory");
-}
-
 // Tensor-memory layout of one lane (512 columns of 32 bits = 128 complex doubles).  Threads tau and tau + 128 of a
 // group share a lane (and have the same L = tau % 16, hence the same P2 twiddles); both groups read the same copy.
 //   [  0,  64)  P2 twiddles w_256^{L l1}                        (shared by the two halves)
@@ -110,18 +89,21 @@ struct StreamArgs {
   int lines;                // 128-byte lines per input row
   long long* dbg;           // lab builds: per-CTA time stamps (globaltimer ns), else null
   int skew_ns;              // lab builds: group 1 starts its first pair this much later (phase offset between the groups)
+  unsigned* tickets;        // dynamic scheduling (TMA variant, grid >= P): one self-resetting ticket counter per plan row, else null
 };
 
 // Work split: when there are at least as many CTAs as plan rows, every CTA works on ONE plan row (its tables are
 // loaded once) and the CTAs of a plan row share its pairs evenly; otherwise CTAs take contiguous item ranges.
 // (Drawing pairs from a per-plan-row atomic counter instead was measured and is not faster: r01n.)
-__device__ __forceinline__ void st_item_range(const StreamArgs& a, long long& lo, long long& hi) {
+__device__ __forceinline__ void st_item_range(const StreamArgs& a, long long& lo, long long& hi, int& row_ctas) {
   const int G = (int)gridDim.x, b = (int)blockIdx.x;
+  row_ctas = 0;
   if (G >= a.P) {
     const int base = G / a.P, rem = G % a.P;     // the first `rem` plan rows get base + 1 CTAs
     int p, j, c;
     if (b < rem * (base + 1)) { p = b / (base + 1); j = b - p * (base + 1); c = base + 1; }
     else { const int bb = b - rem * (base + 1); p = rem + bb / base; j = bb - (p - rem) * base; c = base; }
+    row_ctas = c;
     lo = (long long)p * a.pairs_per_p + (long long)a.pairs_per_p * j / c;
     hi = (long long)p * a.pairs_per_p + (long long)a.pairs_per_p * (j + 1) / c;
   } else {
@@ -142,6 +124,12 @@ __device__ __forceinline__ void st_item_range(const StreamArgs& a, long long& lo
 #else
 #define ST_STAMP(slot) do { } while (0)
 #endif
+
+// Next pair of a plan row's queue.  One hardware atomic per draw (a compare-and-swap loop collapses under the contention
+// of ~300 groups: measured 5x slower overall).  The counter wraps to zero by itself: the groups that share the row make
+// exactly pairs + groups draws in a launch (every group draws until its first ticket >= pairs), and atomicInc(word, wrap)
+// returns to 0 after wrap + 1 draws, so no launch has to reset it.
+__device__ __forceinline__ int st_draw_ticket(unsigned* word, const unsigned wrap) { return (int)atomicInc(word, wrap); }
 
 // twtab [3][16][256]: P1, P2, P1' twiddles (entry-major: thread tau reads element [.][.][tau], coalesced) ;
 // uttab [P][16][256]: kernel spectrum at the bins thread tau holds after FFT #1 ((-1)^k and 1/N folded in) ;
@@ -177,12 +165,23 @@ __global__ void __launch_bounds__(512, 1) fftlog_stream_kernel(const StreamArgs 
     if (two) bulk_g2s(stage + N / 2, ra + a.in_row, N * 4u, &s_mbar[g]);
   };
 
+  __shared__ int s_next[NG];
+  // dynamic scheduling: the groups of the CTAs that share a plan row draw its pairs from a queue, one pair ahead of their use
+  // (the draw decides what the bulk copies fetch); evens out the 10 % spread of the CTA end times of the static split
+  const bool dynamic = TMA && a.tickets != nullptr;
   ST_STAMP(0);
   // programmatic dependent launch: let the next kernel of the stream start its CTAs as SMs become free (its prologue -- TMEM
   // allocation, plan tables -- then overlaps the tail of this grid); it waits below, before touching caller data
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   long long lo, hi;
-  st_item_range(a, lo, hi);
+  int row_ctas;
+  st_item_range(a, lo, hi, row_ctas);
+  const unsigned ticket_wrap = (unsigned)(a.pairs_per_p + NG * row_ctas - 1);
+  if (dynamic) {        // this CTA's plan row (the host guarantees grid >= P and non-empty static ranges): the whole row is one segment
+    const int prow = (int)(lo / a.pairs_per_p);
+    lo = (long long)prow * a.pairs_per_p;
+    hi = lo + a.pairs_per_p;
+  }
 
   // L2 prefetch of the two rows of pair `pair` of plan row p (one 128-byte line per thread covers both rows)
   auto prefetch_rows = [&](const int p, const int pair, const bool l1 = false) {
@@ -281,6 +280,15 @@ __global__ void __launch_bounds__(512, 1) fftlog_stream_kernel(const StreamArgs 
     ST_STAMP(2);
     // everything above read plan tables only; rows may have been written by the previous kernel of the stream
     if (first_pair) asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (dynamic) {
+      if (tau == 0) {
+        const int t0 = st_draw_ticket(a.tickets + p, ticket_wrap);
+        s_next[g] = t0;
+        if (t0 < pair_hi) stage_rows(p, t0);
+      }
+      named_sync(1 + g, T);
+      pair = s_next[g];
+    } else
     if (TMA && tau == 0 && pair < pair_hi) stage_rows(p, pair);     // nobody reads the staging buffer any more (barrier above)
 
     while (pair < pair_hi) {
@@ -316,7 +324,13 @@ __global__ void __launch_bounds__(512, 1) fftlog_stream_kernel(const StreamArgs 
         st_p1(tau, v8, S, tb);
       }
       if (!(ABL & 1)) row_a_bad = named_sync_or(1 + g, T, bad_a);
-      if (TMA && tau == 0 && pair + NG < pair_hi) stage_rows(p, pair + NG);   // every thread of the group has its samples in registers
+      if (TMA && tau == 0) {                                                  // every thread of the group has its samples in registers
+        if (dynamic) {
+          const int tn = st_draw_ticket(a.tickets + p, ticket_wrap);
+          s_next[g] = tn;                                                       // read by the group after its second barrier
+          if (tn < pair_hi) stage_rows(p, tn);
+        } else if (pair + NG < pair_hi) stage_rows(p, pair + NG);
+      }
       st_p2(tau, S, tb);
       __syncwarp();
       st_p3_mul_p1(tau, S, tb);
@@ -332,6 +346,7 @@ __global__ void __launch_bounds__(512, 1) fftlog_stream_kernel(const StreamArgs 
       } else
       st_p2b(tau, S, M);
       if (!(ABL & 1)) row_b_bad = named_sync_or(1 + g, T, bad_b);
+      const int next_pair = dynamic ? s_next[g] : pair + NG;
       double2 v[16];
       st_col_load(tau, S, v);
       Tm4 tf;
@@ -351,7 +366,7 @@ __global__ void __launch_bounds__(512, 1) fftlog_stream_kernel(const StreamArgs 
         }
       }
       if (first_pair) { ST_STAMP(3); first_pair = false; }
-      pair += NG;
+      pair = next_pair;
     }
     ST_STAMP(4);
   }

@@ -150,6 +150,8 @@ def test_multipoles_config2_shapes():
 
 @pytest.mark.parametrize('kernel,n,B,ells,per_ell', [
     ('stream', 2048, 601, [0, 2, 4], True),     # full window, odd batch, one input row per ell
+    ('stream', 2048, 2001, [0, 2, 4], True),    # enough pairs per plan row for the dynamically scheduled TMA variant, odd batch
+    ('stream', 2048, 2600, [1], False),         # dynamic scheduling, one plan row shared by all CTAs
     ('stream', 2048, 300, [0, 2], False),       # the same row for every ell (no P axis in the input)
     ('stream', 2000, 77, [0, 2, 4], True),      # window narrower than N/2: masked loads and stores
     ('stream', 1919, 40, [1], False),           # odd n, single plan row
