@@ -789,13 +789,14 @@ static int launch_stream(const cpf_plan* pl, const FftlogArgs& a, cudaStream_t s
   if (fullwin && want_tma && ((uintptr_t)a.in % 16 == 0) && (s.in_row % 2 == 0) && (s.in_p % 2 == 0)) {
     kern = (kern_t)fftlog_stream_kernel<true, 0, true>;
     smem_bytes = ST_SMEM_BYTES_TMA;
-    // dynamic scheduling when every CTA owns one plan row and has a queue worth drawing from (opt-in until measured: CPF_STREAM_DYNAMIC=1)
+    // dynamic scheduling when every CTA owns one plan row and has a queue worth drawing from (CPF_STREAM_DYNAMIC=0: static split)
     const char* dyn_env = getenv("CPF_STREAM_DYNAMIC");
     const long long ctas_per_row = (grid + a.P - 1) / a.P;
-    if ((dyn_env && dyn_env[0] == '1') && grid >= a.P && a.P <= kTicketSlotWords && a.pairs_per_p >= 8 * ctas_per_row) {
+    if (!(dyn_env && dyn_env[0] == '0') && grid >= a.P && a.P <= kTicketSlotWords && a.pairs_per_p >= 8 * ctas_per_row) {
       unsigned* ring = nullptr;
       CPF_TRY(ticket_ring(dev, &ring));
       s.tickets = ring + (size_t)(g_ticket_seq.fetch_add(1u) % kTicketSlots) * kTicketSlotWords;
+      kern = (kern_t)fftlog_stream_kernel<true, 0, true, true>;
     }
   }
 #ifdef CPF_LAB

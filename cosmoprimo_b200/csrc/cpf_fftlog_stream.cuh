@@ -141,10 +141,11 @@ __device__ __forceinline__ int st_draw_ticket(unsigned* word, const unsigned wra
 // issued by one thread right after the first group barrier of the current pair (every thread has consumed the staged rows by
 // then), a whole pair ahead of their use; threads then read their 8 + 8 samples with conflict-free 64-bit shared loads instead
 // of waiting for global loads.
-template <bool FULLWIN, int ABL = 0, bool TMA = false>
+template <bool FULLWIN, int ABL = 0, bool TMA = false, bool DYN = false>
 __global__ void __launch_bounds__(512, 1) fftlog_stream_kernel(const StreamArgs a, const double2* __restrict__ twtab,
                                                                const double2* __restrict__ uttab, const double2* __restrict__ m256) {
   static_assert(!TMA || FULLWIN, "the staged variant covers the full window only");
+  static_assert(!DYN || TMA, "dynamic scheduling is built on the staged variant");
   constexpr int T = 256, N = 4096, NG = 2;
   extern __shared__ double2 smem[];
   __shared__ uint32_t s_tmem_base;
@@ -168,7 +169,7 @@ __global__ void __launch_bounds__(512, 1) fftlog_stream_kernel(const StreamArgs 
   __shared__ int s_next[NG];
   // dynamic scheduling: the groups of the CTAs that share a plan row draw its pairs from a queue, one pair ahead of their use
   // (the draw decides what the bulk copies fetch); evens out the 10 % spread of the CTA end times of the static split
-  const bool dynamic = TMA && a.tickets != nullptr;
+  constexpr bool dynamic = DYN;
   ST_STAMP(0);
   // programmatic dependent launch: let the next kernel of the stream start its CTAs as SMs become free (its prologue -- TMEM
   // allocation, plan tables -- then overlaps the tail of this grid); it waits below, before touching caller data

@@ -6,7 +6,7 @@ mkdir -p $OUT
 timeout 900 python -m pytest tests -m gpu -q > $OUT/pytest_$TAG.log 2>&1
 echo "pytest rc=$?" >> $OUT/pytest_$TAG.log
 tail -n 5 $OUT/pytest_$TAG.log
-for dyn in 1 0 1 0; do
+for dyn in 1 0 1 0; do  # CPF_STREAM_DYNAMIC is opt-in: 1 = tickets, 0 = static split
   CPF_STREAM_DYNAMIC=$dyn timeout 600 python bench.py --no-cpu-baseline > $OUT/bench_dyn${dyn}_$TAG.json 2>> $OUT/bench_$TAG.err
   python -c "import json; d=json.load(open('$OUT/bench_dyn${dyn}_$TAG.json')); print('dynamic $dyn', d['value'], d['roofline']['frac'], d['e2e']['value'])"
 done
