@@ -1,7 +1,7 @@
 // cpf_eh.cu — on-device Eisenstein & Hu linear P(k, z) rows: the input generator of every FFTLog workload
 // (cosmoprimo/eisenstein_hu.py, see cpf_eh_core.h), written directly in the (rows, nk) layout cpf_fftlog reads, optionally
-// as Kaiser multipoles ell = 0, 2, 4.  One CTA per cosmology: thread 0 derives the ~20 fitting coefficients, all threads
-// then evaluate the transfer function on the shared k grid once and write one row per redshift of that cosmology (the
+// as Kaiser multipoles ell = 0, 2, 4.  The ~20 fitting coefficients are derived by one thread per cosmology (eh_coeffs_kernel); then one
+// CTA per cosmology: all threads evaluate the transfer function on the shared k grid once and write one row per redshift of that cosmology (the
 // z dependence is the growth factor only).
 #include "cpf_common.h"
 #include "cpf_eh_core.h"
@@ -10,21 +10,24 @@ namespace cpf {
 
 #define EH_MAX_NZ 1024
 
-__global__ void __launch_bounds__(256) eh_pk_kernel(const double* __restrict__ params, const double* __restrict__ z, const long long B,
-                                                    const int nz, const double* __restrict__ k, const int nk, const double T_cmb,
-                                                    const double omega_r, const double k_pivot, const int kaiser,
+// fitting coefficients: one thread per cosmology (~25 dependent pow / log / sqrt calls: 20 us of latency that a whole CTA used
+// to sit through while its thread 0 worked)
+__global__ void eh_coeffs_kernel(const double* __restrict__ params, const long long B, const double T_cmb, const double omega_r,
+                                 const double k_pivot, EHCoeffs* __restrict__ coeffs) {
+  const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const double* p = params + 5 * b;
+  coeffs[b] = eh_coeffs(p[0], p[1], p[2], p[3], p[4], 0., T_cmb, omega_r, k_pivot);
+}
+
+__global__ void __launch_bounds__(256, 4) eh_pk_kernel(const EHCoeffs* __restrict__ coeffs, const double* __restrict__ z, const long long B,
+                                                    const int nz, const double* __restrict__ k, const int nk, const int kaiser,
                                                     double* __restrict__ out, double* __restrict__ derived) {
-  __shared__ EHCoeffs sc;
   __shared__ double g2[EH_MAX_NZ], gf[EH_MAX_NZ];
   const int P = kaiser ? 3 : 1;
   for (long long b = blockIdx.x; b < B; b += gridDim.x) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      const double* p = params + 5 * b;
-      sc = eh_coeffs(p[0], p[1], p[2], p[3], p[4], 0., T_cmb, omega_r, k_pivot);
-    }
-    __syncthreads();
-    const EHCoeffs c = sc;
+    __syncthreads();                       // g2 / gf of the previous cosmology are no longer read
+    const EHCoeffs c = coeffs[b];          // the same 23 doubles for every thread: broadcast loads
     for (int iz = threadIdx.x; iz < nz; iz += blockDim.x) {
       double gs, fr;
       eh_growth(c, z ? z[b * nz + iz] : 0., gs, fr);
@@ -100,8 +103,11 @@ int cpf_eh_pk(const double* params, const double* z, int64_t B, int nz, const do
       p_der = (double*)dder.p;
     }
   }
+  ScratchBuf dcoef;
+  CPF_CUDA(dcoef.alloc((size_t)B * sizeof(EHCoeffs), stream));
+  eh_coeffs_kernel<<<(unsigned)((B + 63) / 64), 64, 0, stream>>>(p_params, B, T_cmb, omega_r, k_pivot, (EHCoeffs*)dcoef.p);
   const unsigned grid = (unsigned)(B < 148LL * 64 ? B : 148LL * 64);
-  eh_pk_kernel<<<grid, 256, 0, stream>>>(p_params, p_z, B, nz, p_k, nk, T_cmb, omega_r, k_pivot, kaiser ? 1 : 0, p_out, p_der);
+  eh_pk_kernel<<<grid, 256, 0, stream>>>((const EHCoeffs*)dcoef.p, p_z, B, nz, p_k, nk, kaiser ? 1 : 0, p_out, p_der);
   CPF_CUDA(cudaGetLastError());
   if (!on_device) {
     CPF_CUDA(cudaMemcpyAsync(out, p_out, ocells * sizeof(double), cudaMemcpyDeviceToHost, stream));
