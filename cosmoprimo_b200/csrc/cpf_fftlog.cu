@@ -63,6 +63,7 @@ struct FftlogArgs {
   int P, in_has_P, n, N, log2N, in_left, out_left, n_out, keep_padding;
   int ex_l_mode, ex_r_mode;
   double ex_l_val, ex_r_val;
+  unsigned* tickets;       // ping-pong kernel with dynamic scheduling: one self-resetting ticket counter per plan row, else null
 };
 
 // Two real rows ride one complex FFT, so a NaN / Inf in one row would spoil its partner, which the reference's row-wise
@@ -701,42 +702,7 @@ static int launch_fast_r(const FftlogArgs& a, bool pruned, bool cpost, long long
   return cpost ? launch_fast<R1, false, true>(a, nblocks, stream) : launch_fast<R1, false, false>(a, nblocks, stream);
 }
 
-template <int R1>
-static int launch_pp(const FftlogArgs& a, const double2* tab, cudaStream_t stream) {
-  typedef Geo<R1> G;
-  constexpr int NG = 512 / G::T;
-  size_t smem = (size_t)NG * G::SMEM_ELEMS * sizeof(double2);
-  typedef void (*kern_t)(const FftlogArgs, const double2*);
-  kern_t kern = fftlog_pp_kernel<R1, false>;
-  // full window + 16-byte aligned rows: input rows staged by bulk copies (CPF_STREAM_TMA=0: direct loads)
-  const char* tma_env = getenv("CPF_STREAM_TMA");
-  const bool fullwin = a.n == G::N / 2 && a.in_left == G::N / 4 && !a.keep_padding;
-  if (fullwin && R1 < 16 && !(tma_env && tma_env[0] == '0') && ((uintptr_t)a.in % 16 == 0)) {
-    kern = fftlog_pp_kernel<R1, true>;
-    smem += (size_t)NG * G::N * sizeof(double);
-  }
-  CPF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int dev = 0, sms = 0;
-  CPF_CUDA(cudaGetDevice(&dev));
-  CPF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  long long grid = (a.pairs_per_p + NG - 1) / NG;
-  if (grid > sms) grid = sms;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3(512);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  const char* pdl_env = getenv("CPF_STREAM_PDL");
-  cfg.attrs = attr;
-  cfg.numAttrs = (pdl_env && pdl_env[0] == '0') ? 0 : 1;
-  CPF_CUDA(cudaLaunchKernelEx(&cfg, kern, a, tab));
-  return CPF_OK;
-}
-
-// Ticket counters of the dynamically scheduled stream kernel: a per-device ring of kTicketSlots slots of kTicketSlotWords
+// Ticket counters of the dynamically scheduled persistent kernels: a per-device ring of kTicketSlots slots of kTicketSlotWords
 // counters.  A launch takes the next slot; its counters are back at zero when it completes (st_draw_ticket), and launches that
 // overlap (programmatic dependent launch, other streams) are on different slots unless more than kTicketSlots are in flight.
 constexpr int kTicketSlots = 64, kTicketSlotWords = 64;
@@ -753,6 +719,52 @@ static int ticket_ring(int device, unsigned** out) {
   CPF_CUDA(cudaMemset(p, 0, (size_t)kTicketSlots * kTicketSlotWords * sizeof(unsigned)));
   g_ticket_rings.emplace_back(device, p);
   *out = p;
+  return CPF_OK;
+}
+
+template <int R1>
+static int launch_pp(const FftlogArgs& a, const double2* tab, cudaStream_t stream) {
+  typedef Geo<R1> G;
+  constexpr int NG = 512 / G::T;
+  size_t smem = (size_t)NG * G::SMEM_ELEMS * sizeof(double2);
+  typedef void (*kern_t)(const FftlogArgs, const double2*);
+  kern_t kern = fftlog_pp_kernel<R1, false>;
+  // full window + 16-byte aligned rows: input rows staged by bulk copies (CPF_STREAM_TMA=0: direct loads)
+  const char* tma_env = getenv("CPF_STREAM_TMA");
+  const bool fullwin = a.n == G::N / 2 && a.in_left == G::N / 4 && !a.keep_padding;
+  int dev = 0, sms = 0;
+  CPF_CUDA(cudaGetDevice(&dev));
+  CPF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  long long grid = (a.pairs_per_p + NG - 1) / NG;
+  if (grid > sms) grid = sms;
+  FftlogArgs b = a;
+  b.tickets = nullptr;
+  if (fullwin && R1 < 16 && !(tma_env && tma_env[0] == '0') && ((uintptr_t)a.in % 16 == 0)) {
+    kern = fftlog_pp_kernel<R1, true>;
+    smem += (size_t)NG * G::N * sizeof(double);
+    // ticket counters bring nothing here (r02u: 175-176 vs 176-178 M transforms/s at nk = 1024): the interleaved static split of
+    // this kernel is already balanced; kept behind CPF_PP_DYNAMIC=1 (covered by the GPU tests through that variable)
+    const char* dyn_env = getenv("CPF_PP_DYNAMIC");
+    if ((dyn_env && dyn_env[0] == '1') && a.P <= kTicketSlotWords && a.pairs_per_p >= 8LL * grid * NG) {
+      unsigned* ring = nullptr;
+      CPF_TRY(ticket_ring(dev, &ring));
+      b.tickets = ring + (size_t)(g_ticket_seq.fetch_add(1u) % kTicketSlots) * kTicketSlotWords;
+      kern = fftlog_pp_kernel<R1, true, true>;
+    }
+  }
+  CPF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(512);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  const char* pdl_env = getenv("CPF_STREAM_PDL");
+  cfg.attrs = attr;
+  cfg.numAttrs = (pdl_env && pdl_env[0] == '0') ? 0 : 1;
+  CPF_CUDA(cudaLaunchKernelEx(&cfg, kern, b, tab));
   return CPF_OK;
 }
 
@@ -1102,6 +1114,7 @@ int cpf_fftlog(const cpf_plan* pl, const double* in, int64_t batch, int in_has_P
   if (guard.err != cudaSuccess) return fail(CPF_ECUDA, "cudaSetDevice(%d): %s", pl->device, cudaGetErrorString(guard.err));
 
   FftlogArgs a;
+  a.tickets = nullptr;
   a.pre = pl->d_pre;
   a.post_re = pl->d_post_re;
   a.post_im = pl->d_post_im;

@@ -127,13 +127,17 @@ constexpr uint32_t PP_COL_TW1 = 0, PP_COL_TW2 = 64, PP_COL_UT = 128, PP_COL_PRE 
 // barrier ids: 0 = __syncthreads, 1..8 = groups
 // TMA (full window: n = N/2, in_left = N/4, 16-byte aligned rows): the rows of a group's next pair are staged in shared memory by
 // bulk copies issued after the first group barrier of the current pair, as in fftlog_stream_kernel.
-template <int R1, bool TMA = false>
+// DYN (with TMA): the groups draw their pairs from the plan row's ticket counter (st_draw_ticket in cpf_fftlog_stream.cuh's sense:
+// one atomicInc per draw, wrapping to zero after pairs + groups draws) instead of taking every (grid x NG)-th pair.
+template <int R1, bool TMA = false, bool DYN = false>
 __global__ void __launch_bounds__(512, 1) fftlog_pp_kernel(const FftlogArgs a, const double2* __restrict__ tmtab) {
+  static_assert(!DYN || TMA, "dynamic scheduling is built on the staged variant");
   typedef Geo<R1> G;
   constexpr int T = G::T, N = G::N, NG = 512 / T, RS = G::RS;
   extern __shared__ double2 smem[];
   __shared__ uint32_t s_tmem_base;
   __shared__ __align__(8) uint64_t s_mbar[NG];
+  __shared__ long long s_next[NG];
   const int warp = threadIdx.x >> 5;
   const int g = threadIdx.x / T, t = threadIdx.x - g * T;
   double2* S = smem + g * G::SMEM_ELEMS;
@@ -182,9 +186,19 @@ __global__ void __launch_bounds__(512, 1) fftlog_pp_kernel(const FftlogArgs a, c
     tmem_fence_after();
 
     if (p == 0) asm volatile("griddepcontrol.wait;" ::: "memory");      // plan tables only so far; rows may come from the previous kernel
-    if (TMA && t == 0 && (long long)blockIdx.x * NG + g < a.pairs_per_p) stage_rows(p, (long long)blockIdx.x * NG + g);
-    for (long long it = 0; it < iters; ++it) {
-      const long long pair = (it * gridDim.x + blockIdx.x) * NG + g;
+    const unsigned ticket_wrap = (unsigned)(a.pairs_per_p + (long long)gridDim.x * NG - 1);
+    long long pair = (long long)blockIdx.x * NG + g;
+    if (DYN) {
+      if (t == 0) {
+        const long long t0 = (long long)atomicInc(a.tickets + p, ticket_wrap);
+        s_next[g] = t0;
+        if (t0 < a.pairs_per_p) stage_rows(p, t0);
+      }
+      named_sync(1 + g, T);
+      pair = s_next[g];
+    } else if (TMA && t == 0 && pair < a.pairs_per_p) stage_rows(p, pair);
+    for (long long it = 0; it < (DYN ? (1LL << 62) : iters); ++it) {
+      if (!DYN) pair = (it * gridDim.x + blockIdx.x) * NG + g;
       const bool active = pair < a.pairs_per_p;
       if (!active) break;
       const long long b0 = 2 * pair, b1 = b0 + 1;
@@ -287,9 +301,16 @@ __global__ void __launch_bounds__(512, 1) fftlog_pp_kernel(const FftlogArgs a, c
       // ---- FFT #1 ----
       pass1(std::true_type());
       const bool row_a_bad = named_sync_or(1 + g, T, bad_a);
-      if (TMA && t == 0 && pair + per_iter < a.pairs_per_p) stage_rows(p, pair + per_iter);   // the staged rows are in registers everywhere
+      if (TMA && t == 0) {                                                                   // the staged rows are in registers everywhere
+        if (DYN) {
+          const long long tn = (long long)atomicInc(a.tickets + p, ticket_wrap);
+          s_next[g] = tn;                                                                      // read by the group after its next barrier
+          if (tn < a.pairs_per_p) stage_rows(p, tn);
+        } else if (pair + per_iter < a.pairs_per_p) stage_rows(p, pair + per_iter);
+      }
       pass2();
       const bool row_b_bad = named_sync_or(1 + g, T, bad_b);
+      const long long next_pair = DYN ? s_next[g] : 0;
       {
         const int k1 = t & (R1 - 1), l1 = t >> G::B1;
         const double2* row = S + k1 * RS + 16 * l1;
@@ -340,6 +361,7 @@ __global__ void __launch_bounds__(512, 1) fftlog_pp_kernel(const FftlogArgs a, c
           }
         }
       }
+      if (DYN) pair = next_pair;
     }
   }
   tmem_fence_before();

@@ -158,6 +158,8 @@ def test_multipoles_config2_shapes():
     ('stream', 2048, 2, [0, 2, 4], True),       # as many CTAs as plan rows
     ('stream', 2048, 1, [0, 1, 2, 3, 4], True),  # fewer CTAs than plan rows: a CTA walks over several plan rows
     ('pp', 1024, 333, [0, 2], True),            # N = 2048: ping-pong kernel, four groups per CTA
+    ('pp', 1024, 12001, [0, 2], True),          # enough pairs for the dynamically scheduled TMA variant, odd batch
+    ('pp', 512, 19000, [1], False),             # N = 1024, dynamic scheduling, one plan row
     ('pp', 1000, 65, [2], False),
     ('pp', 512, 129, [0, 2, 4], True),          # N = 1024: eight groups per CTA
     ('pp', 2048, 67, [0, 2], True),             # N = 4096 through the ping-pong kernel
@@ -173,6 +175,8 @@ def test_persistent_kernels(monkeypatch, kernel, n, B, ells, per_ell):
     monkeypatch.setenv('CPF_FFTLOG_KERNEL', 'fast')
     ref_fast = obj(fun if per_ell else fun[:, None, :])[1]
     monkeypatch.setenv('CPF_FFTLOG_KERNEL', kernel)
+    if kernel == 'pp' and B > 10000:
+        monkeypatch.setenv('CPF_PP_DYNAMIC', '1')       # the opt-in ticket-counter variant of the ping-pong kernel
     s, xi = obj(fun if per_ell else fun[:, None, :])
     assert xi.shape == (B, len(ells), n) and np.isfinite(xi).all()
     post = obj.padded_postfactor[:, obj.padded_size_out_left:obj.padded_size_out_left + n]
