@@ -334,6 +334,102 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_secondary(args):
+    """
+    `--secondary`: the other BASELINE.json configs on one GPU, each with the oracle port of the reference timed beside it on one
+    host core (bounded sample; SURVEY.md section 8d asks for the reference's CPU path next to every GPU number).  One JSON line.
+    Not part of the driver's contract: the default invocation is unchanged.
+    """
+    import torch
+    from cosmoprimo_b200 import synthetic as S, _lib
+    from cosmoprimo_b200.fftlog import TophatVariance
+    from cosmoprimo_b200.interp import spline_eval_rows, Interpolator1D
+    from cosmoprimo_b200.interpolator import PowerSpectrumInterpolator1D
+    from cosmoprimo_b200.eisenstein_hu import EisensteinHu
+    from cosmoprimo_b200.bao_filter import PowerSpectrumBAOFilter
+    from oracle import fftlog_oracle as O, spline_oracle as SO, wallish_oracle as WO
+    _lib.require_device()
+
+    def gpu_time(fn, reps=5, warm=2):
+        for _ in range(warm): fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps): fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) * 1e-3 / reps
+
+    def cpu_time(fn, reps=3):
+        fn()
+        t0 = time.perf_counter()
+        for _ in range(reps): fn()
+        return (time.perf_counter() - t0) / reps
+
+    res = {'secondary': True, 'cpu': 'oracle port (numpy {} / scipy), 1 core, bounded samples'.format(np.__version__), 'data': 'synthetic'}
+    n = 2048
+    k = np.geomspace(1e-5, 1e2, n)
+    r = np.linspace(1., 20., 10)
+    # config 3: sigma(r, z), 10 000 cosmologies x 100 redshifts, generated, transformed and reduced on the device
+    ncosmo, nz = 10000, 100
+    par = S.lhs_cosmologies(ncosmo, seed=42)
+    eh = EisensteinHu(par['h'], par['omega_b'], par['omega_cdm'], par['n_s'], logA=par['logA'])
+    zgrid = np.linspace(0., 3., nz)[None, :]
+    tv = TophatVariance(k)
+    s_grid = tv.y if tv.y.ndim == 1 else tv.y[0]
+    t = gpu_time(lambda: spline_eval_rows(s_grid, tv(eh.pk(k, z=zgrid).reshape(ncosmo * nz, n))[1], r)**0.5, reps=3, warm=1)
+    sub = {name: val[:2] for name, val in par.items()}
+    pk_cpu = (S.eh_pk(k, sub)[:, None, :] * np.ones((1, 128, 1))).reshape(256, n)
+    plan = O.plan_tophat_variance(k)
+
+    def sigma_cpu():
+        s, var = O.execute(plan, pk_cpu)
+        return SO.interpolator1d(s, var.T, assume_sorted=True)(r)**0.5
+    tc = cpu_time(sigma_cpu)
+    res['config3_sigma_rz'] = {'unit': 'rows/s', 'gpu': ncosmo * nz / t, 'gpu_rows': ncosmo * nz, 'cpu_1core': 256 / tc, 'cpu_rows': 256,
+                               'gpu_path': 'EH generator + TophatVariance + row splines at 10 radii, all on the device',
+                               'cpu_path': 'TophatVariance (numpy FFTs) + scipy CubicSpline + evaluation at 10 radii, spectra given'}
+    tg = gpu_time(lambda: eh.pk(k, z=zgrid), reps=3, warm=1)
+    tcg = cpu_time(lambda: S.eh_pk(k, {name: np.repeat(val[:8], 32) for name, val in par.items()}, z=np.tile(np.linspace(0., 3., 32), 8)))
+    res['eh_generator'] = {'unit': 'rows/s', 'gpu': ncosmo * nz / tg, 'cpu_1core': 256 / tcg,
+                           'cpu_path': 'numpy restatement of the reference engine (cosmoprimo_b200/synthetic.py), one redshift per row'}
+    del eh
+    torch.cuda.empty_cache()
+    # config 4: Wallish2018 over 65 536 spectra (filter only: the two evaluations of the input interpolator are inputs)
+    ktab = np.geomspace(1e-5, 1e2, 512)
+    base = S.eh_pk(ktab, S.lhs_cosmologies(256, seed=42)).T
+    ncols = 65536
+    pk = torch.from_numpy(np.tile(base, (1, ncols // 256)) * (1 + 1e-3 * np.arange(ncols) / ncols)).cuda()
+    interp = PowerSpectrumInterpolator1D(ktab, pk)
+    filt = PowerSpectrumBAOFilter(interp, engine='wallish2018')
+    klin = np.linspace(interp.extrap_kmin, 2., 4096)
+    pklin, pkout = interp(klin), interp(filt.k)
+    lib = _lib.load()
+    kl, ko = torch.from_numpy(klin).cuda(), torch.from_numpy(filt.k).cuda()
+    out = torch.empty_like(pkout)
+    stream = torch.cuda.current_stream().cuda_stream
+    tw = gpu_time(lambda: _lib.check(lib.cpf_wallish2018(kl.data_ptr(), pklin.data_ptr(), 4096, ko.data_ptr(), pkout.data_ptr(), filt.k.size, ncols,
+                                                         out.data_ptr(), None, 1, 0, stream)), reps=3, warm=1)
+    tf = gpu_time(lambda: filt(interp), reps=3, warm=1)
+    pl_cpu, po_cpu = pklin[:, :32].cpu().numpy(), pkout[:, :32].cpu().numpy()
+    twc = cpu_time(lambda: WO.wallish2018(klin, pl_cpu, filt.k, po_cpu), reps=2)
+    res['config4_wallish2018'] = {'unit': 'P(k)/s', 'gpu_filter_only': ncols / tw, 'gpu_with_input_evaluations': ncols / tf, 'gpu_spectra': ncols,
+                                  'cpu_1core_filter_only': 32 / twc, 'cpu_spectra': 32,
+                                  'cpu_path': 'scipy dst / CubicSpline restatement of Wallish2018PowerSpectrumBAOFilter._compute (per-column Python loop as in the reference)'}
+    del pk, interp, filt, pklin, pkout, out
+    torch.cuda.empty_cache()
+    # spline evaluation of a log-log P(k) table (the step in front of every transform): 540 knots x 4096 spectra -> 2048 wavenumbers
+    ktab = np.geomspace(1e-4, 50., 540)
+    tab = S.eh_pk(ktab, S.lhs_cosmologies(256, seed=3)).T
+    tab_d = torch.from_numpy(np.tile(tab, (1, 16))).cuda()
+    kq = np.geomspace(1e-4, 50., n)
+    ti = gpu_time(lambda: Interpolator1D(ktab, tab_d, interp_x='log', interp_fun='log', assume_sorted=True).eval_rows(kq))
+    tic = cpu_time(lambda: SO.interpolator1d(ktab, tab, interp_x='log', interp_fun='log', assume_sorted=True)(kq))
+    res['spline_fit_and_eval'] = {'unit': 'spectra/s', 'gpu': tab_d.shape[1] / ti, 'cpu_1core': tab.shape[1] / tic,
+                                  'what': 'natural cubic spline fit (540 knots, log-log) + evaluation at 2048 wavenumbers'}
+    print(json.dumps(res))
+
+
 def main():
     parser = argparse.ArgumentParser()
     parser.add_argument('--gpus', type=int, default=1)
@@ -341,8 +437,11 @@ def main():
     parser.add_argument('--warmup', type=int, default=10)
     parser.add_argument('--impl', type=str, default='ours', choices=['ours', 'reference'])
     parser.add_argument('--no-cpu-baseline', action='store_true')
+    parser.add_argument('--secondary', action='store_true', help='the other BASELINE configs with the oracle timed beside them (one GPU)')
     args = parser.parse_args()
-    if args.impl == 'reference':
+    if args.secondary:
+        run_secondary(args)
+    elif args.impl == 'reference':
         run_reference(args)
     else:
         run_ours(args)
