@@ -122,3 +122,68 @@ def test_wallish2018_on_2d_interpolator():
     peak = lambda v: np.any((v[1:-1] > v[:-2]) & (v[1:-1] > v[2:]))
     z0 = np.zeros(1)
     assert peak(interp.to_xi()(sfine, z0)[:, 0] * sfine**2) and not peak(xi(sfine, z0)[:, 0] * sfine**2)
+
+
+@pytest.mark.gpu
+def test_sigma_r_against_quadrature():
+    """Known answer independent of the reference's FFTLog: sigma(r) by adaptive quadrature of the top-hat integral (the reference's
+    own check, tests/test_fftlog.py:16-23, 134-146, rtol 1e-5), for the FFTLog + row-spline path and for the interpolator method."""
+    from scipy import integrate
+    from cosmoprimo_b200 import synthetic as S
+    from cosmoprimo_b200.fftlog import TophatVariance
+    from cosmoprimo_b200.interp import spline_eval_rows
+    from cosmoprimo_b200.interpolator import PowerSpectrumInterpolator1D
+    ktab = np.geomspace(1e-6, 1e2, 1500)
+    interp = PowerSpectrumInterpolator1D(ktab, S.eh_pk(ktab))
+
+    def wtophat(x):
+        return 3. * (np.sin(x) - x * np.cos(x)) / x**3
+
+    def sigma_quad(r, kmin=1e-6, kmax=100., epsrel=1e-5):
+        integrand = lambda logk: float(interp(np.exp(logk))) * (wtophat(r * np.exp(logk)) * np.exp(logk))**2 * np.exp(logk)
+        return np.sqrt(1. / 2. / np.pi**2 * integrate.quad(integrand, np.log(kmin), np.log(kmax), epsrel=epsrel, limit=400)[0])
+
+    r = np.linspace(1., 20., 10)
+    ref = np.array([sigma_quad(rr) for rr in r])
+    k = np.logspace(-5, 2, 1000)
+    r2, var = TophatVariance(k, lowring=True)(interp(k))
+    np.testing.assert_allclose(np.sqrt(spline_eval_rows(r2, var[None, :], r)[:, 0]), ref, rtol=1e-5)
+    np.testing.assert_allclose(interp.sigma_r(r), ref, rtol=1e-5)
+
+
+@pytest.mark.gpu
+def test_nan_tables_and_bounds_contract():
+    """The reference's test_nan (tests/test_interpolator.py:328-337) and the bounds part of test_extrap_2d (:232-300)."""
+    from cosmoprimo_b200 import synthetic as S
+    from cosmoprimo_b200.interpolator import PowerSpectrumInterpolator1D, PowerSpectrumInterpolator2D
+    k = np.logspace(-4, 2, 1000)
+    pk = k**2
+    pk[:2] *= -1                                               # log10 of a negative number: the whole fit is poisoned
+    with np.errstate(invalid='ignore'):
+        assert np.isnan(PowerSpectrumInterpolator1D(k, pk)(k)).all()
+        z = np.linspace(0., 2., 4)
+        assert np.isnan(PowerSpectrumInterpolator2D(k, z, pk[..., None][..., [0] * len(z)])(k, z=1.)).all()
+    # bounds: NaN outside the extrapolation range / redshift table, ValueError with bounds_error
+    z = np.linspace(0., 4., 10)
+    D2 = S.growth_factor(z, 0.3137721026737606, 0.6736)**2
+    tab = S.eh_pk(k)[:, None] * D2
+    k_extrap = np.logspace(-6, 3, 1000)
+    k_eval = k_extrap[1:-1]
+    interp = PowerSpectrumInterpolator2D(k, z, tab, extrap_kmin=k_extrap[0], extrap_kmax=k_extrap[-1])
+    assert np.isfinite(interp(k_eval, z)).all()
+    assert np.isnan(interp(k_eval[0] / 2., z)).all() and np.isnan(interp(k_eval[-1] * 2., z)).all()
+    assert np.isnan(interp(k_eval, z[-1] * 2.)).all()
+    for kk, zz in [(k_eval / 2., z), (k_eval * 2., z), (k_eval, z * 2.)]:
+        with pytest.raises(ValueError):
+            interp(kk, zz, bounds_error=True)
+    xi = interp.to_xi()
+    s_eval = xi.s
+    assert np.isfinite(xi(s_eval, z)).all()
+    assert np.isnan(xi(s_eval[0] / 2., z)).all() and np.isnan(xi(s_eval[-1] * 2., z)).all() and np.isnan(xi(s_eval, z[-1] * 2.)).all()
+    for ss, zz in [(s_eval / 2., z), (s_eval * 2., z), (s_eval, z * 2.)]:
+        with pytest.raises(ValueError):
+            xi(ss, zz, bounds_error=True)
+    # round trip xi -> P(k) at z = 0 within 1 % over the tabulated range (tests/test_interpolator.py:300)
+    back = xi.to_pk()
+    sel = (k > 1e-3) & (k < 10.)
+    np.testing.assert_allclose(back(k[sel], 0.), tab[sel, 0], rtol=1e-2)
