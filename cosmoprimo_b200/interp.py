@@ -296,12 +296,14 @@ _DEVICE_COPIES = {}
 def _device_copy(a, dev):
     """Device copy of a small host grid, cached by content: the same knots / radii come back on every sigma(r) call and a
     pageable host-to-device copy synchronises the stream."""
+    torch = _buf._torch()
+    if a.nbytes > 65536:                       # large query sets are not worth remembering
+        return torch.as_tensor(a, device=torch.device('cuda', dev))
     key = (dev, a.size, a.tobytes())
     hit = _DEVICE_COPIES.get(key)
     if hit is None:
         if len(_DEVICE_COPIES) >= 16:
             _DEVICE_COPIES.pop(next(iter(_DEVICE_COPIES)))
-        torch = _buf._torch()
         hit = _DEVICE_COPIES[key] = torch.as_tensor(a, device=torch.device('cuda', dev))
     return hit
 
