@@ -56,15 +56,17 @@ struct WallishSmem {
   int* redi;      // [256]
   int* box;       // [8]
   WallishGap* gaps;   // [4]
+  double* wtab;   // [32] Thomas pivots (copied from global memory once: they sit in the dependency chain of the first chunks)
   __device__ explicit WallishSmem(double2* base) {
     S = base; X = base + WallishGeo::BUF; DD = base + 2 * WallishGeo::BUF;
     red = reinterpret_cast<double*>(base + 3 * WallishGeo::BUF);
     redi = reinterpret_cast<int*>(red + 256);
     box = redi + 256;
     gaps = reinterpret_cast<WallishGap*>(box + 8);
+    wtab = reinterpret_cast<double*>(gaps + 4);
   }
 };
-static constexpr size_t kWallishSmemBytes = 3 * (size_t)WallishGeo::BUF * sizeof(double2) + 256 * sizeof(double) + 264 * sizeof(int) + 4 * sizeof(WallishGap);
+static constexpr size_t kWallishSmemBytes = 3 * (size_t)WallishGeo::BUF * sizeof(double2) + 256 * sizeof(double) + 264 * sizeof(int) + 4 * sizeof(WallishGap) + 32 * sizeof(double);
 
 __device__ __forceinline__ void fft4096(const int t, double2 (&v)[16], double2* S, const double2* tw1, const double2* tw2) {
   fft_pass1<16, false>(t, v, S, tw1);
@@ -130,14 +132,15 @@ __global__ void __launch_bounds__(256, 1) wallish_fused_kernel(const WallishArgs
   double2 v[16];
   // sign * log(k P) in Makhoul order, packed per pair by wallish_pack_kernel                  (bao_filter.py:371)
   double2* zrow = a.packed + (long long)blockIdx.x * G::N;
+  if (t < 32) sm.wtab[t] = a.wtab[t];            // visible after the barriers of the first FFT
 #pragma unroll
   for (int r = 0; r < 16; ++r) v[r] = __ldcs(zrow + t + 256 * r);
   dst2_in_smem(t, v, sm, a.tw1, a.tw2, a.twd);                                              // :372
   // second derivatives of the clamped splines through the even / odd coefficients           (:377-382)
-  wallish_forward(t, sm.X, sm.S, a.wtab);
+  wallish_forward(t, sm.X, sm.S, sm.wtab);
   __syncthreads();
   WallishBest chunk;
-  wallish_backward_dd(t, sm.X, sm.S, sm.DD, a.wtab, &chunk);
+  wallish_backward_dd(t, sm.X, sm.S, sm.DD, sm.wtab, &chunk);
   // boxes (:392-395): argmax over [20, H-20), then over [first + 5, H-20); per-chunk maxima come out of the backward pass,
   // warps reduce them with shuffles, thread q < 4 merges the four warps of its sequence
   wallish_best_reduce(t, chunk, sm.red, sm.redi);
@@ -177,10 +180,10 @@ __global__ void __launch_bounds__(256, 1) wallish_fused_kernel(const WallishArgs
   if (t < 8) {
     const int q = t >> 1;
     const int b0 = sm.box[2 * q], b1 = sm.box[2 * q + 1];
-    sm.red[t] = wallish_gap_ok(b0, b1) ? wallish_gap_chain(gr + t * G::WARM, b0, b1, t & 1, a.wtab) : 0.;
+    sm.red[t] = wallish_gap_ok(b0, b1) ? wallish_gap_chain(gr + t * G::WARM, b0, b1, t & 1, sm.wtab) : 0.;
   }
   __syncthreads();
-  if (t < 4) sm.gaps[t] = wallish_gap_finish(sm.X, t >> 1, t & 1, sm.box[2 * t], sm.box[2 * t + 1], sm.red[2 * t], sm.red[2 * t + 1], a.wtab);
+  if (t < 4) sm.gaps[t] = wallish_gap_finish(sm.X, t >> 1, t & 1, sm.box[2 * t], sm.box[2 * t + 1], sm.red[2 * t], sm.red[2 * t + 1], sm.wtab);
   __syncthreads();
   {                                                                                         // :402
     // only the knots of the removed box change (64 threads per sequence); a box that reaches the end of the array

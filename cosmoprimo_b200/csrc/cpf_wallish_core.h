@@ -84,6 +84,7 @@ CPF_HD void wallish_forward(const int t, const double2* X, double2* D, const dou
   const int first = c * G::CH, start = first - G::WARM > 0 ? first - G::WARM : 0;
   double2 d = mk2(0., 0.);
   double2 ym = start > 0 ? X[wpos(h, start - 1)] : mk2(0., 0.), y0 = X[wpos(h, start)];
+#pragma unroll 4
   for (int i = start; i < first + G::CH; ++i) {
     const double2 yp = i + 1 < G::H ? X[wpos(h, i + 1)] : mk2(0., 0.);
     const bool edge = (i == 0 || i == G::H - 1);
@@ -121,6 +122,7 @@ CPF_HD void wallish_backward_dd(const int t, const double2* X, const double2* D,
   double2 yn = X[wpos(h, end)];
   WallishBest b;
   b.vx = b.vy = 0.; b.ix = b.iy = -1;
+#pragma unroll 4
   for (int i = end - 1; i >= first; --i) {
     const double cp = wcp(wtab, i, G::H);
     const double2 di = D[wpos(h, i)], yi = X[wpos(h, i)];
