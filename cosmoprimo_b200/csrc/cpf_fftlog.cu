@@ -445,6 +445,8 @@ static int fast_twiddles(int device, int N, const FastTw** out) {
       for (int l = 0; l < 16; ++l) m256[16 * hh + l] = unit_root(hh * l, 256);
     rc = upload((void**)&f->d_st_tw, stw.data(), stw.size() * sizeof(double2));
     if (rc == CPF_OK) rc = upload((void**)&f->d_m256, m256.data(), m256.size() * sizeof(double2));
+    if (rc == CPF_OK && cudaMemcpyToSymbol(c_m256, m256.data(), m256.size() * sizeof(double2)) != cudaSuccess)
+      rc = fail(CPF_ECUDA, "cudaMemcpyToSymbol(c_m256) failed");
   }
   if (rc != CPF_OK) {
     cudaFree(f->d_tw1); cudaFree(f->d_tw2); cudaFree(f->d_st_tw); cudaFree(f->d_m256);
@@ -822,6 +824,7 @@ static int launch_stream(const cpf_plan* pl, const FftlogArgs& a, cudaStream_t s
       case 16: kern = fftlog_stream_kernel<true, 16>; break;
       case 32: kern = fftlog_stream_kernel<true, 32>; break;
       case 48: kern = fftlog_stream_kernel<true, 48>; break;
+      case 64: kern = fftlog_stream_kernel<true, 64>; break;
       default: break;
     }
   }

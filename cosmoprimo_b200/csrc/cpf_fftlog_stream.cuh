@@ -28,6 +28,21 @@ constexpr int ST_SMEM_BYTES = (2 * ST_GROUP_ELEMS + 256) * (int)sizeof(double2);
 constexpr int ST_STAGE_DOUBLES = 2 * 2048;
 constexpr int ST_SMEM_BYTES_TMA = ST_SMEM_BYTES + 2 * ST_STAGE_DOUBLES * (int)sizeof(double);
 
+// Lab variant (ABL bit 64): P2' twiddles w_256^{H l1} from constant memory instead of the 4 KB shared-memory copy.  They are
+// uniform over a half-warp, and the shared-memory loads are ~9 % of the kernel's wavefronts -- but two different constant
+// addresses per warp serialise in the constant cache: 69.0 M transforms/s against 78.2 M (r02z).  Kept for the record.
+__constant__ double2 c_m256[256];
+
+__device__ __forceinline__ void st_p2b_const(const int tau, double2* S) {
+  double2 w[16];
+  st_row_load(tau, S, w);
+  dft_dit<16, false, false>(w);
+  const double2* M16 = c_m256 + 16 * (tau >> 4);
+#pragma unroll
+  for (int l1 = 1; l1 < 16; ++l1) w[l1] = cmul(w[l1], M16[l1]);
+  st_row_store(tau, w, S);
+}
+
 // Tensor-memory layout of one lane (512 columns of 32 bits = 128 complex doubles).  Threads tau and tau + 128 of a
 // group share a lane (and have the same L = tau % 16, hence the same P2 twiddles); both groups read the same copy.
 //   [  0,  64)  P2 twiddles w_256^{L l1}                        (shared by the two halves)
@@ -344,8 +359,8 @@ __global__ void __launch_bounds__(512, 1) fftlog_stream_kernel(const StreamArgs 
 #pragma unroll
         for (int l1 = 1; l1 < 16; ++l1) w[l1] = cmul(w[l1], m);
         st_row_store(tau, w, S);
-      } else
-      st_p2b(tau, S, M);
+      } else if (ABL & 64) st_p2b_const(tau, S);      // lab: P2' twiddles from constant memory (measured 12 % slower: r02z)
+      else st_p2b(tau, S, M);
       if (!(ABL & 1)) row_b_bad = named_sync_or(1 + g, T, bad_b);
       const int next_pair = dynamic ? s_next[g] : pair + NG;
       double2 v[16];
