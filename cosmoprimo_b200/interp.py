@@ -193,7 +193,7 @@ class Interpolator1D(object):
         dev = self._spline.device
         if self._on_device:
             torch = _buf._torch()
-            qbuf = _buf.as_input(torch.as_tensor(q, device=torch.device('cuda', dev)), dtype='f8')
+            qbuf = _buf.as_input(_device_copy(q, dev), dtype='f8')      # the wavenumber grid of sigma_r / to_xi repeats across calls
             stream = _buf.current_stream(dev)
         else:
             qbuf = _buf.as_input(q, dtype='f8')

@@ -109,14 +109,14 @@ class PowerSpectrumInterpolator1D(object):
 
     def __call__(self, k, **kwargs):
         """P(k); NaN outside [extrap_kmin, extrap_kmax]; shape ``k.shape + pk.shape[1:]`` (ref:495-521)."""
-        return self._interp(k, **kwargs) * self._rsigma8sq
+        return _scaled(self._interp(k, **kwargs), self._rsigma8sq)
 
     def sigma_r(self, r, nk=1024):
         r"""
         R.m.s. of perturbations in spheres of radius ``r``: FFTLog top-hat variance on ``nk`` log-spaced wavenumbers, then
         a natural cubic spline in (linear) s evaluated at ``r`` — ``integrate_sigma_r2(method='fftlog')``, ref:285-291.
         """
-        rows = lambda k: (self._interp.eval_rows(k) * self._rsigma8sq, self._interp.shape)
+        rows = lambda k: (_scaled(self._interp.eval_rows(k), self._rsigma8sq), self._interp.shape)
         out = integrate_sigma_r2(r, self, kmin=self.extrap_kmin, kmax=self.extrap_kmax, nk=nk, device=self._device, pk_rows=rows)**0.5
         if _buf.is_device_array(out):
             return out
@@ -175,7 +175,7 @@ class CorrelationFunctionInterpolator1D(object):
     extrap_smin, extrap_smax = smin, smax
 
     def __call__(self, s, **kwargs):
-        return self._interp(s, **kwargs) * self._rsigma8sq
+        return _scaled(self._interp(s, **kwargs), self._rsigma8sq)
 
     def to_pk(self, ns=1024, fftlog_kwargs=None, **kwargs):
         """Power spectrum by FFTLog (ref:1194-1215)."""
@@ -222,6 +222,11 @@ def integrate_sigma_r2(r, pk, kmin=1e-7, kmax=1e2, nk=None, device=None, pk_rows
     if _buf.is_device_array(sigma2):
         return sigma2.to(_buf._torch().float32) if dtype == np.float32 else sigma2
     return sigma2.astype(dtype)
+
+
+def _scaled(a, factor):
+    """a * factor, without a pass over the array when the factor is exactly 1 (no sigma8 rescaling requested)."""
+    return a if (np.ndim(factor) == 0 and factor == 1.) else a * factor
 
 
 def _times(a, b):
@@ -325,8 +330,8 @@ class PowerSpectrumInterpolator2D(object):
         if _buf.is_device_array(tmp):
             torch = _buf._torch()
             tmp = torch.where(torch.as_tensor(mask, device=tmp.device), tmp, torch.full_like(tmp, float('nan')))
-            return (tmp.to(torch.float32 if dtype == np.float32 else torch.float64)).reshape(shape) * self._rsigma8sq
-        return np.where(mask, tmp, np.nan).astype(dtype).reshape(shape) * self._rsigma8sq
+            return _scaled((tmp.to(torch.float32 if dtype == np.float32 else torch.float64)).reshape(shape), self._rsigma8sq)
+        return _scaled(np.where(mask, tmp, np.nan).astype(dtype).reshape(shape), self._rsigma8sq)
 
     def sigma_rz(self, r, z, nk=None):
         """R.m.s. of perturbations in spheres of radius ``r`` at redshifts ``z``: (r.size, z.size) (ref:846-876)."""
@@ -467,8 +472,8 @@ class CorrelationFunctionInterpolator2D(object):
         if _buf.is_device_array(tmp):
             torch = _buf._torch()
             tmp = torch.where(torch.as_tensor(mask, device=tmp.device), tmp, torch.full_like(tmp, float('nan')))
-            return (tmp.to(torch.float32 if dtype == np.float32 else torch.float64)).reshape(shape) * self._rsigma8sq
-        return np.where(mask, tmp, np.nan).astype(dtype).reshape(shape) * self._rsigma8sq
+            return _scaled((tmp.to(torch.float32 if dtype == np.float32 else torch.float64)).reshape(shape), self._rsigma8sq)
+        return _scaled(np.where(mask, tmp, np.nan).astype(dtype).reshape(shape), self._rsigma8sq)
 
     def to_pk(self, ns=1024, fftlog_kwargs=None, **kwargs):
         """Power spectrum by FFTLog (ref:1476-1498)."""
