@@ -57,6 +57,8 @@ struct WallishSmem {
   int* box;       // [8]
   WallishGap* gaps;   // [4]
   double* wtab;   // [32] Thomas pivots (copied from global memory once: they sit in the dependency chain of the first chunks)
+  double2* E;     // [256] chunk results of the two-step eliminations (value with zero inflow)
+  double* Mf;     // [256] ... and the factor the inflow is multiplied with
   __device__ explicit WallishSmem(double2* base) {
     S = base; X = base + WallishGeo::BUF; DD = base + 2 * WallishGeo::BUF;
     red = reinterpret_cast<double*>(base + 3 * WallishGeo::BUF);
@@ -64,9 +66,11 @@ struct WallishSmem {
     box = redi + 256;
     gaps = reinterpret_cast<WallishGap*>(box + 8);
     wtab = reinterpret_cast<double*>(gaps + 4);
+    E = reinterpret_cast<double2*>(wtab + 32);
+    Mf = reinterpret_cast<double*>(E + 256);
   }
 };
-static constexpr size_t kWallishSmemBytes = 3 * (size_t)WallishGeo::BUF * sizeof(double2) + 256 * sizeof(double) + 264 * sizeof(int) + 4 * sizeof(WallishGap) + 32 * sizeof(double);
+static constexpr size_t kWallishSmemBytes = 3 * (size_t)WallishGeo::BUF * sizeof(double2) + 256 * sizeof(double) + 264 * sizeof(int) + 4 * sizeof(WallishGap) + 32 * sizeof(double) + 256 * sizeof(double2) + 256 * sizeof(double);
 
 __device__ __forceinline__ void fft4096(const int t, double2 (&v)[16], double2* S, const double2* tw1, const double2* tw2) {
   fft_pass1<16, false>(t, v, S, tw1);
@@ -137,10 +141,14 @@ __global__ void __launch_bounds__(256, 1) wallish_fused_kernel(const WallishArgs
   for (int r = 0; r < 16; ++r) v[r] = __ldcs(zrow + t + 256 * r);
   dst2_in_smem(t, v, sm, a.tw1, a.tw2, a.twd);                                              // :372
   // second derivatives of the clamped splines through the even / odd coefficients           (:377-382)
-  wallish_forward(t, sm.X, sm.S, sm.wtab);
+  wallish_forward_local(t, sm.X, sm.E, sm.Mf, sm.wtab);
+  __syncthreads();
+  wallish_forward_store(t, sm.X, sm.S, sm.E, sm.Mf, sm.wtab);
+  __syncthreads();
+  wallish_backward_local(t, sm.S, sm.E, sm.Mf, sm.wtab);
   __syncthreads();
   WallishBest chunk;
-  wallish_backward_dd(t, sm.X, sm.S, sm.DD, sm.wtab, &chunk);
+  wallish_backward_dd(t, sm.X, sm.S, sm.DD, sm.E, sm.Mf, sm.wtab, &chunk);
   // boxes (:392-395): argmax over [20, H-20), then over [first + 5, H-20); per-chunk maxima come out of the backward pass,
   // warps reduce them with shuffles, thread q < 4 merges the four warps of its sequence
   wallish_best_reduce(t, chunk, sm.red, sm.redi);

@@ -58,12 +58,16 @@ int main(int argc, char** argv) {
   for (int t = 0; t < 256; ++t) wallish_dst2_post(t, *(Regs*)&v[t * 16], S.data(), X.data(), twd.data());
   std::vector<double> out;
   for (int kk = 0; kk < G::N; ++kk) { out.push_back(X[wpos(kk & 1, kk >> 1)].x); out.push_back(X[wpos(kk & 1, kk >> 1)].y); }
-  for (int t = 0; t < 256; ++t) wallish_forward(t, X.data(), S.data(), wtab);
-  for (int t = 0; t < 256; ++t) wallish_backward_dd(t, X.data(), S.data(), DD.data(), wtab);
+  std::vector<double2> E(256);
+  std::vector<double> Mf(256);
+  for (int t = 0; t < 256; ++t) wallish_forward_local(t, X.data(), E.data(), Mf.data(), wtab);
+  for (int t = 0; t < 256; ++t) wallish_forward_store(t, X.data(), S.data(), E.data(), Mf.data(), wtab);
+  for (int t = 0; t < 256; ++t) wallish_backward_local(t, S.data(), E.data(), Mf.data(), wtab);
+  for (int t = 0; t < 256; ++t) wallish_backward_dd(t, X.data(), S.data(), DD.data(), E.data(), Mf.data(), wtab);
   for (int h = 0; h < 2; ++h) for (int i = 0; i < G::H; ++i) { out.push_back(DD[wpos(h, i)].x); out.push_back(DD[wpos(h, i)].y); }
   // argmax boxes: per-chunk maxima from the backward pass, merged in thread order (the kernel merges with warp shuffles)
   std::vector<WallishBest> chunk(256), cand(256);
-  for (int t = 0; t < 256; ++t) wallish_backward_dd(t, X.data(), S.data(), DD.data(), wtab, &chunk[t]);
+  for (int t = 0; t < 256; ++t) wallish_backward_dd(t, X.data(), S.data(), DD.data(), E.data(), Mf.data(), wtab, &chunk[t]);
   auto merge = [&](const std::vector<WallishBest>& b, int q) {
     double v = 0.; int i = -1;
     for (int t = 128 * (q >> 1); t < 128 * (q >> 1) + 128; ++t) wallish_best_merge(v, i, (q & 1) ? b[t].vy : b[t].vx, (q & 1) ? b[t].iy : b[t].ix);
