@@ -15,8 +15,14 @@
 //     threads tau and tau + 128 share a lane and the same P2 twiddles, which makes room for the 8 + 8 pre/post factors
 //     of a thread in tensor memory too; the P2' twiddles are uniform over a half-warp and come from a 4 KB shared
 //     table with broadcast reads;
-//   * the rows of the next pair are loaded into registers right after the last DFT of the current pair, before its
-//     post-factor multiply and stores, and the pair after that is prefetched into L2.
+//   * full window (n = N/2): the two rows of a group's next pair arrive in a shared-memory staging buffer through TMA bulk
+//     copies issued one pair ahead (template parameter TMA); other windows load their samples directly, with the pair after
+//     next prefetched into L2;
+//   * the groups of the CTAs that share a plan row draw their pairs from a self-resetting ticket counter (DYN), which evens
+//     out the different speeds of the SMs; small launches keep the static split;
+//   * launched with programmatic stream serialisation: the prologue (TMEM allocation, tables) overlaps the tail of the previous
+//     kernel of the stream, `griddepcontrol.wait` precedes the first access to caller data;
+//   * non-finite samples are zeroed on load and their row is written as NaN (two rows share one complex FFT).
 #pragma once
 
 #include "cpf_stream_core.h"
