@@ -174,21 +174,30 @@ __global__ void __launch_bounds__(256, 1) wallish_fused_kernel(const WallishArgs
     }
   }
   __syncthreads();
-  // cut + re-spline (:396-401): right-hand sides of the 8 one-sided eliminations by all threads (DD is free now), the 8
-  // chains on 8 threads, the 2x2 solves on 4
-  double* gr = reinterpret_cast<double*>(sm.DD);
+  // cut + re-spline (:396-401): the 8 one-sided eliminations (4 sequences x 2 sides, at most WARM = 32 rows each) run one per warp,
+  // one row per lane: a row's step d -> (r - lo d) w is the affine map d -> a d + b with a = -lo w, b = r w, and the maps are
+  // composed in row order by a shuffle tree (5 rounds) instead of a 32-step chain on one thread (14 % of the kernel's stall
+  // samples sat on the barrier behind those chains).  Then the 2x2 solves on 4 threads.
   {
-    const int e = t >> 5, q = e >> 1;                  // warp e runs elimination e: sequence q, side e & 1
+    static_assert(G::WARM == 32, "one elimination row per lane");
+    const int e = t >> 5, lane = t & 31, q = e >> 1, side = e & 1;
     const int b0 = sm.box[2 * q], b1 = sm.box[2 * q + 1];
-    const bool ok = wallish_gap_ok(b0, b1);
-    for (int step = t & 31; step < G::WARM; step += 32)
-      gr[e * G::WARM + step] = ok ? wallish_gap_rhs(sm.X, q >> 1, q & 1, wallish_gap_row(b0, b1, e & 1, step)) : 0.;
-  }
-  __syncthreads();
-  if (t < 8) {
-    const int q = t >> 1;
-    const int b0 = sm.box[2 * q], b1 = sm.box[2 * q + 1];
-    sm.red[t] = wallish_gap_ok(b0, b1) ? wallish_gap_chain(gr + t * G::WARM, b0, b1, t & 1, sm.wtab) : 0.;
+    double fa = 1., fb = 0.;                             // identity for lanes without a row
+    if (wallish_gap_ok(b0, b1)) {
+      const int i = wallish_gap_row(b0, b1, side, lane);
+      if (i >= 0) {
+        const bool edge = (i == 0 || i == G::H - 1);
+        const double w = wpivot(sm.wtab, side ? G::H - 1 - i : i, G::H);
+        fa = edge ? 0. : -w;
+        fb = wallish_gap_rhs(sm.X, q >> 1, q & 1, i) * w;
+      }
+    }
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {             // lane l ends up with the composition of rows l .. l + 2 off - 1, in order
+      const double ha = __shfl_down_sync(0xffffffffu, fa, off), hb = __shfl_down_sync(0xffffffffu, fb, off);
+      if (lane + off < 32) { fb = fma(ha, fb, hb); fa = ha * fa; }
+    }
+    if (lane == 0) sm.red[e] = fb;                       // reduced right-hand side at the last eliminated row (zero inflow)
   }
   __syncthreads();
   if (t < 4) sm.gaps[t] = wallish_gap_finish(sm.X, t >> 1, t & 1, sm.box[2 * t], sm.box[2 * t + 1], sm.red[2 * t], sm.red[2 * t + 1], sm.wtab);
