@@ -39,8 +39,13 @@ UNIT = 'transforms/s'
 # algorithmic work per transform, SURVEY.md §8(d) / BASELINE.md §3
 BYTES_PER_TRANSFORM = 16 * NK
 FLOPS_PER_TRANSFORM = 2 * 2.5 * (2 * NK) * np.log2(2 * NK) + 2 * NK + 6 * (NK + 1) + NK     # = 264198
-CPU_SAMPLE_COSMO = 256     # cosmologies per worker and repetition in the CPU legs
 QUICK = bool(os.environ.get('CPF_BENCH_QUICK'))   # profiler runs: no time-based warm-up / sustain loops
+
+
+def scale_aware(G, G_ref, post):
+    """SURVEY.md 8(d) parity metric: per row, max |dG| |w| / max |G_ref w| with w = 1/post (the biased space, where FFT rounding is uniform)."""
+    w = 1. / np.abs(post)
+    return np.max(np.abs(G - G_ref) * w, axis=-1) / np.max(np.abs(G_ref) * w, axis=-1)
 
 
 def make_inputs(ncosmo, seed):
@@ -51,73 +56,158 @@ def make_inputs(ncosmo, seed):
 
 
 # ---------------------------------------------------------------------------------------------------------------
-# CPU legs (oracle port of the reference path).  Workers are spawned processes that import numpy + oracle only.
+# CPU legs: the UNMODIFIED reference from baseline/_ref (kind "reference"), driven through its own public API
+#     cosmoprimo.fftlog.PowerToCorrelation(k, ell=[0, 2, 4], engine='numpy')(fun)
+# on all host cores (numpy's pocketfft is single-threaded: one process per core, each with its slice of the SAME 4096 cosmologies,
+# seed 42, that the GPU arm transforms).  Falls back to the oracle port (kind "port", the same numpy calls) only if the reference
+# cannot be imported.  Workers are spawned processes that never import torch or the CUDA library.
 # ---------------------------------------------------------------------------------------------------------------
-_W = {}
+def workload_config():
+    return {'workload': 'P(k)->xi multipoles ell=0,2,4, nk=2048, 4096 synthetic EH cosmologies per GPU (BASELINE configs[1])',
+            'transforms_per_step_per_gpu': NCOSMO * len(ELLS), 'nk': NK, 'padded_size': 2 * NK, 'seed': 42,
+            'l2': 'inputs+outputs (403 MB/step) larger than L2, no flush', 'partition': 'rows split over ranks, no collective'}
 
 
-def _cpu_init(root, seed_base):
-    os.environ['OMP_NUM_THREADS'] = '1'
+def reference_available():
+    base = os.path.join(ROOT, 'baseline')
+    sys.path.insert(0, base)
+    try:
+        import install_reference
+        return install_reference.activate() is not None
+    except Exception:
+        return False
+    finally:
+        sys.path.remove(base)
+
+
+def _cpu_worker(root, index, cores, ncosmo, engine, nthreads, start, done, reps, stop, ready):
+    os.environ['OMP_NUM_THREADS'] = str(nthreads)
+    sys.dont_write_bytecode = True
     if root not in sys.path:
         sys.path.insert(0, root)
-    from oracle import fftlog_oracle as O
-    k, fun = make_inputs(CPU_SAMPLE_COSMO, seed_base + os.getpid() % 1000)
-    _W['O'], _W['plan'], _W['fun'] = O, O.plan_power_to_correlation(k, ell=ELLS), fun
+    try:
+        from cosmoprimo_b200 import synthetic
+        k = np.geomspace(1e-5, 1e2, NK)
+        lo, hi = ncosmo * index // cores, ncosmo * (index + 1) // cores
+        par = {name: val[lo:hi] for name, val in synthetic.lhs_cosmologies(ncosmo, seed=42).items()}
+        fun = synthetic.kaiser_multipoles(synthetic.eh_pk(k, par), np.full(hi - lo, 0.76))
+        if engine == 'port':
+            from oracle import fftlog_oracle as O
+            plan = O.plan_power_to_correlation(k, ell=ELLS)
+            call = lambda: O.execute(plan, fun)
+        else:
+            assert reference_available()
+            from cosmoprimo.fftlog import PowerToCorrelation
+            kw = {'nthreads': nthreads} if engine == 'fftw' else {}
+            fftlog = PowerToCorrelation(k, ell=ELLS, engine=engine, **kw)
+            call = lambda: fftlog(fun)
+        call()
+        ready.value = 1
+    except Exception as exc:       # reported by the parent
+        sys.stderr.write('cpu worker {}: {!r}\n'.format(index, exc))
+        ready.value = -1
+        call = lambda: None
+    while True:
+        start.wait()
+        if stop.value:
+            break
+        for _ in range(reps.value):
+            call()
+        done.wait()
 
 
-def _cpu_step(reps):
-    O, plan, fun = _W['O'], _W['plan'], _W['fun']
-    t0 = time.perf_counter()
-    for _ in range(reps):
-        O.execute(plan, fun)
-    return reps * fun.shape[0] * fun.shape[1], time.perf_counter() - t0
+class CpuArm(object):
+    """`cores` persistent worker processes; step() = every worker transforms its slice of the 4096-cosmology batch `reps` times."""
 
-
-class CpuPool(object):
-
-    def __init__(self, cores=None):
+    def __init__(self, engine, cores=None, ncosmo=NCOSMO, nthreads=1):
         import multiprocessing as mp
-        from concurrent.futures import ProcessPoolExecutor
+        ctx = mp.get_context('spawn')
         self.cores = cores or len(os.sched_getaffinity(0))
-        self.pool = ProcessPoolExecutor(max_workers=self.cores, mp_context=mp.get_context('spawn'),
-                                        initializer=_cpu_init, initargs=(ROOT, 1000))
-        self.step(1)   # start every worker
+        self.engine, self.ncosmo, self.nthreads = engine, ncosmo, nthreads
+        self.start, self.done = ctx.Barrier(self.cores + 1), ctx.Barrier(self.cores + 1)
+        self.reps, self.stop = ctx.Value('i', 1), ctx.Value('i', 0)
+        self.ready = [ctx.Value('i', 0) for _ in range(self.cores)]
+        self.procs = [ctx.Process(target=_cpu_worker, args=(ROOT, i, self.cores, ncosmo, engine, nthreads, self.start, self.done, self.reps, self.stop,
+                                                            self.ready[i]), daemon=True) for i in range(self.cores)]
+        for p in self.procs:
+            p.start()
+        self.step(1)   # every worker has built its plan and input
+        if any(r.value != 1 for r in self.ready):
+            self.close()
+            raise RuntimeError('a CPU worker could not set up engine {!r}'.format(engine))
 
-    def step(self, reps):
-        """All workers transform their sample `reps` times concurrently; returns (transforms, wall seconds)."""
+    def step(self, reps=1):
+        """Returns (transforms, wall seconds) of one step."""
+        self.reps.value = reps
+        self.start.wait()
         t0 = time.perf_counter()
-        res = list(self.pool.map(_cpu_step, [reps] * self.cores))
-        return sum(r[0] for r in res), time.perf_counter() - t0
+        self.done.wait()
+        return reps * self.ncosmo * len(ELLS), time.perf_counter() - t0
 
     def close(self):
-        self.pool.shutdown()
+        self.stop.value = 1
+        try:
+            self.start.wait(timeout=10)
+        except Exception:
+            pass
+        for p in self.procs:
+            p.join(timeout=10)
+            if p.is_alive():
+                p.kill()
+
+    def describe(self):
+        what = {'numpy': "UNMODIFIED reference from baseline/_ref: cosmoprimo.fftlog.PowerToCorrelation(k, ell=[0,2,4], engine='numpy')(fun)",
+                'fftw': "UNMODIFIED reference from baseline/_ref: engine='fftw' (pyfftw, nthreads={})".format(self.nthreads),
+                'port': 'oracle port of the reference numpy engine (reference not importable here)'}[self.engine]
+        return '{}; numpy {} pocketfft; {} processes x 1 thread, each a slice of the same {} cosmologies x 3 ell (seed 42) = {} transforms per step'.format(
+            what, np.__version__, self.cores, self.ncosmo, self.ncosmo * len(ELLS))
 
 
-def cpu_sample_desc(cores, reps):
-    return ('oracle port of cosmoprimo numpy engine (numpy {} pocketfft, 1 thread/process): {} processes x {} reps x '
-            '({} cosmologies x 3 ell, nk={}) per step').format(np.__version__, cores, reps, CPU_SAMPLE_COSMO, NK)
+def cpu_arm(cores=None):
+    if reference_available():
+        try:
+            return CpuArm('numpy', cores=cores), 'reference'
+        except RuntimeError:
+            pass
+    return CpuArm('port', cores=cores), 'port'
+
+
+def pyfftw_leg(cores):
+    """the reference's engine='fftw' with nthreads = cores, if pyfftw imports on this box; else say so."""
+    try:
+        import pyfftw  # noqa: F401
+    except Exception:
+        return {'pyfftw': 'pyfftw unavailable', 'nthreads': None}
+    try:
+        arm = CpuArm('fftw', cores=1, nthreads=cores)
+        n, t = arm.step(1)
+        arm.close()
+        return {'pyfftw': 'available', 'nthreads': cores, 'value': n / t, 'unit': UNIT}
+    except Exception as exc:
+        return {'pyfftw': 'pyfftw import ok but engine failed: {!r}'.format(exc), 'nthreads': cores}
 
 
 def run_reference(args):
     rank = int(os.environ.get('RANK', 0))
     if rank != 0:
         return
-    reps = 2
-    pool = CpuPool()
+    arm, kind = cpu_arm()
     for _ in range(max(args.warmup, 1)):
-        pool.step(reps)
-    total, t0 = 0, time.perf_counter()
+        arm.step(1)
+    total, elapsed = 0, 0.
     for _ in range(args.steps):
-        total += pool.step(reps)[0]
-    elapsed = time.perf_counter() - t0
-    pool.close()
+        n, t = arm.step(1)
+        total, elapsed = total + n, elapsed + t
+    single = CpuArm(arm.engine, cores=1, ncosmo=256)
+    n1, t1 = single.step(1)
+    single.close()
+    arm.close()
     value = total / elapsed
     out = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
            'warmup': args.warmup, 'ms_per_step': 1e3 * elapsed / args.steps, 'higher_is_better': True, 'scaling': 'weak',
-           'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-           'config': {'workload': 'P(k)->xi multipoles ell=0,2,4, nk=2048, synthetic EH cosmologies (BASELINE configs[1])',
-                      'batch': '{} cosmologies x 3 ell per worker and rep'.format(CPU_SAMPLE_COSMO), 'nk': NK, 'padded_size': 2 * NK},
-           'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': pool.cores, 'kind': 'port', 'sample': cpu_sample_desc(pool.cores, reps)},
+           'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': workload_config(),
+           'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': arm.cores, 'kind': kind, 'sample': arm.describe(), 'value_1core': n1 / t1,
+                            'threads_per_process': 1, 'pyfftw': pyfftw_leg(arm.cores)},
            'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
            'gpu_launches': 0}
     print(json.dumps(out))
@@ -273,9 +363,10 @@ def run_ours(args):
     torch.cuda.synchronize()
     e2e_elapsed = max_over_ranks(time.perf_counter() - t0)
     e2e_value = world * per_step * e2e_steps / e2e_elapsed
-    # the host path runs the per-pair kernel on 16 MB chunks, the device path the persistent kernel: same transform, different rounding
+    # `out` is the result of the TIMED launches (persistent stream kernel); `h_out` went through the host path (16 MB chunks)
     d_out = out.cpu().numpy()
-    assert np.max(np.abs(h_out - d_out)) <= 1e-13 * np.max(np.abs(d_out))
+    post = fftlog.padded_postfactor[:, fftlog.padded_size_out_left:fftlog.padded_size_out_left + NK]
+    assert float(np.max(scale_aware(h_out, d_out, post))) <= 1e-12       # two kernel families, same transform: per row, scale-aware
 
     if rank != 0:
         return
@@ -303,32 +394,33 @@ def run_ours(args):
     result = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': warm,
               'ms_per_step': 1e3 * elapsed / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
               'dtype': 'f64', 'data': 'synthetic',
-              'config': {'workload': 'P(k)->xi multipoles ell=0,2,4, nk=2048, 4096 synthetic EH cosmologies per GPU (BASELINE configs[1])',
-                         'transforms_per_step_per_gpu': per_step, 'nk': NK, 'padded_size': 2 * NK,
-                         'l2': 'inputs+outputs (403 MB/step) larger than L2, no flush', 'partition': 'rows split over ranks, no collective'},
+              'config': workload_config(),
               'clocks': clocks,
               'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(fun.nbytes), 'd2h_bytes_per_step': int(h_out.nbytes), 'steps': e2e_steps},
               'gpu_launches': args.steps, 'roofline': roof}
 
     if world == 1 and not args.no_cpu_baseline:
-        # CPU baseline + parity of the GPU result against the oracle on the same sample
+        # parity of the TIMED kernel's own output (every row of the 4096-cosmology batch would take the CPU minutes: the first 256 cosmologies,
+        # 768 rows) against the oracle, scale-aware per row, and of the host-path output on the same rows
         from oracle import fftlog_oracle as O
-        ref = O.execute(O.plan_power_to_correlation(k, ell=ELLS), fun[:64])[1]
-        post = fftlog.padded_postfactor[:, fftlog.padded_size_out_left:fftlog.padded_size_out_left + NK]
-        result['parity'] = {'scale_aware_max_err': float(np.max(O.scale_aware_error(h_out[:64], ref, post))), 'rows': 64 * 3, 'tol': 1e-10}
-        pool = CpuPool()
-        reps = 2
-        pool.step(reps)
+        nchk = 256
+        ref = O.execute(O.plan_power_to_correlation(k, ell=ELLS), fun[:nchk])[1]
+        result['parity'] = {'scale_aware_max_err': float(np.max(O.scale_aware_error(d_out[:nchk], ref, post))), 'what': 'output of the timed fftlog_stream_kernel launches vs oracle',
+                            'host_path_scale_aware_max_err': float(np.max(O.scale_aware_error(h_out[:nchk], ref, post))), 'rows': nchk * 3, 'tol': 1e-10}
+        assert result['parity']['scale_aware_max_err'] <= 1e-10 and result['parity']['host_path_scale_aware_max_err'] <= 1e-10
+        # CPU baseline: the reference itself (baseline/_ref) on all host cores, the same 4096 cosmologies; best of 5 steps
+        arm, kind = cpu_arm()
+        arm.step(1)
         best = 0.
         for _ in range(5):
-            n, t = pool.step(reps)
+            n, t = arm.step(1)
             best = max(best, n / t)
-        pool.close()
-        single = CpuPool(cores=1)
-        n, t = single.step(reps)
+        single = CpuArm(arm.engine, cores=1, ncosmo=256)
+        n1, t1 = single.step(1)
         single.close()
-        result['cpu_baseline'] = {'value': best, 'unit': UNIT, 'cores': pool.cores, 'kind': 'port', 'sample': cpu_sample_desc(pool.cores, reps),
-                                  'value_1core': n / t}
+        arm.close()
+        result['cpu_baseline'] = {'value': best, 'unit': UNIT, 'cores': arm.cores, 'kind': kind, 'sample': arm.describe(), 'value_1core': n1 / t1,
+                                  'threads_per_process': 1, 'pyfftw': pyfftw_leg(arm.cores)}
     print(json.dumps(result))
     if world > 1:
         dist.destroy_process_group()

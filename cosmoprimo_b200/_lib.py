@@ -30,6 +30,8 @@ SIGNATURES = {
     'cpf_version': (_i, []),
     'cpf_last_error': (ctypes.c_char_p, []),
     'cpf_device_count': (_i, [ctypes.POINTER(_i)]),
+    'cpf_trim': (_i, [_i]),
+    'cpf_counter': (_i64, [_i]),
     'cpf_plan_create': (_i, [ctypes.POINTER(_vp), _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i]),
     'cpf_plan_destroy': (_i, [_vp]),
     'cpf_plan_kernel_family': (_i, [_vp, _i, _d, _i, _d, _i]),

@@ -45,28 +45,23 @@ struct DeviceGuard {
   }
 };
 
-// Stream-ordered scratch buffer: freed (stream-ordered) when it goes out of scope.
+// Scratch memory comes from a PRIVATE stream-ordered pool per device (never the device's default pool, whose attributes belong to the
+// host application: torch / JAX allocate next to this library).  The pool keeps at most CPF_SCRATCH_KEEP_MB (default 2048) MiB of
+// unused memory across synchronisations, so that repeated calls recycle their scratch instead of going back to the driver (~100 us per
+// allocation, milliseconds for GB-sized scratch) while a large one-off call cannot hold on to tens of GB; cpf_trim() returns it all.
+cudaMemPool_t scratch_pool(int device);      // cpf_fftlog.cu; nullptr on failure (alloc then reports the CUDA error)
+
 struct ScratchBuf {
   void* p = nullptr;
   cudaStream_t s = nullptr;
   cudaError_t alloc(size_t bytes, cudaStream_t stream) {
     s = stream;
-    keep_pool_warm();
-    return cudaMallocAsync(&p, bytes ? bytes : 1, stream);
-  }
-  // The default memory pool hands its free blocks back to the driver at every synchronisation (release threshold 0), which
-  // makes each cudaMallocAsync after a sync a fresh driver allocation (~100 us, milliseconds for GB-sized scratch).  Raise
-  // the threshold once per device so that scratch memory is recycled inside the pool.
-  static void keep_pool_warm() {
-    static bool done[64] = {};
     int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || done[dev]) return;
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-      uint64_t threshold = UINT64_MAX;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
-    }
-    done[dev] = true;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    cudaMemPool_t pool = scratch_pool(dev);
+    if (!pool) return cudaErrorMemoryAllocation;
+    return cudaMallocFromPoolAsync(&p, bytes ? bytes : 1, pool, stream);
   }
   ~ScratchBuf() {
     if (p) cudaFreeAsync(p, s);

@@ -64,7 +64,19 @@ struct FftlogArgs {
   int ex_l_mode, ex_r_mode;
   double ex_l_val, ex_r_val;
   unsigned* tickets;       // ping-pong kernel with dynamic scheduling: one self-resetting ticket counter per plan row, else null
+  unsigned* t_finished;    // ... the slot's CTA exit counter (self-resetting) and its completion word in mapped host memory
+  unsigned* t_done;
+  unsigned t_seq;
 };
+
+// Last instruction of a dynamically scheduled kernel: the CTA that exits last publishes the launch's sequence number in mapped host
+// memory, which is how the host knows that the slot's counters are back at zero before it hands the slot to another launch.
+__device__ __forceinline__ void ticket_release(unsigned* finished, unsigned* done, const unsigned seq) {
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicInc(finished, gridDim.x - 1) == gridDim.x - 1) { *reinterpret_cast<volatile unsigned*>(done) = seq; __threadfence_system(); }
+  }
+}
 
 // Two real rows ride one complex FFT, so a NaN / Inf in one row would spoil its partner, which the reference's row-wise
 // numpy FFTs do not do.  Every kernel therefore replaces non-finite samples by zero on load, ORs "row a is bad" / "row b is
@@ -348,6 +360,30 @@ static double2 unit_root(long long num, long long den) {   // exp(-2 pi i num/de
   return r;
 }
 
+std::atomic<long long> g_stat_dynamic{0}, g_stat_fallback{0};      // cpf_counter
+
+// private scratch pool per device (see cpf_common.h)
+static std::mutex g_pool_mutex;
+static cudaMemPool_t g_pools[64] = {};
+
+cudaMemPool_t scratch_pool(int device) {
+  if (device < 0 || device >= 64) return nullptr;
+  std::lock_guard<std::mutex> lock(g_pool_mutex);
+  if (g_pools[device]) return g_pools[device];
+  cudaMemPoolProps props = {};
+  props.allocType = cudaMemAllocationTypePinned;
+  props.handleTypes = cudaMemHandleTypeNone;
+  props.location.type = cudaMemLocationTypeDevice;
+  props.location.id = device;
+  cudaMemPool_t pool = nullptr;
+  if (cudaMemPoolCreate(&pool, &props) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  uint64_t keep = 2048ull << 20;
+  if (const char* e = getenv("CPF_SCRATCH_KEEP_MB")) { const long long v = atoll(e); if (v >= 0) keep = (uint64_t)v << 20; }
+  cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  g_pools[device] = pool;
+  return pool;
+}
+
 int upload(void** dptr, const void* src, size_t bytes) {
   CPF_CUDA(cudaMalloc(dptr, bytes ? bytes : 1));
   CPF_CUDA(cudaMemcpy(*dptr, src, bytes, cudaMemcpyHostToDevice));
@@ -509,12 +545,6 @@ static int stage_pool(int device, StagePool** out) {
     CPF_CUDA(cudaEventCreateWithFlags(&sp->out_free[i], cudaEventDisableTiming));
   }
   CPF_CUDA(cudaEventCreateWithFlags(&sp->start, cudaEventDisableTiming));
-  // keep freed scratch in the pool instead of returning it to the OS after every call
-  cudaMemPool_t pool;
-  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-    uint64_t thr = UINT64_MAX;
-    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-  }
   g_stage_pools.push_back(sp);
   *out = sp;
   return CPF_OK;
@@ -559,6 +589,27 @@ int cpf_device_count(int* count) {
   cudaError_t e = cudaGetDeviceCount(&c);
   if (e != cudaSuccess) return fail(CPF_ECUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
   *count = c;
+  return CPF_OK;
+}
+
+int64_t cpf_counter(int which) {
+  switch (which) {
+    case CPF_COUNTER_DYNAMIC_LAUNCHES: return cpf::g_stat_dynamic.load();
+    case CPF_COUNTER_TICKET_FALLBACKS: return cpf::g_stat_fallback.load();
+    default: return -1;
+  }
+}
+
+int cpf_trim(int device) {
+  cudaMemPool_t pool = nullptr;
+  {
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    if (device >= 0 && device < 64) pool = g_pools[device];
+  }
+  if (!pool) return CPF_OK;             // nothing was ever allocated on that device
+  DeviceGuard guard(device);
+  CPF_CUDA(cudaDeviceSynchronize());
+  CPF_CUDA(cudaMemPoolTrimTo(pool, 0));
   return CPF_OK;
 }
 
@@ -704,23 +755,77 @@ static int launch_fast_r(const FftlogArgs& a, bool pruned, bool cpost, long long
   return cpost ? launch_fast<R1, false, true>(a, nblocks, stream) : launch_fast<R1, false, false>(a, nblocks, stream);
 }
 
-// Ticket counters of the dynamically scheduled persistent kernels: a per-device ring of kTicketSlots slots of kTicketSlotWords
-// counters.  A launch takes the next slot; its counters are back at zero when it completes (st_draw_ticket), and launches that
-// overlap (programmatic dependent launch, other streams) are on different slots unless more than kTicketSlots are in flight.
+// Ticket counters of the dynamically scheduled persistent kernels: a per-device ring of slots, each with kTicketSlotWords counters (one
+// per plan row), a CTA exit counter and a completion word in mapped host memory.  A launch takes the next slot of the ring; its counters
+// are back at zero when it completes (st_draw_ticket).  Before a slot is handed out again the host checks that its previous launch has
+// published its sequence number (ticket_release): a slot whose launch is still queued or running -- more launches in flight than slots,
+// whatever the streams -- or never finished is NOT reused, and the new launch takes the static split instead.  No reset kernel, no
+// synchronisation, one host read per launch.  CPF_TICKET_SLOTS (1..64, read once) shrinks the ring (tests).
 constexpr int kTicketSlots = 64, kTicketSlotWords = 64;
+struct TicketRing {
+  int device;
+  unsigned* counters;             // [kTicketSlots][kTicketSlotWords] device
+  unsigned* finished;             // [kTicketSlots] device
+  unsigned* done_dev;             // [kTicketSlots] device view of done_host
+  volatile unsigned* done_host;   // [kTicketSlots] mapped, page-locked
+  unsigned assigned[kTicketSlots];
+  unsigned next;
+};
+struct TicketLease {
+  unsigned *counters, *finished, *done;
+  unsigned seq;
+};
 static std::atomic<unsigned> g_ticket_seq{0};
 static std::mutex g_ticket_mutex;
-static std::vector<std::pair<int, unsigned*>> g_ticket_rings;
+static std::vector<TicketRing*> g_ticket_rings;
 
-static int ticket_ring(int device, unsigned** out) {
+static int ticket_slots() {
+  static const int n = [] {
+    const char* e = getenv("CPF_TICKET_SLOTS");
+    const int v = e ? atoi(e) : kTicketSlots;
+    return v < 1 ? 1 : (v > kTicketSlots ? kTicketSlots : v);
+  }();
+  return n;
+}
+
+// *ok = false: every candidate slot is still in flight, the caller uses the static split
+static int ticket_acquire(int device, TicketLease* lease, bool* ok) {
   std::lock_guard<std::mutex> lock(g_ticket_mutex);
-  for (auto& e : g_ticket_rings)
-    if (e.first == device) { *out = e.second; return CPF_OK; }
-  unsigned* p = nullptr;
-  CPF_CUDA(cudaMalloc(&p, (size_t)kTicketSlots * kTicketSlotWords * sizeof(unsigned)));
-  CPF_CUDA(cudaMemset(p, 0, (size_t)kTicketSlots * kTicketSlotWords * sizeof(unsigned)));
-  g_ticket_rings.emplace_back(device, p);
-  *out = p;
+  TicketRing* ring = nullptr;
+  for (auto* e : g_ticket_rings)
+    if (e->device == device) ring = e;
+  if (!ring) {
+    ring = new TicketRing();
+    ring->device = device;
+    ring->next = 0;
+    memset(ring->assigned, 0, sizeof(ring->assigned));
+    void* host = nullptr;
+    CPF_CUDA(cudaMalloc(&ring->counters, (size_t)kTicketSlots * kTicketSlotWords * sizeof(unsigned)));
+    CPF_CUDA(cudaMemset(ring->counters, 0, (size_t)kTicketSlots * kTicketSlotWords * sizeof(unsigned)));
+    CPF_CUDA(cudaMalloc(&ring->finished, kTicketSlots * sizeof(unsigned)));
+    CPF_CUDA(cudaMemset(ring->finished, 0, kTicketSlots * sizeof(unsigned)));
+    CPF_CUDA(cudaHostAlloc(&host, kTicketSlots * sizeof(unsigned), cudaHostAllocMapped | cudaHostAllocPortable));
+    memset(host, 0, kTicketSlots * sizeof(unsigned));
+    ring->done_host = static_cast<volatile unsigned*>(host);
+    CPF_CUDA(cudaHostGetDevicePointer((void**)&ring->done_dev, host, 0));
+    g_ticket_rings.push_back(ring);
+  }
+  const unsigned slot = ring->next % (unsigned)ticket_slots();
+  if (ring->assigned[slot] != 0 && ring->done_host[slot] != ring->assigned[slot]) {      // its last launch has not completed yet
+    *ok = false;
+    g_stat_fallback.fetch_add(1);
+    return CPF_OK;
+  }
+  ring->next++;
+  unsigned seq = g_ticket_seq.fetch_add(1u) + 1u;
+  if (seq == 0) seq = g_ticket_seq.fetch_add(1u) + 1u;
+  ring->assigned[slot] = seq;
+  lease->counters = ring->counters + (size_t)slot * kTicketSlotWords;
+  lease->finished = ring->finished + slot;
+  lease->done = ring->done_dev + slot;
+  lease->seq = seq;
+  *ok = true;
+  g_stat_dynamic.fetch_add(1);
   return CPF_OK;
 }
 
@@ -748,10 +853,13 @@ static int launch_pp(const FftlogArgs& a, const double2* tab, cudaStream_t strea
     // this kernel is already balanced; kept behind CPF_PP_DYNAMIC=1 (covered by the GPU tests through that variable)
     const char* dyn_env = getenv("CPF_PP_DYNAMIC");
     if ((dyn_env && dyn_env[0] == '1') && a.P <= kTicketSlotWords && a.pairs_per_p >= 8LL * grid * NG) {
-      unsigned* ring = nullptr;
-      CPF_TRY(ticket_ring(dev, &ring));
-      b.tickets = ring + (size_t)(g_ticket_seq.fetch_add(1u) % kTicketSlots) * kTicketSlotWords;
-      kern = fftlog_pp_kernel<R1, true, true>;
+      TicketLease lease;
+      bool ok = false;
+      CPF_TRY(ticket_acquire(dev, &lease, &ok));
+      if (ok) {
+        b.tickets = lease.counters; b.t_finished = lease.finished; b.t_done = lease.done; b.t_seq = lease.seq;
+        kern = fftlog_pp_kernel<R1, true, true>;
+      }
     }
   }
   CPF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -799,7 +907,8 @@ static int launch_stream(const cpf_plan* pl, const FftlogArgs& a, cudaStream_t s
   int smem_bytes = ST_SMEM_BYTES;
   const char* tma_env = getenv("CPF_STREAM_TMA");
   const bool want_tma = !tma_env || tma_env[0] != '0';
-  s.tickets = nullptr;
+  s.tickets = s.t_finished = s.t_done = nullptr;
+  s.t_seq = 0;
   if (fullwin && want_tma && ((uintptr_t)a.in % 16 == 0) && (s.in_row % 2 == 0) && (s.in_p % 2 == 0)) {
     kern = (kern_t)fftlog_stream_kernel<true, 0, true>;
     smem_bytes = ST_SMEM_BYTES_TMA;
@@ -807,10 +916,13 @@ static int launch_stream(const cpf_plan* pl, const FftlogArgs& a, cudaStream_t s
     const char* dyn_env = getenv("CPF_STREAM_DYNAMIC");
     const long long ctas_per_row = (grid + a.P - 1) / a.P;
     if (!(dyn_env && dyn_env[0] == '0') && grid >= a.P && a.P <= kTicketSlotWords && a.pairs_per_p >= 8 * ctas_per_row) {
-      unsigned* ring = nullptr;
-      CPF_TRY(ticket_ring(dev, &ring));
-      s.tickets = ring + (size_t)(g_ticket_seq.fetch_add(1u) % kTicketSlots) * kTicketSlotWords;
-      kern = (kern_t)fftlog_stream_kernel<true, 0, true, true>;
+      TicketLease lease;
+      bool ok = false;
+      CPF_TRY(ticket_acquire(dev, &lease, &ok));
+      if (ok) {
+        s.tickets = lease.counters; s.t_finished = lease.finished; s.t_done = lease.done; s.t_seq = lease.seq;
+        kern = (kern_t)fftlog_stream_kernel<true, 0, true, true>;
+      }
     }
   }
 #ifdef CPF_LAB
@@ -1036,6 +1148,7 @@ static int run_staged(int device, const double* in, size_t in_row_doubles, doubl
   cap = cap < 2 ? 2 : (cap & ~1LL);                 // even, so that row pairs never straddle chunks
   long long small = (long long)(small_bytes / (row_bytes ? row_bytes : 1));
   small = small < 2 ? 2 : (small & ~1LL);
+  if (small > cap) small = cap;                     // chunk_schedule never emits more than max(small, cap) rows: keep that <= buf_rows
   const std::vector<long long> sched = chunk_schedule(rows, small, cap);
   void* zout = nullptr;
   const bool direct_out = !out_dev && host_direct_out_enabled() && pinned_device_pointer(out, &zout);
@@ -1117,7 +1230,8 @@ int cpf_fftlog(const cpf_plan* pl, const double* in, int64_t batch, int in_has_P
   if (guard.err != cudaSuccess) return fail(CPF_ECUDA, "cudaSetDevice(%d): %s", pl->device, cudaGetErrorString(guard.err));
 
   FftlogArgs a;
-  a.tickets = nullptr;
+  a.tickets = a.t_finished = a.t_done = nullptr;
+  a.t_seq = 0;
   a.pre = pl->d_pre;
   a.post_re = pl->d_post_re;
   a.post_im = pl->d_post_im;

@@ -366,6 +366,7 @@ __global__ void __launch_bounds__(512, 1) fftlog_pp_kernel(const FftlogArgs a, c
   }
   tmem_fence_before();
   __syncthreads();
+  if (DYN) ticket_release(a.t_finished, a.t_done, a.t_seq);
   if (warp == 0) tmem_dealloc_all(s_tmem_base);
 }
 

@@ -111,6 +111,9 @@ struct StreamArgs {
   long long* dbg;           // lab builds: per-CTA time stamps (globaltimer ns), else null
   int skew_ns;              // lab builds: group 1 starts its first pair this much later (phase offset between the groups)
   unsigned* tickets;        // dynamic scheduling (TMA variant, grid >= P): one self-resetting ticket counter per plan row, else null
+  unsigned* t_finished;     // ... with the slot's CTA exit counter and completion word (ticket_release, cpf_fftlog.cu)
+  unsigned* t_done;
+  unsigned t_seq;
 };
 
 // Work split: when there are at least as many CTAs as plan rows, every CTA works on ONE plan row (its tables are
@@ -395,6 +398,7 @@ __global__ void __launch_bounds__(512, 1) fftlog_stream_kernel(const StreamArgs 
   ST_STAMP(5);
   tmem_fence_before();
   __syncthreads();
+  if (dynamic) ticket_release(a.t_finished, a.t_done, a.t_seq);      // every draw of this CTA is done
   if (warp == 0) tmem_dealloc_all(s_tmem_base);
   ST_STAMP(6);
 }

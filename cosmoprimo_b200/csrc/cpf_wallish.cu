@@ -307,6 +307,7 @@ __global__ void wallish_final_kernel(const double* __restrict__ knots, const dou
   if (col >= ncols) return;
   const double k = kout[q];
   const int i = idx[q];
+  if (i < 0) { pknow[(long long)q * ncols + col] = nan(""); return; }
   const long long o = (long long)i * ncols + col;
   const double smooth = spline_poly(knots[i], knots[i + 1], vals[o], vals[o + ncols], slopes[o], slopes[o + ncols], k, 0);   // :420
   const double th = k > 1. ? exp(-400. * (k - 1.) * (k - 1.)) : 1.;                                                          // :425-431, scale=20
@@ -492,8 +493,9 @@ int cpf_wallish2018(const double* klin, const double* pklin, int nlin, const dou
   for (int i = 1; i < nknots; ++i) if (!(h_knots[i] > h_knots[i - 1])) return fail(CPF_EINVAL, "cpf_wallish2018: spliced knots are not increasing");
   std::vector<int> h_idx(nk);
   for (int q = 0; q < nk; ++q) {
-    if (h_kout[q] < h_knots[0] || h_kout[q] > h_knots[nknots - 1]) return fail(CPF_EINVAL, "cpf_wallish2018: kout outside the spliced knots");
-    h_idx[q] = spline_interval(h_knots.data(), nknots, h_kout[q]);
+    // outside the spliced knots the reference's CubicSpline(extrapolate=False) yields NaN (:420), hence pknow = NaN there (:422-423)
+    const bool outside = h_kout[q] < h_knots[0] || h_kout[q] > h_knots[nknots - 1];
+    h_idx[q] = outside ? -1 : spline_interval(h_knots.data(), nknots, h_kout[q]);
   }
 
   const size_t lin_bytes = (size_t)nlin * ncols * sizeof(double), out_bytes = (size_t)nk * ncols * sizeof(double);

@@ -10,6 +10,8 @@ arrays (torch / ``__cuda_array_interface__`` / DLPack) in -> torch tensors out.
 """
 
 import ctypes
+import threading
+import collections
 
 import numpy as np
 
@@ -290,7 +292,8 @@ class Interpolator2D(object):
         return tmp.astype(dtype).reshape(shape)
 
 
-_DEVICE_COPIES = {}
+_DEVICE_COPIES = collections.OrderedDict()       # LRU, guarded by a lock like the plan caches of fftlog.py (calls may come from several threads)
+_DEVICE_COPIES_LOCK = threading.Lock()
 
 
 def _device_copy(a, dev):
@@ -300,11 +303,16 @@ def _device_copy(a, dev):
     if a.nbytes > 65536:                       # large query sets are not worth remembering
         return torch.as_tensor(a, device=torch.device('cuda', dev))
     key = (dev, a.size, a.tobytes())
-    hit = _DEVICE_COPIES.get(key)
-    if hit is None:
-        if len(_DEVICE_COPIES) >= 16:
-            _DEVICE_COPIES.pop(next(iter(_DEVICE_COPIES)))
-        hit = _DEVICE_COPIES[key] = torch.as_tensor(a, device=torch.device('cuda', dev))
+    with _DEVICE_COPIES_LOCK:
+        hit = _DEVICE_COPIES.get(key)
+        if hit is not None:
+            _DEVICE_COPIES.move_to_end(key)
+            return hit
+    new = torch.as_tensor(a, device=torch.device('cuda', dev))
+    with _DEVICE_COPIES_LOCK:
+        hit = _DEVICE_COPIES.setdefault(key, new)
+        while len(_DEVICE_COPIES) > 16:
+            _DEVICE_COPIES.popitem(last=False)
     return hit
 
 

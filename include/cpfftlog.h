@@ -43,6 +43,15 @@ int cpf_version(void);
 const char* cpf_last_error(void);
 /* number of visible CUDA devices; *count = 0 with CPF_ECUDA when no driver/GPU is present */
 int cpf_device_count(int* count);
+/* Scratch memory (staging buffers of host-pointer calls, work arrays of cpf_wallish2018 / cpf_spline_eval_rows) comes from a private
+ * stream-ordered pool per device that keeps at most CPF_SCRATCH_KEEP_MB (environment, default 2048) MiB between calls; the device's
+ * default pool and its attributes are never touched.  cpf_trim synchronises the device and returns all unused scratch to the driver. */
+int cpf_trim(int device);
+/* process-wide diagnostic counters (tests): launches that used the ticket-counter scheduling / launches that took the static split because
+ * their ticket slot was still owned by a launch in flight; -1 for an unknown id */
+#define CPF_COUNTER_DYNAMIC_LAUNCHES 0
+#define CPF_COUNTER_TICKET_FALLBACKS 1
+int64_t cpf_counter(int which);
 
 /* ---- FFTLog plan: replaces the tables FFTlog._setup builds and the engine get_fft_engine returns -------------
  * (fftlog.py:144-184, 119-132, 641-663).  The host computes the tables exactly as the reference does (scipy

@@ -12,6 +12,24 @@ if ROOT not in sys.path:
 GOLDEN_DIR = os.path.join(ROOT, 'tests', 'golden')
 
 
+def reference(module=None):
+    """
+    The UNMODIFIED reference package, imported from baseline/_ref (installed by baseline/install_reference.py; it travels to the
+    GPU box) or, in the build container, from /root/reference.  Skips the calling test when neither exists.
+    """
+    import importlib
+    base = os.path.join(ROOT, 'baseline')
+    sys.path.insert(0, base)
+    try:
+        import install_reference
+    finally:
+        sys.path.remove(base)
+    if install_reference.activate() is None:
+        pytest.skip('reference not installed (run `python baseline/install_reference.py` where /root/reference exists)')
+    sys.dont_write_bytecode = True
+    return importlib.import_module('cosmoprimo' + ('.' + module if module else ''))
+
+
 def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: test needs a CUDA device (run on the B200 box with -m gpu)')
     # the shared library is built in-tree; build it here if it is missing or stale (nvcc cross-compiles without a GPU)
