@@ -74,7 +74,7 @@ struct FftlogArgs {
 __device__ __forceinline__ void ticket_release(unsigned* finished, unsigned* done, const unsigned seq) {
   if (threadIdx.x == 0) {
     __threadfence();
-    if (atomicInc(finished, gridDim.x - 1) == gridDim.x - 1) { *reinterpret_cast<volatile unsigned*>(done) = seq; __threadfence_system(); }
+    if (atomicInc(finished, gridDim.x - 1) == gridDim.x - 1) *reinterpret_cast<volatile unsigned*>(done) = seq;
   }
 }
 
@@ -438,8 +438,8 @@ struct FastTw {
   int device, N;
   double2* d_tw1;                 // per-pair kernel: [6, 256] factored pass-1 twiddles (cpf_fft_core.h)
   double2* d_tw2;                 // per-pair kernel: [6, 16]
-  double2* d_st_tw;               // stream kernel (N = 4096): P1 / P2 / P1' twiddles [3, 16, 256]
-  double2* d_m256;                // stream kernel: P2' twiddles w_256^{h l}, [16, 16]
+  double* d_st_tw;                // stream kernel (N = 4096): scaled twiddles + ratios of P1 / P2 / P1', [3, 32, 256] (st_build_tables)
+  double* d_m256;                 // stream kernel: P2' twiddles and P3' ratios, [2, 16, 16]
   std::vector<double2> pp_tw;     // host: twiddle part of the ping-pong records, [T][32]
 };
 static std::mutex g_fast_mutex;
@@ -452,7 +452,8 @@ static int fast_twiddles(int device, int N, const FastTw** out) {
   const int R1 = N / 256, T = 16 * R1, C = 16 / R1;
   FastTw* f = new FastTw();
   f->device = device; f->N = N;
-  f->d_tw1 = f->d_tw2 = f->d_st_tw = f->d_m256 = nullptr;
+  f->d_tw1 = f->d_tw2 = nullptr;
+  f->d_st_tw = f->d_m256 = nullptr;
   static const int expo[6] = {1, 2, 3, 4, 8, 12};
   std::vector<double2> tw1(6 * 256), tw2(6 * 16);
   for (int e = 0; e < 6; ++e) {
@@ -468,21 +469,11 @@ static int fast_twiddles(int device, int N, const FastTw** out) {
   int rc = upload((void**)&f->d_tw1, tw1.data(), tw1.size() * sizeof(double2));
   if (rc == CPF_OK) rc = upload((void**)&f->d_tw2, tw2.data(), tw2.size() * sizeof(double2));
   if (rc == CPF_OK && N == 4096) {
-    std::vector<double2> stw((size_t)48 * 256), m256(256);
-    for (int t = 0; t < 256; ++t) {
-      const int H = t >> 4, L = t & 15;
-      for (int k = 0; k < 16; ++k) {
-        stw[(size_t)k * 256 + t] = unit_root((long long)t * k, N);                        // P1 : w_4096^{tau k1}
-        stw[(size_t)(16 + k) * 256 + t] = unit_root(L * k, 256);                          // P2 : w_256^{L l1}
-        stw[(size_t)(32 + k) * 256 + t] = unit_root((long long)(H + 16 * L) * k, N);      // P1': w_4096^{(H + 16 L) k1'}
-      }
-    }
-    for (int hh = 0; hh < 16; ++hh)
-      for (int l = 0; l < 16; ++l) m256[16 * hh + l] = unit_root(hh * l, 256);
-    rc = upload((void**)&f->d_st_tw, stw.data(), stw.size() * sizeof(double2));
-    if (rc == CPF_OK) rc = upload((void**)&f->d_m256, m256.data(), m256.size() * sizeof(double2));
-    if (rc == CPF_OK && cudaMemcpyToSymbol(c_m256, m256.data(), m256.size() * sizeof(double2)) != cudaSuccess)
-      rc = fail(CPF_ECUDA, "cudaMemcpyToSymbol(c_m256) failed");
+    // scaled twiddles + butterfly ratios of the stream kernel (cpf_stream_core.h)
+    std::vector<double> stw((size_t)3 * 32 * 256), m256(512);
+    st_build_tables(stw.data(), m256.data());
+    rc = upload((void**)&f->d_st_tw, stw.data(), stw.size() * sizeof(double));
+    if (rc == CPF_OK) rc = upload((void**)&f->d_m256, m256.data(), m256.size() * sizeof(double));
   }
   if (rc != CPF_OK) {
     cudaFree(f->d_tw1); cudaFree(f->d_tw2); cudaFree(f->d_st_tw); cudaFree(f->d_m256);
@@ -901,7 +892,7 @@ static int launch_stream(const cpf_plan* pl, const FftlogArgs& a, cudaStream_t s
   CPF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   long long grid = (s.items + 1) / 2;
   if (grid > sms) grid = sms;
-  typedef void (*kern_t)(const StreamArgs, const double2*, const double2*, const double2*);
+  typedef void (*kern_t)(const StreamArgs, const double*, const double2*, const double2*);
   kern_t kern = fullwin ? (kern_t)fftlog_stream_kernel<true> : (kern_t)fftlog_stream_kernel<false>;
   // staged variant: bulk copies need 16-byte aligned rows; CPF_STREAM_TMA=0 selects the direct-load kernel (A/B runs)
   int smem_bytes = ST_SMEM_BYTES;
@@ -936,7 +927,6 @@ static int launch_stream(const cpf_plan* pl, const FftlogArgs& a, cudaStream_t s
       case 16: kern = fftlog_stream_kernel<true, 16>; break;
       case 32: kern = fftlog_stream_kernel<true, 32>; break;
       case 48: kern = fftlog_stream_kernel<true, 48>; break;
-      case 64: kern = fftlog_stream_kernel<true, 64>; break;
       default: break;
     }
   }
@@ -963,7 +953,7 @@ static int launch_stream(const cpf_plan* pl, const FftlogArgs& a, cudaStream_t s
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = (pdl_env && pdl_env[0] == '0') ? 0 : 1;
-  CPF_CUDA(cudaLaunchKernelEx(&cfg, kern, s, (const double2*)pl->fast->d_st_tw, (const double2*)pl->d_st_ut, (const double2*)pl->fast->d_m256));
+  CPF_CUDA(cudaLaunchKernelEx(&cfg, kern, s, (const double*)pl->fast->d_st_tw, (const double2*)pl->d_st_ut, (const double2*)pl->fast->d_m256));
 #ifdef CPF_LAB
   if (s.dbg && getenv("CPF_STREAM_DBG")[0] == '2') {     // print the time line of this launch (synchronises)
     std::vector<long long> h(8 * 256);

@@ -34,28 +34,13 @@ constexpr int ST_SMEM_BYTES = (2 * ST_GROUP_ELEMS + 256) * (int)sizeof(double2);
 constexpr int ST_STAGE_DOUBLES = 2 * 2048;
 constexpr int ST_SMEM_BYTES_TMA = ST_SMEM_BYTES + 2 * ST_STAGE_DOUBLES * (int)sizeof(double);
 
-// Lab variant (ABL bit 64): P2' twiddles w_256^{H l1} from constant memory instead of the 4 KB shared-memory copy.  They are
-// uniform over a half-warp, and the shared-memory loads are ~9 % of the kernel's wavefronts -- but two different constant
-// addresses per warp serialise in the constant cache: 69.0 M transforms/s against 78.2 M (r02z).  Kept for the record.
-__constant__ double2 c_m256[256];
-
-__device__ __forceinline__ void st_p2b_const(const int tau, double2* S) {
-  double2 w[16];
-  st_row_load(tau, S, w);
-  dft_dit<16, false, false>(w);
-  const double2* M16 = c_m256 + 16 * (tau >> 4);
-#pragma unroll
-  for (int l1 = 1; l1 < 16; ++l1) w[l1] = cmul(w[l1], M16[l1]);
-  st_row_store(tau, w, S);
-}
-
-// Tensor-memory layout of one lane (512 columns of 32 bits = 128 complex doubles).  Threads tau and tau + 128 of a
-// group share a lane (and have the same L = tau % 16, hence the same P2 twiddles); both groups read the same copy.
-//   [  0,  64)  P2 twiddles w_256^{L l1}                        (shared by the two halves)
+// Tensor-memory layout of one lane (512 columns of 32 bits = 256 doubles).  Threads tau and tau + 128 of a group share a lane (and have
+// the same L = tau % 16, hence the same P2 twiddles and P3 ratios); both groups read the same copy.  Regions as in cpf_stream_core.h:
+//   [  0,  64)  ST_TW2 : t of the P2 twiddles w_256^{L l1} + ratios of the P3 DFT          (shared by the two halves)
 //   half h = tau / 128 at 64 + 224 h:
-//   [+  0,+ 64) P1 twiddles  w_4096^{tau k1}
-//   [+ 64,+128) kernel spectrum at the bins H + 16 L + 256 l2
-//   [+128,+192) P1' twiddles w_4096^{(H + 16 L) k1'}
+//   [+  0,+ 64) ST_TW1 : t of the P1 twiddles w_4096^{tau k1} + ratios of the P2 DFT
+//   [+ 64,+128) ST_UT  : kernel spectrum at the bins H + 16 L + 256 l2
+//   [+128,+192) ST_TW1B: t of the P1' twiddles w_4096^{(H + 16 L) k1'} + ratios of the P2' DFT
 //   [+192,+208) pre-factor  at window elements tau + 256 r, r < 8   (8 doubles)
 //   [+208,+224) post-factor at window elements tau + 256 r, r < 8   (8 doubles)
 constexpr uint32_t ST_COL_HALF0 = 64, ST_COL_HALF = 224, ST_COL_PRE = 192, ST_COL_POST = 208;
@@ -72,6 +57,8 @@ struct TmemTables {
     tmem_ld4((TABLE == ST_TW2 ? lane : half + st_table_col(TABLE)) + 16u * ch, buf[b]);
   }
   __device__ __forceinline__ void wait(const int b) { tmem_wait4(buf[b]); }
+  template <int SET>
+  __device__ __forceinline__ double getd(const int, const int, const int b, const int i) const { return buf[b].getd(i); }
   template <int SET>
   __device__ __forceinline__ double2 get(const int, const int, const int b, const int i) const { return buf[b].get(i); }
 };
@@ -155,18 +142,19 @@ __device__ __forceinline__ void st_item_range(const StreamArgs& a, long long& lo
 // returns to 0 after wrap + 1 draws, so no launch has to reset it.
 __device__ __forceinline__ int st_draw_ticket(unsigned* word, const unsigned wrap) { return (int)atomicInc(word, wrap); }
 
-// twtab [3][16][256]: P1, P2, P1' twiddles (entry-major: thread tau reads element [.][.][tau], coalesced) ;
+// twtab [3][32][256] doubles: the ST_TW1, ST_TW2, ST_TW1B regions of cpf_stream_core.h (st_build_tables; entry-major: thread tau reads
+// element [.][.][tau], coalesced) ;
 // uttab [P][16][256]: kernel spectrum at the bins thread tau holds after FFT #1 ((-1)^k and 1/N folded in) ;
-// m256 [16][16] = w_256^{h l}
-// ABL (lab builds only, -DCPF_LAB): ablation bits — 1: no group barriers (racy), 2: no P2' twiddle loads, 4: no global
-// loads/stores, 8: no pre/post-factor loads (results are wrong on purpose); 16: L1 prefetch of the group's next pair,
-// 32: L2 prefetch three pairs ahead instead of two (results unchanged).
+// m256 [2][16][16] doubles: t of the P2' twiddles w_256^{h l} and the ratios of the P3' DFT (uniform over a half-warp: shared memory)
+// ABL (lab builds only, -DCPF_LAB): ablation bits — 1: no group barriers (racy), 4: no global loads/stores, 8: no pre/post-factor
+// loads (results are wrong on purpose); 16: L1 prefetch of the group's next pair, 32: L2 prefetch three pairs ahead instead of two
+// (results unchanged).
 // TMA (full window only): the two rows of a group's next pair are brought into a shared-memory staging buffer by bulk copies
 // issued by one thread right after the first group barrier of the current pair (every thread has consumed the staged rows by
 // then), a whole pair ahead of their use; threads then read their 8 + 8 samples with conflict-free 64-bit shared loads instead
 // of waiting for global loads.
 template <bool FULLWIN, int ABL = 0, bool TMA = false, bool DYN = false>
-__global__ void __launch_bounds__(512, 1) fftlog_stream_kernel(const StreamArgs a, const double2* __restrict__ twtab,
+__global__ void __launch_bounds__(512, 1) fftlog_stream_kernel(const StreamArgs a, const double* __restrict__ twtab,
                                                                const double2* __restrict__ uttab, const double2* __restrict__ m256) {
   static_assert(!TMA || FULLWIN, "the staged variant covers the full window only");
   static_assert(!DYN || TMA, "dynamic scheduling is built on the staged variant");
@@ -178,6 +166,7 @@ __global__ void __launch_bounds__(512, 1) fftlog_stream_kernel(const StreamArgs 
   const int g = threadIdx.x >> 8, tau = threadIdx.x & 255;
   double2* S = smem + g * ST_GROUP_ELEMS;
   double2* M = smem + NG * ST_GROUP_ELEMS;
+  const double* Md = reinterpret_cast<const double*>(M);
   double* stage = reinterpret_cast<double*>(M + 256) + g * ST_STAGE_DOUBLES;     // TMA only
   unsigned stage_parity = 0;
   if (TMA && tau == 0) { mbar_init(&s_mbar[g], 1); mbar_fence_init(); }
@@ -223,11 +212,11 @@ __global__ void __launch_bounds__(512, 1) fftlog_stream_kernel(const StreamArgs 
   // batch-invariant twiddles: group 0 brings P1 and P2, group 1 brings P1' (the same lanes are visible to both);
   // the loads are in flight while tensor memory is being allocated
   double2 d[4][4];
-  const double2* rec = twtab + (g == 0 ? 0 : 32 * T) + tau;
+  const double* rec = twtab + (g == 0 ? 0 : 2 * 32 * T) + tau;          // group 0: region 0 (then 1), group 1: region 2
 #pragma unroll
   for (int ch = 0; ch < 4; ++ch)
 #pragma unroll
-    for (int q = 0; q < 4; ++q) d[ch][q] = rec[(4 * ch + q) * T];
+    for (int q = 0; q < 4; ++q) d[ch][q] = mk2(rec[(8 * ch + 2 * q) * T], rec[(8 * ch + 2 * q + 1) * T]);
   if (warp == 0) tmem_alloc_all(&s_tmem_base);
   if (threadIdx.x < 256) M[threadIdx.x] = m256[threadIdx.x];
   tmem_fence_before();
@@ -244,7 +233,7 @@ __global__ void __launch_bounds__(512, 1) fftlog_stream_kernel(const StreamArgs 
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch)
 #pragma unroll
-        for (int q = 0; q < 4; ++q) d[ch][q] = rec[(16 + 4 * ch + q) * T];
+        for (int q = 0; q < 4; ++q) d[ch][q] = mk2(rec[(32 + 8 * ch + 2 * q) * T], rec[(32 + 8 * ch + 2 * q + 1) * T]);
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) tmem_st4(tb.lane + 16u * ch, d[ch]);
     }
@@ -360,23 +349,14 @@ __global__ void __launch_bounds__(512, 1) fftlog_stream_kernel(const StreamArgs 
       __syncwarp();
       st_p3_mul_p1(tau, S, tb);
       __syncwarp();
-      if (ABL & 2) {
-        double2 w[16];
-        st_row_load(tau, S, w);
-        dft_dit<16, false, false>(w);
-        const double2 m = M[16 * (tau >> 4) + 1];
-#pragma unroll
-        for (int l1 = 1; l1 < 16; ++l1) w[l1] = cmul(w[l1], m);
-        st_row_store(tau, w, S);
-      } else if (ABL & 64) st_p2b_const(tau, S);      // lab: P2' twiddles from constant memory (measured 12 % slower: r02z)
-      else st_p2b(tau, S, M);
+      st_p2b(tau, S, tb, Md);
       if (!(ABL & 1)) row_b_bad = named_sync_or(1 + g, T, bad_b);
       const int next_pair = dynamic ? s_next[g] : pair + NG;
       double2 v[16];
       st_col_load(tau, S, v);
       Tm4 tf;
       tmem_ld4(tb.half + ST_COL_POST, tf);
-      st_p3b_compute(v);
+      st_p3b_compute(v, Md + 256 + 16 * (tau >> 4));
       tmem_wait4(tf);
       double* ob = oa + a.out_row;
 #pragma unroll

@@ -12,10 +12,11 @@
 using namespace cpf;
 
 struct HostTables {
-  const double2* tab;   // this thread's [ST_NTAB][16]
+  const double* tab;   // this thread's [ST_NTAB][32] doubles
   template <int TABLE, int SET> void issue(int, int) {}
   void wait(int) {}
-  template <int SET> double2 get(int table, int ch, int, int i) const { return tab[table * 16 + 4 * ch + i]; }
+  template <int SET> double getd(int table, int ch, int, int i) const { return tab[table * 32 + 8 * ch + i]; }
+  template <int SET> double2 get(int table, int ch, int, int i) const { return mk2(tab[table * 32 + 8 * ch + 2 * i], tab[table * 32 + 8 * ch + 2 * i + 1]); }
 };
 
 static double2 root(long long num, long long den) {
@@ -25,27 +26,28 @@ static double2 root(long long num, long long den) {
 
 int main() {
   const int N = 4096, T = 256;
-  std::vector<double2> z(N), ut(N), S(ST_GROUP_ELEMS), M(256), tabs((size_t)T * ST_NTAB * 16);
+  std::vector<double2> z(N), ut(N), S(ST_GROUP_ELEMS);
+  std::vector<double> M(512), tw((size_t)3 * 32 * T), tabs((size_t)T * ST_NTAB * 32);
   srand(4321);
   for (int j = 0; j < N; ++j) {
     z[j] = j < N / 2 ? mk2(rand() / (double)RAND_MAX - 0.5, rand() / (double)RAND_MAX - 0.5) : mk2(0, 0);
     ut[j] = mk2(rand() / (double)RAND_MAX - 0.5, rand() / (double)RAND_MAX - 0.5);
   }
-  for (int h = 0; h < 16; ++h)
-    for (int l = 0; l < 16; ++l) M[16 * h + l] = root(h * l, 256);
+  st_build_tables(tw.data(), M.data());          // the very tables the library uploads
   for (int t = 0; t < T; ++t) {
     const int H = t >> 4, L = t & 15;
-    double2* tb = &tabs[(size_t)t * ST_NTAB * 16];
+    double* tb = &tabs[(size_t)t * ST_NTAB * 32];
+    const int region_of[3] = {ST_TW1, ST_TW2, ST_TW1B};
+    for (int reg = 0; reg < 3; ++reg)
+      for (int e = 0; e < 32; ++e) tb[region_of[reg] * 32 + e] = tw[((size_t)reg * 32 + e) * T + t];
     for (int k = 0; k < 16; ++k) {
-      tb[ST_TW1 * 16 + k] = root((long long)t * k, N);
-      tb[ST_TW2 * 16 + k] = root(L * k, 256);
-      tb[ST_UT * 16 + k] = ut[H + 16 * L + 256 * k];
-      tb[ST_TW1B * 16 + k] = root((long long)(H + 16 * L) * k, N);
+      tb[ST_UT * 32 + 2 * k] = ut[H + 16 * L + 256 * k].x;
+      tb[ST_UT * 32 + 2 * k + 1] = ut[H + 16 * L + 256 * k].y;
     }
   }
   // poison the exchange buffer: reads of slots nobody wrote show up as NaN
   for (auto& s : S) s = mk2(NAN, NAN);
-  auto tables = [&](int t) { HostTables h; h.tab = &tabs[(size_t)t * ST_NTAB * 16]; return h; };
+  auto tables = [&](int t) { HostTables h; h.tab = &tabs[(size_t)t * ST_NTAB * 32]; return h; };
   const int warp_order[8] = {5, 2, 7, 0, 3, 6, 1, 4};
   std::vector<double2> out((size_t)T * 16);
   for (int pass = 0; pass < 2; ++pass) {   // two pairs back to back: the second P1 overwrites what P3' just read
@@ -60,12 +62,12 @@ int main() {
       const int w = warp_order[wi];
       for (int t = 32 * w; t < 32 * w + 32; ++t) { HostTables h = tables(t); st_p2(t, S.data(), h); }
       for (int t = 32 * w + 31; t >= 32 * w; --t) { HostTables h = tables(t); st_p3_mul_p1(t, S.data(), h); }
-      for (int t = 32 * w; t < 32 * w + 32; ++t) st_p2b(t, S.data(), M.data());
+      for (int t = 32 * w; t < 32 * w + 32; ++t) { HostTables h = tables(t); st_p2b(t, S.data(), h, M.data()); }
     }
     // group barrier
     for (int t = T - 1; t >= 0; --t) {
       double2 v[16];
-      st_p3b(t, v, S.data());
+      st_p3b(t, v, S.data(), M.data());
       for (int r = 0; r < 8; ++r) out[(size_t)t * 16 + r] = v[r];
       if (pass == 0) {                      // the next pair's P1 of this thread may run before other threads' P3'
         double2 v8[8];

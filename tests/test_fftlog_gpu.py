@@ -348,15 +348,15 @@ import sys, numpy as np, torch
 sys.path.insert(0, {root!r})
 from cosmoprimo_b200 import fftlog as F, synthetic as S, _lib
 lib = _lib.load()
-n, B = 2048, 2600
+n, B = 2048, 20000
 k = np.geomspace(1e-5, 1e2, n)
 pk = torch.from_numpy(S.eh_pk(k, S.lhs_cosmologies(B, seed=5))).cuda()
 obj = F.PowerToCorrelation(k, ell=[1])
 ref = obj(pk)[1].clone()
 torch.cuda.synchronize()
-streams = [torch.cuda.Stream() for _ in range(24)]
+streams = [torch.cuda.Stream() for _ in range(8)]
 outs = []
-for rep in range(8):                       # 192 launches queued on 24 streams: far more in flight than ticket slots
+for rep in range(6):                       # 48 launches of 0.26 ms queued on 8 streams: the host runs ahead, far more in flight than 2 slots
     for st in streams:
         with torch.cuda.stream(st):
             outs.append(obj(pk)[1])
@@ -369,14 +369,14 @@ print('RESULT', bad, lib.cpf_counter(0), lib.cpf_counter(1))
 @pytest.mark.parametrize('slots', [2, 64])
 def test_ticket_ring_with_more_launches_in_flight_than_slots(slots):
     """VERDICT r1 'weak' 13: launches that would share a ticket slot with a launch still in flight must not skip pairs.  With a ring of 2 slots
-    and 192 launches queued on 24 streams most launches find their slot busy and take the static split; all results are bit-identical."""
+    and 48 launches queued on 8 streams most launches find their slot busy and take the static split; all results are bit-identical."""
     import os, subprocess, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     env = dict(os.environ, CPF_TICKET_SLOTS=str(slots), CPF_FFTLOG_KERNEL='stream')
     res = subprocess.run([sys.executable, '-c', TICKET_STRESS.format(root=root)], env=env, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stderr[-2000:]
     bad, dynamic, fallback = (int(x) for x in res.stdout.strip().splitlines()[-1].split()[1:])
-    assert bad == 0 and dynamic >= 1 and dynamic + fallback == 193
+    assert bad == 0 and dynamic >= 1 and dynamic + fallback == 49
     if slots == 2:
         assert fallback > 0        # the guard was exercised
 
