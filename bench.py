@@ -426,6 +426,130 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_roundtrip(args):
+    """
+    `--workload roundtrip` = BASELINE.json configs[4]: a 1 M-transform P(k) <-> xi round-trip sweep (500 000 rows of nk = 2048, P -> xi with
+    PowerToCorrelation, then xi -> P with CorrelationToPower on the output grid: two plans, ref interpolator.py:1476-1498 is the xi -> P leg)
+    PARTITIONED over the ranks with cosmoprimo_b200.distributed.shard: strong scaling, no data-path collective.  The rows are 5000 Latin-hypercube
+    cosmologies x 100 redshifts, generated on the owning device by the EH generator.  The optional gather of the result shards over NCCL
+    (distributed.gather_rows) is timed separately and never enters `value`.  A step = both legs over the rank's shard.
+    """
+    import torch
+    from cosmoprimo_b200 import _lib, synthetic as S
+    from cosmoprimo_b200.fftlog import PowerToCorrelation, CorrelationToPower
+    from cosmoprimo_b200.eisenstein_hu import EisensteinHu
+    from cosmoprimo_b200.distributed import shard, gather_rows, shard_bounds
+
+    rank = int(os.environ.get('RANK', 0))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    if world > 1:
+        import torch.distributed as dist
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+            torch.cuda.set_device(local_rank)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    _lib.require_device()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ncosmo, nz = args.roundtrip_cosmologies, 100
+    nrows = ncosmo * nz
+    k = np.geomspace(1e-5, 1e2, NK)
+    par = S.lhs_cosmologies(ncosmo, seed=42)
+    names = ['h', 'omega_b', 'omega_cdm', 'n_s', 'logA']
+    table = torch.from_numpy(np.stack([par[name] for name in names], axis=-1)).to(dev)          # (ncosmo, 5) on the device
+    mine = shard(table, rank, world).cpu().numpy()                                              # this rank's contiguous block of cosmologies
+    eh = EisensteinHu(mine[:, 0], mine[:, 1], mine[:, 2], mine[:, 3], logA=mine[:, 4], device=local_rank)
+    pk = eh.pk(k, z=np.linspace(0., 3., nz)[None, :]).reshape(-1, NK)                           # (rows of this rank, nk) on the device
+    rows_local = pk.shape[0]
+    assert rows_local == (shard_bounds(ncosmo, rank, world)[1] - shard_bounds(ncosmo, rank, world)[0]) * nz
+    p2x = PowerToCorrelation(k, ell=0, engine='cuda', device=local_rank)
+    x2p = CorrelationToPower(p2x.y if p2x.y.ndim == 1 else p2x.y[0], ell=0, engine='cuda', device=local_rank)
+
+    def step():
+        return x2p(p2x(pk)[1])[1]
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        back = step()
+    torch.cuda.synchronize()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        back = step()
+    e1.record()
+    barrier()
+    elapsed = max_over_ranks(e0.elapsed_time(e1) * 1e-3)
+    t0 = time.perf_counter()
+    while time.perf_counter() - t0 < (0. if QUICK else 0.5):
+        step()
+        torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
+    value = 2. * nrows * args.steps / elapsed
+    # size-independent property of the sweep: P -> xi -> P returns the input where the transform pair is well conditioned (0.01 < k < 1 h/Mpc)
+    mid = (k > 1e-2) & (k < 1.)
+    sel = torch.from_numpy(np.nonzero(mid)[0]).to(dev)
+    rel = float((back.index_select(1, sel) / pk.index_select(1, sel) - 1.).abs().max().item())
+    rel = max_over_ranks(rel)
+    # optional gather of the result shards over NCCL, timed separately (never in `value`)
+    gather = None
+    if world > 1:
+        for _ in range(2):
+            full = gather_rows(back, nrows)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(3):
+            full = gather_rows(back, nrows)
+        g1.record()
+        barrier()
+        tg = max_over_ranks(g0.elapsed_time(g1) * 1e-3 / 3)
+        lo, hi = shard_bounds(nrows, rank, world)
+        ok = bool(torch.equal(full[lo:hi], back)) and tuple(full.shape) == (nrows, NK)
+        gather = {'ms': 1e3 * tg, 'bytes_received_per_rank': int(full.numel() * 8), 'algbw_GBps': full.numel() * 8 / tg / 1e9,
+                  'busbw_GBps': full.numel() * 8 * (world - 1) / world / tg / 1e9, 'verified': ok, 'backend': 'nccl all_gather_into_tensor'}
+        del full
+    if rank == 0:
+        f64 = __import__('ctypes').c_double(0.)
+        _lib.check(_lib.load().cpf_measure_fp64_peak(local_rank, __import__('ctypes').byref(f64)))
+        per_gpu = value / world
+        roof = per_gpu * FLOPS_PER_TRANSFORM / f64.value
+        print(json.dumps({'metric': 'fftlog_roundtrip_transforms_per_sec_fp64_nk2048', 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': warm,
+                          'ms_per_step': 1e3 * elapsed / args.steps, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+                          'config': {'workload': '1 M-transform P(k) <-> xi round-trip sweep partitioned over the ranks (BASELINE configs[4])', 'rows': nrows, 'rows_per_rank': rows_local,
+                                     'nk': NK, 'padded_size': 2 * NK, 'plans': 2, 'partition': 'distributed.shard: contiguous blocks of cosmologies, no collective in the timed region',
+                                     'l2': 'each leg streams {:.1f} GB per rank, larger than L2'.format(2 * rows_local * NK * 8 / 1e9)},
+                          'clocks': clocks, 'gpu_launches': 2 * args.steps, 'roundtrip_max_rel_err_0.01<k<1': rel, 'gather_rows': gather,
+                          'roofline': {'bound': 'fp64', 'frac': roof, 'achieved': per_gpu * FLOPS_PER_TRANSFORM / 1e12, 'peak': f64.value / 1e12, 'unit': 'TFLOP/s', 'per': 'GPU'}}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_secondary(args):
     """
     `--secondary`: the other BASELINE.json configs on one GPU, each with the oracle port of the reference timed beside it on one
@@ -459,6 +583,28 @@ def run_secondary(args):
         return (time.perf_counter() - t0) / reps
 
     res = {'secondary': True, 'cpu': 'oracle port (numpy {} / scipy), 1 core, bounded samples'.format(np.__version__), 'data': 'synthetic'}
+    # the other transform sizes of BASELINE.md section 3: nk = 1024 (N = 2048) and nk = 4096 (N = 8192), device-resident P(k) -> xi multipoles,
+    # with their fp64 rooflines (flops of SURVEY 8d / measured DFMA peak)
+    import ctypes
+    from cosmoprimo_b200.fftlog import PowerToCorrelation
+    f64 = ctypes.c_double(0.)
+    _lib.check(_lib.load().cpf_measure_fp64_peak(0, ctypes.byref(f64)))
+    hbm = measured_peaks()[0] * 1e9
+    for nk_, ncosmo_ in [(1024, 8192), (2048, 4096), (4096, 2048)]:
+        kk = np.geomspace(1e-5, 1e2, nk_)
+        fun_ = torch.from_numpy(S.kaiser_multipoles(S.eh_pk(kk, S.lhs_cosmologies(ncosmo_, seed=42)), np.full(ncosmo_, 0.76))).cuda()
+        obj_ = PowerToCorrelation(kk, ell=ELLS)
+        tt = gpu_time(lambda: obj_(fun_), reps=50, warm=5)
+        N_ = 2 * nk_
+        flops_ = 2 * 2.5 * N_ * np.log2(N_) + N_ + 6 * (N_ // 2 + 1) + nk_
+        bound_ = 1. / max(flops_ / f64.value, 16. * nk_ / hbm)
+        rate_ = 3 * ncosmo_ / tt
+        sub_ = fun_[:32].cpu().numpy()
+        plan_ = O.plan_power_to_correlation(kk, ell=ELLS)
+        tc_ = cpu_time(lambda: O.execute(plan_, sub_))
+        res['fftlog_nk%d' % nk_] = {'unit': 'transforms/s', 'gpu': rate_, 'transforms_per_launch': 3 * ncosmo_, 'roofline_transforms_per_s': bound_, 'roofline_frac': rate_ / bound_,
+                                     'algorithmic_flops_per_transform': flops_, 'cpu_1core': 96 / tc_}
+        del fun_, obj_
     n = 2048
     k = np.geomspace(1e-5, 1e2, n)
     r = np.linspace(1., 20., 10)
@@ -505,7 +651,18 @@ def run_secondary(args):
     tf = gpu_time(lambda: filt(interp), reps=3, warm=1)
     pl_cpu, po_cpu = pklin[:, :32].cpu().numpy(), pkout[:, :32].cpu().numpy()
     twc = cpu_time(lambda: WO.wallish2018(klin, pl_cpu, filt.k, po_cpu), reps=2)
+    # parity at the BASELINE size (VERDICT r1 missing 6): boxes of every one of the 65 536 columns from the timed entry point, against the oracle on
+    # a strided sample of 1024 columns (bit-identical inputs): number of columns whose four box indices differ (expected 0) and max |pknow/ref - 1|
+    boxes = torch.empty((ncols, 4), dtype=torch.int32, device='cuda')
+    _lib.check(lib.cpf_wallish2018(kl.data_ptr(), pklin.data_ptr(), 4096, ko.data_ptr(), pkout.data_ptr(), filt.k.size, ncols, out.data_ptr(), boxes.data_ptr(), 1, 0, stream))
+    torch.cuda.synchronize()
+    sample = np.arange(0, ncols, ncols // 1024)
+    ref_s, dbg_s = WO.wallish2018(klin, pklin[:, sample].cpu().numpy(), filt.k, pkout[:, sample].cpu().numpy(), return_debug=True)
+    mism = np.any(boxes.cpu().numpy()[sample] != dbg_s['boxes'], axis=1)
+    perr = np.abs(out[:, sample].cpu().numpy() / ref_s - 1.)
     res['config4_wallish2018'] = {'unit': 'P(k)/s', 'gpu_filter_only': ncols / tw, 'gpu_with_input_evaluations': ncols / tf, 'gpu_spectra': ncols,
+                                  'wallish_box_mismatches': int(mism.sum()), 'columns_compared': int(sample.size), 'max_rel_err_pknow_matching_columns': float(perr[:, ~mism].max()),
+                                  'all_finite': bool(torch.isfinite(out).all().item()), 'roofline_pk_per_s': f64.value / 8.9e5, 'roofline_frac': ncols / tw / (f64.value / 8.9e5),
                                   'cpu_1core_filter_only': 32 / twc, 'cpu_spectra': 32,
                                   'cpu_path': 'scipy dst / CubicSpline restatement of Wallish2018PowerSpectrumBAOFilter._compute (per-column Python loop as in the reference)'}
     del pk, interp, filt, pklin, pkout, out
@@ -529,12 +686,16 @@ def main():
     parser.add_argument('--warmup', type=int, default=10)
     parser.add_argument('--impl', type=str, default='ours', choices=['ours', 'reference'])
     parser.add_argument('--no-cpu-baseline', action='store_true')
+    parser.add_argument('--workload', type=str, default='multipoles', choices=['multipoles', 'roundtrip'], help="'roundtrip' = BASELINE configs[4], strong scaling")
+    parser.add_argument('--roundtrip-cosmologies', type=int, default=5000, help='x 100 redshifts = rows of the round-trip sweep')
     parser.add_argument('--secondary', action='store_true', help='the other BASELINE configs with the oracle timed beside them (one GPU)')
     args = parser.parse_args()
     if args.secondary:
         run_secondary(args)
     elif args.impl == 'reference':
         run_reference(args)
+    elif args.workload == 'roundtrip':
+        run_roundtrip(args)
     else:
         run_ours(args)
 

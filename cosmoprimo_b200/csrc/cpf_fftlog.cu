@@ -222,6 +222,113 @@ __global__ void __launch_bounds__(16 * R1, 512 / (16 * R1)) fftlog_fast_kernel(c
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// N = 8192 (nk = 4096, cosmoprimo/fftlog.py:149-150): one CTA of 512 threads per pair of rows, two groups of 256 threads,
+// each running the 4096-point register FFT on its own exchange buffer.  The 8192-point transforms are split by one
+// radix-2 stage that needs no exchange:
+//   FFT #1, decimation in frequency: A[2k + g] = FFT_4096( (a[n] + (-1)^g a[n + 4096]) w_8192^{g n} )[k]; group g owns the bins of parity g
+//            (with zero padding a[n + 4096] = 0 after the N/4 rotation: both groups load the same 4096 samples);
+//   FFT #2, decimation in time:      g[j] = E[j] + w_8192^j O[j],  g[j + 4096] = E[j] - w_8192^j O[j], E / O = FFT_4096 of the even / odd bins
+//            (group 0 / group 1); the halves are exchanged through shared memory once, and with the cropped output only g[j], j < 4096,
+//            is formed: group 0 finishes the elements of register rows 0..7, group 1 those of rows 8..15.
+// ---------------------------------------------------------------------------------------------------------------
+template <bool PRUNED, bool CPOST>
+__global__ void __launch_bounds__(512, 1) fftlog_split2_kernel(const FftlogArgs a, const double2* __restrict__ tw8192) {
+  typedef Geo<16> G;
+  extern __shared__ double2 smem2[];
+  constexpr int T = 256, M = 4096, N = 8192;
+  constexpr int SHIFT = PRUNED ? N / 4 : 0;
+  const int g = threadIdx.x >> 8, t = threadIdx.x & 255;
+  double2* S = smem2 + g * G::SMEM_ELEMS;
+  double2* Sother = smem2 + (1 - g) * G::SMEM_ELEMS;
+  const long long q = blockIdx.x;
+  const int p = (int)(q / a.pairs_per_p);
+  const long long b0 = 2 * (q - p * a.pairs_per_p), b1 = b0 + 1;
+  const bool has1 = b1 < a.batch;
+  const double* rowA = a.in + (a.in_has_P ? (b0 * a.P + p) : b0) * (long long)a.n;
+  const double* rowB = has1 ? a.in + (a.in_has_P ? (b1 * a.P + p) : b1) * (long long)a.n : rowA;
+  const double* pre = a.pre + (size_t)p * N;
+
+  double2 v[16];
+  bool bad_a = false, bad_b = false;
+#pragma unroll
+  for (int r = 0; r < 16; ++r) {
+    const int nn = t + T * r;                          // n < 4096
+    const int j = nn + SHIFT, i = j - a.in_left;
+    double x, y;
+    if (PRUNED) {
+      const bool ok = (unsigned)i < (unsigned)a.n;
+      x = ok ? __ldcs(rowA + i) : 0.;
+      y = (ok && has1) ? __ldcs(rowB + i) : 0.;
+    } else {
+      x = padded_value(rowA, i, a);
+      y = has1 ? padded_value(rowB, i, a) : 0.;
+    }
+    x = scrub(x, bad_a);
+    y = scrub(y, bad_b);
+    const double pr = pre[j];
+    double2 z = mk2(x * pr, y * pr);
+    if (!PRUNED) {                                     // upper half of the padded row
+      const int j2 = j + M, i2 = j2 - a.in_left;
+      const double x2 = scrub(padded_value(rowA, i2, a), bad_a), y2 = has1 ? scrub(padded_value(rowB, i2, a), bad_b) : 0.;
+      const double pr2 = pre[j2];
+      z = g == 0 ? mk2(fma(x2, pr2, z.x), fma(y2, pr2, z.y)) : mk2(fma(-x2, pr2, z.x), fma(-y2, pr2, z.y));
+    }
+    v[r] = g == 0 ? z : cmul(z, __ldg(tw8192 + nn));
+  }
+  // FFT #1 (both groups in lock step: CTA barriers)
+  fft_pass1<16, false>(t, v, S, a.tw1);
+  const bool row_a_bad = __syncthreads_or(bad_a);
+  fft_pass2<16>(t, S, a.tw2);
+  const bool row_b_bad = __syncthreads_or(bad_b);
+  fft_pass3<16, false>(t, v, S);
+  // kernel multiply: this thread holds bins 2 (t + 256 r) + g; bins above N/2 use conj(u[N - bin])
+  const double2* uh = a.ut + (size_t)p * (N / 2 + 1);
+#pragma unroll
+  for (int r = 0; r < 8; ++r) v[r] = cmul(v[r], uh[2 * (t + T * r) + g]);
+#pragma unroll
+  for (int r = 8; r < 16; ++r) v[r] = cmul_conj(v[r], uh[N - 2 * (t + T * r) - g]);
+  __syncthreads();
+  // FFT #2
+  fft_pass1<16, false>(t, v, S, a.tw1);
+  __syncthreads();
+  fft_pass2<16>(t, S, a.tw2);
+  __syncthreads();
+  fft_pass3<16, false>(t, v, S);
+  if (g == 1) {
+#pragma unroll
+    for (int r = 0; r < 16; ++r) v[r] = cmul(v[r], __ldg(tw8192 + t + T * r));       // O'[j] = w_8192^j O[j]
+  }
+  __syncthreads();                                      // pass-3 reads are done in both groups
+  // hand the other group what it needs: cropped output: group 0 finishes rows r < 8, group 1 rows r >= 8; otherwise both need everything
+#pragma unroll
+  for (int r = 0; r < 16; ++r)
+    if (!PRUNED || (g == 0 ? r >= 8 : r < 8)) S[t + T * r] = v[r];
+  __syncthreads();
+  const size_t osz = (size_t)a.n_out * (CPOST ? 2 : 1);
+  double* outA = a.out + (size_t)(b0 * a.P + p) * osz;
+  double* outB = a.out + (size_t)(b1 * a.P + p) * osz;
+  const double* post_re = a.post_re + (size_t)p * N;
+  const double* post_im = CPOST ? a.post_im + (size_t)p * N : nullptr;
+#pragma unroll
+  for (int r = 0; r < 16; ++r) {
+    if (PRUNED && (g == 0 ? r >= 8 : r < 8)) continue;
+    const double2 w = Sother[t + T * r];
+    double2 res;
+    int j;
+    if (PRUNED) { res = mk2(v[r].x + w.x, v[r].y + w.y); j = t + T * r + SHIFT; }        // E + O' either way
+    else if (g == 0) { res = mk2(v[r].x + w.x, v[r].y + w.y); j = t + T * r; }            // g[j] = E + O'
+    else { res = mk2(w.x - v[r].x, w.y - v[r].y); j = t + T * r + M; }                    // g[j + 4096] = E - O'
+    const int o = a.keep_padding ? j : j - a.out_left;
+    if ((unsigned)o < (unsigned)a.n_out) {
+      const double pr = post_re[j];
+      const double pi = CPOST ? post_im[j] : 0.;
+      store_out(a, outA, o, res.x, pr, pi, CPOST, row_a_bad);
+      if (has1) store_out(a, outB, o, res.y, pr, pi, CPOST, row_b_bad);
+    }
+  }
+}
+
 }  // namespace cpf
 
 #include "cpf_fftlog_pp.cuh"
@@ -485,6 +592,22 @@ static int fast_twiddles(int device, int N, const FastTw** out) {
   return CPF_OK;
 }
 
+// w_8192^n, n < 4096, of the split kernel: once per device, never freed
+static std::mutex g_tw8192_mutex;
+static std::vector<std::pair<int, double2*>> g_tw8192;
+static int split2_twiddles(int device, const double2** out) {
+  std::lock_guard<std::mutex> lock(g_tw8192_mutex);
+  for (auto& e : g_tw8192)
+    if (e.first == device) { *out = e.second; return CPF_OK; }
+  std::vector<double2> tw(4096);
+  for (int n = 0; n < 4096; ++n) tw[n] = unit_root(n, 8192);
+  double2* d = nullptr;
+  CPF_TRY(upload((void**)&d, tw.data(), tw.size() * sizeof(double2)));
+  g_tw8192.emplace_back(device, d);
+  *out = d;
+  return CPF_OK;
+}
+
 // per-device twiddle cache for the unfused engine entry points
 struct GenericTw {
   int device, N;
@@ -549,6 +672,8 @@ struct cpf_plan {
   int n, N, P, in_left, out_left, device, log2N;
   bool post_complex;
   int fast_R1;
+  bool split2 = false;        // N = 8192: two 4096-point register FFTs per transform (fftlog_split2_kernel)
+  const double2* d_tw8192 = nullptr;   // w_8192^n, n < 4096 (shared, not owned)
   bool window_prunable;
   void* d_block = nullptr;    // one device allocation holds every per-plan table below
   double* d_pre = nullptr;
@@ -634,6 +759,7 @@ int cpf_plan_create(cpf_plan** out, int n, int N, int P, int in_left, int out_le
   pl->log2N = ilog2(N);
   pl->post_complex = post_im != nullptr;
   pl->fast_R1 = fast_radix(N);
+  pl->split2 = (N == 8192);
   pl->window_prunable = in_left >= N / 4 && in_left + n <= 3 * (N / 4) && out_left >= N / 4 && out_left + n <= 3 * (N / 4);
 
   const size_t PN = (size_t)P * N;
@@ -663,14 +789,15 @@ int cpf_plan_create(cpf_plan** out, int n, int N, int P, int in_left, int out_le
   std::vector<double2> pp_tab;
   int rc = CPF_OK;
   do {
-    if (pl->fast_R1) {
-      if ((rc = fast_twiddles(device, N, &pl->fast))) break;
+    if (pl->fast_R1 || pl->split2) {
+      if ((rc = fast_twiddles(device, pl->split2 ? 4096 : N, &pl->fast))) break;
+      if (pl->split2 && (rc = split2_twiddles(device, &pl->d_tw8192))) break;
       std::vector<double2> uhs(uh);
       for (int p = 0; p < P; ++p)
         for (int m = 1; m < nb; m += 2) { uhs[(size_t)p * nb + m].x = -uhs[(size_t)p * nb + m].x; uhs[(size_t)p * nb + m].y = -uhs[(size_t)p * nb + m].y; }
       o_ut = put(uh.data(), uh.size() * sizeof(double2));
       o_uts = put(uhs.data(), uhs.size() * sizeof(double2));
-      if (pl->window_prunable && !post_im) {
+      if (pl->fast_R1 && pl->window_prunable && !post_im) {
         if (pl->fast_R1 == 16) {
           o_st_ut = put(nullptr, (size_t)P * 16 * 256 * sizeof(double2));
           build_stream_ut(P, uhs, reinterpret_cast<double2*>(stage.data() + o_st_ut));
@@ -715,13 +842,13 @@ int cpf_plan_create(cpf_plan** out, int n, int N, int P, int in_left, int out_le
 }
 
 static bool use_pruned(const cpf_plan* pl, int ex_l_mode, double ex_l_val, int ex_r_mode, double ex_r_val, int keep_padding) {
-  return pl->fast_R1 && pl->window_prunable && !keep_padding && ex_l_mode == CPF_EXTRAP_CONST && ex_r_mode == CPF_EXTRAP_CONST &&
+  return (pl->fast_R1 || pl->split2) && pl->window_prunable && !keep_padding && ex_l_mode == CPF_EXTRAP_CONST && ex_r_mode == CPF_EXTRAP_CONST &&
          ex_l_val == 0. && ex_r_val == 0.;
 }
 
 int cpf_plan_kernel_family(const cpf_plan* plan, int ex_l_mode, double ex_l_val, int ex_r_mode, double ex_r_val, int keep_padding) {
   if (!plan) return -1;
-  if (!plan->fast_R1) return 0;
+  if (!plan->fast_R1 && !plan->split2) return 0;
   return use_pruned(plan, ex_l_mode, ex_l_val, ex_r_mode, ex_r_val, keep_padding) ? 2 : 1;
 }
 
@@ -1043,6 +1170,19 @@ static int launch_fftlog(const cpf_plan* pl, FftlogArgs a, bool pruned, cudaStre
       case 8: return launch_fast_r<8>(a, pruned, pl->post_complex, nblocks, stream);
       default: return launch_fast_r<4>(a, pruned, pl->post_complex, nblocks, stream);
     }
+  }
+  if (pl->split2) {
+    a.ut = pruned ? pl->d_uts : pl->d_ut;
+    a.tw1 = pl->fast->d_tw1;
+    a.tw2 = pl->fast->d_tw2;
+    const size_t smem2 = 2 * (size_t)Geo<16>::SMEM_ELEMS * sizeof(double2);
+    typedef void (*kern2_t)(const FftlogArgs, const double2*);
+    kern2_t kern = pruned ? (pl->post_complex ? (kern2_t)fftlog_split2_kernel<true, true> : (kern2_t)fftlog_split2_kernel<true, false>)
+                          : (pl->post_complex ? (kern2_t)fftlog_split2_kernel<false, true> : (kern2_t)fftlog_split2_kernel<false, false>);
+    CPF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    kern<<<(unsigned)nblocks, 512, smem2, stream>>>(a, pl->d_tw8192);
+    CPF_CUDA(cudaGetLastError());
+    return CPF_OK;
   }
   a.ut = pl->d_ut;
   a.tw1 = pl->d_tw;

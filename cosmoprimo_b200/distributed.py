@@ -54,8 +54,13 @@ def gather_rows(local, nrows_total):
     sizes = [shard_bounds(nrows_total, r, world) for r in range(world)]
     if t.shape[0] != sizes[dist.get_rank()][1] - sizes[dist.get_rank()][0]:
         raise ValueError('local shard has {} rows, expected {}'.format(t.shape[0], sizes[dist.get_rank()][1] - sizes[dist.get_rank()][0]))
-    # all_gather wants equal shapes: pad every shard to the largest one (they differ by at most one row), trim after
     most = max(b - a for a, b in sizes)
+    if all(b - a == most for a, b in sizes):
+        # equal shards (the usual case): one collective straight into the result, no staging copies
+        out = t.new_empty((nrows_total,) + tuple(t.shape[1:]))
+        dist.all_gather_into_tensor(out, t)
+        return out.numpy() if is_numpy else out
+    # all_gather wants equal shapes: pad every shard to the largest one (they differ by at most one row), trim after
     if t.shape[0] < most:
         t = torch.cat([t, t.new_zeros((most - t.shape[0],) + tuple(t.shape[1:]))], dim=0)
     parts = [torch.empty_like(t) for _ in sizes]

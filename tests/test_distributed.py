@@ -59,3 +59,53 @@ def test_two_rank_partition_and_gather():
     assert [r[1] for r in res] == [4, 3]
     assert all(r[2] for r in res)
     assert all(p.exitcode == 0 for p in procs)
+
+
+def _gpu_worker(rank, world, port, root, queue):
+    sys.path.insert(0, root)
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch
+    import torch.distributed as dist
+    from cosmoprimo_b200 import fftlog as F, synthetic as S
+    from cosmoprimo_b200.distributed import shard, gather_rows, shard_bounds
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    try:
+        res = []
+        for B in [64, 63]:                      # equal shards (all_gather_into_tensor) and, on two ranks, shards of 32 + 31 rows (padded all_gather)
+            n = 1024
+            k = np.geomspace(1e-5, 1e2, n)
+            pk = torch.from_numpy(S.eh_pk(k, S.lhs_cosmologies(B, seed=3))).cuda()
+            mine = shard(pk)                                         # CUDA tensor in, CUDA view out
+            assert mine.is_cuda and mine.shape[0] == shard_bounds(B, rank, world)[1] - shard_bounds(B, rank, world)[0]
+            p2x = F.PowerToCorrelation(k, device=rank)
+            local = p2x(mine)[1]                                     # the per-rank transform on the cuda engine
+            full = gather_rows(local, B)                             # NCCL
+            assert full.is_cuda and tuple(full.shape) == (B, n)
+            ref = p2x(pk)[1]                                         # the same rows in one piece on this rank
+            res.append(bool(torch.equal(full, ref)))
+        queue.put((rank, res))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_partition_and_nccl_gather_on_cuda_tensors():
+    """VERDICT r1 row g: distributed.shard / gather_rows on CUDA tensors with the cuda engine and NCCL (two ranks when the box has two GPUs,
+    otherwise a one-rank NCCL group: the same code path, all_gather_into_tensor included)."""
+    import torch
+    import torch.multiprocessing as mp
+    world = min(2, torch.cuda.device_count())
+    assert world >= 1
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context('spawn')
+    queue = ctx.Queue()
+    procs = [ctx.Process(target=_gpu_worker, args=(r, world, port, root, queue)) for r in range(world)]
+    for p in procs: p.start()
+    for p in procs: p.join(300)
+    res = sorted(queue.get(timeout=10) for _ in range(world))
+    assert all(all(r[1]) for r in res), res
+    assert all(p.exitcode == 0 for p in procs)
