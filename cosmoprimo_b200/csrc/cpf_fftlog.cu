@@ -15,6 +15,7 @@
 //
 // One CTA handles one pair of rows (T = N/16 threads, 16 complex values per thread in registers, three register
 // passes per FFT, two shared-memory exchanges per FFT); nothing but the input rows and the output rows touches HBM.
+#include <cooperative_groups.h>
 #include <math.h>
 #include <stdarg.h>
 #include <stdlib.h>
@@ -222,6 +223,13 @@ __global__ void __launch_bounds__(16 * R1, 512 / (16 * R1)) fftlog_fast_kernel(c
   }
 }
 
+}  // namespace cpf
+
+#include "cpf_fftlog_pp.cuh"
+#include "cpf_fftlog_stream.cuh"
+
+namespace cpf {
+
 // ---------------------------------------------------------------------------------------------------------------
 // N = 8192 (nk = 4096, cosmoprimo/fftlog.py:149-150): one CTA of 512 threads per pair of rows, two groups of 256 threads,
 // each running the 4096-point register FFT on its own exchange buffer.  The 8192-point transforms are split by one
@@ -233,15 +241,15 @@ __global__ void __launch_bounds__(16 * R1, 512 / (16 * R1)) fftlog_fast_kernel(c
 //            is formed: group 0 finishes the elements of register rows 0..7, group 1 those of rows 8..15.
 // ---------------------------------------------------------------------------------------------------------------
 template <bool PRUNED, bool CPOST>
-__global__ void __launch_bounds__(512, 1) fftlog_split2_kernel(const FftlogArgs a, const double2* __restrict__ tw8192) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 2) fftlog_split2_kernel(const FftlogArgs a, const double2* __restrict__ tw8192) {
   typedef Geo<16> G;
-  extern __shared__ double2 smem2[];
+  extern __shared__ double2 S[];
   constexpr int T = 256, M = 4096, N = 8192;
   constexpr int SHIFT = PRUNED ? N / 4 : 0;
-  const int g = threadIdx.x >> 8, t = threadIdx.x & 255;
-  double2* S = smem2 + g * G::SMEM_ELEMS;
-  double2* Sother = smem2 + (1 - g) * G::SMEM_ELEMS;
-  const long long q = blockIdx.x;
+  cooperative_groups::cluster_group cluster = cooperative_groups::this_cluster();
+  const int g = (int)cluster.block_rank(), t = threadIdx.x;      // the two CTAs of a cluster are the two groups (two CTAs per SM: four groups resident)
+  const double2* Sother = cluster.map_shared_rank(S, 1 - g);      // the other group's exchange buffer, through distributed shared memory
+  const long long q = blockIdx.x >> 1;
   const int p = (int)(q / a.pairs_per_p);
   const long long b0 = 2 * (q - p * a.pairs_per_p), b1 = b0 + 1;
   const bool has1 = b1 < a.batch;
@@ -276,9 +284,9 @@ __global__ void __launch_bounds__(512, 1) fftlog_split2_kernel(const FftlogArgs 
     }
     v[r] = g == 0 ? z : cmul(z, __ldg(tw8192 + nn));
   }
-  // FFT #1 (both groups in lock step: CTA barriers)
+  // FFT #1: the groups run free of each other until the final exchange
   fft_pass1<16, false>(t, v, S, a.tw1);
-  const bool row_a_bad = __syncthreads_or(bad_a);
+  const bool row_a_bad = __syncthreads_or(bad_a);                 // both groups loaded the same rows: the same flags in both
   fft_pass2<16>(t, S, a.tw2);
   const bool row_b_bad = __syncthreads_or(bad_b);
   fft_pass3<16, false>(t, v, S);
@@ -299,12 +307,12 @@ __global__ void __launch_bounds__(512, 1) fftlog_split2_kernel(const FftlogArgs 
 #pragma unroll
     for (int r = 0; r < 16; ++r) v[r] = cmul(v[r], __ldg(tw8192 + t + T * r));       // O'[j] = w_8192^j O[j]
   }
-  __syncthreads();                                      // pass-3 reads are done in both groups
+  __syncthreads();                                      // this group's pass-3 reads of S are done
   // hand the other group what it needs: cropped output: group 0 finishes rows r < 8, group 1 rows r >= 8; otherwise both need everything
 #pragma unroll
   for (int r = 0; r < 16; ++r)
     if (!PRUNED || (g == 0 ? r >= 8 : r < 8)) S[t + T * r] = v[r];
-  __syncthreads();
+  cluster.sync();                                       // both buffers are written and visible across the cluster
   const size_t osz = (size_t)a.n_out * (CPOST ? 2 : 1);
   double* outA = a.out + (size_t)(b0 * a.P + p) * osz;
   double* outB = a.out + (size_t)(b1 * a.P + p) * osz;
@@ -327,14 +335,8 @@ __global__ void __launch_bounds__(512, 1) fftlog_split2_kernel(const FftlogArgs 
       if (has1) store_out(a, outB, o, res.y, pr, pi, CPOST, row_b_bad);
     }
   }
+  cluster.sync();                                       // neither CTA leaves while the other still reads its shared memory
 }
-
-}  // namespace cpf
-
-#include "cpf_fftlog_pp.cuh"
-#include "cpf_fftlog_stream.cuh"
-
-namespace cpf {
 
 // ---------------------------------------------------------------------------------------------------------------
 // generic path: any power-of-two N <= CPF_MAX_N, whole transform in shared memory, radix-2
@@ -1175,12 +1177,13 @@ static int launch_fftlog(const cpf_plan* pl, FftlogArgs a, bool pruned, cudaStre
     a.ut = pruned ? pl->d_uts : pl->d_ut;
     a.tw1 = pl->fast->d_tw1;
     a.tw2 = pl->fast->d_tw2;
-    const size_t smem2 = 2 * (size_t)Geo<16>::SMEM_ELEMS * sizeof(double2);
+    const size_t smem2 = (size_t)Geo<16>::SMEM_ELEMS * sizeof(double2);
     typedef void (*kern2_t)(const FftlogArgs, const double2*);
     kern2_t kern = pruned ? (pl->post_complex ? (kern2_t)fftlog_split2_kernel<true, true> : (kern2_t)fftlog_split2_kernel<true, false>)
                           : (pl->post_complex ? (kern2_t)fftlog_split2_kernel<false, true> : (kern2_t)fftlog_split2_kernel<false, false>);
     CPF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-    kern<<<(unsigned)nblocks, 512, smem2, stream>>>(a, pl->d_tw8192);
+    if (2 * nblocks > 2147483647LL) return fail(CPF_EUNSUPPORTED, "cpf_fftlog: batch too large for one launch");
+    kern<<<(unsigned)(2 * nblocks), 256, smem2, stream>>>(a, pl->d_tw8192);      // clusters of two CTAs (__cluster_dims__)
     CPF_CUDA(cudaGetLastError());
     return CPF_OK;
   }

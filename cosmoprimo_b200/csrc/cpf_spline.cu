@@ -320,6 +320,9 @@ struct cpf_spline {
   double* d_x = nullptr;   // (log10 of) abscissae
   double* d_y = nullptr;   // (log10 of) ordinates [nx, ncols]
   double* d_s = nullptr;   // slopes [nx, ncols]
+  // the three arrays come from the library's private stream-ordered pool (no device-wide synchronisation at create / destroy, unlike
+  // cudaMalloc / cudaFree); they are released in stream order behind the last stream that used the spline
+  mutable cudaStream_t last_stream = nullptr;
 };
 
 extern "C" {
@@ -327,9 +330,9 @@ extern "C" {
 int cpf_spline_destroy(cpf_spline* sp) {
   if (!sp) return CPF_OK;
   DeviceGuard guard(sp->device);
-  cudaFree(sp->d_x);
-  cudaFree(sp->d_y);
-  cudaFree(sp->d_s);
+  if (sp->d_x) cudaFreeAsync(sp->d_x, sp->last_stream);
+  if (sp->d_y) cudaFreeAsync(sp->d_y, sp->last_stream);
+  if (sp->d_s) cudaFreeAsync(sp->d_s, sp->last_stream);
   delete sp;
   return CPF_OK;
 }
@@ -357,9 +360,12 @@ int cpf_spline_create(cpf_spline** out, const double* x, const double* y, int nx
   do {
     cudaError_t e;
 #define SP_CUDA(call) if ((e = (call)) != cudaSuccess) { rc = fail(CPF_ECUDA, "%s: %s", #call, cudaGetErrorString(e)); break; }
-    SP_CUDA(cudaMalloc(&sp->d_x, nx * sizeof(double)));
-    SP_CUDA(cudaMalloc(&sp->d_y, (cells ? cells : 1) * sizeof(double)));
-    SP_CUDA(cudaMalloc(&sp->d_s, (cells ? cells : 1) * sizeof(double)));
+    sp->last_stream = stream;
+    cudaMemPool_t pool = scratch_pool(device);
+    if (!pool) { rc = fail(CPF_ECUDA, "cpf_spline_create: no memory pool on device %d", device); break; }
+    SP_CUDA(cudaMallocFromPoolAsync((void**)&sp->d_x, nx * sizeof(double), pool, stream));
+    SP_CUDA(cudaMallocFromPoolAsync((void**)&sp->d_y, (cells ? cells : 1) * sizeof(double), pool, stream));
+    SP_CUDA(cudaMallocFromPoolAsync((void**)&sp->d_s, (cells ? cells : 1) * sizeof(double), pool, stream));
     const double* src_x = x;
     const double* src_y = y;
     double ends[2];
@@ -398,6 +404,7 @@ static int spline_eval_impl(const cpf_spline* sp, const double* xq, int nq, int 
                             void* stream_) {
   if (!sp) return fail(CPF_EINVAL, "cpf_spline_eval: null spline");
   if (nq < 0) return fail(CPF_EINVAL, "cpf_spline_eval: negative query count");
+  sp->last_stream = (cudaStream_t)stream_;
   if (nu < 0 || nu > 3) return fail(CPF_EINVAL, "cpf_spline_eval: derivative order %d not in 0..3", nu);
   if (nq == 0 || sp->ncols == 0) return CPF_OK;
   if (!xq || !out) return fail(CPF_EINVAL, "cpf_spline_eval: null buffer");

@@ -38,7 +38,8 @@ struct WallishArgs {
   const double* pklin;    // [4096, ncols]
   double2* packed;        // [npairs, 4096]: in  = sign * log(k P) of both columns of a pair in Makhoul order (wallish_pack_kernel),
                           //                 out = raw FFT bins of the DST-III (consumed by wallish_unpack_kernel)
-  long long ncols;
+  long long ncols;        // columns of this chunk
+  long long ld;           // doubles between consecutive rows of pklin / pkout / pknow (= total number of columns)
   int i0, i1;             // rows of klin kept (1e-2 < k < 1.5)
   int nl;                 // rows of the knot matrix before them
   double* vals;           // [nknots, ncols] knot values of the final spline
@@ -225,7 +226,7 @@ __global__ void __launch_bounds__(256, 1) wallish_fused_kernel(const WallishArgs
 // ---- layout changes around the fused kernel: both are 64-row x 32-column tile transpositions through shared memory ----
 // pack: pklin [4096, ncols] -> packed [npairs, 4096] double2 = sign * log(k P), Makhoul order (n < N/2: j = 2n, else j = 2(N-1-n)+1).
 // 64 consecutive rows j0 .. j0+63 hold 32 ascending samples n = j0/2 + i (even j) and 32 descending n = N-1-j0/2-i (odd j).
-__global__ void __launch_bounds__(256) wallish_pack_kernel(const double* __restrict__ klin, const double* __restrict__ pklin,
+__global__ void __launch_bounds__(256) wallish_pack_kernel(const double* __restrict__ klin, const double* __restrict__ pklin, const long long ld,
                                                            const long long ncols, double2* __restrict__ packed) {
   typedef WallishGeo G;
   __shared__ double tile[64][33];
@@ -236,7 +237,7 @@ __global__ void __launch_bounds__(256) wallish_pack_kernel(const double* __restr
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int j = j0 + ty + 8 * i;
-    const double v = log(klin[j] * __ldcs(pklin + (long long)j * ncols + col));
+    const double v = log(klin[j] * __ldcs(pklin + (long long)j * ld + col));
     tile[ty + 8 * i][tx] = (j & 1) ? -v : v;
   }
   __syncthreads();
@@ -288,32 +289,32 @@ __global__ void __launch_bounds__(256) wallish_unpack_kernel(const double* __res
 }
 
 // rows of the knot matrix copied from the unfiltered spectrum: k < 5e-4 (first nl rows of kout) and k > 2 (last nr)
-__global__ void wallish_edges_kernel(const double* __restrict__ pkout, const int nk, const long long ncols, const int nl,
+__global__ void wallish_edges_kernel(const double* __restrict__ pkout, const long long ld, const int nk, const long long ncols, const int nl,
                                      const int nmid, const int nr, double* __restrict__ vals) {
   const long long col = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const int r = blockIdx.y;   // 0 .. nl+nr-1
   if (col >= ncols) return;
   const int src = r < nl ? r : nk - nr + (r - nl);
   const int dst = r < nl ? r : nl + nmid + (r - nl);
-  vals[(long long)dst * ncols + col] = pkout[(long long)src * ncols + col];
+  vals[(long long)dst * ncols + col] = pkout[(long long)src * ld + col];
 }
 
 // evaluate the final clamped spline at kout[q] (interval idx[q] precomputed: the knots are shared) and blend
 __global__ void wallish_final_kernel(const double* __restrict__ knots, const double* __restrict__ vals, const double* __restrict__ slopes,
                                      const long long ncols, const double* __restrict__ kout, const int* __restrict__ idx,
-                                     const double* __restrict__ pkout, double* __restrict__ pknow) {
+                                     const double* __restrict__ pkout, const long long ld, double* __restrict__ pknow) {
   const long long col = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const int q = blockIdx.y;
   if (col >= ncols) return;
   const double k = kout[q];
   const int i = idx[q];
-  if (i < 0) { pknow[(long long)q * ncols + col] = nan(""); return; }
+  if (i < 0) { pknow[(long long)q * ld + col] = nan(""); return; }
   const long long o = (long long)i * ncols + col;
   const double smooth = spline_poly(knots[i], knots[i + 1], vals[o], vals[o + ncols], slopes[o], slopes[o + ncols], k, 0);   // :420
   const double th = k > 1. ? exp(-400. * (k - 1.) * (k - 1.)) : 1.;                                                          // :425-431, scale=20
-  const double pk = pkout[(long long)q * ncols + col];
+  const double pk = pkout[(long long)q * ld + col];
   const double wiggles = (pk / smooth - 1.) * th + 1.;                                                                      // :422
-  pknow[(long long)q * ncols + col] = pk / wiggles;                                                                          // :423
+  pknow[(long long)q * ld + col] = pk / wiggles;                                                                          // :423
 }
 
 // ---- standalone DST-II / DST-III (orthonormal), N = 4096, along axis 0 of [4096, ncols] ------------------------------
@@ -499,7 +500,10 @@ int cpf_wallish2018(const double* klin, const double* pklin, int nlin, const dou
   }
 
   const size_t lin_bytes = (size_t)nlin * ncols * sizeof(double), out_bytes = (size_t)nk * ncols * sizeof(double);
-  const size_t knot_bytes = (size_t)nknots * ncols * sizeof(double);
+  // columns are processed in chunks so that the work arrays (packed: 64 KB, knot values + slopes: 59 KB per spectrum) stay within the
+  // private scratch pool's release threshold whatever the batch
+  const long long chunk = ncols < 8192 ? ncols : 8192;
+  const size_t knot_bytes = (size_t)nknots * chunk * sizeof(double);
   ScratchBuf d_klin, d_pklin, d_kout, d_pkout, d_pknow, d_boxes, d_knots, d_idx, d_vals, d_slopes, d_fac, d_packed;
   const double *p_klin = klin, *p_pklin = pklin, *p_kout = kout, *p_pkout = pkout;
   double* p_pknow = pknow;
@@ -526,34 +530,35 @@ int cpf_wallish2018(const double* klin, const double* pklin, int nlin, const dou
   CPF_CUDA(d_vals.alloc(knot_bytes, stream));
   CPF_CUDA(d_slopes.alloc(knot_bytes, stream));
   CPF_CUDA(d_fac.alloc(4 * (size_t)nknots * sizeof(double), stream));
-  const long long npairs = (ncols + 1) / 2;
-  CPF_CUDA(d_packed.alloc((size_t)npairs * WallishGeo::N * sizeof(double2), stream));
+  CPF_CUDA(d_packed.alloc((size_t)((chunk + 1) / 2) * WallishGeo::N * sizeof(double2), stream));
   // the factors of the final clamped spline depend on the spliced knots only: computed here, on the host copy
   std::vector<double> h_fac(4 * (size_t)nknots);
   spline_factor_host(h_knots.data(), nknots, 1, h_fac.data());
   CPF_CUDA(cudaMemcpyAsync(d_fac.p, h_fac.data(), h_fac.size() * sizeof(double), cudaMemcpyHostToDevice, stream));
   CPF_CUDA(cudaMemcpyAsync(d_knots.p, h_knots.data(), nknots * sizeof(double), cudaMemcpyHostToDevice, stream));
   CPF_CUDA(cudaMemcpyAsync(d_idx.p, h_idx.data(), nk * sizeof(int), cudaMemcpyHostToDevice, stream));
-
-  WallishArgs a;
-  a.klin = p_klin; a.pklin = p_pklin; a.packed = (double2*)d_packed.p; a.ncols = ncols; a.i0 = i0; a.i1 = i1; a.nl = nl;
-  a.vals = (double*)d_vals.p; a.boxes = p_boxes;
-  a.tw1 = wt.tw1; a.tw2 = wt.tw2; a.twd = wt.twd; a.wtab = wt.wtab;
   CPF_CUDA(cudaFuncSetAttribute(wallish_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWallishSmemBytes));
-  const dim3 tgrid((unsigned)((ncols + 31) / 32), WallishGeo::N / 64);
-  wallish_pack_kernel<<<tgrid, 256, 0, stream>>>(p_klin, p_pklin, ncols, a.packed);
-  wallish_fused_kernel<<<(unsigned)npairs, 256, kWallishSmemBytes, stream>>>(a);
-  wallish_unpack_kernel<<<tgrid, 256, 0, stream>>>(p_klin, a.packed, ncols, i0, i1, nl, a.vals);
-  CPF_CUDA(cudaGetLastError());
-  const unsigned ctile = (unsigned)((ncols + 127) / 128);
-  if (nl + nr > 0) {
-    wallish_edges_kernel<<<dim3(ctile, (unsigned)(nl + nr)), 128, 0, stream>>>(p_pkout, nk, ncols, nl, nmid, nr, (double*)d_vals.p);
+  for (long long c0 = 0; c0 < ncols; c0 += chunk) {
+    const long long cc = ncols - c0 < chunk ? ncols - c0 : chunk;
+    WallishArgs a;
+    a.klin = p_klin; a.pklin = p_pklin + c0; a.packed = (double2*)d_packed.p; a.ncols = cc; a.ld = ncols; a.i0 = i0; a.i1 = i1; a.nl = nl;
+    a.vals = (double*)d_vals.p; a.boxes = p_boxes ? p_boxes + 4 * c0 : nullptr;
+    a.tw1 = wt.tw1; a.tw2 = wt.tw2; a.twd = wt.twd; a.wtab = wt.wtab;
+    const dim3 tgrid((unsigned)((cc + 31) / 32), WallishGeo::N / 64);
+    wallish_pack_kernel<<<tgrid, 256, 0, stream>>>(p_klin, a.pklin, ncols, cc, a.packed);
+    wallish_fused_kernel<<<(unsigned)((cc + 1) / 2), 256, kWallishSmemBytes, stream>>>(a);
+    wallish_unpack_kernel<<<tgrid, 256, 0, stream>>>(p_klin, a.packed, cc, i0, i1, nl, a.vals);
+    CPF_CUDA(cudaGetLastError());
+    const unsigned ctile = (unsigned)((cc + 127) / 128);
+    if (nl + nr > 0) {
+      wallish_edges_kernel<<<dim3(ctile, (unsigned)(nl + nr)), 128, 0, stream>>>(p_pkout + c0, ncols, nk, cc, nl, nmid, nr, (double*)d_vals.p);
+      CPF_CUDA(cudaGetLastError());
+    }
+    CPF_TRY(spline_fit_device((const double*)d_knots.p, (const double*)d_vals.p, nknots, cc, 1, (double*)d_slopes.p, (double*)d_fac.p, stream, true));
+    wallish_final_kernel<<<dim3(ctile, (unsigned)nk), 128, 0, stream>>>((const double*)d_knots.p, (const double*)d_vals.p, (const double*)d_slopes.p,
+                                                                          cc, p_kout, (const int*)d_idx.p, p_pkout + c0, ncols, p_pknow + c0);
     CPF_CUDA(cudaGetLastError());
   }
-  CPF_TRY(spline_fit_device((const double*)d_knots.p, (const double*)d_vals.p, nknots, ncols, 1, (double*)d_slopes.p, (double*)d_fac.p, stream, true));
-  wallish_final_kernel<<<dim3(ctile, (unsigned)nk), 128, 0, stream>>>((const double*)d_knots.p, (const double*)d_vals.p, (const double*)d_slopes.p,
-                                                                        ncols, p_kout, (const int*)d_idx.p, p_pkout, p_pknow);
-  CPF_CUDA(cudaGetLastError());
   if (!on_device) {
     CPF_CUDA(cudaMemcpyAsync(pknow, p_pknow, out_bytes, cudaMemcpyDeviceToHost, stream));
     if (boxes) CPF_CUDA(cudaMemcpyAsync(boxes, p_boxes, (size_t)ncols * 4 * sizeof(int), cudaMemcpyDeviceToHost, stream));

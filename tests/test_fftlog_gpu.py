@@ -351,7 +351,7 @@ import sys, numpy as np, torch
 sys.path.insert(0, {root!r})
 from cosmoprimo_b200 import fftlog as F, synthetic as S, _lib
 lib = _lib.load()
-n, B = 2048, 20000
+n, B = 2048, 2600
 k = np.geomspace(1e-5, 1e2, n)
 pk = torch.from_numpy(S.eh_pk(k, S.lhs_cosmologies(B, seed=5))).cuda()
 obj = F.PowerToCorrelation(k, ell=[1])
@@ -359,7 +359,10 @@ ref = obj(pk)[1].clone()
 torch.cuda.synchronize()
 streams = [torch.cuda.Stream() for _ in range(8)]
 outs = []
-for rep in range(6):                       # 48 launches of 0.26 ms queued on 8 streams: the host runs ahead, far more in flight than 2 slots
+torch.cuda._sleep(int(1.5e9))              # keep the GPU busy (~0.75 s) while the launches below are queued: all of them are in flight at once
+for st in streams:
+    st.wait_stream(torch.cuda.current_stream())
+for rep in range(6):                       # 48 launches queued on 8 streams behind the sleep kernel
     for st in streams:
         with torch.cuda.stream(st):
             outs.append(obj(pk)[1])

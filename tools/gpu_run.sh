@@ -44,6 +44,10 @@ for STEP in "$@"; do
       tail -5 $OUT/sanitizer_${ARG:-memcheck}_$TAG.log ;;
     sass)
       bash tools/sass_summary.sh > $OUT/sass_$TAG.txt 2>&1; cat $OUT/sass_$TAG.txt ;;
+    ncupy)   # ncupy:<script>,<kernel regex>[,<skip>]: ncu --set full of one launch of a kernel in tools/lab/<script>.py
+      IFS=, read SCRIPT REGEX SKIP <<< "$ARG"
+      timeout 900 ncu --set full --clock-control none --import-source on -k regex:$REGEX -s ${SKIP:-3} -c 1 -f -o $OUT/prof_${SCRIPT}_$TAG \
+          python tools/lab/$SCRIPT.py > $OUT/ncu_${SCRIPT}_$TAG.log 2>&1; tail -2 $OUT/ncu_${SCRIPT}_$TAG.log ;;
     py)
       timeout 1200 python tools/lab/$ARG.py > $OUT/${ARG}_$TAG.log 2>&1; echo "rc=$?" >> $OUT/${ARG}_$TAG.log; tail -40 $OUT/${ARG}_$TAG.log ;;
     *) echo "unknown step $STEP" ;;
