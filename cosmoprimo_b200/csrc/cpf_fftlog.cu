@@ -68,6 +68,7 @@ struct FftlogArgs {
   unsigned* t_finished;    // ... the slot's CTA exit counter (self-resetting) and its completion word in mapped host memory
   unsigned* t_done;
   unsigned t_seq;
+  int ahead;               // split kernel: a CTA prefetches into L2 the rows of the pair `ahead` pairs after its own (one wave of resident clusters)
 };
 
 // Last instruction of a dynamically scheduled kernel: the CTA that exits last publishes the launch's sequence number in mapped host
@@ -257,6 +258,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 2) fftlog_split
   const double* rowB = has1 ? a.in + (a.in_has_P ? (b1 * a.P + p) : b1) * (long long)a.n : rowA;
   const double* pre = a.pre + (size_t)p * N;
 
+  // L2 prefetch of the two rows of a pair that a later wave of clusters transforms (group 0: row a, group 1: row b; one 128-byte line per
+  // thread covers a row of up to 4096 samples): the input loads of that wave then hit L2 instead of HBM
+  if (a.ahead > 0) {
+    const long long qn = q + a.ahead;
+    if (qn / a.pairs_per_p == p) {                       // same plan row: same input indexing
+      const long long bn = 2 * (qn - p * a.pairs_per_p) + g;
+      if (bn < a.batch && 16 * t < a.n) {
+        const double* rn = a.in + (a.in_has_P ? (bn * a.P + p) : bn) * (long long)a.n + 16 * t;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(rn));
+      }
+    }
+  }
   double2 v[16];
   bool bad_a = false, bad_b = false;
 #pragma unroll
@@ -312,16 +325,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 2) fftlog_split
 #pragma unroll
   for (int r = 0; r < 16; ++r)
     if (!PRUNED || (g == 0 ? r >= 8 : r < 8)) S[t + T * r] = v[r];
-  cluster.sync();                                       // both buffers are written and visible across the cluster
+  cluster.barrier_arrive();                             // this group's half is written ...
   const size_t osz = (size_t)a.n_out * (CPOST ? 2 : 1);
   double* outA = a.out + (size_t)(b0 * a.P + p) * osz;
   double* outB = a.out + (size_t)(b1 * a.P + p) * osz;
   const double* post_re = a.post_re + (size_t)p * N;
   const double* post_im = CPOST ? a.post_im + (size_t)p * N : nullptr;
+  cluster.barrier_wait();                               // ... and so is the other group's, visible across the cluster
+  double2 wo[16];
 #pragma unroll
   for (int r = 0; r < 16; ++r) {
     if (PRUNED && (g == 0 ? r >= 8 : r < 8)) continue;
-    const double2 w = Sother[t + T * r];
+    wo[r] = Sother[t + T * r];
+  }
+  cluster.barrier_arrive();                             // done reading the other group's shared memory (waited for at the very end)
+#pragma unroll
+  for (int r = 0; r < 16; ++r) {
+    if (PRUNED && (g == 0 ? r >= 8 : r < 8)) continue;
+    const double2 w = wo[r];
     double2 res;
     int j;
     if (PRUNED) { res = mk2(v[r].x + w.x, v[r].y + w.y); j = t + T * r + SHIFT; }        // E + O' either way
@@ -335,7 +356,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 2) fftlog_split
       if (has1) store_out(a, outB, o, res.y, pr, pi, CPOST, row_b_bad);
     }
   }
-  cluster.sync();                                       // neither CTA leaves while the other still reads its shared memory
+  cluster.barrier_wait();                               // neither CTA leaves while the other still reads its shared memory
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1183,6 +1204,12 @@ static int launch_fftlog(const cpf_plan* pl, FftlogArgs a, bool pruned, cudaStre
                           : (pl->post_complex ? (kern2_t)fftlog_split2_kernel<false, true> : (kern2_t)fftlog_split2_kernel<false, false>);
     CPF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
     if (2 * nblocks > 2147483647LL) return fail(CPF_EUNSUPPORTED, "cpf_fftlog: batch too large for one launch");
+    {
+      int dev = 0, sms = 0;
+      CPF_CUDA(cudaGetDevice(&dev));
+      CPF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+      a.ahead = sms;                                    // two CTAs per SM = `sms` clusters per wave
+    }
     kern<<<(unsigned)(2 * nblocks), 256, smem2, stream>>>(a, pl->d_tw8192);      // clusters of two CTAs (__cluster_dims__)
     CPF_CUDA(cudaGetLastError());
     return CPF_OK;
@@ -1365,6 +1392,7 @@ int cpf_fftlog(const cpf_plan* pl, const double* in, int64_t batch, int in_has_P
   FftlogArgs a;
   a.tickets = a.t_finished = a.t_done = nullptr;
   a.t_seq = 0;
+  a.ahead = 0;
   a.pre = pl->d_pre;
   a.post_re = pl->d_post_re;
   a.post_im = pl->d_post_im;

@@ -113,3 +113,69 @@ class EisensteinHu(object):
     def derived(self, z=None, on_device=False):
         """(..., 4): rs_drag [Mpc/h], z_drag, growth_factor(z, znorm=0)**2, growth_rate(z); leading shape as :meth:`pk`."""
         return self._run(None, z, False, on_device, want_pk=False)[1]
+
+
+class EHCosmology(object):
+    """
+    The handful of cosmology-dependent numbers the polynomial / peak-average BAO filters need (``cosmoprimo/bao_filter.py`` uses
+    ``cosmo.rs_drag`` and ``Fourier(cosmo, engine='eisenstein_hu_nowiggle').pk_interpolator()(k, z=0)``): one flat LCDM cosmology without
+    massive neutrinos, evaluated with the Eisenstein & Hu formulae exactly as the reference's engines do
+    (``cosmoprimo/eisenstein_hu.py:34-66`` for ``rs_drag``, ``cosmoprimo/eisenstein_hu_nowiggle.py:17-51`` for the no-wiggle transfer function,
+    ``cosmoprimo/eisenstein_hu.py:189-214, 321-324`` for the primordial spectrum and the potential / curvature factors).  Host numpy code: one
+    cosmology per filter, nothing batched.  Reference ``Cosmology`` objects are accepted by the filters as well (duck typing).
+    """
+
+    def __init__(self, h, omega_b, omega_cdm, n_s, A_s=None, logA=None, T_cmb=T_CMB, k_pivot=K_PIVOT):
+        if (A_s is None) == (logA is None):
+            raise ValueError('provide either A_s or logA')
+        self.h, self.omega_b, self.omega_cdm, self.n_s = float(h), float(omega_b), float(omega_cdm), float(n_s)
+        self.A_s = float(A_s) if A_s is not None else 1e-10 * float(np.exp(logA))
+        self.T_cmb, self.k_pivot = float(T_cmb), float(k_pivot)
+        # ref eisenstein_hu.py:34-66
+        self.omega_m = self.omega_cdm + self.omega_b
+        self.frac_b = self.omega_b / self.omega_m
+        self.theta_cmb = self.T_cmb / 2.7
+        self.z_eq = 2.5e4 * self.omega_m * self.theta_cmb**(-4) - 1.
+        self.k_eq = 0.0746 * self.omega_m * self.theta_cmb**(-2)
+        b1 = 0.313 * self.omega_m**(-0.419) * (1 + 0.607 * self.omega_m**0.674)
+        b2 = 0.238 * self.omega_m**0.223
+        self.z_drag = 1345 * self.omega_m**0.251 / (1. + 0.659 * self.omega_m**0.828) * (1. + b1 * self.omega_b**b2)
+        r_drag = 31.5 * self.omega_b * self.theta_cmb**(-4) * (1000. / (1 + self.z_drag))
+        r_eq = 31.5 * self.omega_b * self.theta_cmb**(-4) * (1000. / (1 + self.z_eq))
+        self._rs_drag_mpc = 2. / (3. * self.k_eq) * np.sqrt(6. / r_eq) * np.log((np.sqrt(1 + r_drag) + np.sqrt(r_drag + r_eq)) / (1 + np.sqrt(r_eq)))
+        # ref eisenstein_hu_nowiggle.py:20-23
+        self.alpha_gamma = 1. - 0.328 * np.log(431. * self.omega_m) * self.frac_b + 0.38 * np.log(22.3 * self.omega_m) * self.frac_b**2
+
+    @property
+    def rs_drag(self):
+        """Sound horizon at the drag epoch in Mpc/h, as ``Cosmology.rs_drag`` of the reference."""
+        return self._rs_drag_mpc * self.h
+
+    def _pk_from_transfer(self, k, transfer):
+        # ref eisenstein_hu.py:189-214 (primordial, k_pivot in 1/Mpc) and :321-324; growth factor at z = 0 with the reference's `znorm=0` convention
+        from . import synthetic
+        k = np.asarray(k, dtype='f8')
+        Omega0_m = self.omega_m / self.h**2
+        potential_to_density = (3. * Omega0_m * 100**2 / (2. * synthetic.C_KMS**2 * k**2))**(-2)
+        curvature_to_potential = 9. / 25. * 2. * np.pi**2 / k**3 / self.h**3
+        primordial = self.h**3 * self.A_s * (k / (self.k_pivot / self.h))**(self.n_s - 1.)
+        return transfer**2 * potential_to_density * curvature_to_potential * primordial * synthetic.growth_factor(0., Omega0_m, self.h)**2
+
+    def transfer_nowiggle(self, k):
+        """No-wiggle transfer function on ``k`` [h/Mpc] (ref eisenstein_hu_nowiggle.py:35-51)."""
+        kk = np.asarray(k, dtype='f8') * self.h
+        ks = kk * self._rs_drag_mpc
+        gamma_eff = self.omega_m * (self.alpha_gamma + (1 - self.alpha_gamma) / (1 + (0.43 * ks)**4))
+        q = kk * self.theta_cmb**2 / gamma_eff
+        L0 = np.log(2 * np.e + 1.8 * q)
+        C0 = 14.2 + 731.0 / (1 + 62.5 * q)
+        return L0 / (L0 + C0 * q**2)
+
+    def pk_nowiggle(self, k):
+        """Linear no-wiggle P(k, z=0) [(Mpc/h)^3]."""
+        return self._pk_from_transfer(k, self.transfer_nowiggle(k))
+
+    def pk_lin(self, k):
+        """Linear P(k, z=0) with baryon wiggles (Eisenstein & Hu 1998 full fitting formula)."""
+        from . import synthetic
+        return synthetic.eh_pk(k, dict(h=self.h, omega_b=self.omega_b, omega_cdm=self.omega_cdm, n_s=self.n_s, logA=np.log(1e10 * self.A_s)), z=0.)

@@ -326,8 +326,43 @@ def make_interp2d():
     print('wrote {} ({:.2f} MB)'.format(fn, os.path.getsize(fn) / 1e6))
 
 
+def make_filters():
+    """The least-squares / peak-average BAO filters: reference outputs on EH spectra of one cosmology at four redshifts.
+    The inputs the filters draw from the cosmology layer (rs_drag, no-wiggle spectra) are stored too, so that a failure can be attributed."""
+    from cosmoprimo import Cosmology
+    from cosmoprimo.cosmology import Fourier
+    from cosmoprimo.bao_filter import PowerSpectrumBAOFilter, CorrelationFunctionBAOFilter
+    par = dict(h=0.70, omega_b=0.0235, omega_cdm=0.125, n_s=0.95, A_s=2.2e-9)
+    par_fid = dict(h=0.6736, omega_b=0.02237, omega_cdm=0.12, n_s=0.9649, A_s=2.083e-9)
+    cosmo = Cosmology(m_ncdm=None, engine='eisenstein_hu', **par)
+    cosmo_fid = Cosmology(m_ncdm=None, engine='eisenstein_hu', **par_fid)
+    interp2d = cosmo.get_fourier().pk_interpolator()                     # from_callable: exact EH spectrum, growth factor applied per z
+    ktab = np.geomspace(1e-5, 1e2, 1500)
+    z = np.array([0., 0.5, 1., 2.])
+    from cosmoprimo.interpolator import PowerSpectrumInterpolator1D
+    interp = PowerSpectrumInterpolator1D(ktab, interp2d(ktab, z))        # tabulated, four columns
+    arrays = dict(par=np.array([par[n] for n in ['h', 'omega_b', 'omega_cdm', 'n_s', 'A_s']]), par_fid=np.array([par_fid[n] for n in ['h', 'omega_b', 'omega_cdm', 'n_s', 'A_s']]),
+                  rs_drag=cosmo.rs_drag, rs_drag_fid=cosmo_fid.rs_drag, extrap_kmin=interp.extrap_kmin, extrap_kmax=interp.extrap_kmax)
+    f = PowerSpectrumBAOFilter(interp, engine='ehpoly', cosmo=cosmo)
+    arrays.update(k=f.k, pk=f.pk, ehpoly_pknow=f.pknow, pk_nowiggle=Fourier(cosmo, engine='eisenstein_hu_nowiggle', set_engine=False).pk_interpolator()(f.k, z=0.))
+    f = PowerSpectrumBAOFilter(interp, engine='ehpoly', cosmo=cosmo, cosmo_fid=cosmo_fid, krange=(2e-3, 0.8), rescale_krange=True)
+    arrays.update(ehpoly2_pknow=f.pknow)
+    f = PowerSpectrumBAOFilter(interp, engine='peakaverage', cosmo=cosmo, cosmo_fid=cosmo_fid)
+    arrays.update(peakaverage_pknow=f.pknow, peakaverage_k_peaks0=f.k_peaks[0], peakaverage_k_peaks1=f.k_peaks[1], peakaverage_pad=np.array(f.pad_peaks))
+    f1 = PowerSpectrumBAOFilter(PowerSpectrumInterpolator1D(ktab, interp2d(ktab, 0.5)), engine='peakaverage', cosmo=cosmo, cosmo_fid=cosmo_fid)
+    arrays.update(peakaverage_pknow_1col=f1.pknow)
+    xi = interp.to_xi()
+    fx = CorrelationFunctionBAOFilter(xi, engine='kirkby2013', cosmo=cosmo)
+    arrays.update(s=fx.s, xi=fx.xi, kirkby_xinow=fx.xinow, extrap_smin=xi.extrap_smin, extrap_smax=xi.extrap_smax)
+    fx = CorrelationFunctionBAOFilter(xi, engine='kirkby2013', cosmo=cosmo, cosmo_fid=cosmo_fid, srange_left=(45., 80.), srange_right=(155., 195.))
+    arrays.update(kirkby2_xinow=fx.xinow)
+    fn = os.path.join(GOLDEN, 'filters_golden.npz')
+    np.savez_compressed(fn, **arrays)
+    print('wrote {} ({:.2f} MB)'.format(fn, os.path.getsize(fn) / 1e6))
+
+
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['fftlog', 'spline', 'wallish', 'eh', 'interp2d']
+    which = sys.argv[1:] or ['fftlog', 'spline', 'wallish', 'eh', 'interp2d', 'filters']
     print('reference: cosmoprimo {} from {}; numpy {}'.format(cosmoprimo.__version__, os.path.dirname(cosmoprimo.__file__), np.__version__))
     for name in which:
         fn = globals().get('make_' + name, None)
