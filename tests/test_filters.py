@@ -137,8 +137,8 @@ def test_kirkby2013_filter(device):
 def test_new_filters_register_in_reference():
     """The reference's factories build our classes by name once they are registered (ref bao_filter.py:22-31, 691-700, 912-933), with the
     reference's own Cosmology objects standing in for EHCosmology."""
+    Cosmology = reference().Cosmology          # puts baseline/_ref on the path
     refb = B.register_in_reference()
-    Cosmology = reference().Cosmology
     d = golden()
     cosmo = Cosmology(m_ncdm=None, engine='eisenstein_hu', **dict(zip(NAMES, d['par'])))
     fid = Cosmology(m_ncdm=None, engine='eisenstein_hu', **dict(zip(NAMES, d['par_fid'])))

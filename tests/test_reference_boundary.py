@@ -23,6 +23,7 @@ def test_engine_instance_passes_through_reference_factory():
 
 def test_filter_registers_in_reference_registry():
     """ref bao_filter.py:22-31, 912-921: the factory looks the engine name up in the metaclass registry."""
+    reference()
     refb = B.register_in_reference()
     reg = refb.RegisteredPowerSpectrumBAOFilter._registry
     assert reg['wallish2018_cuda'] is B.Wallish2018PowerSpectrumBAOFilter

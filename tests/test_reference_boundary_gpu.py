@@ -86,6 +86,7 @@ def reference_boxes(filt):
 def test_register_in_reference():
     """Zero-patch route 2: after register_in_reference() the reference's own factory builds our filter for engine='wallish2018_cuda' and it
     agrees with the reference's engine='wallish2018' on the identical interpolator (ref bao_filter.py:22-31, 361-423, 912-921)."""
+    reference()                                # puts baseline/_ref on the path
     refb = B.register_in_reference()
     interp = reference_interpolator(33, seed=21)
     ours = refb.PowerSpectrumBAOFilter(interp, engine='wallish2018_cuda')
