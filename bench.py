@@ -296,6 +296,9 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     _lib.require_device()
+    # each rank next to its own GPU: cores and pinned memory of the GPU's NUMA node (before any pinned allocation)
+    from cosmoprimo_b200.distributed import bind_to_device_numa
+    numa = bind_to_device_numa(local_rank) if not os.environ.get('CPF_NO_NUMA_BIND') else {'disabled': True}
 
     def barrier():
         if world > 1:
@@ -363,6 +366,42 @@ def run_ours(args):
     torch.cuda.synchronize()
     e2e_elapsed = max_over_ranks(time.perf_counter() - t0)
     e2e_value = world * per_step * e2e_steps / e2e_elapsed
+    # e2e variants (same metric, same transforms per step): (a) PAGEABLE numpy input and output, what a user gets without pinning anything;
+    # (b) the north-star path "5 parameters per cosmology in -> EH generator on the device -> FFTLog -> xi to the host": half the PCIe bytes
+    e2e_variants = {}
+    if not QUICK:
+        p_fun = np.array(fun)                                  # plain pageable copy
+        for _ in range(2):
+            p_out = fftlog(p_fun)[1]
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            p_out = fftlog(p_fun)[1]
+        torch.cuda.synchronize()
+        e2e_variants['pageable_in_out'] = {'value': world * per_step * 3 / max_over_ranks(time.perf_counter() - t0), 'unit': UNIT}
+        del p_fun, p_out
+        from cosmoprimo_b200 import synthetic as S_
+        from cosmoprimo_b200.eisenstein_hu import EisensteinHu
+        par = S_.lhs_cosmologies(NCOSMO, seed=42 + rank)
+        pinned_out = torch.empty((NCOSMO, len(ELLS), NK), dtype=torch.float64).pin_memory()
+
+        def params_in():
+            eh = EisensteinHu(par['h'], par['omega_b'], par['omega_cdm'], par['n_s'], logA=par['logA'], device=local_rank)     # 5 x 4096 doubles to the device
+            xi = fftlog(eh.pk(k, z=np.full(NCOSMO, 0.5), kaiser=True))[1]
+            pinned_out.copy_(xi, non_blocking=True)
+            return pinned_out
+        for _ in range(2):
+            params_in()
+        torch.cuda.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            params_in()
+        torch.cuda.synchronize()
+        e2e_variants['parameters_in_xi_out'] = {'value': world * per_step * e2e_steps / max_over_ranks(time.perf_counter() - t0), 'unit': UNIT,
+                                                'h2d_bytes_per_step': 5 * 8 * NCOSMO, 'd2h_bytes_per_step': int(pinned_out.numel() * 8),
+                                                'path': 'cpf_eh_pk (Kaiser multipoles, z = 0.5) -> cpf_fftlog on the device, result copied into a pinned host buffer'}
+        del pinned_out
     # `out` is the result of the TIMED launches (persistent stream kernel); `h_out` went through the host path (16 MB chunks)
     d_out = out.cpu().numpy()
     post = fftlog.padded_postfactor[:, fftlog.padded_size_out_left:fftlog.padded_size_out_left + NK]
@@ -396,7 +435,8 @@ def run_ours(args):
               'dtype': 'f64', 'data': 'synthetic',
               'config': workload_config(),
               'clocks': clocks,
-              'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(fun.nbytes), 'd2h_bytes_per_step': int(h_out.nbytes), 'steps': e2e_steps},
+              'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(fun.nbytes), 'd2h_bytes_per_step': int(h_out.nbytes), 'steps': e2e_steps,
+                      'GBps_each_way_per_gpu': e2e_value / world * BYTES_PER_TRANSFORM / 2 / 1e9, 'numa_binding_rank0': numa, 'variants': e2e_variants},
               'gpu_launches': args.steps, 'roofline': roof}
 
     if world == 1 and not args.no_cpu_baseline:

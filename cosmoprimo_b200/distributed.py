@@ -67,3 +67,43 @@ def gather_rows(local, nrows_total):
     dist.all_gather(parts, t)
     out = torch.cat([part[:b - a] for part, (a, b) in zip(parts, sizes)], dim=0)
     return out.numpy() if is_numpy else out
+
+
+def bind_to_device_numa(device):
+    """
+    Bind the calling process to the CPU cores (and, when libnuma is present, the memory) of the NUMA node the GPU ``device`` hangs off, so that
+    each rank's pinned staging buffers and copy threads sit next to its own PCIe root instead of all on node 0 (eight ranks
+    shared one memory controller).  Linux sysfs only; returns a dict describing what was done (for the bench record), never raises.
+    """
+    import os
+    info = {'device': int(device), 'numa_node': None, 'cpus': None, 'membind': False}
+    try:
+        import torch
+        prop = torch.cuda.get_device_properties(device)
+        bdf = '{:04x}:{:02x}:{:02x}.0'.format(prop.pci_domain_id, prop.pci_bus_id, prop.pci_device_id)
+        info['pci'] = bdf
+        with open('/sys/bus/pci/devices/{}/numa_node'.format(bdf)) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return info
+        info['numa_node'] = node
+        with open('/sys/devices/system/node/node{}/cpulist'.format(node)) as f:
+            cpus = set()
+            for part in f.read().strip().split(','):
+                lo, _, hi = part.partition('-')
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info['cpus'] = len(allowed)
+        try:
+            import ctypes
+            numa = ctypes.CDLL('libnuma.so.1')
+            if numa.numa_available() >= 0:
+                numa.numa_set_preferred(node)
+                info['membind'] = True
+        except OSError:
+            pass
+    except Exception as exc:      # best effort: a container without sysfs, an old torch without the PCI ids, ...
+        info['error'] = repr(exc)
+    return info
