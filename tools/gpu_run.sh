@@ -36,9 +36,9 @@ for STEP in "$@"; do
           python bench.py --steps 5 --warmup 3 --no-cpu-baseline > $OUT/ncu_full_$TAG.log 2>&1; tail -2 $OUT/ncu_full_$TAG.log ;;
     ncuwallish)
       timeout 900 ncu --set full --clock-control none --import-source on -k regex:${ARG:-wallish} -s 2 -c 3 -f -o $OUT/prof_wallish_$TAG \
-          python tools/lab/wallish_run.py 4096 > $OUT/ncu_wallish_$TAG.log 2>&1; tail -2 $OUT/ncu_wallish_$TAG.log
+          python tools/lab/wallish_run.py 8192 > $OUT/ncu_wallish_$TAG.log 2>&1; tail -2 $OUT/ncu_wallish_$TAG.log
       timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $OUT/launches_wallish_$TAG.csv \
-          python tools/lab/wallish_run.py 4096 >> $OUT/ncu_wallish_$TAG.log 2>&1 ;;
+          python tools/lab/wallish_run.py 8192 >> $OUT/ncu_wallish_$TAG.log 2>&1 ;;
     sanitizer)
       timeout 1500 compute-sanitizer --tool ${ARG:-memcheck} python -m pytest tests -m gpu -x -q -k "golden or persistent or wallish" > $OUT/sanitizer_${ARG:-memcheck}_$TAG.log 2>&1
       tail -5 $OUT/sanitizer_${ARG:-memcheck}_$TAG.log ;;
