@@ -1,29 +1,30 @@
 // cpf_wallish.cu — Wallish2018 no-wiggle filter (cosmoprimo/bao_filter.py:361-431) and the orthonormal DST-II/III it is
 // built on (scipy.fftpack.dst / idst, bao_filter.py:372, 412), on sm_100a.
 //
-// Pipeline of cpf_wallish2018 for ncols spectra (reference layout: wavenumber along axis 0, one column per spectrum):
-//   1. wallish_fused_kernel  — one CTA per PAIR of columns, everything in shared memory (cpf_wallish_core.h):
-//        log(k P) -> DST-II (one packed complex FFT-4096, the FFTLog register FFT) -> clamped-spline second derivatives
-//        of the even / odd coefficients -> argmax boxes -> cut + re-spline -> DST-III -> exp(.)/k on 1e-2 < k < 1.5,
-//        written straight into the knot-value matrix of the final spline.
-//   2. wallish_edges_kernel  — rows of that matrix taken from the unfiltered spectrum (k < 5e-4 and k > 2, :415-419).
-//   3. spline_factor_kernel + spline_solve_kernel (cpf_spline.cu) — clamped spline on the 3666 shared knots (:420).
-//   4. wallish_final_kernel  — evaluate at self.k, blend with the Gaussian top-hat (:421-423).
+// cpf_wallish2018 is ONE kernel, wallish_fused_kernel: one CTA of 256 threads per PAIR of spectra (columns of the reference layout,
+// wavenumber along axis 0), two CTAs per SM, everything between the load of pklin and the store of pknow in ONE 68 KB shared-memory
+// buffer and in registers (cpf_wallish_core.h):
+//   log(k P) -> DST-II (one packed complex FFT-4096, the FFTLog register FFT) -> clamped-spline second derivatives of the even / odd
+//   coefficients -> argmax boxes -> cut + re-spline -> DST-III -> exp(.)/k on 1e-2 < k < 1.5 -> spliced with the unfiltered spectrum
+//   at k < 5e-4 and k > 2 -> clamped spline on those knots, evaluated at self.k -> blend with the Gaussian top-hat (:415-423).
+// HBM traffic per spectrum: 8 * 4096 B of pklin in, 8 * nk B of pk in and of pknow out; no intermediate leaves the SM.
 #include <math.h>
 #include <mutex>
+#include <string.h>
 #include <vector>
 
 #include "cpf_common.h"
+#include "cpf_fastmath.h"
 #include "cpf_fft_core.h"
 #include "cpf_spline_core.h"
 #include "cpf_wallish_core.h"
+#include "cpf_wallish_final.h"
+
+#ifndef CPF_WALLISH_L2_HINT
+#define CPF_WALLISH_L2_HINT 256
+#endif
 
 namespace cpf {
-
-// defined in cpf_spline.cu
-int spline_fit_device(const double* d_x, const double* d_y, int nx, long long ncols, int bc, double* d_s, double* d_fac,
-                      cudaStream_t stream, bool fac_ready);
-void spline_factor_host(const double* x, int nx, int bc, double* fac);
 
 struct WallishTables {
   int device;
@@ -35,43 +36,52 @@ struct WallishTables {
 
 struct WallishArgs {
   const double* klin;     // [4096]
-  const double* pklin;    // [4096, ncols]
-  double2* packed;        // [npairs, 4096]: in  = sign * log(k P) of both columns of a pair in Makhoul order (wallish_pack_kernel),
-                          //                 out = raw FFT bins of the DST-III (consumed by wallish_unpack_kernel)
-  long long ncols;        // columns of this chunk
-  long long ld;           // doubles between consecutive rows of pklin / pkout / pknow (= total number of columns)
-  int i0, i1;             // rows of klin kept (1e-2 < k < 1.5)
-  int nl;                 // rows of the knot matrix before them
-  double* vals;           // [nknots, ncols] knot values of the final spline
+  const double* pklin;    // [4096, ld]
+  const double* pkout;    // [nk, ld]
+  double* pknow;          // [nk, ld]
+  long long ncols;
+  long long ld;           // doubles between consecutive rows of pklin / pkout / pknow
+  int vec;                // pairs of columns are 16-byte aligned in all three arrays
   int* boxes;             // [ncols, 4] or null
+  unsigned long long* dbg; // lab: per-phase cycle totals (thread 0 of every CTA), or null
   const double2 *tw1, *tw2, *twd;
   const double* wtab;
+  // final stage (cpf_wallish_final.h)
+  int i0, i1, nl, nr, lz, rz, nmid, nc, nk, nrounds, slbase;
+  WallishFinFac fc;       // elimination factors of the spliced spline
+  const double* rklin;    // [4096] 1 / klin
+  const int* slotT;
+  const int* qstart;
+  const int* qinfo;
+  const double* qh;
+  const double* qth;      // [nk] Gaussian top-hat at self.k (:425-431)
 };
 
-// shared-memory carve-up of the fused kernels
+// shared-memory carve-up
 struct WallishSmem {
-  double2* S;     // FFT exchange buffer, then natural-order spectrum, then reduced right-hand sides
-  double2* X;     // DST coefficients, de-interleaved + padded
-  double2* DD;    // second derivatives
+  double2* B;     // FFT exchange buffer / spectrum in natural order / DST coefficients (de-interleaved + padded) / knots + slope slots of the final spline
+  double2* E;     // [256] chunk results of the two-step eliminations (value with zero inflow), forward
+  double2* Eb;    // [256] ... backward
+  double* Mf;     // [256] ... and the factors the inflow is multiplied with
+  double* Mb;     // [256]
   double* red;    // [256]
   int* redi;      // [256]
   int* box;       // [8]
   WallishGap* gaps;   // [4]
   double* wtab;   // [32] Thomas pivots (copied from global memory once: they sit in the dependency chain of the first chunks)
-  double2* E;     // [256] chunk results of the two-step eliminations (value with zero inflow)
-  double* Mf;     // [256] ... and the factor the inflow is multiplied with
   __device__ explicit WallishSmem(double2* base) {
-    S = base; X = base + WallishGeo::BUF; DD = base + 2 * WallishGeo::BUF;
-    red = reinterpret_cast<double*>(base + 3 * WallishGeo::BUF);
-    redi = reinterpret_cast<int*>(red + 256);
+    B = base; E = base + WallishGeo::BUF; Eb = E + 256;
+    Mf = reinterpret_cast<double*>(Eb + 256);
+    Mb = Mf + 256;
+    red = Mb + 256;
+    wtab = red + 256;
+    gaps = reinterpret_cast<WallishGap*>(wtab + 32);
+    redi = reinterpret_cast<int*>(gaps + 4);
     box = redi + 256;
-    gaps = reinterpret_cast<WallishGap*>(box + 8);
-    wtab = reinterpret_cast<double*>(gaps + 4);
-    E = reinterpret_cast<double2*>(wtab + 32);
-    Mf = reinterpret_cast<double*>(E + 256);
   }
 };
-static constexpr size_t kWallishSmemBytes = 3 * (size_t)WallishGeo::BUF * sizeof(double2) + 256 * sizeof(double) + 264 * sizeof(int) + 4 * sizeof(WallishGap) + 32 * sizeof(double) + 256 * sizeof(double2) + 256 * sizeof(double);
+static constexpr size_t kWallishSmemBytes = ((size_t)WallishGeo::BUF + 512) * sizeof(double2) + (3 * 256 + 32) * sizeof(double) + 4 * sizeof(WallishGap) + 264 * sizeof(int);
+static_assert(2 * (kWallishSmemBytes + 1024) <= 227 * 1024, "two CTAs per SM");
 
 __device__ __forceinline__ void fft4096(const int t, double2 (&v)[16], double2* S, const double2* tw1, const double2* tw2) {
   fft_pass1<16, false>(t, v, S, tw1);
@@ -81,15 +91,28 @@ __device__ __forceinline__ void fft4096(const int t, double2 (&v)[16], double2* 
   fft_pass3<16, false>(t, v, S);
 }
 
-// DST-II (orthonormal) of the two packed real sequences whose Makhoul-permuted samples are in v; result in sm.X
-__device__ __forceinline__ void dst2_in_smem(const int t, double2 (&v)[16], const WallishSmem& sm, const double2* tw1,
-                                             const double2* tw2, const double2* twd) {
-  fft4096(t, v, sm.S, tw1, tw2);
+// DST-II (orthonormal) of the two packed real sequences whose Makhoul-permuted samples are in v; coefficients in B (padded layout)
+__device__ __forceinline__ void dst2_in_smem(const int t, double2 (&v)[16], double2* B, const double2* tw1, const double2* tw2, const double2* twd) {
+  fft4096(t, v, B, tw1, tw2);
   __syncthreads();
 #pragma unroll
-  for (int r = 0; r < 16; ++r) sm.S[t + 256 * r] = v[r];
+  for (int r = 0; r < 16; ++r) B[t + 256 * r] = v[r];
   __syncthreads();
-  wallish_dst2_post(t, v, sm.S, sm.X, twd);
+  wallish_dst2_coef(t, v, B, twd);
+  __syncthreads();
+  wallish_dst2_store(t, v, B);
+  __syncthreads();
+}
+
+// the part of dst2_in_smem after the FFT
+__device__ __forceinline__ void dst2_post_in_smem(const int t, double2 (&v)[16], double2* B, const double2* twd) {
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < 16; ++r) B[t + 256 * r] = v[r];
+  __syncthreads();
+  wallish_dst2_coef(t, v, B, twd);
+  __syncthreads();
+  wallish_dst2_store(t, v, B);
   __syncthreads();
 }
 
@@ -98,6 +121,26 @@ __device__ __forceinline__ int makhoul_src(const int n, double& sign) {
   if (n < WallishGeo::N / 2) { sign = 1.; return 2 * n; }
   sign = -1.;
   return 2 * (WallishGeo::N - 1 - n) + 1;
+}
+
+// the two columns of a pair at row `row` of a [rows, ld] array
+__device__ __forceinline__ double2 load_pair(const double* base, const long long ld, const long long row, const long long col0, const bool has1, const int vec) {
+  const double* p = base + row * ld + col0;
+  if (vec && has1) {
+    // a pair is 16 bytes of a row; the CTAs that run at the same time work on neighbouring pairs, so the whole 256-byte stretch of the row
+    // is asked for at once (L2 prefetch size): 8 x fewer, 8 x longer DRAM accesses than one 32-byte sector per pair
+    double2 r;
+#if CPF_WALLISH_L2_HINT == 256
+    asm volatile("ld.global.L2::256B.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+#elif CPF_WALLISH_L2_HINT == 128
+    asm volatile("ld.global.L2::128B.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+#else
+    r = __ldcs(reinterpret_cast<const double2*>(p));
+#endif
+    return r;
+  }
+  const double a = __ldcs(p);
+  return mk2(a, has1 ? __ldcs(p + 1) : a);
 }
 
 // warp-level argmax of the chunk candidates of both columns; lane 0 of warp w (sequence parity h = w / 4) leaves the
@@ -127,29 +170,106 @@ __device__ __forceinline__ int wallish_best_final(const int q, const double* red
   return i;
 }
 
-__global__ void __launch_bounds__(256, 1) wallish_fused_kernel(const WallishArgs a) {
+// ---- phases of the fused kernel ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void store_pair(double* base, const long long ld, const long long row, const long long col0, const bool has1, const int vec,
+                                           const double2 val) {
+  double* dst = base + row * ld + col0;
+  if (vec && has1) __stcs(reinterpret_cast<double2*>(dst), val);
+  else { dst[0] = val.x; if (has1) dst[1] = val.y; }
+}
+
+// output wavenumbers that are knots of the spliced spline (self.k < 5e-4, self.k > 2): it returns pk there, wiggles = 1, pknow = pk
+__device__ __forceinline__ void wallish_copy_edges(const WallishArgs& a, const int t, const long long col0, const bool has1) {
+  for (int c = t; c < a.nl + a.nr; c += WallishGeo::T) {
+    const int q = c < a.nl ? c : a.nk - a.nr + (c - a.nl);
+    store_pair(a.pknow, a.ld, q, col0, has1, a.vec, load_pair(a.pkout, a.ld, q, col0, has1, a.vec));
+  }
+}
+
+// v[r] = sign * log(k P) in Makhoul order, straight from the reference layout (16 bytes per row and pair)      (bao_filter.py:371)
+// ROLL: the samples land in the (free) buffer by asynchronous 16-byte copies, the logarithms are taken in place by a rolled loop
+template <bool ROLL>
+__device__ __forceinline__ void wallish_load_log(const WallishArgs& a, const WallishSmem& sm, const int t, const long long col0, const bool has1,
+                                                 double2 (&v)[16]) {
   typedef WallishGeo G;
-  extern __shared__ double2 smem_raw[];
-  const WallishSmem sm(smem_raw);
-  const int t = threadIdx.x;
-  const long long col0 = 2LL * blockIdx.x;
-  const bool has1 = col0 + 1 < a.ncols;
-  double2 v[16];
-  // sign * log(k P) in Makhoul order, packed per pair by wallish_pack_kernel                  (bao_filter.py:371)
-  double2* zrow = a.packed + (long long)blockIdx.x * G::N;
-  if (t < 32) sm.wtab[t] = a.wtab[t];            // visible after the barriers of the first FFT
+  if (!ROLL) {
 #pragma unroll
-  for (int r = 0; r < 16; ++r) v[r] = __ldcs(zrow + t + 256 * r);
-  dst2_in_smem(t, v, sm, a.tw1, a.tw2, a.twd);                                              // :372
-  // second derivatives of the clamped splines through the even / odd coefficients           (:377-382)
-  wallish_forward_local(t, sm.X, sm.E, sm.Mf, sm.wtab);
+    for (int r = 0; r < 16; ++r) {
+      double sign;
+      const int j = makhoul_src(t + 256 * r, sign);
+      v[r] = load_pair(a.pklin, a.ld, j, col0, has1, a.vec);
+    }
+    wallish_copy_edges(a, t, col0, has1);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      double sign;
+      const int j = makhoul_src(t + 256 * r, sign);
+      const double k = __ldg(a.klin + j);
+      v[r] = mk2(sign * fast_log(k * v[r].x), sign * fast_log(k * v[r].y));
+    }
+    return;
+  }
+  if (a.vec && has1) {
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      const int n = t + 256 * r;
+      double sign;
+      const int j = makhoul_src(n, sign);
+      const unsigned dst = (unsigned)__cvta_generic_to_shared(sm.B + n);
+#if CPF_WALLISH_L2_HINT == 256
+      asm volatile("cp.async.cg.shared.global.L2::256B [%0], [%1], 16;" ::"r"(dst), "l"(a.pklin + (long long)j * a.ld + col0) : "memory");
+#elif CPF_WALLISH_L2_HINT == 128
+      asm volatile("cp.async.cg.shared.global.L2::128B [%0], [%1], 16;" ::"r"(dst), "l"(a.pklin + (long long)j * a.ld + col0) : "memory");
+#else
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(a.pklin + (long long)j * a.ld + col0) : "memory");
+#endif
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  } else {
+#pragma unroll 1
+    for (int r = 0; r < 16; ++r) {
+      const int n = t + 256 * r;
+      double sign;
+      const int j = makhoul_src(n, sign);
+      sm.B[n] = load_pair(a.pklin, a.ld, j, col0, has1, 0);
+    }
+  }
+  wallish_copy_edges(a, t, col0, has1);
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll 1
+  for (int r4 = 0; r4 < 16; r4 += 4) {                  // four samples per step: their k and shared-memory loads are in flight together
+    double k[4];
+    double2 x[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int n = t + 256 * (r4 + i);
+      double sign;
+      k[i] = __ldg(a.klin + makhoul_src(n, sign));
+      x[i] = sm.B[n];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int n = t + 256 * (r4 + i);
+      const double sign = n < G::N / 2 ? 1. : -1.;
+      sm.B[n] = mk2(sign * fast_log(k[i] * x[i].x), sign * fast_log(k[i] * x[i].y));
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 16; ++r) v[r] = sm.B[t + 256 * r];
+  __syncthreads();                                     // pass 1 of the FFT scatters into other threads' slots
+}
+
+// between the two FFTs: DST-II coefficients -> second derivatives -> boxes -> cut + re-spline -> DST-III input in v
+__device__ __forceinline__ void wallish_middle(const WallishArgs& a, const WallishSmem& sm, const int t, const long long col0, const bool has1,
+                                               double2 (&v)[16], double2 (&d)[16]) {
+  typedef WallishGeo G;
+  dst2_post_in_smem(t, v, sm.B, a.twd);                                                      // :372
+  // second derivatives of the clamped splines through the even / odd coefficients           (:377-382); chunks live in registers
+  wallish_forward_local(t, sm.B, d, sm.E, sm.Mf, sm.wtab);
   __syncthreads();
-  wallish_forward_store(t, sm.X, sm.S, sm.E, sm.Mf, sm.wtab);
+  wallish_forward_fix_backward_local(t, d, sm.E, sm.Mf, sm.Eb, sm.Mb, sm.wtab);
   __syncthreads();
-  wallish_backward_local(t, sm.S, sm.E, sm.Mf, sm.wtab);
-  __syncthreads();
-  WallishBest chunk;
-  wallish_backward_dd(t, sm.X, sm.S, sm.DD, sm.E, sm.Mf, sm.wtab, &chunk);
+  const WallishBest chunk = wallish_backward_dd(t, sm.B, d, sm.Eb, sm.Mb, sm.wtab);
   // boxes (:392-395): argmax over [20, H-20), then over [first + 5, H-20); per-chunk maxima come out of the backward pass,
   // warps reduce them with shuffles, thread q < 4 merges the four warps of its sequence
   wallish_best_reduce(t, chunk, sm.red, sm.redi);
@@ -158,7 +278,7 @@ __global__ void __launch_bounds__(256, 1) wallish_fused_kernel(const WallishArgs
   __syncthreads();
   {
     const int h = t >> 7;
-    const WallishBest cand = wallish_chunk_candidate(t, sm.DD, sm.box[4 * h] + G::MARGIN_SECOND, sm.box[4 * h + 2] + G::MARGIN_SECOND, chunk);
+    const WallishBest cand = wallish_chunk_candidate(t, d, sm.box[4 * h] + G::MARGIN_SECOND, sm.box[4 * h + 2] + G::MARGIN_SECOND, chunk);
     wallish_best_reduce(t, cand, sm.red, sm.redi);     // red / redi were consumed before the previous barrier
   }
   __syncthreads();
@@ -177,8 +297,7 @@ __global__ void __launch_bounds__(256, 1) wallish_fused_kernel(const WallishArgs
   __syncthreads();
   // cut + re-spline (:396-401): the 8 one-sided eliminations (4 sequences x 2 sides, at most WARM = 32 rows each) run one per warp,
   // one row per lane: a row's step d -> (r - lo d) w is the affine map d -> a d + b with a = -lo w, b = r w, and the maps are
-  // composed in row order by a shuffle tree (5 rounds) instead of a 32-step chain on one thread (14 % of the kernel's stall
-  // samples sat on the barrier behind those chains).  Then the 2x2 solves on 4 threads.
+  // composed in row order by a shuffle tree (5 rounds) instead of a 32-step chain on one thread.  Then the 2x2 solves on 4 threads.
   {
     static_assert(G::WARM == 32, "one elimination row per lane");
     const int e = t >> 5, lane = t & 31, q = e >> 1, side = e & 1;
@@ -190,7 +309,7 @@ __global__ void __launch_bounds__(256, 1) wallish_fused_kernel(const WallishArgs
         const bool edge = (i == 0 || i == G::H - 1);
         const double w = wpivot(sm.wtab, side ? G::H - 1 - i : i, G::H);
         fa = edge ? 0. : -w;
-        fb = wallish_gap_rhs(sm.X, q >> 1, q & 1, i) * w;
+        fb = wallish_gap_rhs(sm.B, q >> 1, q & 1, i) * w;
       }
     }
 #pragma unroll
@@ -201,7 +320,7 @@ __global__ void __launch_bounds__(256, 1) wallish_fused_kernel(const WallishArgs
     if (lane == 0) sm.red[e] = fb;                       // reduced right-hand side at the last eliminated row (zero inflow)
   }
   __syncthreads();
-  if (t < 4) sm.gaps[t] = wallish_gap_finish(sm.X, t >> 1, t & 1, sm.box[2 * t], sm.box[2 * t + 1], sm.red[2 * t], sm.red[2 * t + 1], sm.wtab);
+  if (t < 4) sm.gaps[t] = wallish_gap_finish(sm.B, t >> 1, t & 1, sm.box[2 * t], sm.box[2 * t + 1], sm.red[2 * t], sm.red[2 * t + 1], sm.wtab);
   __syncthreads();
   {                                                                                         // :402
     // only the knots of the removed box change (64 threads per sequence); a box that reaches the end of the array
@@ -210,120 +329,145 @@ __global__ void __launch_bounds__(256, 1) wallish_fused_kernel(const WallishArgs
     const WallishGap g = sm.gaps[q];
     const int iend = g.ok ? g.b1 : G::H - 1;
     for (int i = g.b0 + (t & 63); i <= iend; i += 64) {
-      double* y = reinterpret_cast<double*>(sm.X + wpos(h, i)) + col;
+      double* y = reinterpret_cast<double*>(sm.B + wpos(h, i)) + col;
       *y = wallish_fill(*y, i, g);
     }
   }
   __syncthreads();
-  // DST-III and exp(.)/k on the kept rows                                                   (:409-416)
-  wallish_dst3_pre(t, sm.X, v, a.twd);
-  fft4096(t, v, sm.S, a.tw1, a.tw2);
-  // FFT bins of the DST-III, bin order (coalesced); exp(.)/k and the transposition happen in wallish_unpack_kernel
-#pragma unroll
-  for (int r = 0; r < 16; ++r) __stcs(zrow + t + 256 * r, v[r]);
+  // DST-III (:409-412)
+  wallish_dst3_pre(t, sm.B, v, a.twd);
+  __syncthreads();                                      // the coefficients are in registers: the buffer is the FFT's again
 }
 
-// ---- layout changes around the fused kernel: both are 64-row x 32-column tile transpositions through shared memory ----
-// pack: pklin [4096, ncols] -> packed [npairs, 4096] double2 = sign * log(k P), Makhoul order (n < N/2: j = 2n, else j = 2(N-1-n)+1).
-// 64 consecutive rows j0 .. j0+63 hold 32 ascending samples n = j0/2 + i (even j) and 32 descending n = N-1-j0/2-i (odd j).
-__global__ void __launch_bounds__(256) wallish_pack_kernel(const double* __restrict__ klin, const double* __restrict__ pklin, const long long ld,
-                                                           const long long ncols, double2* __restrict__ packed) {
+// knots of the spliced spline (:413-419): exp(.)/k of the DST-III output on the kept rows, the unfiltered spectrum on the edge knots
+// ROLL: raw values to their slots, exp(.)/k applied in place by a rolled loop
+template <bool ROLL>
+__device__ __forceinline__ void wallish_knots(const WallishArgs& a, const WallishSmem& sm, const int t, const long long col0, const bool has1,
+                                              const double2 (&v)[16]) {
   typedef WallishGeo G;
-  __shared__ double tile[64][33];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int j0 = blockIdx.y * 64;
-  const long long c0 = (long long)blockIdx.x * 32;
-  const long long col = c0 + tx < ncols ? c0 + tx : ncols - 1;      // odd column count: the last pair repeats its column
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int j = j0 + ty + 8 * i;
-    const double v = log(klin[j] * __ldcs(pklin + (long long)j * ld + col));
-    tile[ty + 8 * i][tx] = (j & 1) ? -v : v;
-  }
-  __syncthreads();
-  // unit u = (pair p, parity): 32 lanes write 32 consecutive samples
-  for (int u = ty; u < 32; u += 8) {
-    const int p = u >> 1, odd = u & 1;
-    const long long pair = (c0 >> 1) + p;
-    if (2 * pair >= ncols) continue;
-    int jj, n;
-    if (!odd) { jj = 2 * tx; n = (j0 >> 1) + tx; }
-    else { jj = 2 * (31 - tx) + 1; n = G::N - 1 - (j0 >> 1) - (31 - tx); }
-    packed[pair * G::N + n] = mk2(tile[jj][2 * p], tile[jj][2 * p + 1]);
-  }
-}
-
-// unpack: packed [npairs, 4096] FFT bins m of the DST-III -> vals [nl + (j - i0), col] = exp(sign * bin / N) / k_j for rows
-// i0 <= j < i1 (bao_filter.py:412-416); j odd <-> m = (j+1)/2, j even <-> m = N - j/2 (m = 0 for j = 0), sign as in
-// wallish_dst3_out_index.
-__global__ void __launch_bounds__(256) wallish_unpack_kernel(const double* __restrict__ klin, const double2* __restrict__ packed,
-                                                             const long long ncols, const int i0, const int i1, const int nl,
-                                                             double* __restrict__ vals) {
-  typedef WallishGeo G;
-  __shared__ double tile[64][33];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int j0 = blockIdx.y * 64;
-  const long long c0 = (long long)blockIdx.x * 32;
-  for (int u = ty; u < 32; u += 8) {
-    const int p = u >> 1, odd = u & 1;
-    const long long pair = (c0 >> 1) + p;
-    if (2 * pair >= ncols) continue;
-    int jj, m;
-    if (odd) { jj = 2 * tx + 1; m = ((j0 + jj) + 1) >> 1; }
-    else { jj = 2 * (31 - tx); m = (G::N - ((j0 + jj) >> 1)) & (G::N - 1); }
-    const double2 z = __ldcs(packed + pair * G::N + m);
-    tile[jj][2 * p] = z.x;
-    tile[jj][2 * p + 1] = z.y;
-  }
-  __syncthreads();
-  const long long col = c0 + tx;
-  if (col >= ncols) return;
   const double inv = 1. / G::N;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int j = j0 + ty + 8 * i;
-    if (j < i0 || j >= i1) continue;
-    const double sign = (j & 1) ? -1. : 1.;           // j = 0 (m = 0) and even j: +1; odd j: -1
-    vals[(long long)(nl + j - i0) * ncols + col] = exp(sign * inv * tile[ty + 8 * i][tx]) / klin[j];
+  for (int r = 0; r < 16; ++r) {
+    double sign;
+    const int j = wallish_dst3_out_index(t + 256 * r, sign);
+    if (j >= a.i0 && j < a.i1) {
+      if (ROLL) sm.B[ypos(a.lz + (j - a.i0))] = v[r];
+      else {
+        const double rk = __ldg(a.rklin + j);
+        sm.B[ypos(a.lz + (j - a.i0))] = mk2(fast_exp(sign * inv * v[r].x) * rk, fast_exp(sign * inv * v[r].y) * rk);
+      }
+    }
+  }
+  for (int c = t; c < a.lz + a.rz; c += G::T) {
+    const int row = c < a.lz ? a.nl - a.lz + c : a.nk - a.nr + (c - a.lz);
+    const int knot = c < a.lz ? c : a.nmid + c;
+    sm.B[ypos(knot)] = load_pair(a.pkout, a.ld, row, col0, has1, a.vec);
+  }
+  if (ROLL) {
+    __syncthreads();
+#pragma unroll 1
+    for (int c0 = t; c0 < a.nmid; c0 += 4 * G::T) {       // four knots per step: their 1/k and shared-memory loads are in flight together
+      double rk[4];
+      double2 x[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = c0 + G::T * i;
+        if (c < a.nmid) { rk[i] = __ldg(a.rklin + a.i0 + c); x[i] = sm.B[ypos(a.lz + c)]; }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = c0 + G::T * i;
+        if (c < a.nmid) {
+          const double sc = ((a.i0 + c) & 1) ? -inv : inv;   // sign of wallish_dst3_out_index: odd rows -1, even rows +1
+          sm.B[ypos(a.lz + c)] = mk2(fast_exp(sc * x[i].x) * rk[i], fast_exp(sc * x[i].y) * rk[i]);
+        }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// clamped spline on the spliced knots (:420), chunks in registers; evaluation at self.k and blend (:420-423)
+__device__ __forceinline__ void wallish_final(const WallishArgs& a, const WallishSmem& sm, const int t, const long long col0, const bool has1,
+                                              double2 (&d)[16]) {
+  typedef WallishGeo G;
+  wallish_fin_forward_local(t, a.nc, sm.B, a.fc, d, sm.E, sm.Mf);
+  __syncthreads();
+  wallish_fin_fix_backward_local(t, a.fc, d, sm.E, sm.Mf, sm.Eb, sm.Mb);
+  __syncthreads();
+  wallish_fin_backward_fix(t, a.fc, d, sm.Eb, sm.Mb);
+  // the slopes next to an output wavenumber travel through the slot array
+  double2* SL = sm.B + a.slbase;
+  for (int round = 0; round < a.nrounds; ++round) {
+    if (round) __syncthreads();
+    wallish_fin_scatter(t, round, a.slotT, d, SL);
+    __syncthreads();
+    int q0 = __ldg(a.qstart + round), q1 = __ldg(a.qstart + round + 1);
+    if (q0 < a.nl) q0 = a.nl;                           // the knots themselves were copied by wallish_copy_edges
+    if (q1 > a.nk - a.nr) q1 = a.nk - a.nr;
+    for (int q = q0 + t; q < q1; q += 2 * G::T) {       // two output wavenumbers per step: their table and spectrum loads overlap
+      const int qb = q + G::T;
+      const bool two = qb < q1;
+      const double2 pka = load_pair(a.pkout, a.ld, q, col0, has1, a.vec);
+      const double2 pkb = two ? load_pair(a.pkout, a.ld, qb, col0, has1, a.vec) : pka;
+      const double2 ra = wallish_fin_eval(q, a.qinfo, a.qh, sm.B, SL, pka, __ldg(a.qth + q));
+      const double2 rb = wallish_fin_eval(two ? qb : q, a.qinfo, a.qh, sm.B, SL, pkb, __ldg(a.qth + (two ? qb : q)));
+      store_pair(a.pknow, a.ld, q, col0, has1, a.vec, ra);
+      if (two) store_pair(a.pknow, a.ld, qb, col0, has1, a.vec, rb);
+    }
   }
 }
 
-// rows of the knot matrix copied from the unfiltered spectrum: k < 5e-4 (first nl rows of kout) and k > 2 (last nr)
-__global__ void wallish_edges_kernel(const double* __restrict__ pkout, const long long ld, const int nk, const long long ncols, const int nl,
-                                     const int nmid, const int nr, double* __restrict__ vals) {
-  const long long col = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  const int r = blockIdx.y;   // 0 .. nl+nr-1
-  if (col >= ncols) return;
-  const int src = r < nl ? r : nk - nr + (r - nl);
-  const int dst = r < nl ? r : nl + nmid + (r - nl);
-  vals[(long long)dst * ncols + col] = pkout[(long long)src * ld + col];
-}
-
-// evaluate the final clamped spline at kout[q] (interval idx[q] precomputed: the knots are shared) and blend
-__global__ void wallish_final_kernel(const double* __restrict__ knots, const double* __restrict__ vals, const double* __restrict__ slopes,
-                                     const long long ncols, const double* __restrict__ kout, const int* __restrict__ idx,
-                                     const double* __restrict__ pkout, const long long ld, double* __restrict__ pknow) {
-  const long long col = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  const int q = blockIdx.y;
-  if (col >= ncols) return;
-  const double k = kout[q];
-  const int i = idx[q];
-  if (i < 0) { pknow[(long long)q * ld + col] = nan(""); return; }
-  const long long o = (long long)i * ncols + col;
-  const double smooth = spline_poly(knots[i], knots[i + 1], vals[o], vals[o + ncols], slopes[o], slopes[o + ncols], k, 0);   // :420
-  const double th = k > 1. ? exp(-400. * (k - 1.) * (k - 1.)) : 1.;                                                          // :425-431, scale=20
-  const double pk = pkout[(long long)q * ld + col];
-  const double wiggles = (pk / smooth - 1.) * th + 1.;                                                                      // :422
-  pknow[(long long)q * ld + col] = pk / wiggles;                                                                          // :423
+// V (lab): bit 0: the two FFTs share their code (a two-trip loop); bit 1: rolled logarithms; bit 2: rolled exponentials
+template <int V>
+__global__ void __launch_bounds__(256, 2) wallish_fused_kernel(const WallishArgs a) {
+  extern __shared__ double2 smem_raw[];
+  const WallishSmem sm(smem_raw);
+  const int t = threadIdx.x;
+  const long long npairs = (a.ncols + 1) / 2;
+  if (t < 32) sm.wtab[t] = a.wtab[t];            // visible after the barriers of the first FFT
+  for (long long pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+    const long long col0 = 2 * pair;
+    const bool has1 = col0 + 1 < a.ncols;     // odd column count: the last pair repeats its column
+    double2 v[16];
+    double2 d[16];
+    long long c0 = clock64();
+    auto stamp = [&](const int ph) {
+      if (a.dbg && t == 0) { const long long c1 = clock64(); atomicAdd(a.dbg + ph, (unsigned long long)(c1 - c0)); c0 = c1; }
+    };
+    if (V & 1) {
+#pragma unroll 1
+      for (int leg = 0; leg < 2; ++leg) {
+        if (leg == 0) wallish_load_log<(V & 2) != 0>(a, sm, t, col0, has1, v);
+        fft4096(t, v, sm.B, a.tw1, a.tw2);
+        if (leg == 0) wallish_middle(a, sm, t, col0, has1, v, d);
+      }
+    } else {
+      wallish_load_log<(V & 2) != 0>(a, sm, t, col0, has1, v);
+      stamp(0);
+      fft4096(t, v, sm.B, a.tw1, a.tw2);
+      stamp(1);
+      wallish_middle(a, sm, t, col0, has1, v, d);
+      stamp(2);
+      fft4096(t, v, sm.B, a.tw1, a.tw2);
+    }
+    __syncthreads();
+    stamp(3);
+    wallish_knots<(V & 4) != 0>(a, sm, t, col0, has1, v);
+    stamp(4);
+    wallish_final(a, sm, t, col0, has1, d);
+    stamp(5);
+    __syncthreads();                                      // the buffer goes back to the next pair's FFT
+  }
 }
 
 // ---- standalone DST-II / DST-III (orthonormal), N = 4096, along axis 0 of [4096, ncols] ------------------------------
 template <int TYPE>
-__global__ void __launch_bounds__(256, 1) dst_kernel(const double* __restrict__ in, double* __restrict__ out, const long long ncols,
+__global__ void __launch_bounds__(256, 2) dst_kernel(const double* __restrict__ in, double* __restrict__ out, const long long ncols,
                                                      const double2* tw1, const double2* tw2, const double2* twd) {
   typedef WallishGeo G;
   extern __shared__ double2 smem_raw[];
-  const WallishSmem sm(smem_raw);
+  double2* B = smem_raw;
   const int t = threadIdx.x;
   const long long col0 = 2LL * blockIdx.x;
   const bool has1 = col0 + 1 < ncols;
@@ -336,9 +480,9 @@ __global__ void __launch_bounds__(256, 1) dst_kernel(const double* __restrict__ 
       const double* row = in + (long long)j * ncols + col0;
       v[r] = mk2(sign * row[0], has1 ? sign * row[1] : 0.);
     }
-    dst2_in_smem(t, v, sm, tw1, tw2, twd);
+    dst2_in_smem(t, v, B, tw1, tw2, twd);
     for (int kk = t; kk < G::N; kk += 256) {
-      const double2 x = sm.X[wpos(kk & 1, kk >> 1)];
+      const double2 x = B[wpos(kk & 1, kk >> 1)];
       double* dst = out + (long long)kk * ncols + col0;
       dst[0] = x.x;
       if (has1) dst[1] = x.y;
@@ -346,11 +490,12 @@ __global__ void __launch_bounds__(256, 1) dst_kernel(const double* __restrict__ 
   } else {
     for (int kk = t; kk < G::N; kk += 256) {
       const double* row = in + (long long)kk * ncols + col0;
-      sm.X[wpos(kk & 1, kk >> 1)] = mk2(row[0], has1 ? row[1] : 0.);
+      B[wpos(kk & 1, kk >> 1)] = mk2(row[0], has1 ? row[1] : 0.);
     }
     __syncthreads();
-    wallish_dst3_pre(t, sm.X, v, twd);
-    fft4096(t, v, sm.S, tw1, tw2);
+    wallish_dst3_pre(t, B, v, twd);
+    __syncthreads();
+    fft4096(t, v, B, tw1, tw2);
     const double inv = 1. / G::N;
 #pragma unroll
     for (int r = 0; r < 16; ++r) {
@@ -468,7 +613,7 @@ int cpf_wallish2018(const double* klin, const double* pklin, int nlin, const dou
   WallishTables wt;
   CPF_TRY(wallish_tables(device, &wt));
 
-  // the two wavenumber grids are needed on the host (knot selection, interval search) and on the device
+  // the two wavenumber grids are needed on the host (knot selection, interval search, spline factors) and on the device
   std::vector<double> h_klin(nlin), h_kout(nk);
   if (on_device) {
     CPF_CUDA(cudaMemcpyAsync(h_klin.data(), klin, nlin * sizeof(double), cudaMemcpyDeviceToHost, stream));
@@ -480,91 +625,96 @@ int cpf_wallish2018(const double* klin, const double* pklin, int nlin, const dou
   }
   for (int i = 1; i < nlin; ++i) if (!(h_klin[i] > h_klin[i - 1])) return fail(CPF_EINVAL, "cpf_wallish2018: klin must be strictly increasing");
   for (int i = 1; i < nk; ++i) if (!(h_kout[i] > h_kout[i - 1])) return fail(CPF_EINVAL, "cpf_wallish2018: kout must be strictly increasing");
-  int i0 = 0, i1 = nlin, nl = 0, nr = 0;
-  while (i0 < nlin && !(h_klin[i0] > 1e-2)) ++i0;                    // mask = (k > 1e-2) & (k < 1.5)   (:415)
-  while (i1 > i0 && !(h_klin[i1 - 1] < 1.5)) --i1;
-  while (nl < nk && h_kout[nl] < 5e-4) ++nl;                         // mask_left = self.k < 5e-4        (:417)
-  while (nr < nk - nl && h_kout[nk - 1 - nr] > 2.) ++nr;             // mask_right = self.k > 2
-  const int nmid = i1 - i0, nknots = nl + nmid + nr;
-  if (nknots < 2) return fail(CPF_EINVAL, "cpf_wallish2018: fewer than two knots survive the k cuts");
-  std::vector<double> h_knots(nknots);
-  for (int i = 0; i < nl; ++i) h_knots[i] = h_kout[i];
-  for (int i = 0; i < nmid; ++i) h_knots[nl + i] = h_klin[i0 + i];
-  for (int i = 0; i < nr; ++i) h_knots[nl + nmid + i] = h_kout[nk - nr + i];
-  for (int i = 1; i < nknots; ++i) if (!(h_knots[i] > h_knots[i - 1])) return fail(CPF_EINVAL, "cpf_wallish2018: spliced knots are not increasing");
-  std::vector<int> h_idx(nk);
-  for (int q = 0; q < nk; ++q) {
-    // outside the spliced knots the reference's CubicSpline(extrapolate=False) yields NaN (:420), hence pknow = NaN there (:422-423)
-    const bool outside = h_kout[q] < h_knots[0] || h_kout[q] > h_knots[nknots - 1];
-    h_idx[q] = outside ? -1 : spline_interval(h_knots.data(), nknots, h_kout[q]);
+  WallishFinalPlan fp;
+  const char* cap_env = getenv("CPF_WALLISH_SLOT_CAP");                   // tests: forces the multi-round evaluation
+  const std::string why = wallish_final_plan(h_klin.data(), nlin, h_kout.data(), nk, &fp, cap_env ? atoi(cap_env) : 0);
+  if (!why.empty()) return fail(CPF_EINVAL, "cpf_wallish2018: %s", why.c_str());
+  std::vector<double> h_qth(nk);
+  for (int q = 0; q < nk; ++q) {                                          // _tophat(self.k, kmax=1, scale=20) (:425-431)
+    const double k = h_kout[q];
+    h_qth[q] = k > 1. ? exp(-400. * (k - 1.) * (k - 1.)) : 1.;
   }
 
   const size_t lin_bytes = (size_t)nlin * ncols * sizeof(double), out_bytes = (size_t)nk * ncols * sizeof(double);
-  // columns are processed in chunks so that the work arrays (packed: 64 KB, knot values + slopes: 59 KB per spectrum) stay within the
-  // private scratch pool's release threshold whatever the batch
-  const long long chunk = ncols < 8192 ? ncols : 8192;
-  const size_t knot_bytes = (size_t)nknots * chunk * sizeof(double);
-  ScratchBuf d_klin, d_pklin, d_kout, d_pkout, d_pknow, d_boxes, d_knots, d_idx, d_vals, d_slopes, d_fac, d_packed;
-  const double *p_klin = klin, *p_pklin = pklin, *p_kout = kout, *p_pkout = pkout;
+  ScratchBuf d_klin, d_pklin, d_pkout, d_pknow, d_boxes, d_tab;
+  const double *p_klin = klin, *p_pklin = pklin, *p_pkout = pkout;
   double* p_pknow = pknow;
   int* p_boxes = boxes;
   if (!on_device) {
     CPF_CUDA(d_klin.alloc(nlin * sizeof(double), stream));
     CPF_CUDA(d_pklin.alloc(lin_bytes, stream));
-    CPF_CUDA(d_kout.alloc(nk * sizeof(double), stream));
     CPF_CUDA(d_pkout.alloc(out_bytes, stream));
     CPF_CUDA(d_pknow.alloc(out_bytes, stream));
     CPF_CUDA(cudaMemcpyAsync(d_klin.p, klin, nlin * sizeof(double), cudaMemcpyHostToDevice, stream));
     CPF_CUDA(cudaMemcpyAsync(d_pklin.p, pklin, lin_bytes, cudaMemcpyHostToDevice, stream));
-    CPF_CUDA(cudaMemcpyAsync(d_kout.p, kout, nk * sizeof(double), cudaMemcpyHostToDevice, stream));
     CPF_CUDA(cudaMemcpyAsync(d_pkout.p, pkout, out_bytes, cudaMemcpyHostToDevice, stream));
-    p_klin = (const double*)d_klin.p; p_pklin = (const double*)d_pklin.p; p_kout = (const double*)d_kout.p; p_pkout = (const double*)d_pkout.p;
+    p_klin = (const double*)d_klin.p; p_pklin = (const double*)d_pklin.p; p_pkout = (const double*)d_pkout.p;
     p_pknow = (double*)d_pknow.p;
     if (boxes) {
       CPF_CUDA(d_boxes.alloc((size_t)ncols * 4 * sizeof(int), stream));
       p_boxes = (int*)d_boxes.p;
     }
   }
-  CPF_CUDA(d_knots.alloc(nknots * sizeof(double), stream));
-  CPF_CUDA(d_idx.alloc(nk * sizeof(int), stream));
-  CPF_CUDA(d_vals.alloc(knot_bytes, stream));
-  CPF_CUDA(d_slopes.alloc(knot_bytes, stream));
-  CPF_CUDA(d_fac.alloc(4 * (size_t)nknots * sizeof(double), stream));
-  CPF_CUDA(d_packed.alloc((size_t)((chunk + 1) / 2) * WallishGeo::N * sizeof(double2), stream));
-  // the factors of the final clamped spline depend on the spliced knots only: computed here, on the host copy
-  std::vector<double> h_fac(4 * (size_t)nknots);
-  spline_factor_host(h_knots.data(), nknots, 1, h_fac.data());
-  CPF_CUDA(cudaMemcpyAsync(d_fac.p, h_fac.data(), h_fac.size() * sizeof(double), cudaMemcpyHostToDevice, stream));
-  CPF_CUDA(cudaMemcpyAsync(d_knots.p, h_knots.data(), nknots * sizeof(double), cudaMemcpyHostToDevice, stream));
-  CPF_CUDA(cudaMemcpyAsync(d_idx.p, h_idx.data(), nk * sizeof(int), cudaMemcpyHostToDevice, stream));
-  CPF_CUDA(cudaFuncSetAttribute(wallish_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWallishSmemBytes));
-  for (long long c0 = 0; c0 < ncols; c0 += chunk) {
-    const long long cc = ncols - c0 < chunk ? ncols - c0 : chunk;
-    WallishArgs a;
-    a.klin = p_klin; a.pklin = p_pklin + c0; a.packed = (double2*)d_packed.p; a.ncols = cc; a.ld = ncols; a.i0 = i0; a.i1 = i1; a.nl = nl;
-    a.vals = (double*)d_vals.p; a.boxes = p_boxes ? p_boxes + 4 * c0 : nullptr;
-    a.tw1 = wt.tw1; a.tw2 = wt.tw2; a.twd = wt.twd; a.wtab = wt.wtab;
-    const dim3 tgrid((unsigned)((cc + 31) / 32), WallishGeo::N / 64);
-    wallish_pack_kernel<<<tgrid, 256, 0, stream>>>(p_klin, a.pklin, ncols, cc, a.packed);
-    wallish_fused_kernel<<<(unsigned)((cc + 1) / 2), 256, kWallishSmemBytes, stream>>>(a);
-    wallish_unpack_kernel<<<tgrid, 256, 0, stream>>>(p_klin, a.packed, cc, i0, i1, nl, a.vals);
-    CPF_CUDA(cudaGetLastError());
-    const unsigned ctile = (unsigned)((cc + 127) / 128);
-    if (nl + nr > 0) {
-      wallish_edges_kernel<<<dim3(ctile, (unsigned)(nl + nr)), 128, 0, stream>>>(p_pkout + c0, ncols, nk, cc, nl, nmid, nr, (double*)d_vals.p);
-      CPF_CUDA(cudaGetLastError());
-    }
-    CPF_TRY(spline_fit_device((const double*)d_knots.p, (const double*)d_vals.p, nknots, cc, 1, (double*)d_slopes.p, (double*)d_fac.p, stream, true));
-    wallish_final_kernel<<<dim3(ctile, (unsigned)nk), 128, 0, stream>>>((const double*)d_knots.p, (const double*)d_vals.p, (const double*)d_slopes.p,
-                                                                          cc, p_kout, (const int*)d_idx.p, p_pkout + c0, ncols, p_pknow + c0);
-    CPF_CUDA(cudaGetLastError());
+  // the tables of the final stage in one allocation / one copy: doubles first (facT, qh, qth, rklin), then the ints (slotT, qstart, qinfo)
+  const size_t n_fac = fp.facT.size(), n_qh = fp.qh.size(), n_slot = fp.slotT.size(), n_qs = fp.qstart.size(), n_qi = fp.qinfo.size();
+  const size_t tab_bytes = (n_fac + n_qh + (size_t)nk + (size_t)nlin) * sizeof(double) + (n_slot + n_qs + n_qi) * sizeof(int);
+  std::vector<char> h_tab(tab_bytes);
+  {
+    double* pd = reinterpret_cast<double*>(h_tab.data());
+    memcpy(pd, fp.facT.data(), n_fac * sizeof(double));
+    memcpy(pd + n_fac, fp.qh.data(), n_qh * sizeof(double));
+    memcpy(pd + n_fac + n_qh, h_qth.data(), (size_t)nk * sizeof(double));
+    for (int i = 0; i < nlin; ++i) pd[n_fac + n_qh + nk + i] = 1. / h_klin[i];
+    int* pi = reinterpret_cast<int*>(pd + n_fac + n_qh + nk + nlin);
+    memcpy(pi, fp.slotT.data(), n_slot * sizeof(int));
+    memcpy(pi + n_slot, fp.qstart.data(), n_qs * sizeof(int));
+    memcpy(pi + n_slot + n_qs, fp.qinfo.data(), n_qi * sizeof(int));
   }
+  CPF_CUDA(d_tab.alloc(tab_bytes, stream));
+  CPF_CUDA(cudaMemcpyAsync(d_tab.p, h_tab.data(), tab_bytes, cudaMemcpyHostToDevice, stream));
+  WallishArgs a;
+  a.klin = p_klin; a.pklin = p_pklin; a.pkout = p_pkout; a.pknow = p_pknow; a.ncols = ncols; a.ld = ncols;
+  a.vec = (ncols % 2 == 0) && ((uintptr_t)p_pklin % 16 == 0) && ((uintptr_t)p_pkout % 16 == 0) && ((uintptr_t)p_pknow % 16 == 0);
+  a.boxes = p_boxes;
+  a.dbg = nullptr;
+  ScratchBuf d_dbg;
+  if (getenv("CPF_WALLISH_DBG")) { CPF_CUDA(d_dbg.alloc(8 * sizeof(unsigned long long), stream)); CPF_CUDA(cudaMemsetAsync(d_dbg.p, 0, 64, stream)); a.dbg = (unsigned long long*)d_dbg.p; }
+  a.tw1 = wt.tw1; a.tw2 = wt.tw2; a.twd = wt.twd; a.wtab = wt.wtab;
+  a.i0 = fp.i0; a.i1 = fp.i1; a.nl = fp.nl; a.nr = fp.nr; a.lz = fp.lz; a.rz = fp.rz; a.nmid = fp.nmid; a.nc = fp.nc; a.nk = nk;
+  a.nrounds = fp.nrounds; a.slbase = fp.slbase;
+  a.fc.facT = reinterpret_cast<const double*>(d_tab.p);
+  a.fc.t0 = fp.ut0; a.fc.t1 = fp.ut1; a.fc.Lw = fp.uLw; a.fc.cp = fp.ucp; a.fc.P = fp.uP; a.fc.Q = fp.uQ;
+  a.qh = a.fc.facT + n_fac;
+  a.qth = a.qh + n_qh;
+  a.rklin = a.qth + nk;
+  a.slotT = reinterpret_cast<const int*>(a.rklin + nlin);
+  a.qstart = a.slotT + n_slot;
+  a.qinfo = a.qstart + n_qs;
+  int sms = 0;
+  CPF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  const long long npairs = (ncols + 1) / 2;
+  unsigned grid = (unsigned)npairs;
+  int variant = 2;
+  if (const char* e = getenv("CPF_WALLISH_PERSISTENT")) { if (e[0] == '1' && npairs > 2LL * sms) grid = 2u * (unsigned)sms; }
+  if (const char* e = getenv("CPF_WALLISH_VARIANT")) variant = atoi(e) & 7;
+  typedef void (*wkern_t)(const WallishArgs);
+  static const wkern_t kerns[8] = {wallish_fused_kernel<0>, wallish_fused_kernel<1>, wallish_fused_kernel<2>, wallish_fused_kernel<3>,
+                                   wallish_fused_kernel<4>, wallish_fused_kernel<5>, wallish_fused_kernel<6>, wallish_fused_kernel<7>};
+  CPF_CUDA(cudaFuncSetAttribute(kerns[variant], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWallishSmemBytes));
+  kerns[variant]<<<grid, 256, kWallishSmemBytes, stream>>>(a);
+  CPF_CUDA(cudaGetLastError());
   if (!on_device) {
     CPF_CUDA(cudaMemcpyAsync(pknow, p_pknow, out_bytes, cudaMemcpyDeviceToHost, stream));
     if (boxes) CPF_CUDA(cudaMemcpyAsync(boxes, p_boxes, (size_t)ncols * 4 * sizeof(int), cudaMemcpyDeviceToHost, stream));
   }
-  // host vectors (knots, idx) must outlive the async uploads; scratch is stream-ordered
+  // the host table image must outlive its upload; scratch is stream-ordered
   CPF_CUDA(cudaStreamSynchronize(stream));
+  if (a.dbg) {
+    unsigned long long h[8];
+    CPF_CUDA(cudaMemcpy(h, a.dbg, sizeof(h), cudaMemcpyDeviceToHost));
+    fprintf(stderr, "wallish phases (cycles per pair, thread 0): load+log %.0f  fft %.0f  middle %.0f  fft %.0f  knots %.0f  final %.0f\n", (double)h[0] / npairs,
+            (double)h[1] / npairs, (double)h[2] / npairs, (double)h[3] / npairs, (double)h[4] / npairs, (double)h[5] / npairs);
+  }
   return CPF_OK;
 }
 

@@ -27,7 +27,8 @@ struct WallishGeo {
   static constexpr int T = 256;             // threads per CTA
   static constexpr int CH = 16;             // knots per thread in the chunked eliminations
   static constexpr int WARM = 32;           // warm-up knots: (2 - sqrt 3)^32 = 5e-19, below the rounding of the exact solve
-  static constexpr int HP = H + H / CH;     // padded half length (one pad element per 16: conflict-free chunk access)
+  static constexpr int HP = H + H / CH + 4;   // padded half length (one pad element per 16: conflict-free chunk access; + 4: the even and the odd
+                                              // sequence sit 4 bank groups apart, accesses that alternate between them are conflict-free too)
   static constexpr int BUF = 2 * HP;        // elements of one shared-memory array (>= 16*257 exchange elements)
   static constexpr int MARGIN_FIRST = 20, MARGIN_SECOND = 5, OFF_LO = -10, OFF_HI = 20;   // bao_filter.py:387-389
 };
@@ -70,55 +71,103 @@ CPF_HD void wallish_dst2_post(const int t, const double2 (&zk)[16], const double
   }
 }
 
-// ---- forward elimination of one chunk (both columns at once) -----------------------------------------------------
-// Y: knot values (padded layout, parity h), D: reduced right-hand sides.  sq != 0: the values are y_i * x_i^2.
+// ---- DST-II post-processing with ONE buffer: the thread's bins zk[r] (k = t + 256 r) are replaced in registers by the DST-II
+// coefficient of index N-1-k (A holds the bins in natural order); after a barrier wallish_dst2_store scatters them into the
+// same buffer in the de-interleaved, padded layout the spline phases read.
+CPF_HD void wallish_dst2_coef(const int t, double2 (&zk)[16], const double2* A, const double2* tw) {
+  typedef WallishGeo G;
+#pragma unroll
+  for (int r = 0; r < 16; ++r) {
+    const int k = t + G::T * r;
+    const double2 z = zk[r], zm = A[(G::N - k) & (G::N - 1)];
+    const double2 va = mk2(0.5 * (z.x + zm.x), 0.5 * (z.y - zm.y));
+    const double2 vb = mk2(0.5 * (z.y + zm.y), 0.5 * (zm.x - z.x));
+    const double2 w = CPF_LDG(tw + k);
+    const double sc = 2. * (k == 0 ? CPF_DST_S_LAST : CPF_DST_S);
+    zk[r] = mk2(sc * (w.x * va.x - w.y * va.y), sc * (w.x * vb.x - w.y * vb.y));
+  }
+}
+
+CPF_HD void wallish_dst2_store(const int t, const double2 (&zk)[16], double2* X) {
+  typedef WallishGeo G;
+#pragma unroll
+  for (int r = 0; r < 16; ++r) {
+    const int kk = G::N - 1 - (t + G::T * r);
+    X[wpos(kk & 1, kk >> 1)] = zk[r];
+  }
+}
+
+// ---- clamped splines through the even / odd coefficients, chunks in registers ----------------------------------------
+// Y: knot values (padded layout, parity h).  sq != 0: the values are y_i * x_i^2.
 CPF_HD double2 wallish_y(const double2* Y, const int h, const int i, const int sq) {
   double2 y = Y[wpos(h, i)];
   if (sq) { const double x2 = (double)(i + 1) * (double)(i + 1); y.x *= x2; y.y *= x2; }
   return y;
 }
 
-// Two-step chunked elimination.  The recurrence d_i = (r_i - lo_i d_{i-1}) w_i is affine in the value flowing in from the left:
-// d_last = E + M d_{first-1}, with M = prod(-lo_i w_i) ~ (-0.27)^16 = 7e-10 per 16-knot chunk.  Step 1 (local): every thread runs
-// its own chunk from zero inflow and publishes (E, M).  Step 2 (store): the true inflow is E_{c-1} + M_{c-1} E_{c-2} (the next term,
-// M^2 E_{c-3} ~ 5e-19, is below the rounding of the exact solve) and the chunk is run again, storing D.  32 steps per thread instead
-// of the 48 of a 32-knot warm-up, same truncation.
-CPF_HD void wallish_forward_chunk(const int t, const double2* X, double2* D, const double* wtab, double2 d, double2* e_out, double* m_out) {
+// Thread t = 128 h + c owns the 16 knots first = 16 c .. first + 15 of parity h and keeps their reduced right-hand sides /
+// slopes / second derivatives in d[16] (registers; no second and third shared-memory array: two CTAs fit one SM).
+// The recurrence d_i = (r_i - lo_i d_{i-1}) w_i is affine in the value flowing in from the left chunk:
+//   d_i = d_i(0) + m_i d_in,  m_i = prod_{j <= i} (-lo_j w_j),  m_15 ~ (-0.27)^16 = 7e-10.
+// Step 1 (wallish_forward_local): every thread runs its chunk from zero inflow and publishes (E, M) = (d_15(0), m_15).
+// Step 2 (wallish_forward_fix): the true inflow is E_{c-1} + M_{c-1} E_{c-2} (the next term, ~ 5e-19 E, is below the rounding of the
+// exact solve); the chunk is corrected by d_i += m_i d_in instead of being run again.  The back substitution
+// s_i = d_i - cp_i s_{i+1} is treated the same way from the right.
+CPF_HD void wallish_forward_local(const int t, const double2* X, double2 (&d)[16], double2* E, double* M, const double* wtab) {
   typedef WallishGeo G;
-  const int h = t >> 7, c = t & 127;
-  const int first = c * G::CH;
+  const int h = t >> 7, first = (t & 127) * G::CH;
   double m = 1.;
+  double2 dp = mk2(0., 0.);
   double2 ym = first > 0 ? X[wpos(h, first - 1)] : mk2(0., 0.), y0 = X[wpos(h, first)];
-#pragma unroll 4
-  for (int i = first; i < first + G::CH; ++i) {
+#pragma unroll
+  for (int j = 0; j < G::CH; ++j) {
+    const int i = first + j;
     const double2 yp = i + 1 < G::H ? X[wpos(h, i + 1)] : mk2(0., 0.);
     const bool edge = (i == 0 || i == G::H - 1);
     const double w = wpivot(wtab, i, G::H);
     const double rx = edge ? 0. : 3. * (yp.x - ym.x), ry = edge ? 0. : 3. * (yp.y - ym.y);
     const double lo = edge ? 0. : 1.;
-    d = mk2((rx - lo * d.x) * w, (ry - lo * d.y) * w);
+    dp = mk2((rx - lo * dp.x) * w, (ry - lo * dp.y) * w);
     m *= -lo * w;
-    if (D) D[wpos(h, i)] = d;
+    d[j] = dp;
     ym = y0; y0 = yp;
   }
-  if (e_out) { *e_out = d; *m_out = m; }
+  E[t] = dp;
+  M[t] = m;
 }
 
-CPF_HD void wallish_forward_local(const int t, const double2* X, double2* E, double* M, const double* wtab) {
-  wallish_forward_chunk(t, X, nullptr, wtab, mk2(0., 0.), E + t, M + t);
-}
-
-CPF_HD void wallish_forward_store(const int t, const double2* X, double2* D, const double2* E, const double* M, const double* wtab) {
-  const int c = t & 127;
+// inflow correction of the forward pass, then the back substitution from zero inflow: d[j] <- s_j(0); publishes (Eb, Mb)
+CPF_HD void wallish_forward_fix_backward_local(const int t, double2 (&d)[16], const double2* E, const double* M, double2* Eb, double* Mb,
+                                               const double* wtab) {
+  typedef WallishGeo G;
+  const int c = t & 127, first = c * G::CH;
   double2 din = mk2(0., 0.);
   if (c >= 1) {
     din = E[t - 1];
     if (c >= 2) { din.x += M[t - 1] * E[t - 2].x; din.y += M[t - 1] * E[t - 2].y; }
   }
-  wallish_forward_chunk(t, X, D, wtab, din, nullptr, nullptr);
+  double m = 1.;
+#pragma unroll
+  for (int j = 0; j < G::CH; ++j) {
+    const int i = first + j;
+    const bool edge = (i == 0 || i == G::H - 1);
+    m *= edge ? 0. : -wpivot(wtab, i, G::H);
+    d[j].x = fma(m, din.x, d[j].x);
+    d[j].y = fma(m, din.y, d[j].y);
+  }
+  double2 s = mk2(0., 0.);
+  m = 1.;
+#pragma unroll
+  for (int j = G::CH - 1; j >= 0; --j) {
+    const double cp = wcp(wtab, first + j, G::H);
+    s = mk2(d[j].x - cp * s.x, d[j].y - cp * s.y);
+    m *= -cp;
+    d[j] = s;
+  }
+  Eb[t] = s;
+  Mb[t] = m;
 }
 
-// ---- back substitution of one chunk, fused with the second derivative at the knots (bao_filter.py:379, 382) ----
 // best second derivative of a thread's 16-knot chunk inside the search range [MARGIN_FIRST, H - MARGIN_FIRST) of both
 // columns (index -1: no knot of the chunk is in range); ties keep the lowest index (numpy argmax)
 struct WallishBest {
@@ -132,72 +181,57 @@ CPF_HD void wallish_best_update(WallishBest& b, const double x, const double y, 
   if (i >= loy && i < hi && (b.iy < 0 || y > b.vy || (y == b.vy && i < b.iy))) { b.vy = y; b.iy = i; }
 }
 
-// back substitution s_i = d_i - cp_i s_{i+1}, affine in the slope flowing in from the right: s_first = E + M s_{last+1}, M = prod(-cp_i).
-// Step 1 (local): zero inflow, publish (E, M).  Step 2: true inflow E_{c+1} + M_{c+1} E_{c+2}, second derivatives and chunk maxima.
-CPF_HD void wallish_backward_local(const int t, const double2* D, double2* E, double* M, const double* wtab) {
+// inflow correction of the back substitution fused with the second derivatives at the knots (bao_filter.py:379, 382):
+// d[j] <- dd_{first + j}; returns the chunk's best
+CPF_HD WallishBest wallish_backward_dd(const int t, const double2* X, double2 (&d)[16], const double2* Eb, const double* Mb, const double* wtab) {
   typedef WallishGeo G;
   const int h = t >> 7, c = t & 127;
   const int first = c * G::CH, last = first + G::CH - 1;
-  double2 s = mk2(0., 0.);
-  double m = 1.;
-#pragma unroll 4
-  for (int i = last; i >= first; --i) {
-    const double cp = wcp(wtab, i, G::H);
-    const double2 di = D[wpos(h, i)];
-    s = mk2(di.x - cp * s.x, di.y - cp * s.y);
-    m *= -cp;
-  }
-  E[t] = s;
-  M[t] = m;
-}
-
-CPF_HD void wallish_backward_dd(const int t, const double2* X, const double2* D, double2* DD, const double2* E, const double* M,
-                                const double* wtab, WallishBest* best = nullptr) {
-  typedef WallishGeo G;
-  const int h = t >> 7, c = t & 127;
-  const int first = c * G::CH, last = first + G::CH - 1;
-  double2 s = mk2(0., 0.);              // s_{last+1}: slope flowing in from the right (nothing beyond the last knot)
+  double2 sin_ = mk2(0., 0.);           // s_{last+1}: slope flowing in from the right (nothing beyond the last knot)
   if (c <= 126) {
-    s = E[t + 1];
-    if (c <= 125) { s.x += M[t + 1] * E[t + 2].x; s.y += M[t + 1] * E[t + 2].y; }
+    sin_ = Eb[t + 1];
+    if (c <= 125) { sin_.x += Mb[t + 1] * Eb[t + 2].x; sin_.y += Mb[t + 1] * Eb[t + 2].y; }
   }
+  double2 sn = sin_;
   double2 yn = last + 1 < G::H ? X[wpos(h, last + 1)] : mk2(0., 0.);
+  double m = 1.;
+  double2 ddlast = mk2(0., 0.);
   WallishBest b;
   b.vx = b.vy = 0.; b.ix = b.iy = -1;
-#pragma unroll 4
-  for (int i = last; i >= first; --i) {
-    const double cp = wcp(wtab, i, G::H);
-    const double2 di = D[wpos(h, i)], yi = X[wpos(h, i)];
-    const double2 sn = s;
-    s = mk2(di.x - cp * sn.x, di.y - cp * sn.y);
+#pragma unroll
+  for (int j = G::CH - 1; j >= 0; --j) {
+    const int i = first + j;
+    m *= -wcp(wtab, i, G::H);
+    const double2 yi = X[wpos(h, i)];
+    const double2 s = mk2(fma(m, sin_.x, d[j].x), fma(m, sin_.y, d[j].y));
     if (i < G::H - 1) {
       // dd_i = 2 c1 = 2 (3 m_i - 2 s_i - s_{i+1}), m_i = y_{i+1} - y_i; last knot: -6 m_{n-2} + 2 s_{n-2} + 4 s_{n-1}
       const double mx = yn.x - yi.x, my = yn.y - yi.y;
       const double2 dd = mk2(2. * (3. * mx - 2. * s.x - sn.x), 2. * (3. * my - 2. * s.y - sn.y));
-      DD[wpos(h, i)] = dd;
+      d[j] = dd;
       wallish_best_update(b, dd.x, dd.y, i, G::MARGIN_FIRST, G::MARGIN_FIRST);
-      if (i == G::H - 2) DD[wpos(h, G::H - 1)] = mk2(-6. * mx + 2. * s.x + 4. * sn.x, -6. * my + 2. * s.y + 4. * sn.y);
+      if (i == G::H - 2) ddlast = mk2(-6. * mx + 2. * s.x + 4. * sn.x, -6. * my + 2. * s.y + 4. * sn.y);
     }
+    sn = s;
     yn = yi;
   }
-  if (best) *best = b;
+  if (last == G::H - 1) d[G::CH - 1] = ddlast;
+  return b;
 }
 
 // candidate of a thread's chunk for the second search range [lb, H - MARGIN_FIRST) (lb per column): the chunk best when
 // the whole chunk lies above lb, a re-scan of the chunk's knots >= lb when lb falls inside it, nothing below
-CPF_HD WallishBest wallish_chunk_candidate(const int t, const double2* DD, const int lbx, const int lby, const WallishBest& chunk) {
+CPF_HD WallishBest wallish_chunk_candidate(const int t, const double2 (&dd)[16], const int lbx, const int lby, const WallishBest& chunk) {
   typedef WallishGeo G;
-  const int h = t >> 7, first = (t & 127) * G::CH, last = first + G::CH - 1;
+  const int first = (t & 127) * G::CH, last = first + G::CH - 1;
   WallishBest b;
   b.vx = b.vy = 0.; b.ix = b.iy = -1;
   if (first >= lbx) { b.vx = chunk.vx; b.ix = chunk.ix; }
   if (first >= lby) { b.vy = chunk.vy; b.iy = chunk.iy; }
   if ((first < lbx && last >= lbx) || (first < lby && last >= lby)) {
     const int lox = first < lbx ? lbx : G::H, loy = first < lby ? lby : G::H;     // columns already settled are skipped
-    for (int i = first; i <= last; ++i) {
-      const double2 dd = DD[wpos(h, i)];
-      wallish_best_update(b, dd.x, dd.y, i, lox, loy);
-    }
+#pragma unroll
+    for (int j = 0; j < G::CH; ++j) wallish_best_update(b, dd[j].x, dd[j].y, first + j, lox, loy);
   }
   return b;
 }
@@ -340,6 +374,141 @@ CPF_HD int wallish_dst3_out_index(const int m, double& sign) {
   if (m <= G::N / 2) { sign = -1.; return 2 * m - 1; }
   sign = 1.;
   return 2 * (G::N - m);
+}
+
+// ---- final stage (bao_filter.py:415-423) inside the fused kernel ----------------------------------------------------
+// The spliced clamped spline -- nl unfiltered knots (self.k < 5e-4), the filtered spectrum on 1e-2 < k < 1.5, nr unfiltered knots
+// (self.k > 2) -- is solved per pair of spectra in shared memory and evaluated at self.k.  Only the lz <= 64 / rz <= 64 edge knots next
+// to the filtered ones are kept: the slope system is strictly diagonally dominant, the influence of a knot decays by >= 2 per knot
+// (2^-64 = 5e-20), and the output wavenumbers outside [5e-4, 2] are knots themselves (the spline returns pk there, wiggles = 1).
+// Knot c of the nc kept ones sits at ypos(c) (one pad element per 16: conflict-free chunk access); thread t owns the knots
+// 16 t .. 16 t + 15.  The per-knot factors Lw, cp, P, Q of cpf_spline_core.h (spline_factor_step) depend on the knots only and come
+// from a table in thread-major order: factor f of knot 16 t + j at facT[(4 j + f) * 256 + t] (coalesced; zeros beyond nc).
+// Same two-step scheme as above with four inflow terms (non-uniform knots: |Lw|, |cp| <= 1/2, M <= 1.5e-5 per chunk, M^4 = 5e-20).
+CPF_HD int ypos(const int i) { return i + (i >> 4); }
+
+CPF_HD double2 wallish_inflow4(const double2* E, const double* M, const int t, const int dir) {
+  // dir = -1: E_{t-1} + M_{t-1} (E_{t-2} + M_{t-2} (E_{t-3} + M_{t-3} E_{t-4})), chunks below 0 / above 255 do not exist
+  double2 acc = mk2(0., 0.);
+#pragma unroll
+  for (int j = 4; j >= 1; --j) {
+    const int c = t + dir * j;
+    if (c < 0 || c > WallishGeo::T - 1) continue;
+    const double m = j < 4 ? M[c] : 0.;
+    const double2 e = E[c];
+    acc = mk2(fma(m, acc.x, e.x), fma(m, acc.y, e.y));
+  }
+  return acc;
+}
+
+// Factors of the final solve.  Where the knots are uniform (the filtered ones, away from the splice points) the factors have converged to
+// constants: threads t0 <= t < t1 take them from here instead of loading 48 table entries each (the table was 130 KB of L2 -> SM
+// traffic per pair of spectra, three times the spectra themselves).
+struct WallishFinFac {
+  const double* facT;
+  int t0, t1;
+  double Lw, cp, P, Q;
+};
+
+template <bool UNI>
+CPF_HD void wallish_fin_forward_local_t(const int t, const int nc, const double2* Y, const WallishFinFac& fc, double2 (&d)[16], double2* E, double* M) {
+  typedef WallishGeo G;
+  const int first = t * G::CH;
+  double m = 1.;
+  double2 dp = mk2(0., 0.);
+  double2 ym = (first > 0 && first - 1 < nc) ? Y[ypos(first - 1)] : mk2(0., 0.), y0 = first < nc ? Y[ypos(first)] : mk2(0., 0.);
+#pragma unroll
+  for (int j = 0; j < G::CH; ++j) {
+    const int i = first + j;
+    const double2 yp = i + 1 < nc ? Y[ypos(i + 1)] : mk2(0., 0.);
+    const double Lw = UNI ? fc.Lw : CPF_LDG(fc.facT + (4 * j + 0) * G::T + t);
+    const double P = UNI ? fc.P : CPF_LDG(fc.facT + (4 * j + 2) * G::T + t), Q = UNI ? fc.Q : CPF_LDG(fc.facT + (4 * j + 3) * G::T + t);
+    const double ax = y0.x - ym.x, ay = y0.y - ym.y, bx = yp.x - y0.x, by = yp.y - y0.y;
+    dp = mk2(fma(P, ax, fma(Q, bx, -Lw * dp.x)), fma(P, ay, fma(Q, by, -Lw * dp.y)));
+    m *= -Lw;
+    d[j] = dp;
+    ym = y0; y0 = yp;
+  }
+  E[t] = dp;
+  M[t] = m;
+}
+
+CPF_HD void wallish_fin_forward_local(const int t, const int nc, const double2* Y, const WallishFinFac& fc, double2 (&d)[16], double2* E, double* M) {
+  if (t >= fc.t0 && t < fc.t1) wallish_fin_forward_local_t<true>(t, nc, Y, fc, d, E, M);
+  else wallish_fin_forward_local_t<false>(t, nc, Y, fc, d, E, M);
+}
+
+template <bool UNI>
+CPF_HD void wallish_fin_fix_backward_local_t(const int t, const WallishFinFac& fc, double2 (&d)[16], const double2* E, const double* M, double2* Eb, double* Mb) {
+  typedef WallishGeo G;
+  const double2 din = wallish_inflow4(E, M, t, -1);
+  double m = 1.;
+#pragma unroll
+  for (int j = 0; j < G::CH; ++j) {
+    m *= -(UNI ? fc.Lw : CPF_LDG(fc.facT + (4 * j + 0) * G::T + t));
+    d[j].x = fma(m, din.x, d[j].x);
+    d[j].y = fma(m, din.y, d[j].y);
+  }
+  double2 s = mk2(0., 0.);
+  m = 1.;
+#pragma unroll
+  for (int j = G::CH - 1; j >= 0; --j) {
+    const double cp = UNI ? fc.cp : CPF_LDG(fc.facT + (4 * j + 1) * G::T + t);
+    s = mk2(fma(-cp, s.x, d[j].x), fma(-cp, s.y, d[j].y));
+    m *= -cp;
+    d[j] = s;
+  }
+  Eb[t] = s;
+  Mb[t] = m;
+}
+
+CPF_HD void wallish_fin_fix_backward_local(const int t, const WallishFinFac& fc, double2 (&d)[16], const double2* E, const double* M, double2* Eb, double* Mb) {
+  if (t >= fc.t0 && t < fc.t1) wallish_fin_fix_backward_local_t<true>(t, fc, d, E, M, Eb, Mb);
+  else wallish_fin_fix_backward_local_t<false>(t, fc, d, E, M, Eb, Mb);
+}
+
+// d[j] <- slope at knot 16 t + j
+template <bool UNI>
+CPF_HD void wallish_fin_backward_fix_t(const int t, const WallishFinFac& fc, double2 (&d)[16], const double2* Eb, const double* Mb) {
+  typedef WallishGeo G;
+  const double2 sin_ = wallish_inflow4(Eb, Mb, t, +1);
+  double m = 1.;
+#pragma unroll
+  for (int j = G::CH - 1; j >= 0; --j) {
+    m *= -(UNI ? fc.cp : CPF_LDG(fc.facT + (4 * j + 1) * G::T + t));
+    d[j].x = fma(m, sin_.x, d[j].x);
+    d[j].y = fma(m, sin_.y, d[j].y);
+  }
+}
+
+CPF_HD void wallish_fin_backward_fix(const int t, const WallishFinFac& fc, double2 (&d)[16], const double2* Eb, const double* Mb) {
+  if (t >= fc.t0 && t < fc.t1) wallish_fin_backward_fix_t<true>(t, fc, d, Eb, Mb);
+  else wallish_fin_backward_fix_t<false>(t, fc, d, Eb, Mb);
+}
+
+// slopes needed by the queries of round r go to their slots (slotT[(16 r + j) * 256 + t], -1: not needed)
+CPF_HD void wallish_fin_scatter(const int t, const int round, const int* slotT, const double2 (&d)[16], double2* SL) {
+  typedef WallishGeo G;
+#pragma unroll
+  for (int j = 0; j < G::CH; ++j) {
+    const int sl = CPF_LDG(slotT + (G::CH * round + j) * G::T + t);
+    if (sl >= 0) SL[sl] = d[j];
+  }
+}
+
+// query q: qinfo[4 q ..] = {pos0, pos1, slot0, slot1} (pos0 = -1: self.k[q] is a spliced-in knot, the spline returns pk; -2: outside the
+// knots, extrapolate=False gives NaN), qh[4 q ..] = Hermite factors h00, h01, h10 dx, h11 dx; th = Gaussian top-hat (:425-431)
+CPF_HD double2 wallish_fin_eval(const int q, const int* qinfo, const double* qh, const double2* Y, const double2* SL, const double2 pk,
+                                const double th) {
+  const int pos0 = CPF_LDG(qinfo + 4 * q);
+  if (pos0 == -1) return pk;
+  if (pos0 < 0) return mk2(nan(""), nan(""));
+  const int pos1 = CPF_LDG(qinfo + 4 * q + 1), sl0 = CPF_LDG(qinfo + 4 * q + 2), sl1 = CPF_LDG(qinfo + 4 * q + 3);
+  const double h0 = CPF_LDG(qh + 4 * q), h1 = CPF_LDG(qh + 4 * q + 1), h2 = CPF_LDG(qh + 4 * q + 2), h3 = CPF_LDG(qh + 4 * q + 3);
+  const double2 y0 = Y[pos0], y1 = Y[pos1], s0 = SL[sl0], s1 = SL[sl1];
+  const double sa = fma(h0, y0.x, fma(h1, y1.x, fma(h2, s0.x, h3 * s1.x)));         // :420
+  const double sb = fma(h0, y0.y, fma(h1, y1.y, fma(h2, s0.y, h3 * s1.y)));
+  return mk2(pk.x / ((pk.x / sa - 1.) * th + 1.), pk.y / ((pk.y / sb - 1.) * th + 1.));     // :422-423
 }
 
 }  // namespace cpf

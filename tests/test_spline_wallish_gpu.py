@@ -231,3 +231,15 @@ def test_wallish_output_outside_spliced_knots_is_nan():
         assert np.isnan(ref).any() and np.array_equal(np.isnan(filt.pknow), np.isnan(ref))
         m = np.isfinite(ref)
         assert np.max(np.abs(filt.pknow[m] / ref[m] - 1.)) < 1e-10
+
+
+def test_wallish_multi_round_evaluation(monkeypatch):
+    """The slopes next to the output wavenumbers travel through a slot array in the shared buffer; with more output wavenumbers than slots the
+    evaluation runs in rounds.  CPF_WALLISH_SLOT_CAP shrinks the slot array so that the 1024 default wavenumbers need > 10 rounds: same bits."""
+    d = load_golden('wallish_golden.npz').data
+    klin, pklin, kout, pkout = (d['w0_%s' % n] for n in ['klin', 'pklin', 'kout', 'pkout'])
+    one = PowerSpectrumBAOFilter(fake_interpolator(klin, pklin, kout, pkout), engine='wallish2018_cuda').pknow
+    monkeypatch.setenv('CPF_WALLISH_SLOT_CAP', '37')
+    many = PowerSpectrumBAOFilter(fake_interpolator(klin, pklin, kout, pkout), engine='wallish2018_cuda').pknow
+    assert np.array_equal(one, many)
+    assert np.max(np.abs(many / d['w0_pknow'] - 1.)) < 1e-10

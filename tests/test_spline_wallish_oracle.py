@@ -68,16 +68,19 @@ def test_wallish_kernel_emulation():
     with tempfile.TemporaryDirectory() as tmp:
         exe = os.path.join(tmp, 'emul_wallish')
         subprocess.run(['g++', '-O2', '-std=c++17', '-o', exe, os.path.join(here, 'emul', 'emul_wallish.cpp')], check=True)
-        for idx, c0 in [(0, 0), (0, 4), (1, 0)]:
+        for idx, c0, cap in [(0, 0, 0), (0, 4, 37), (1, 0, 0)]:        # cap: slot array shrunk, several evaluation rounds
             klin, pklin = d['w%d_klin' % idx], d['w%d_pklin' % idx]
             _, dbg = WO.wallish2018(klin, pklin, d['w%d_kout' % idx], d['w%d_pkout' % idx], return_debug=True)
             fin, fout = os.path.join(tmp, 'in.bin'), os.path.join(tmp, 'out.bin')
-            np.concatenate([klin, pklin[:, c0], pklin[:, c0 + 1]]).tofile(fin)
-            subprocess.run([exe, fin, fout], check=True)
+            kout, pkout = d['w%d_kout' % idx], d['w%d_pkout' % idx]
+            np.concatenate([klin, pklin[:, c0], pklin[:, c0 + 1], [float(kout.size)], kout, pkout[:, c0], pkout[:, c0 + 1]]).tofile(fin)
+            subprocess.run([exe, fin, fout, str(cap)], check=True)
             r = np.fromfile(fout)
             X, dd = r[:2 * N].reshape(N, 2), r[2 * N:4 * N].reshape(2, N // 2, 2)
             boxes = r[4 * N:4 * N + 8].astype(int).reshape(2, 2, 2)        # [parity, column, (b0, b1)]
-            Xnow, pl = r[4 * N + 8:6 * N + 8].reshape(N, 2), r[6 * N + 8:].reshape(N, 2)
+            Xnow, pl = r[4 * N + 8:6 * N + 8].reshape(N, 2), r[6 * N + 8:8 * N + 8].reshape(N, 2)
+            pknow = r[8 * N + 8:8 * N + 8 + 2 * kout.size].reshape(kout.size, 2)
+            nuni, nrounds, nc, lz, rz = r[-5:].astype(int)
             assert np.max(np.abs(X[:256] - d['w%d_dst_head' % idx][:, c0:c0 + 2])) < 1e-14 * np.max(np.abs(X))
             for h, name in enumerate(['dd_even', 'dd_odd']):
                 ref = dbg[name][:, c0:c0 + 2]
@@ -91,3 +94,10 @@ def test_wallish_kernel_emulation():
             m = (klin > 1e-2) & (klin < 1.5)
             ref_pl = (np.exp(dbg['kpknow']) / klin[:, None])[:, c0:c0 + 2]
             assert np.max(np.abs(pl[m] / ref_pl[m] - 1)) < 1e-11
+            # final stage (spliced clamped spline in the buffer, truncated edges, slot rounds) against the reference's pknow
+            ref_pknow = d['w%d_pknow' % idx][:, c0:c0 + 2]
+            assert np.array_equal(np.isnan(pknow), np.isnan(ref_pknow))
+            ok = ~np.isnan(ref_pknow)
+            assert np.max(np.abs(pknow[ok] / ref_pknow[ok] - 1)) < 1e-11
+            assert (nrounds == 1 if cap == 0 else nrounds > 10) and nc == lz + m.sum() + rz
+            assert nuni > 150          # threads on the uniform stretch of the spliced knots take constant factors
