@@ -42,6 +42,8 @@ SIGNATURES = {
     'cpf_spline_eval': (_i, [_vp, _vp, _i, _i, _vp, _i, _vp]),
     'cpf_spline_eval_t': (_i, [_vp, _vp, _i, _i, _vp, _i, _vp]),
     'cpf_spline_destroy': (_i, [_vp]),
+    'cpf_spline_create_padlog': (_i, [ctypes.POINTER(_vp), _vp, _vp, _i, _i64, _i, _vp, _i, _i, _vp]),
+    'cpf_column_nan_flags': (_i, [_vp, _i, _i64, _i, _vp, _i, _vp]),
     'cpf_spline_eval_rows': (_i, [_vp, _vp, _i, _i64, _vp, _i, _i, _i, _i, _vp, _i, _i, _vp]),
     'cpf_dst': (_i, [_i, _vp, _i, _i64, _vp, _i, _i, _vp]),
     'cpf_wallish2018': (_i, [_vp, _vp, _i, _vp, _vp, _i, _i64, _vp, _vp, _i, _i, _vp]),

@@ -12,6 +12,7 @@
 // The matrix depends on x only, so its LU factors are computed once per grid and shared by all columns; it is strictly
 // diagonally dominant by rows, so elimination without pivoting is stable (LAPACK's dgtsv, which scipy calls, only
 // pivots when dominance fails).
+#include <string.h>
 #include <vector>
 
 #include "cpf_common.h"
@@ -51,6 +52,63 @@ void spline_factor_host(const double* x, const int nx, const int bc, double* fac
 __global__ void log10_kernel(const double* __restrict__ in, double* __restrict__ out, const long long count, const int apply) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i < count) out[i] = apply ? log10(in[i]) : in[i];
+}
+
+
+// ---- log-log tables with power-law continuation knots (interpolator.py:42-87 `_pad_log`, 343-351; NaN rules of jax.py:161-172) ----
+// y [nx, ncols] tabulated spectra -> ly [nx + 4, ncols] = log10(y) in rows 2 .. nx + 1 and, in rows 0, 1, nx + 2, nx + 3, the straight
+// lines through the two lowest / two highest samples evaluated at the continuation knots lx[0], lx[1], lx[nx + 2], lx[nx + 3] (lx =
+// log10 of the padded knots).  nan_count[col] += number of NaN cells of the column (log10 of a negative sample is NaN; of zero, -inf,
+// which the reference lets through as well).  One thread per (column, chunk of PADLOG_ROWS rows): a warp touches 256 contiguous bytes.
+#define PADLOG_ROWS 64
+__global__ void __launch_bounds__(128) padlog_kernel(const double* __restrict__ y, const double* __restrict__ lx, const int nx,
+                                                     const long long ncols, double* __restrict__ ly, int* __restrict__ nan_count) {
+  const long long col = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (col >= ncols) return;
+  const int r0 = blockIdx.y * PADLOG_ROWS, r1 = min(nx, r0 + PADLOG_ROWS);
+  int bad = 0;
+#pragma unroll 4
+  for (int i = r0; i < r1; ++i) {
+    const double v = log10(__ldcs(y + (long long)i * ncols + col));
+    bad += isnan(v) ? 1 : 0;
+    ly[(long long)(i + 2) * ncols + col] = v;
+  }
+  if (blockIdx.y == 0) {                         // continuation below the table: slope of the two lowest samples
+    const double a = log10(y[col]), b = log10(y[ncols + col]);
+    const double x0 = lx[2], slope = (b - a) / (lx[3] - x0);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const double v = a + slope * (lx[j] - x0);
+      bad += isnan(v) ? 1 : 0;
+      ly[(long long)j * ncols + col] = v;
+    }
+  }
+  if (blockIdx.y == gridDim.y - 1) {             // continuation above the table: slope of the two highest samples
+    const double a = log10(y[(long long)(nx - 2) * ncols + col]), b = log10(y[(long long)(nx - 1) * ncols + col]);
+    const double x1 = lx[nx + 1], slope = (b - a) / (x1 - lx[nx]);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const double v = b + slope * (lx[nx + 2 + j] - x1);
+      bad += isnan(v) ? 1 : 0;
+      ly[(long long)(nx + 2 + j) * ncols + col] = v;
+    }
+  }
+  if (bad) atomicAdd(nan_count + col, bad);
+}
+
+// NaN screening of a table (jax.py:161-172): nan_count[col] += number of NaN (or, for a log10 ordinate, negative) cells of the column
+__global__ void __launch_bounds__(128) nan_count_kernel(const double* __restrict__ y, const int nx, const long long ncols, const int neg_is_nan,
+                                                        int* __restrict__ nan_count) {
+  const long long col = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (col >= ncols) return;
+  const int r0 = blockIdx.y * PADLOG_ROWS, r1 = min(nx, r0 + PADLOG_ROWS);
+  int bad = 0;
+#pragma unroll 8
+  for (int i = r0; i < r1; ++i) {
+    const double v = y[(long long)i * ncols + col];
+    bad += (isnan(v) || (neg_is_nan && v < 0.)) ? 1 : 0;
+  }
+  if (bad) atomicAdd(nan_count + col, bad);
 }
 
 // ---- per-column forward elimination + back substitution ------------------------------------------------------------
@@ -272,7 +330,8 @@ __global__ void __launch_bounds__(32) spline_row_weights_kernel(const double* __
 // dot kernel: one warp per row; out[q, row] = sum_j w[q, j] y[row, first_q + j].  Window loads are contiguous runs.
 __global__ void __launch_bounds__(256) spline_rows_dot_kernel(const double* __restrict__ y, const int nx, const long long rows,
                                                               const double* __restrict__ wq, const int* __restrict__ meta,
-                                                              const int nq, const int LW, double* __restrict__ out) {
+                                                              const int nq, const int LW, const int post_sqrt,
+                                                              double* __restrict__ out) {
   const int lane = threadIdx.x & 31;
   const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -288,7 +347,7 @@ __global__ void __launch_bounds__(256) spline_rows_dot_kernel(const double* __re
     } else {
       acc = nan("");
     }
-    if (lane == (q & 31)) out[(long long)q * rows + row] = acc;
+    if (lane == (q & 31)) out[(long long)q * rows + row] = post_sqrt ? sqrt(acc) : acc;     // sigma(r) from sigma^2(r), interpolator.py:573
   }
 }
 
@@ -366,29 +425,29 @@ int cpf_spline_create(cpf_spline** out, const double* x, const double* y, int nx
     SP_CUDA(cudaMallocFromPoolAsync((void**)&sp->d_x, nx * sizeof(double), pool, stream));
     SP_CUDA(cudaMallocFromPoolAsync((void**)&sp->d_y, (cells ? cells : 1) * sizeof(double), pool, stream));
     SP_CUDA(cudaMallocFromPoolAsync((void**)&sp->d_s, (cells ? cells : 1) * sizeof(double), pool, stream));
-    const double* src_x = x;
-    const double* src_y = y;
-    double ends[2];
-    if (!on_device) {
-      SP_CUDA(stage_x.alloc(nx * sizeof(double), stream));
-      SP_CUDA(cudaMemcpyAsync(stage_x.p, x, nx * sizeof(double), cudaMemcpyHostToDevice, stream));
-      src_x = (const double*)stage_x.p;
-      if (cells) {
-        SP_CUDA(stage_y.alloc(cells * sizeof(double), stream));
-        SP_CUDA(cudaMemcpyAsync(stage_y.p, y, cells * sizeof(double), cudaMemcpyHostToDevice, stream));
-        src_y = (const double*)stage_y.p;
-      }
-      ends[0] = x[0]; ends[1] = x[nx - 1];
-    } else {
-      SP_CUDA(cudaMemcpyAsync(&ends[0], x, sizeof(double), cudaMemcpyDeviceToHost, stream));
-      SP_CUDA(cudaMemcpyAsync(&ends[1], x + nx - 1, sizeof(double), cudaMemcpyDeviceToHost, stream));
+    // knots on the host: their (optional) logarithms and the elimination factors are O(nx) serial work that took a single device thread
+    // longer than the whole fit; one small upload instead
+    std::vector<double> hx((size_t)nx), tab(5 * (size_t)nx);
+    if (on_device) {
+      SP_CUDA(cudaMemcpyAsync(hx.data(), x, nx * sizeof(double), cudaMemcpyDeviceToHost, stream));
       SP_CUDA(cudaStreamSynchronize(stream));
+    } else {
+      memcpy(hx.data(), x, nx * sizeof(double));
     }
-    sp->xmin_raw = ends[0]; sp->xmax_raw = ends[1];
-    log10_kernel<<<(nx + 255) / 256, 256, 0, stream>>>(src_x, sp->d_x, nx, sp->log_x);
-    if (cells) log10_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, stream>>>(src_y, sp->d_y, (long long)cells, sp->log_y);
+    sp->xmin_raw = hx[0]; sp->xmax_raw = hx[nx - 1];
+    for (int i = 0; i < nx; ++i) tab[i] = sp->log_x ? log10(hx[i]) : hx[i];
+    spline_factor_host(tab.data(), nx, bc, tab.data() + nx);
     SP_CUDA(fac.alloc(4 * (size_t)nx * sizeof(double), stream));
-    if ((rc = spline_fit_device(sp->d_x, sp->d_y, nx, ncols, bc, sp->d_s, (double*)fac.p, stream, false)) != CPF_OK) break;
+    SP_CUDA(cudaMemcpyAsync(sp->d_x, tab.data(), nx * sizeof(double), cudaMemcpyHostToDevice, stream));
+    SP_CUDA(cudaMemcpyAsync(fac.p, tab.data() + nx, 4 * (size_t)nx * sizeof(double), cudaMemcpyHostToDevice, stream));
+    const double* src_y = y;
+    if (!on_device && cells) {
+      SP_CUDA(stage_y.alloc(cells * sizeof(double), stream));
+      SP_CUDA(cudaMemcpyAsync(stage_y.p, y, cells * sizeof(double), cudaMemcpyHostToDevice, stream));
+      src_y = (const double*)stage_y.p;
+    }
+    if (cells) log10_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, stream>>>(src_y, sp->d_y, (long long)cells, sp->log_y);
+    if ((rc = spline_fit_device(sp->d_x, sp->d_y, nx, ncols, bc, sp->d_s, (double*)fac.p, stream, true)) != CPF_OK) break;
     if (!on_device) SP_CUDA(cudaStreamSynchronize(stream));   // staging buffers of the caller may go away
 #undef SP_CUDA
   } while (0);
@@ -397,6 +456,97 @@ int cpf_spline_create(cpf_spline** out, const double* x, const double* y, int nx
     return rc;
   }
   *out = sp;
+  return CPF_OK;
+}
+
+
+int cpf_spline_create_padlog(cpf_spline** out, const double* x_padded, const double* y, int nx, int64_t ncols, int extrap,
+                             uint8_t* col_flags, int on_device, int device, void* stream_) {
+  if (!out) return fail(CPF_EINVAL, "cpf_spline_create_padlog: null handle pointer");
+  *out = nullptr;
+  if (!x_padded || (!y && ncols > 0) || (!col_flags && ncols > 0)) return fail(CPF_EINVAL, "cpf_spline_create_padlog: null buffer");
+  if (nx < 2) return fail(CPF_EINVAL, "cpf_spline_create_padlog: need at least 2 tabulated knots, got %d", nx);
+  if (ncols < 0) return fail(CPF_EINVAL, "cpf_spline_create_padlog: negative column count");
+  const int np = nx + 4;
+  for (int i = 0; i < np; ++i)
+    if (!(x_padded[i] > 0.) || (i && !(x_padded[i] > x_padded[i - 1])))
+      return fail(CPF_EINVAL, "cpf_spline_create_padlog: the padded knots must be positive and strictly increasing (knot %d)", i);
+  int ndev = 0;
+  CPF_TRY(cpf_device_count(&ndev));
+  if (device < 0 || device >= ndev) return fail(CPF_EINVAL, "cpf_spline_create_padlog: device %d out of range (%d visible)", device, ndev);
+  DeviceGuard guard(device);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  cpf_spline* sp = new cpf_spline();
+  sp->nx = np; sp->bc = 0; sp->log_x = 1; sp->log_y = 1; sp->extrap = extrap ? 1 : 0;
+  sp->device = device; sp->ncols = ncols;
+  sp->xmin_raw = x_padded[0]; sp->xmax_raw = x_padded[np - 1];
+  const size_t cells = (size_t)np * (size_t)ncols, in_bytes = (size_t)nx * (size_t)ncols * sizeof(double);
+  int rc = CPF_OK;
+  ScratchBuf fac, stage_x, stage_y, counts;
+  std::vector<int> h_counts((size_t)ncols);
+  do {
+    cudaError_t e;
+#define SP_CUDA(call) if ((e = (call)) != cudaSuccess) { rc = fail(CPF_ECUDA, "%s: %s", #call, cudaGetErrorString(e)); break; }
+    sp->last_stream = stream;
+    cudaMemPool_t pool = scratch_pool(device);
+    if (!pool) { rc = fail(CPF_ECUDA, "cpf_spline_create_padlog: no memory pool on device %d", device); break; }
+    SP_CUDA(cudaMallocFromPoolAsync((void**)&sp->d_x, np * sizeof(double), pool, stream));
+    SP_CUDA(cudaMallocFromPoolAsync((void**)&sp->d_y, (cells ? cells : 1) * sizeof(double), pool, stream));
+    SP_CUDA(cudaMallocFromPoolAsync((void**)&sp->d_s, (cells ? cells : 1) * sizeof(double), pool, stream));
+    std::vector<double> tab(5 * (size_t)np);
+    for (int i = 0; i < np; ++i) tab[i] = log10(x_padded[i]);
+    spline_factor_host(tab.data(), np, 0, tab.data() + np);
+    SP_CUDA(fac.alloc(4 * (size_t)np * sizeof(double), stream));
+    SP_CUDA(cudaMemcpyAsync(sp->d_x, tab.data(), np * sizeof(double), cudaMemcpyHostToDevice, stream));
+    SP_CUDA(cudaMemcpyAsync(fac.p, tab.data() + np, 4 * (size_t)np * sizeof(double), cudaMemcpyHostToDevice, stream));
+    if (ncols > 0) {
+      const double* src_y = y;
+      if (!on_device) {
+        SP_CUDA(stage_y.alloc(in_bytes, stream));
+        SP_CUDA(cudaMemcpyAsync(stage_y.p, y, in_bytes, cudaMemcpyHostToDevice, stream));
+        src_y = (const double*)stage_y.p;
+      }
+      SP_CUDA(counts.alloc((size_t)ncols * sizeof(int), stream));
+      SP_CUDA(cudaMemsetAsync(counts.p, 0, (size_t)ncols * sizeof(int), stream));
+      const dim3 grid((unsigned)((ncols + 127) / 128), (unsigned)((nx + PADLOG_ROWS - 1) / PADLOG_ROWS));
+      padlog_kernel<<<grid, 128, 0, stream>>>(src_y, sp->d_x, nx, ncols, sp->d_y, (int*)counts.p);
+      SP_CUDA(cudaMemcpyAsync(h_counts.data(), counts.p, (size_t)ncols * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    }
+    // NaN columns propagate through their own (independent) solves, so the fit does not wait for the flags
+    if ((rc = spline_fit_device(sp->d_x, sp->d_y, np, ncols, 0, sp->d_s, (double*)fac.p, stream, true)) != CPF_OK) break;
+    SP_CUDA(cudaStreamSynchronize(stream));     // flags for the caller; the caller's host arrays may go away
+#undef SP_CUDA
+  } while (0);
+  if (rc != CPF_OK) {
+    cpf_spline_destroy(sp);
+    return rc;
+  }
+  for (int64_t c = 0; c < ncols; ++c) col_flags[c] = (uint8_t)(h_counts[c] == np ? 1 : (h_counts[c] > 0 ? 2 : 0));
+  *out = sp;
+  return CPF_OK;
+}
+
+int cpf_column_nan_flags(const double* y, int nx, int64_t ncols, int neg_is_nan, uint8_t* col_flags, int device, void* stream_) {
+  if (ncols < 0 || nx < 0) return fail(CPF_EINVAL, "cpf_column_nan_flags: negative size");
+  if (ncols == 0) return CPF_OK;
+  if (!y || !col_flags) return fail(CPF_EINVAL, "cpf_column_nan_flags: null buffer");
+  int ndev = 0;
+  CPF_TRY(cpf_device_count(&ndev));
+  if (device < 0 || device >= ndev) return fail(CPF_EINVAL, "cpf_column_nan_flags: device %d out of range (%d visible)", device, ndev);
+  DeviceGuard guard(device);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  ScratchBuf counts;
+  std::vector<int> h_counts((size_t)ncols, 0);
+  if (nx > 0) {
+    CPF_CUDA(counts.alloc((size_t)ncols * sizeof(int), stream));
+    CPF_CUDA(cudaMemsetAsync(counts.p, 0, (size_t)ncols * sizeof(int), stream));
+    const dim3 grid((unsigned)((ncols + 127) / 128), (unsigned)((nx + PADLOG_ROWS - 1) / PADLOG_ROWS));
+    nan_count_kernel<<<grid, 128, 0, stream>>>(y, nx, ncols, neg_is_nan ? 1 : 0, (int*)counts.p);
+    CPF_CUDA(cudaGetLastError());
+    CPF_CUDA(cudaMemcpyAsync(h_counts.data(), counts.p, (size_t)ncols * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    CPF_CUDA(cudaStreamSynchronize(stream));
+  }
+  for (int64_t c = 0; c < ncols; ++c) col_flags[c] = (uint8_t)(h_counts[c] == nx ? 1 : (h_counts[c] > 0 ? 2 : 0));
   return CPF_OK;
 }
 
@@ -487,12 +637,12 @@ int cpf_spline_eval_rows(const double* x, const double* y, int nx, int64_t rows,
   CPF_CUDA(dmeta.alloc((size_t)nq * 3 * sizeof(int), stream));
   const size_t wsmem = 2 * (size_t)LW * sizeof(double);
   const int use_smem = wsmem <= 48 * 1024;
-  spline_row_weights_kernel<<<nq, 32, use_smem ? wsmem : 0, stream>>>(p_x, nx, bc, W, LW, p_q, nq, extrap ? 1 : 0, use_smem,
+  spline_row_weights_kernel<<<nq, 32, use_smem ? wsmem : 0, stream>>>(p_x, nx, bc, W, LW, p_q, nq, (extrap & 1) ? 1 : 0, use_smem,
                                                                      (double*)dw.p, (double*)dwork.p, (int*)dmeta.p);
   CPF_CUDA(cudaGetLastError());
   const int wpb = 8;
   spline_rows_dot_kernel<<<(unsigned)((rows + wpb - 1) / wpb), 32 * wpb, 0, stream>>>(p_y, nx, rows, (const double*)dw.p,
-                                                                                    (const int*)dmeta.p, nq, LW, p_out);
+                                                                                    (const int*)dmeta.p, nq, LW, (extrap & 2) ? 1 : 0, p_out);
   CPF_CUDA(cudaGetLastError());
   if (!on_device) {
     CPF_CUDA(cudaMemcpyAsync(out, p_out, ocells * sizeof(double), cudaMemcpyDeviceToHost, stream));

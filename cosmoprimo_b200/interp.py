@@ -99,12 +99,13 @@ class Interpolator1D(object):
         flat = fun_t.reshape(x.size, -1)
         # all-NaN columns are passed through as NaN, any other NaN poisons the whole fit (ref:161-172)
         if on_device:
-            torch = _buf._torch()
-            isnan = torch.isnan(flat)
-            if self.interp_fun == 'log':
-                isnan = isnan | (flat < 0)
-            self._mask_nan = (~isnan.all(dim=0)).cpu().numpy()
-            poisoned = bool(isnan[:, torch.as_tensor(self._mask_nan, device=flat.device)].any().item()) if self._mask_nan.any() else False
+            flat = flat.contiguous()
+            flags = np.zeros(max(int(flat.shape[1]), 1), dtype='u1')                 # one read of the table (cpf_column_nan_flags)
+            _lib.check(_lib.load().cpf_column_nan_flags(flat.data_ptr(), x.size, int(flat.shape[1]), int(self.interp_fun == 'log'), flags.ctypes.data,
+                                                        flat.device.index, _buf.current_stream(flat.device.index)))
+            flags = flags[:int(flat.shape[1])]
+            self._mask_nan = flags != 1
+            poisoned = bool((flags == 2).any())
         else:
             with np.errstate(invalid='ignore'):
                 isnan = np.isnan(flat) | ((flat < 0) if self.interp_fun == 'log' else False)
@@ -128,6 +129,44 @@ class Interpolator1D(object):
             self._spline = _DeviceSpline(xbuf, ybuf, x.size, self._ncols, _BC_CODES[bc_type], self.interp_x == 'log',
                                          self.interp_fun == 'log', self.extrap, dev, stream)
             self._device = dev
+
+    @classmethod
+    def padlog(cls, x_padded, fun, extrap=False, device=None):
+        """
+        The interpolator ``PowerSpectrumInterpolator1D(extrap_pk='log')`` builds (``cosmoprimo/interpolator.py:42-87, 343-351``):
+        natural spline of log10(fun) in log10(x) with two power-law continuation knots on each side, in one pass over ``fun``
+        (``cpf_spline_create_padlog``: logarithms, continuation rows, NaN screening and the fit, no intermediate array).
+        ``x_padded`` (nx + 4,) are the padded knots, ``fun`` (nx, ...) the tabulated values, numpy or CUDA array.
+        """
+        lib = _lib.load()
+        _lib.require_device()
+        self = cls.__new__(cls)
+        self.interp_x = self.interp_fun = 'log'
+        self.extrap = bool(extrap)
+        x = np.ascontiguousarray(x_padded, dtype='f8').ravel()
+        ybuf = _buf.as_input(fun, dtype='f8')
+        nx = x.size - 4
+        if nx < 2 or ybuf.shape[0] != nx:
+            raise ValueError('fun has {} samples along axis 0, x_padded has {} knots (4 of them continuation knots)'.format(ybuf.shape[0], x.size))
+        self.shape = tuple(ybuf.shape[1:])
+        self.xmin, self.xmax = x[0], x[-1]
+        self._ncols = int(np.prod(self.shape, dtype='i8'))
+        self._on_device = ybuf.on_device
+        self._spline = None
+        dev = ybuf.device if ybuf.on_device else (device if device is not None else _buf.default_device())
+        stream = _buf.current_stream(dev) if ybuf.on_device else None
+        flags = np.zeros(max(self._ncols, 1), dtype='u1')
+        handle = ctypes.c_void_p()
+        _lib.check(lib.cpf_spline_create_padlog(ctypes.byref(handle), x.ctypes.data, ybuf.ptr, nx, self._ncols, int(self.extrap),
+                                                flags.ctypes.data, int(ybuf.on_device), dev, stream))
+        spline = _DeviceSpline.__new__(_DeviceSpline)
+        spline.handle, spline.device = handle, dev
+        flags = flags[:self._ncols]
+        # all-NaN columns are passed through as NaN, any other NaN poisons the whole fit (ref:161-172)
+        self._mask_nan = flags != 1
+        if self._mask_nan.any() and not (flags == 2).any():
+            self._spline, self._device = spline, dev
+        return self
 
     def __call__(self, x, bounds_error=False, dx=0):
         """Evaluate the spline (or its ``dx``-th derivative) at ``x``; result has shape ``x.shape + fun.shape[1:]``."""
@@ -316,13 +355,14 @@ def _device_copy(a, dev):
     return hit
 
 
-def spline_eval_rows(x, fun, xq, bc_type='natural', window=64, extrap=False, device=None):
+def spline_eval_rows(x, fun, xq, bc_type='natural', window=64, extrap=False, device=None, sqrt=False):
     """
     Cubic splines along the LAST axis of ``fun`` (rows, nx) -- the layout FFTLog returns -- on the shared knots ``x``
     (nx,), evaluated at ``xq`` (nq,): returns (nq, rows), i.e. what the reference obtains with
     ``Interpolator1D(x, fun.T, assume_sorted=True)(xq)`` (``cosmoprimo/interpolator.py:289``) without the two transposes
     and without a global fit (``cpf_spline_eval_rows``: the value is a weighted sum of the ordinates; the slope system is
-    solved on ``window`` knots either side of the bracketing interval, ``window=0``: all knots).
+    solved on ``window`` knots either side of the bracketing interval, ``window=0``: all knots).  ``sqrt``: the kernel writes the
+    square root of the value (sigma from the variance) instead of a second pass over the result.
     """
     if bc_type not in ('natural', 'clamped'):
         raise ValueError('bc_type must be "natural" or "clamped"')
@@ -344,5 +384,5 @@ def spline_eval_rows(x, fun, xq, bc_type='natural', window=64, extrap=False, dev
         xbuf, qbuf, stream = _buf.as_input(x), _buf.as_input(q), None
     out = _buf.empty_like_kind(ybuf, (q.size, rows))
     _lib.check(lib.cpf_spline_eval_rows(xbuf.ptr, ybuf.ptr, x.size, rows, qbuf.ptr, q.size, 1 if bc_type == 'clamped' else 0, int(window),
-                                        int(bool(extrap)), out.ptr, int(ybuf.on_device), dev, stream))
+                                        int(bool(extrap)) | (2 if sqrt else 0), out.ptr, int(ybuf.on_device), dev, stream))
     return out.obj

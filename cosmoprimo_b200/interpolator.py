@@ -32,12 +32,8 @@ def _pad_log(k, pk, extrap_kmin=_default_extrap_kmin, extrap_kmax=_default_extra
     to it.  ``k`` is a host array (nk,), ``pk`` (nk, ...) numpy or torch.
     """
     xp = _xp(pk)
-    logk = np.log10(np.asarray(k, dtype='f8'))
+    logk, pad_lo, pad_hi = _pad_log_knots(k, extrap_kmin=extrap_kmin, extrap_kmax=extrap_kmax)
     logpk = xp.log10(pk)
-    lo = np.log10(min(extrap_kmin, k[0] * (1 - 1e-9)))
-    hi = np.log10(max(extrap_kmax, k[-1] * (1 + 1e-9)))
-    pad_hi = np.array([logk[-1] * 0.1 + hi * 0.9, hi])
-    pad_lo = np.array([lo, logk[0] * 0.1 + lo * 0.9])
     slope_hi = (logpk[-1] - logpk[-2]) / (logk[-1] - logk[-2])
     slope_lo = (logpk[1] - logpk[0]) / (logk[1] - logk[0])
     rows_hi = [logpk[-1] + slope_hi * (x - logk[-1]) for x in pad_hi]
@@ -46,6 +42,16 @@ def _pad_log(k, pk, extrap_kmin=_default_extrap_kmin, extrap_kmax=_default_extra
     cat = xp.cat if xp is not np else np.concatenate
     logpk = cat([stack(rows_lo), logpk, stack(rows_hi)])
     return np.concatenate([pad_lo, logk, pad_hi]), logpk
+
+
+def _pad_log_knots(k, extrap_kmin=_default_extrap_kmin, extrap_kmax=_default_extrap_kmax):
+    """log10(k) and the two continuation knots on each side (ref:62-67, 75-80): the range end and 90 % of the way to it."""
+    logk = np.log10(np.asarray(k, dtype='f8'))
+    lo = np.log10(min(extrap_kmin, k[0] * (1 - 1e-9)))
+    hi = np.log10(max(extrap_kmax, k[-1] * (1 + 1e-9)))
+    pad_hi = np.array([logk[-1] * 0.1 + hi * 0.9, hi])
+    pad_lo = np.array([lo, logk[0] * 0.1 + lo * 0.9])
+    return logk, pad_lo, pad_hi
 
 
 def _transpose(a):
@@ -80,8 +86,12 @@ class PowerSpectrumInterpolator1D(object):
             if self.interp_k != 'log':
                 raise ValueError('log-log extrapolation requires log-x interpolation')
             self.extrap_kmin, self.extrap_kmax = extrap_kmin, extrap_kmax
-            kk, pp = _pad_log(kk, pp, extrap_kmin=extrap_kmin, extrap_kmax=extrap_kmax)
-            kk, pp = 10**kk, 10**pp
+            if self.interp_order_k != 3:
+                raise NotImplementedError('cosmoprimo_b200 implements the cubic spline (interp_order_k=3) only')
+            # logarithms, continuation knots (`_pad_log`), NaN screening and the fit in one pass over the table
+            logk, pad_lo, pad_hi = _pad_log_knots(kk, extrap_kmin=extrap_kmin, extrap_kmax=extrap_kmax)
+            self._interp = Interpolator1D.padlog(10**np.concatenate([pad_lo, logk, pad_hi]), pp, device=device)
+            return
         self._interp = Interpolator1D(kk, pp, k=self.interp_order_k, interp_x=self.interp_k, interp_fun=self.extrap_pk,
                                       assume_sorted=True, device=device)
 
@@ -117,7 +127,7 @@ class PowerSpectrumInterpolator1D(object):
         a natural cubic spline in (linear) s evaluated at ``r`` — ``integrate_sigma_r2(method='fftlog')``, ref:285-291.
         """
         rows = lambda k: (_scaled(self._interp.eval_rows(k), self._rsigma8sq), self._interp.shape)
-        out = integrate_sigma_r2(r, self, kmin=self.extrap_kmin, kmax=self.extrap_kmax, nk=nk, device=self._device, pk_rows=rows)**0.5
+        out = integrate_sigma_r2(r, self, kmin=self.extrap_kmin, kmax=self.extrap_kmax, nk=nk, device=self._device, pk_rows=rows, sqrt=True)
         if _buf.is_device_array(out):
             return out
         return out.astype(_bcast_dtype(r))
@@ -196,14 +206,14 @@ class CorrelationFunctionInterpolator1D(object):
         return self.sigma_r(8., **kwargs)
 
 
-def integrate_sigma_r2(r, pk, kmin=1e-7, kmax=1e2, nk=None, device=None, pk_rows=None):
+def integrate_sigma_r2(r, pk, kmin=1e-7, kmax=1e2, nk=None, device=None, pk_rows=None, sqrt=False):
     r"""
     Variance of perturbations in spheres of radius ``r``, :math:`\sigma_r^2 = \frac{1}{2\pi^2}\int dk\,k^2 P(k) W^2(kr)`, by
     the reference's default method (``integrate_sigma_r2(method='fftlog')``, ref:200, 285-291): FFTLog top-hat variance on
     ``nk`` (default 1024) log-spaced wavenumbers, then a natural cubic spline in (linear) s evaluated at ``r``.
     ``pk`` is a callable returning (nk,) or (nk, ...) for an array of wavenumbers; result ``r.shape + pk.shape[1:]``.
     ``pk_rows`` (optional, used by the interpolators of this module): callable returning the same values as (B, nk) rows
-    and the trailing shape, so that nothing is transposed between the spline evaluation and FFTLog.
+    and the trailing shape, so that nothing is transposed between the spline evaluation and FFTLog.  ``sqrt``: return sigma_r.
     """
     if nk is None: nk = 1024
     k = np.geomspace(kmin, kmax, nk)
@@ -217,8 +227,15 @@ def integrate_sigma_r2(r, pk, kmin=1e-7, kmax=1e2, nk=None, device=None, pk_rows
         rows = _transpose(p.reshape(nk, -1))
     rr = np.asarray(r, dtype='f8')
     s, var = TophatVariance(k, device=device)(rows)                                        # (B, nk)
-    tmp = (2. * np.pi**2) * spline_eval_rows(s, var, rr.ravel(), device=device)            # ref:289, rows layout
-    sigma2 = 1. / (2. * np.pi**2) * tmp.reshape(rr.shape + lead)
+    if _buf.is_device_array(var):
+        # device rows: the reference's factor 2 pi^2 (ref:289) and its inverse (ref:292) cancel; no pass over the result, and the
+        # square root of sigma_r (``sqrt``) is taken by the kernel that writes it
+        sigma2 = spline_eval_rows(s, var, rr.ravel(), device=device, sqrt=sqrt).reshape(rr.shape + lead)
+    else:
+        tmp = (2. * np.pi**2) * spline_eval_rows(s, var, rr.ravel(), device=device)            # ref:289, rows layout
+        sigma2 = 1. / (2. * np.pi**2) * tmp.reshape(rr.shape + lead)
+        if sqrt:
+            sigma2 = sigma2**0.5
     if _buf.is_device_array(sigma2):
         return sigma2.to(_buf._torch().float32) if dtype == np.float32 else sigma2
     return sigma2.astype(dtype)
@@ -342,7 +359,7 @@ class PowerSpectrumInterpolator2D(object):
         bad = ~((zz >= self.zmin) & (zz <= self.zmax)) if self._is2d else np.zeros(zz.shape, dtype='?')
         zc = np.clip(zz, self.zmin, self.zmax) if self._is2d else zz
         rows = lambda k: (self(k, zc.ravel(), rows=True), zz.shape)
-        toret = integrate_sigma_r2(r, lambda k: self(k, zc), kmin=self.extrap_kmin, kmax=self.extrap_kmax, nk=nk, device=self._device, pk_rows=rows)**0.5
+        toret = integrate_sigma_r2(r, lambda k: self(k, zc), kmin=self.extrap_kmin, kmax=self.extrap_kmax, nk=nk, device=self._device, pk_rows=rows, sqrt=True)
         if bad.any():
             toret[..., _buf._torch().as_tensor(bad, device=toret.device) if _buf.is_device_array(toret) else bad] = float('nan')
         dtype = _bcast_dtype(r, z)

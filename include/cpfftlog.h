@@ -110,6 +110,22 @@ int cpf_irfft_conj(int size, const double* in, int64_t rows, double* out, int in
 typedef struct cpf_spline cpf_spline;
 int cpf_spline_create(cpf_spline** spline, const double* x, const double* y, int nx, int64_t ncols, int bc,
                       int log_x, int log_y, int extrap, int on_device, int device, void* stream);
+/* The construction of PowerSpectrumInterpolator1D / 2D with extrap_pk='log' in ONE pass over the table (replaces `_pad_log`,
+ * interpolator.py:42-87, the `10**` of :349-351 and the log10 / NaN screening of Interpolator1D, jax.py:152-172): natural spline of
+ * log10(y) in log10(x) on nx + 4 knots, where
+ *   x_padded [nx + 4] : HOST, the padded wavenumbers as the reference forms them (two continuation knots, the nx tabulated
+ *                       wavenumbers, two continuation knots), positive and strictly increasing;
+ *   y [nx, ncols]     : the tabulated spectra (host or device); rows 0, 1, nx + 2, nx + 3 of the fitted table continue log10(y) as the
+ *                       straight lines through its two lowest / two highest rows (the reference's power-law extrapolation);
+ *   col_flags [ncols] : HOST, out: 1 = every cell of the column is NaN (a negative sample counts as NaN): the column evaluates to NaN;
+ *                       2 = some cells are: the reference's fit is poisoned as a whole (jax.py:166-172), the caller decides; 0 = clean.
+ * Synchronises the stream (the flags are a host result). */
+int cpf_spline_create_padlog(cpf_spline** spline, const double* x_padded, const double* y, int nx, int64_t ncols, int extrap,
+                             uint8_t* col_flags, int on_device, int device, void* stream);
+/* The NaN screening Interpolator1D applies to a table before fitting it (jax.py:161-172), for DEVICE tables y [nx, ncols]: col_flags
+ * [ncols] (HOST, out) as above -- 1: every cell of the column is NaN (or negative, with neg_is_nan = the log10-ordinate rule), 2: some
+ * are, 0: none.  One read of the table; synchronises the stream. */
+int cpf_column_nan_flags(const double* y, int nx, int64_t ncols, int neg_is_nan, uint8_t* col_flags, int device, void* stream);
 int cpf_spline_eval(const cpf_spline* spline, const double* xq, int nq, int nu, double* out, int on_device,
                     void* stream);
 /* same values, transposed: out [ncols, nq] -- one row per spline, the layout cpf_fftlog reads (saves the `.T` copy of
@@ -124,7 +140,8 @@ int cpf_spline_destroy(cpf_spline* spline);
  * without the two transposes and without a global fit: the value at xq is a weighted sum of the ordinates whose
  * weights depend on (x, xq) only and decay like 0.27^distance, so the slope system is solved on `window` knots either
  * side of the bracketing interval (truncation ~0.27^window; window = 0 or >= nx: all knots = the full solve).
- *   extrap : 0 => NaN outside [x[0], x[nx-1]], 1 => extend the end polynomials
+ *   extrap : bit 0: 0 => NaN outside [x[0], x[nx-1]], 1 => extend the end polynomials; bit 1 (value 2): write the square root of the
+ *            value (sigma(r) from the variance, `sigma_r = integrate_sigma_r2(...)**0.5`, interpolator.py:573)
  */
 int cpf_spline_eval_rows(const double* x, const double* y, int nx, int64_t rows, const double* xq, int nq, int bc,
                          int window, int extrap, double* out, int on_device, int device, void* stream);

@@ -70,6 +70,53 @@ def test_spline_clamped_and_derivatives_vs_oracle():
             assert np.max(np.abs(out - ref)) < 1e-9 * np.max(np.abs(ref)), (bc, nu)
 
 
+def test_padlog_matches_the_composed_construction():
+    """`Interpolator1D.padlog` (one pass: logarithms, continuation knots, NaN screening, fit) against the composition it replaces --
+    `_pad_log`, `10**`, `Interpolator1D(interp_x='log', interp_fun='log')` (ref interpolator.py:42-87, 343-351; jax.py:152-172) -- on host
+    and device tables: clean columns, an all-NaN column (passes through as NaN), a negative sample (poisons the whole fit), a zero."""
+    torch = pytest.importorskip('torch')
+    from cosmoprimo_b200.interpolator import _pad_log, _pad_log_knots
+    rng = np.random.default_rng(5)
+    k = np.geomspace(2e-5, 40., 257)
+    pk = S.eh_pk(k, S.lhs_cosmologies(9, seed=3)).T.copy()                    # (nk, 9)
+    kq = np.concatenate([[1e-7, 1e2], np.geomspace(1e-7, 1e2, 301), [5e-8, 2e2]])
+
+    def composed(table):
+        kk, pp = _pad_log(k, table)
+        return Interpolator1D(10**kk, 10**pp, interp_x='log', interp_fun='log', assume_sorted=True)
+
+    def fused(table):
+        logk, lo, hi = _pad_log_knots(k)
+        return Interpolator1D.padlog(10**np.concatenate([lo, logk, hi]), table)
+
+    ref = composed(pk)(kq)
+    for table in (pk, torch.from_numpy(pk).cuda()):
+        out = fused(table)(kq)
+        out = out.cpu().numpy() if hasattr(out, 'cpu') else out
+        close_with_nans(out, ref, rtol=1e-12)
+    assert np.isnan(ref[-2:]).all() and np.isfinite(ref[:2]).all()             # range ends are inside, beyond them NaN
+    # all-NaN column: that column NaN, the others untouched
+    t = pk.copy(); t[:, 4] = np.nan
+    with np.errstate(invalid='ignore'):
+        close_with_nans(fused(torch.from_numpy(t).cuda())(kq).cpu().numpy(), composed(t)(kq), rtol=1e-12)
+        assert np.isnan(fused(t)(kq)[:, 4]).all() and np.isfinite(fused(t)(kq)[2:-2, 3]).all()
+        # one negative sample: the reference's fit is poisoned as a whole
+        t = pk.copy(); t[100, 2] = -1.
+        out = fused(torch.from_numpy(t).cuda())(kq).cpu().numpy()
+        assert np.isnan(out).all() and np.isnan(composed(t)(kq)).all()
+    # shapes: 1-D table, trailing axes, float32 queries
+    assert fused(pk[:, 0])(kq).shape == kq.shape and fused(pk.reshape(257, 3, 3))(kq[:5]).shape == (5, 3, 3)
+    assert fused(pk)(kq.astype('f4')).dtype == np.float32
+    # through the public class: device table in, device result out, same numbers as the host table
+    a = PowerSpectrumInterpolator1D(k, pk)(kq[2:-2])
+    b = PowerSpectrumInterpolator1D(k, torch.from_numpy(pk).cuda())(kq[2:-2])
+    assert isinstance(b, torch.Tensor) and np.array_equal(a, b.cpu().numpy())
+    # sigma_r: the square root is taken by the kernel on device rows
+    sa = PowerSpectrumInterpolator1D(k, pk).sigma_r(np.array([4., 8., 12.]))
+    sb = PowerSpectrumInterpolator1D(k, torch.from_numpy(pk).cuda()).sigma_r(np.array([4., 8., 12.]))
+    np.testing.assert_allclose(sb.cpu().numpy(), sa, rtol=1e-13)
+
+
 def test_spline_device_buffers_and_shapes():
     torch = pytest.importorskip('torch')
     g = load_golden('spline_golden.npz').data

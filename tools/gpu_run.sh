@@ -2,7 +2,7 @@
 # One parametrised script for every gpurun call (replaces the per-call scripts of round 1).
 #   usage (repo root, on the GPU box):  bash tools/gpu_run.sh <tag> <step> [<step> ...]
 # steps:  smoke | tests[:<pytest -k expr>] | bench[:<steps>] | ref | secondary | extra | launches | ncu[:<kernel regex>] |
-#         ncuwallish | sanitizer | sass | py:<script> (python tools/lab/<script>.py, output in gpurun_out/<script>_<tag>.log)
+#         ncuwallish | sanitizer | sass | launchpy:<script> | py:<script> (python tools/lab/<script>.py, output in gpurun_out/<script>_<tag>.log)
 # Everything lands in gpurun_out/ with the tag in its name; copy what should be judged into profiles/.
 TAG=${1:-r00}; shift
 OUT=gpurun_out
@@ -48,6 +48,18 @@ for STEP in "$@"; do
       IFS=, read SCRIPT REGEX SKIP <<< "$ARG"
       timeout 900 ncu --set full --clock-control none --import-source on -k regex:$REGEX -s ${SKIP:-3} -c 1 -f -o $OUT/prof_${SCRIPT}_$TAG \
           python tools/lab/$SCRIPT.py > $OUT/ncu_${SCRIPT}_$TAG.log 2>&1; tail -2 $OUT/ncu_${SCRIPT}_$TAG.log ;;
+    launchpy)   # launchpy:<script>: launch list (kernel names + durations) of tools/lab/<script>.py
+      timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/launches_${ARG}_$TAG.csv \
+          python tools/lab/$ARG.py > $OUT/ncu_launch_${ARG}_$TAG.log 2>&1; tail -2 $OUT/ncu_launch_${ARG}_$TAG.log
+      python - <<PY
+import csv, collections
+rows = [r for r in csv.reader(open('$OUT/launches_${ARG}_$TAG.csv')) if len(r) > 10 and r[0].isdigit()]
+c = collections.Counter(); t = collections.Counter()
+for r in rows:
+    name = r[4].split('(')[0][:90]; c[name] += 1; t[name] += float(r[-1].replace(',', ''))
+for n, _ in t.most_common(40): print('%6d x %10.1f us  %s' % (c[n], t[n] / 1e3 if False else t[n], n))
+PY
+      ;;
     py)
       timeout 1200 python tools/lab/$ARG.py > $OUT/${ARG}_$TAG.log 2>&1; echo "rc=$?" >> $OUT/${ARG}_$TAG.log; tail -40 $OUT/${ARG}_$TAG.log ;;
     *) echo "unknown step $STEP" ;;
