@@ -227,6 +227,7 @@ __global__ void __launch_bounds__(16 * R1, 512 / (16 * R1)) fftlog_fast_kernel(c
 }  // namespace cpf
 
 #include "cpf_fftlog_pp.cuh"
+#include "cpf_fftlog_pp8k.cuh"
 #include "cpf_fftlog_stream.cuh"
 
 namespace cpf {
@@ -549,6 +550,33 @@ static void build_pp_tables(int N, int R1, int P, const double* pre, const std::
     }
 }
 
+// records of fftlog_pp8k_kernel (cpf_fftlog_pp8k.cuh): N = 8192 as two 4096-point chains; pp_tw are the ping-pong twiddles of N = 4096
+static void build_pp8k_tables(int P, const double* pre, const std::vector<double2>& uhs, const double* post_re, const std::vector<double2>& pp_tw,
+                              std::vector<double2>& tab) {
+  const int N = 8192, T = 256, nb = N / 2 + 1;
+  double2 zero; zero.x = 0.; zero.y = 0.;
+  tab.assign((size_t)P * T * P8_REC, zero);
+  for (int p = 0; p < P; ++p)
+    for (int t = 0; t < T; ++t) {
+      double2* rec = &tab[((size_t)p * T + t) * P8_REC];
+      for (int k1 = 0; k1 < 16; ++k1) rec[k1] = pp_tw[(size_t)t * 32 + k1];
+      for (int c = 0; c < 2; ++c)
+        for (int r = 0; r < 16; ++r) {
+          const int b = 2 * (t + T * r) + c;
+          double2 v = uhs[(size_t)p * nb + (b <= N / 2 ? b : N - b)];
+          if (b > N / 2) v.y = -v.y;
+          rec[16 + 16 * c + r] = v;
+        }
+      double* dpre = reinterpret_cast<double*>(rec + 48);
+      double* dpost = reinterpret_cast<double*>(rec + 56);
+      for (int r = 0; r < 16; ++r) {
+        const size_t j = (size_t)p * N + N / 4 + t + T * r;
+        dpre[r] = pre[j];
+        dpost[r] = post_re[j];
+      }
+    }
+}
+
 // kernel spectrum in the order fftlog_stream_kernel reads it (cpf_fftlog_stream.cuh): [P][16][256], thread tau = 16 H + L
 // holds the bins H + 16 L + 256 l2
 static void build_stream_ut(int P, const std::vector<double2>& uhs, double2* ut) {
@@ -615,19 +643,24 @@ static int fast_twiddles(int device, int N, const FastTw** out) {
   return CPF_OK;
 }
 
-// w_8192^n, n < 4096, of the split kernel: once per device, never freed
+// w_8192^n, n < 4096, of the N = 8192 kernels and the pass-2 twiddles w_256^{m2 l1} ([l1][m2]) of fftlog_pp8k_kernel: once per device, never freed
+struct Tw8192 { int device; double2 *tw, *tw2; };
 static std::mutex g_tw8192_mutex;
-static std::vector<std::pair<int, double2*>> g_tw8192;
-static int split2_twiddles(int device, const double2** out) {
+static std::vector<Tw8192> g_tw8192;
+static int split2_twiddles(int device, const double2** out, const double2** out_tw2) {
   std::lock_guard<std::mutex> lock(g_tw8192_mutex);
   for (auto& e : g_tw8192)
-    if (e.first == device) { *out = e.second; return CPF_OK; }
-  std::vector<double2> tw(4096);
+    if (e.device == device) { *out = e.tw; *out_tw2 = e.tw2; return CPF_OK; }
+  std::vector<double2> tw(4096), tw2(256);
   for (int n = 0; n < 4096; ++n) tw[n] = unit_root(n, 8192);
-  double2* d = nullptr;
-  CPF_TRY(upload((void**)&d, tw.data(), tw.size() * sizeof(double2)));
-  g_tw8192.emplace_back(device, d);
-  *out = d;
+  for (int l1 = 0; l1 < 16; ++l1)
+    for (int m2 = 0; m2 < 16; ++m2) tw2[16 * l1 + m2] = unit_root(m2 * l1, 256);
+  Tw8192 e;
+  e.device = device; e.tw = e.tw2 = nullptr;
+  CPF_TRY(upload((void**)&e.tw, tw.data(), tw.size() * sizeof(double2)));
+  CPF_TRY(upload((void**)&e.tw2, tw2.data(), tw2.size() * sizeof(double2)));
+  g_tw8192.push_back(e);
+  *out = e.tw; *out_tw2 = e.tw2;
   return CPF_OK;
 }
 
@@ -697,6 +730,8 @@ struct cpf_plan {
   int fast_R1;
   bool split2 = false;        // N = 8192: two 4096-point register FFTs per transform (fftlog_split2_kernel)
   const double2* d_tw8192 = nullptr;   // w_8192^n, n < 4096 (shared, not owned)
+  const double2* d_tw2_256 = nullptr;  // w_256^{m2 l1}, [16][16] (shared, not owned)
+  mutable double2* d_pp8k = nullptr;   // N = 8192: per-thread records of fftlog_pp8k_kernel [P, 256, P8_REC], built on first use
   bool window_prunable;
   void* d_block = nullptr;    // one device allocation holds every per-plan table below
   double* d_pre = nullptr;
@@ -757,6 +792,7 @@ int cpf_plan_destroy(cpf_plan* plan) {
   DeviceGuard guard(plan->device);
   cudaFree(plan->d_block);
   cudaFree(plan->d_pp);
+  cudaFree(plan->d_pp8k);
   delete plan;
   return CPF_OK;
 }
@@ -814,7 +850,7 @@ int cpf_plan_create(cpf_plan** out, int n, int N, int P, int in_left, int out_le
   do {
     if (pl->fast_R1 || pl->split2) {
       if ((rc = fast_twiddles(device, pl->split2 ? 4096 : N, &pl->fast))) break;
-      if (pl->split2 && (rc = split2_twiddles(device, &pl->d_tw8192))) break;
+      if (pl->split2 && (rc = split2_twiddles(device, &pl->d_tw8192, &pl->d_tw2_256))) break;
       std::vector<double2> uhs(uh);
       for (int p = 0; p < P; ++p)
         for (int m = 1; m < nb; m += 2) { uhs[(size_t)p * nb + m].x = -uhs[(size_t)p * nb + m].x; uhs[(size_t)p * nb + m].y = -uhs[(size_t)p * nb + m].y; }
@@ -830,6 +866,10 @@ int cpf_plan_create(cpf_plan** out, int n, int N, int P, int in_left, int out_le
         } else {
           build_pp_tables(N, pl->fast_R1, P, pre, uhs, post_re, pl->fast->pp_tw, pp_tab);
         }
+      } else if (pl->split2 && pl->window_prunable && !post_im) {
+        pl->h_uhs.swap(uhs);                        // kept for the lazy records of the persistent N = 8192 kernel
+        pl->h_pre_win.assign(pre, pre + PN);
+        pl->h_post_win.assign(post_re, post_re + PN);
       }
     } else {
       std::vector<double2> ut(PN);
@@ -1142,6 +1182,53 @@ static int ensure_pp_tables(const cpf_plan* pl) {
   return CPF_OK;
 }
 
+// records of the persistent N = 8192 kernel, built the first time it is asked for
+static int ensure_pp8k_tables(const cpf_plan* pl) {
+  std::lock_guard<std::mutex> lock(pl->pp_mutex);
+  if (pl->d_pp8k) return CPF_OK;
+  if (pl->h_uhs.empty()) return fail(CPF_EUNSUPPORTED, "cpf_fftlog: this plan has no tables for the persistent N = 8192 kernel");
+  std::vector<double2> tab;
+  build_pp8k_tables(pl->P, pl->h_pre_win.data(), pl->h_uhs, pl->h_post_win.data(), pl->fast->pp_tw, tab);
+  double2* d = nullptr;
+  CPF_TRY(upload((void**)&d, tab.data(), tab.size() * sizeof(double2)));
+  pl->d_pp8k = d;
+  return CPF_OK;
+}
+
+static int launch_pp8k(const cpf_plan* pl, const FftlogArgs& a, cudaStream_t stream) {
+  int dev = 0, sms = 0;
+  CPF_CUDA(cudaGetDevice(&dev));
+  CPF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  long long grid = a.pairs_per_p;
+  if (grid > sms) grid = sms;
+  typedef void (*kern_t)(const FftlogArgs, const double2*, const double2*, const double2*);
+  kern_t kern = fftlog_pp8k_kernel<false>;
+  int smem = P8_SMEM_BYTES;
+  // full window + 16-byte aligned rows: the rows of a pair are staged by bulk copies (CPF_STREAM_TMA=0: direct loads)
+  const char* tma_env = getenv("CPF_STREAM_TMA");
+  const bool fullwin = a.n == a.N / 2 && a.in_left == a.N / 4 && !a.keep_padding;
+  if (fullwin && !(tma_env && tma_env[0] == '0') && ((uintptr_t)a.in % 16 == 0)) {
+    kern = fftlog_pp8k_kernel<true>;
+    smem = P8_SMEM_BYTES_TMA;
+  }
+  CPF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(512);
+  cfg.dynamicSmemBytes = (size_t)smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  const char* pdl_env = getenv("CPF_STREAM_PDL");
+  cfg.attrs = attr;
+  cfg.numAttrs = (pdl_env && pdl_env[0] == '0') ? 0 : 1;
+  FftlogArgs b = a;
+  b.tickets = nullptr;
+  CPF_CUDA(cudaLaunchKernelEx(&cfg, kern, b, (const double2*)pl->d_pp8k, pl->d_tw2_256, pl->d_tw8192));
+  return CPF_OK;
+}
+
 // Kernel choice for the default call (zero padding, cropped output, real post-factor).  CPF_FFTLOG_KERNEL = fast | pp |
 // stream forces one family (where the plan has its tables); otherwise large launches go to the persistent kernels
 // (stream for N = 4096, ping-pong for N = 2048 / 1024) and small ones to the per-pair kernel, which has no start-up cost.
@@ -1198,6 +1285,16 @@ static int launch_fftlog(const cpf_plan* pl, FftlogArgs a, bool pruned, cudaStre
     a.ut = pruned ? pl->d_uts : pl->d_ut;
     a.tw1 = pl->fast->d_tw1;
     a.tw2 = pl->fast->d_tw2;
+    if (pruned && !pl->post_complex && !pl->h_uhs.empty()) {       // the default call: large launches go to the persistent kernel
+      const int choice = kernel_choice();
+      int dev = 0, sms = 0;
+      CPF_CUDA(cudaGetDevice(&dev));
+      CPF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+      if (choice == K_PP || (choice == K_AUTO && a.pairs_per_p >= 4LL * sms)) {
+        CPF_TRY(ensure_pp8k_tables(pl));
+        return launch_pp8k(pl, a, stream);
+      }
+    }
     const size_t smem2 = (size_t)Geo<16>::SMEM_ELEMS * sizeof(double2);
     typedef void (*kern2_t)(const FftlogArgs, const double2*);
     kern2_t kern = pruned ? (pl->post_complex ? (kern2_t)fftlog_split2_kernel<true, true> : (kern2_t)fftlog_split2_kernel<true, false>)

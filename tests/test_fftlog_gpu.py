@@ -163,6 +163,10 @@ def test_multipoles_config2_shapes():
     ('pp', 1000, 65, [2], False),
     ('pp', 512, 129, [0, 2, 4], True),          # N = 1024: eight groups per CTA
     ('pp', 2048, 67, [0, 2], True),             # N = 4096 through the ping-pong kernel
+    ('pp', 4096, 35, [0, 2, 4], True),          # N = 8192: persistent two-chain kernel (fftlog_pp8k_kernel), TMA-staged rows, odd batch
+    ('pp', 4096, 700, [1], False),              # ... several pairs per CTA, one plan row, the same row for every ell
+    ('pp', 3000, 11, [0, 2], True),             # ... window narrower than N/2: direct masked loads and stores
+    ('auto', 4096, 1301, [0, 2], True),         # ... chosen automatically for a large launch
 ])
 def test_persistent_kernels(monkeypatch, kernel, n, B, ells, per_ell):
     """The persistent kernels (stream for N = 4096, ping-pong for N = 2048 / 1024) are chosen automatically for large
@@ -177,7 +181,13 @@ def test_persistent_kernels(monkeypatch, kernel, n, B, ells, per_ell):
     monkeypatch.setenv('CPF_FFTLOG_KERNEL', kernel)
     if kernel == 'pp' and B > 10000:
         monkeypatch.setenv('CPF_PP_DYNAMIC', '1')       # the opt-in ticket-counter variant of the ping-pong kernel
-    s, xi = obj(fun if per_ell else fun[:, None, :])
+    arg = fun if per_ell else fun[:, None, :]
+    if kernel == 'auto':                                # device-resident rows: one launch, large enough for the automatic choice
+        import torch
+        s, xi = obj(torch.from_numpy(np.ascontiguousarray(arg)).cuda())
+        xi = xi.cpu().numpy()
+    else:
+        s, xi = obj(arg)
     assert xi.shape == (B, len(ells), n) and np.isfinite(xi).all()
     post = obj.padded_postfactor[:, obj.padded_size_out_left:obj.padded_size_out_left + n]
     assert scale_aware_error(xi, ref_fast, post) < 1e-13
@@ -193,6 +203,7 @@ def test_persistent_kernels(monkeypatch, kernel, n, B, ells, per_ell):
     ('fast', 1000, 6, [0, 2]),
     ('auto', 60, 7, [0]),                 # generic shared-memory kernel (N = 128)
     ('auto', 4096, 7, [0, 2]),            # N = 8192: split kernel (two 4096-point FFTs per transform)
+    ('pp', 4096, 7, [0, 2]),              # N = 8192: persistent two-chain kernel
 ])
 def test_non_finite_rows_stay_in_their_row(monkeypatch, kernel, n, B, ells):
     """The reference transforms rows independently (numpy.fft along the last axis): a NaN / Inf sample turns ITS row into NaN

@@ -2,7 +2,7 @@
 # One parametrised script for every gpurun call (replaces the per-call scripts of round 1).
 #   usage (repo root, on the GPU box):  bash tools/gpu_run.sh <tag> <step> [<step> ...]
 # steps:  smoke | tests[:<pytest -k expr>] | bench[:<steps>] | ref | secondary | extra | launches | ncu[:<kernel regex>] |
-#         ncuwallish | sanitizer | sass | launchpy:<script> | py:<script> (python tools/lab/<script>.py, output in gpurun_out/<script>_<tag>.log)
+#         ncuwallish | sanitizer | sass | launchpy:<script> | sh:<script> | py:<script> (python tools/lab/<script>.py, output in gpurun_out/<script>_<tag>.log)
 # Everything lands in gpurun_out/ with the tag in its name; copy what should be judged into profiles/.
 TAG=${1:-r00}; shift
 OUT=gpurun_out
@@ -60,6 +60,8 @@ for r in rows:
 for n, _ in t.most_common(40): print('%6d x %10.1f us  %s' % (c[n], t[n] / 1e3 if False else t[n], n))
 PY
       ;;
+    sh)      # sh:<script>: bash tools/lab/<script>.sh, output in gpurun_out/<script>_<tag>.log
+      timeout 1200 bash tools/lab/$ARG.sh > $OUT/${ARG}_$TAG.log 2>&1; echo "rc=$?" >> $OUT/${ARG}_$TAG.log; tail -40 $OUT/${ARG}_$TAG.log ;;
     py)
       timeout 1200 python tools/lab/$ARG.py > $OUT/${ARG}_$TAG.log 2>&1; echo "rc=$?" >> $OUT/${ARG}_$TAG.log; tail -40 $OUT/${ARG}_$TAG.log ;;
     *) echo "unknown step $STEP" ;;
