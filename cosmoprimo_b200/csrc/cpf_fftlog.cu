@@ -1199,7 +1199,7 @@ static int launch_pp8k(const cpf_plan* pl, const FftlogArgs& a, cudaStream_t str
   int dev = 0, sms = 0;
   CPF_CUDA(cudaGetDevice(&dev));
   CPF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  long long grid = a.pairs_per_p;
+  long long grid = (long long)a.P * a.pairs_per_p;        // a CTA serves one plan row when there are at least P of them
   if (grid > sms) grid = sms;
   typedef void (*kern_t)(const FftlogArgs, const double2*, const double2*, const double2*);
   kern_t kern = fftlog_pp8k_kernel<false>;

@@ -30,6 +30,9 @@ constexpr int P8_SMEM_ELEMS = 2 * Geo<16>::SMEM_ELEMS + 256;
 constexpr int P8_SMEM_BYTES = P8_SMEM_ELEMS * (int)sizeof(double2);
 constexpr int P8_SMEM_BYTES_TMA = P8_SMEM_BYTES + 2 * 4096 * (int)sizeof(double);
 
+// w_32^r = exp(-2 pi i r / 32), r < 16
+__device__ constexpr double kW32[16][2] = {{1.00000000000000000000e+00, -0.00000000000000000000e+00}, {9.80785280403230430579e-01, -1.95090322016128248084e-01}, {9.23879532511286738483e-01, -3.82683432365089781779e-01}, {8.31469612302545235671e-01, -5.55570233019602177649e-01}, {7.07106781186547572737e-01, -7.07106781186547461715e-01}, {5.55570233019602288671e-01, -8.31469612302545235671e-01}, {3.82683432365089837290e-01, -9.23879532511286738483e-01}, {1.95090322016128331351e-01, -9.80785280403230430579e-01}, {6.12323399573676603587e-17, -1.00000000000000000000e+00}, {-1.95090322016128192573e-01, -9.80785280403230430579e-01}, {-3.82683432365089726268e-01, -9.23879532511286738483e-01}, {-5.55570233019601955604e-01, -8.31469612302545457716e-01}, {-7.07106781186547461715e-01, -7.07106781186547572737e-01}, {-8.31469612302545346694e-01, -5.55570233019602177649e-01}, {-9.23879532511286738483e-01, -3.82683432365089892802e-01}, {-9.80785280403230430579e-01, -1.95090322016128608906e-01}};
+
 template <bool TMA>
 __global__ void __launch_bounds__(512, 1) fftlog_pp8k_kernel(const FftlogArgs a, const double2* __restrict__ tmtab, const double2* __restrict__ tw2tab,
                                                              const double2* __restrict__ tw8192) {
@@ -65,10 +68,11 @@ __global__ void __launch_bounds__(512, 1) fftlog_pp8k_kernel(const FftlogArgs a,
   auto gbar = [&]() { named_sync(1 + g, T); };
 
   // DFT outputs w[0..16) times the thread's 16 twiddles in tensor memory at column `col` (chunks of 4, the next chunk in flight while
-  // this one is used), scattered to dst[k * stride]
+  // this one is used), scattered to dst[k * stride]; does the DFT of w first
   auto twiddle_store_tm = [&](double2 (&w)[16], const uint32_t col, double2* dst, const int stride) {
     Tm4 tw[2];
     tmem_ld4(col, tw[0]);
+    dft_dit<16, false, false>(w);             // the first chunk of twiddles arrives behind the butterflies
     tmem_wait4(tw[0]);
 #pragma unroll
     for (int ch = 0; ch < 4; ++ch) {
@@ -87,7 +91,6 @@ __global__ void __launch_bounds__(512, 1) fftlog_pp8k_kernel(const FftlogArgs a,
     double2 w[16];
 #pragma unroll
     for (int n1 = 0; n1 < 16; ++n1) w[bitrev(n1, 4)] = v[n1];
-    dft_dit<16, false, false>(w);
     twiddle_store_tm(w, tb + P8_COL_TW1, S + t, RS);
   };
   auto pass2 = [&]() {
@@ -107,15 +110,25 @@ __global__ void __launch_bounds__(512, 1) fftlog_pp8k_kernel(const FftlogArgs a,
 #pragma unroll
     for (int m2 = 0; m2 < 16; ++m2) v[bitrev(m2, 4)] = row[m2];
   };
-  auto chain_twiddle = [&](double2 (&v)[16]) {        // chain 1: times w_8192^{t + 256 r} (input of FFT #1, output of FFT #2)
+  // chain 1: times w_8192^{t + 256 r} = w_8192^t w_32^r (input of FFT #1, output of FFT #2): one 16-byte load and 15 products with
+  // compile-time constants instead of 16 loads (the loads were 1 k of the 17 k LSU wavefronts per pair and missed L1)
+  auto chain_twiddle = [&](double2 (&v)[16]) {
     if (g == 1) {
+      const double2 base = __ldg(tw8192 + t);
+      v[0] = cmul(v[0], base);
 #pragma unroll
-      for (int r = 0; r < 16; ++r) v[r] = cmul(v[r], __ldg(tw8192 + t + T * r));
+      for (int r = 1; r < 16; ++r) v[r] = cmul(v[r], cmul(base, mk2(kW32[r][0], kW32[r][1])));
     }
   };
 
-  for (int p = 0; p < a.P; ++p) {
-    if (p > 0) { tmem_fence_before(); __syncthreads(); tmem_fence_after(); }   // all reads of the old tables are done
+  // Work split: with at least as many CTAs as plan rows every CTA serves ONE plan row (its tables are loaded once) and the CTAs of a row
+  // take its pairs in turn; otherwise every CTA walks over all plan rows.
+  const bool one_row = (int)gridDim.x >= a.P;
+  const int p_lo = one_row ? (int)blockIdx.x % a.P : 0, p_hi = one_row ? p_lo + 1 : a.P;
+  const long long first = one_row ? (long long)blockIdx.x / a.P : (long long)blockIdx.x;
+  const long long stride = one_row ? ((long long)gridDim.x - p_lo + a.P - 1) / a.P : (long long)gridDim.x;
+  for (int p = p_lo; p < p_hi; ++p) {
+    if (p > p_lo) { tmem_fence_before(); __syncthreads(); tmem_fence_after(); }   // all reads of the old tables are done
     if (threadIdx.x < 256) {
       const double2* rec = tmtab + ((size_t)p * T + t) * P8_REC;
 #pragma unroll 2
@@ -130,16 +143,16 @@ __global__ void __launch_bounds__(512, 1) fftlog_pp8k_kernel(const FftlogArgs a,
     tmem_fence_before();
     __syncthreads();
     tmem_fence_after();
-    if (p == 0) asm volatile("griddepcontrol.wait;" ::: "memory");      // plan tables only so far; rows may come from the previous kernel
-    if (TMA && threadIdx.x == 0 && blockIdx.x < a.pairs_per_p) stage_rows(p, blockIdx.x);
+    if (p == p_lo) asm volatile("griddepcontrol.wait;" ::: "memory");      // plan tables only so far; rows may come from the previous kernel
+    if (TMA && threadIdx.x == 0 && first < a.pairs_per_p) stage_rows(p, first);
 
-    for (long long pair = blockIdx.x; pair < a.pairs_per_p; pair += gridDim.x) {
+    for (long long pair = first; pair < a.pairs_per_p; pair += stride) {
       const long long b0 = 2 * pair, b1 = b0 + 1;
       const bool has1 = b1 < a.batch;
       const double* rowA = a.in + (a.in_has_P ? (b0 * a.P + p) : b0) * (long long)a.n;
       const double* rowB = has1 ? a.in + (a.in_has_P ? (b1 * a.P + p) : b1) * (long long)a.n : rowA;
       if (!TMA) {                                                         // L2 prefetch of the CTA's next pair (one 128-byte line per thread and row)
-        const long long nb0 = 2 * (pair + gridDim.x);
+        const long long nb0 = 2 * (pair + stride);
         if (nb0 < a.batch) {
           const int lines = (a.n * 8 + 127) / 128;
           for (int l = threadIdx.x; l < 2 * lines; l += 512) {
@@ -186,17 +199,17 @@ __global__ void __launch_bounds__(512, 1) fftlog_pp8k_kernel(const FftlogArgs a,
       // ---- FFT #1 ----
       pass1(v);
       const bool row_a_bad = __syncthreads_or(bad_a);                     // every thread has its samples in registers
-      if (TMA && threadIdx.x == 0 && pair + gridDim.x < a.pairs_per_p) stage_rows(p, pair + gridDim.x);
+      if (TMA && threadIdx.x == 0 && pair + stride < a.pairs_per_p) stage_rows(p, pair + stride);
       pass2();
       const bool row_b_bad = named_sync_or(1 + g, T, bad_b);              // both groups loaded the same rows: the same flags in both
       pass3_load(v);
       gbar();   // pass-3 reads of S are done before FFT #2 overwrites it
-      dft_dit<16, false, false>(v);
       // ---- kernel multiply: bins 2 (t + 256 r) + g ----
       {
         const uint32_t col = tb + (g ? P8_COL_UT1 : P8_COL_UT0);
         Tm4 tu[2];
         tmem_ld4(col, tu[0]);
+        dft_dit<16, false, false>(v);
         tmem_wait4(tu[0]);
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
