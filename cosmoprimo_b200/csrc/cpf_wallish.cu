@@ -61,27 +61,30 @@ struct WallishArgs {
 struct WallishSmem {
   double2* B;     // FFT exchange buffer / spectrum in natural order / DST coefficients (de-interleaved + padded) / knots + slope slots of the final spline
   double2* E;     // [256] chunk results of the two-step eliminations (value with zero inflow), forward
-  double2* Eb;    // [256] ... backward
+  double2* Eb;    // ... backward: the SAME memory (WallishCtaSync separates the last read of E from the write of Eb)
   double* Mf;     // [256] ... and the factors the inflow is multiplied with
-  double* Mb;     // [256]
-  double* red;    // [256]
-  int* redi;      // [256]
+  double* Mb;     // the same memory as Mf
+  double* red;    // [32]
+  int* redi;      // [32]
   int* box;       // [8]
   WallishGap* gaps;   // [4]
   double* wtab;   // [32] Thomas pivots (copied from global memory once: they sit in the dependency chain of the first chunks)
   __device__ explicit WallishSmem(double2* base) {
-    B = base; E = base + WallishGeo::BUF; Eb = E + 256;
-    Mf = reinterpret_cast<double*>(Eb + 256);
-    Mb = Mf + 256;
-    red = Mb + 256;
-    wtab = red + 256;
+    B = base; E = base + WallishGeo::BUF; Eb = E;
+    Mf = reinterpret_cast<double*>(E + 256);
+    Mb = Mf;
+    red = Mf + 256;
+    wtab = red + 32;
     gaps = reinterpret_cast<WallishGap*>(wtab + 32);
     redi = reinterpret_cast<int*>(gaps + 4);
-    box = redi + 256;
+    box = redi + 32;
   }
 };
-static constexpr size_t kWallishSmemBytes = ((size_t)WallishGeo::BUF + 512) * sizeof(double2) + (3 * 256 + 32) * sizeof(double) + 4 * sizeof(WallishGap) + 264 * sizeof(int);
-static_assert(2 * (kWallishSmemBytes + 1024) <= 227 * 1024, "two CTAs per SM");
+struct WallishCtaSync {
+  __device__ __forceinline__ void operator()() const { __syncthreads(); }
+};
+static constexpr size_t kWallishSmemBytes = ((size_t)WallishGeo::BUF + 256) * sizeof(double2) + (256 + 32 + 32) * sizeof(double) + 4 * sizeof(WallishGap) + 40 * sizeof(int);
+static_assert(3 * (kWallishSmemBytes + 1024) <= 228 * 1024, "three CTAs per SM");
 
 __device__ __forceinline__ void fft4096(const int t, double2 (&v)[16], double2* S, const double2* tw1, const double2* tw2) {
   fft_pass1<16, false>(t, v, S, tw1);
@@ -267,7 +270,7 @@ __device__ __forceinline__ void wallish_middle(const WallishArgs& a, const Walli
   // second derivatives of the clamped splines through the even / odd coefficients           (:377-382); chunks live in registers
   wallish_forward_local(t, sm.B, d, sm.E, sm.Mf, sm.wtab);
   __syncthreads();
-  wallish_forward_fix_backward_local(t, d, sm.E, sm.Mf, sm.Eb, sm.Mb, sm.wtab);
+  wallish_forward_fix_backward_local(t, d, sm.E, sm.Mf, sm.Eb, sm.Mb, sm.wtab, WallishCtaSync());
   __syncthreads();
   const WallishBest chunk = wallish_backward_dd(t, sm.B, d, sm.Eb, sm.Mb, sm.wtab);
   // boxes (:392-395): argmax over [20, H-20), then over [first + 5, H-20); per-chunk maxima come out of the backward pass,
@@ -393,7 +396,7 @@ __device__ __forceinline__ void wallish_final(const WallishArgs& a, const Wallis
   typedef WallishGeo G;
   wallish_fin_forward_local(t, a.nc, sm.B, a.fc, d, sm.E, sm.Mf);
   __syncthreads();
-  wallish_fin_fix_backward_local(t, a.fc, d, sm.E, sm.Mf, sm.Eb, sm.Mb);
+  wallish_fin_fix_backward_local(t, a.fc, d, sm.E, sm.Mf, sm.Eb, sm.Mb, WallishCtaSync());
   __syncthreads();
   wallish_fin_backward_fix(t, a.fc, d, sm.Eb, sm.Mb);
   // the slopes next to an output wavenumber travel through the slot array
@@ -419,6 +422,8 @@ __device__ __forceinline__ void wallish_final(const WallishArgs& a, const Wallis
 }
 
 // V (lab): bit 0: the two FFTs share their code (a two-trip loop); bit 1: rolled logarithms; bit 2: rolled exponentials
+// Two CTAs per SM: the 128-register budget of the register FFT.  The shared memory would admit three (kWallishSmemBytes), but the
+// 80-register build that goes with them spills in every phase: 9.4 M P(k)/s against 11.6 M (profiles/r2_experiments.md, r3l).
 template <int V>
 __global__ void __launch_bounds__(256, 2) wallish_fused_kernel(const WallishArgs a) {
   extern __shared__ double2 smem_raw[];
@@ -700,8 +705,17 @@ int cpf_wallish2018(const double* klin, const double* pklin, int nlin, const dou
   typedef void (*wkern_t)(const WallishArgs);
   static const wkern_t kerns[8] = {wallish_fused_kernel<0>, wallish_fused_kernel<1>, wallish_fused_kernel<2>, wallish_fused_kernel<3>,
                                    wallish_fused_kernel<4>, wallish_fused_kernel<5>, wallish_fused_kernel<6>, wallish_fused_kernel<7>};
-  CPF_CUDA(cudaFuncSetAttribute(kerns[variant], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWallishSmemBytes));
-  kerns[variant]<<<grid, 256, kWallishSmemBytes, stream>>>(a);
+  wkern_t kern = kerns[variant];
+  size_t smem_bytes = kWallishSmemBytes;
+  if (const char* e = getenv("CPF_WALLISH_SMEM_PAD")) smem_bytes += (size_t)atoi(e);          // lab: lowers the occupancy
+  CPF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+  CPF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+  if (a.dbg) {
+    int occ = 0;
+    CPF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem_bytes));
+    fprintf(stderr, "wallish: %d resident CTAs per SM\n", occ);
+  }
+  kern<<<grid, 256, smem_bytes, stream>>>(a);
   CPF_CUDA(cudaGetLastError());
   if (!on_device) {
     CPF_CUDA(cudaMemcpyAsync(pknow, p_pknow, out_bytes, cudaMemcpyDeviceToHost, stream));

@@ -136,9 +136,14 @@ CPF_HD void wallish_forward_local(const int t, const double2* X, double2 (&d)[16
   M[t] = m;
 }
 
+// SYNC hook of the two fix-and-backward steps: called between the last read of (E, M) and the write of (Eb, Mb).  The kernel passes a CTA
+// barrier and lets Eb / Mb share the memory of E / M (6 KB less shared memory: three CTAs per SM); the CPU emulation keeps separate arrays.
+struct WallishNoSync { CPF_HD void operator()() const {} };
+
 // inflow correction of the forward pass, then the back substitution from zero inflow: d[j] <- s_j(0); publishes (Eb, Mb)
+template <class SYNC = WallishNoSync>
 CPF_HD void wallish_forward_fix_backward_local(const int t, double2 (&d)[16], const double2* E, const double* M, double2* Eb, double* Mb,
-                                               const double* wtab) {
+                                               const double* wtab, const SYNC& sync = SYNC()) {
   typedef WallishGeo G;
   const int c = t & 127, first = c * G::CH;
   double2 din = mk2(0., 0.);
@@ -164,6 +169,7 @@ CPF_HD void wallish_forward_fix_backward_local(const int t, double2 (&d)[16], co
     m *= -cp;
     d[j] = s;
   }
+  sync();
   Eb[t] = s;
   Mb[t] = m;
 }
@@ -439,7 +445,7 @@ CPF_HD void wallish_fin_forward_local(const int t, const int nc, const double2* 
 }
 
 template <bool UNI>
-CPF_HD void wallish_fin_fix_backward_local_t(const int t, const WallishFinFac& fc, double2 (&d)[16], const double2* E, const double* M, double2* Eb, double* Mb) {
+CPF_HD void wallish_fin_fix_backward_local_t(const int t, const WallishFinFac& fc, double2 (&d)[16], const double2* E, const double* M, double2& s_out, double& m_out) {
   typedef WallishGeo G;
   const double2 din = wallish_inflow4(E, M, t, -1);
   double m = 1.;
@@ -458,13 +464,20 @@ CPF_HD void wallish_fin_fix_backward_local_t(const int t, const WallishFinFac& f
     m *= -cp;
     d[j] = s;
   }
-  Eb[t] = s;
-  Mb[t] = m;
+  s_out = s;
+  m_out = m;
 }
 
-CPF_HD void wallish_fin_fix_backward_local(const int t, const WallishFinFac& fc, double2 (&d)[16], const double2* E, const double* M, double2* Eb, double* Mb) {
-  if (t >= fc.t0 && t < fc.t1) wallish_fin_fix_backward_local_t<true>(t, fc, d, E, M, Eb, Mb);
-  else wallish_fin_fix_backward_local_t<false>(t, fc, d, E, M, Eb, Mb);
+template <class SYNC = WallishNoSync>
+CPF_HD void wallish_fin_fix_backward_local(const int t, const WallishFinFac& fc, double2 (&d)[16], const double2* E, const double* M, double2* Eb, double* Mb,
+                                           const SYNC& sync = SYNC()) {
+  double2 s;
+  double m;
+  if (t >= fc.t0 && t < fc.t1) wallish_fin_fix_backward_local_t<true>(t, fc, d, E, M, s, m);
+  else wallish_fin_fix_backward_local_t<false>(t, fc, d, E, M, s, m);
+  sync();
+  Eb[t] = s;
+  Mb[t] = m;
 }
 
 // d[j] <- slope at knot 16 t + j
