@@ -707,15 +707,32 @@ def run_secondary(args):
                                   'cpu_path': 'scipy dst / CubicSpline restatement of Wallish2018PowerSpectrumBAOFilter._compute (per-column Python loop as in the reference)'}
     del pk, interp, filt, pklin, pkout, out
     torch.cuda.empty_cache()
-    # spline evaluation of a log-log P(k) table (the step in front of every transform): 540 knots x 4096 spectra -> 2048 wavenumbers
+    # spline evaluation of a log-log P(k) table (the step in front of every transform): 540 knots x 65 536 spectra -> 2048 wavenumbers, through the
+    # construction PowerSpectrumInterpolator1D uses (one pass: logarithms, continuation knots, NaN screening, fit) and the transposed evaluation;
+    # algorithmic bytes per spectrum = 8 (540 in + 2048 out)
+    from cosmoprimo_b200.interpolator import _pad_log_knots
     ktab = np.geomspace(1e-4, 50., 540)
     tab = S.eh_pk(ktab, S.lhs_cosmologies(256, seed=3)).T
-    tab_d = torch.from_numpy(np.tile(tab, (1, 16))).cuda()
+    nsp = 65536
+    tab_d = torch.from_numpy(np.tile(tab, (1, nsp // 256))).cuda()
     kq = np.geomspace(1e-4, 50., n)
-    ti = gpu_time(lambda: Interpolator1D(ktab, tab_d, interp_x='log', interp_fun='log', assume_sorted=True).eval_rows(kq))
+    logk, lo, hi = _pad_log_knots(ktab)
+    kpad = 10**np.concatenate([lo, logk, hi])
+    ti = gpu_time(lambda: Interpolator1D.padlog(kpad, tab_d).eval_rows(kq), reps=5, warm=2)
     tic = cpu_time(lambda: SO.interpolator1d(ktab, tab, interp_x='log', interp_fun='log', assume_sorted=True)(kq))
-    res['spline_fit_and_eval'] = {'unit': 'spectra/s', 'gpu': tab_d.shape[1] / ti, 'cpu_1core': tab.shape[1] / tic,
-                                  'what': 'natural cubic spline fit (540 knots, log-log) + evaluation at 2048 wavenumbers'}
+    sp_bytes = 8. * (ktab.size + n)
+    res['spline_fit_and_eval'] = {'unit': 'spectra/s', 'gpu': nsp / ti, 'gpu_spectra': nsp, 'cpu_1core': tab.shape[1] / tic,
+                                  'algorithmic_GBps': nsp * sp_bytes / ti / 1e9, 'hbm_frac': nsp * sp_bytes / ti / hbm,
+                                  'what': 'log-log natural cubic spline with continuation knots (540 + 4 knots: cpf_spline_create_padlog) + transposed evaluation at 2048 wavenumbers'}
+    del tab_d
+    torch.cuda.empty_cache()
+    # EH generator with ONE redshift per cosmology (the input of configs[1]): 65 536 cosmologies -> 65 536 rows of 2048 wavenumbers
+    par1 = S.lhs_cosmologies(nsp, seed=7)
+    eh1 = EisensteinHu(par1['h'], par1['omega_b'], par1['omega_cdm'], par1['n_s'], logA=par1['logA'])
+    z1 = np.full(nsp, 0.5)
+    tg1 = gpu_time(lambda: eh1.pk(k, z=z1), reps=5, warm=2)
+    res['eh_generator_single_z'] = {'unit': 'rows/s', 'gpu': nsp / tg1, 'gpu_rows': nsp, 'algorithmic_GBps': nsp * 8. * n / tg1 / 1e9, 'hbm_frac': nsp * 8. * n / tg1 / hbm,
+                                    'what': 'cpf_eh_pk, one redshift per cosmology, nk = 2048 (output bytes only)'}
     print(json.dumps(res))
 
 
