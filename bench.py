@@ -424,7 +424,7 @@ def run_ours(args):
     else:
         roof = {'bound': 'hbm', 'achieved': ach_gbs, 'peak': hbm_gbs, 'unit': 'GB/s', 'frac': ach_gbs / hbm_gbs}
     # DRAM bytes of one launch of the step's kernel from the committed `ncu --set full` capture (profiles/r03i_ncu_stream_kernel.txt)
-    roof.update({'traffic': 347029504, 'traffic_unit': 'bytes/launch (dram__bytes_read.sum + dram__bytes_write.sum, profiles/r03i)', 'kernel': 'fftlog_stream_kernel<fullwin, tma-staged rows, dynamic pairs> (CPF_FFTLOG_KERNEL=%s)' % os.environ.get('CPF_FFTLOG_KERNEL', 'auto'), 'launch_ms': 1e3 * t_launch,
+    roof.update({'traffic': 350454528, 'traffic_unit': 'bytes/launch (dram__bytes_read.sum + dram__bytes_write.sum of one launch under ncu --set full: profiles/r3b_ncu_stream_kernel.txt, the round-2 kernel)', 'kernel': 'fftlog_stream_kernel<fullwin, tma-staged rows, dynamic pairs> (CPF_FFTLOG_KERNEL=%s)' % os.environ.get('CPF_FFTLOG_KERNEL', 'auto'), 'launch_ms': 1e3 * t_launch,
                  'algorithmic_flops_per_launch': per_step * FLOPS_PER_TRANSFORM, 'algorithmic_bytes_per_launch': per_step * BYTES_PER_TRANSFORM,
                  'peak_source': 'fp64: DFMA microbenchmark in this run (cpf_measure_fp64_peak); hbm: ' + hbm_src,
                  'hbm': {'achieved': ach_gbs, 'peak': hbm_gbs, 'unit': 'GB/s', 'frac': ach_gbs / hbm_gbs},
