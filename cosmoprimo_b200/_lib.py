@@ -47,6 +47,7 @@ SIGNATURES = {
     'cpf_spline_eval_rows': (_i, [_vp, _vp, _i, _i64, _vp, _i, _i, _i, _i, _vp, _i, _i, _vp]),
     'cpf_dst': (_i, [_i, _vp, _i, _i64, _vp, _i, _i, _vp]),
     'cpf_wallish2018': (_i, [_vp, _vp, _i, _vp, _vp, _i, _i64, _vp, _vp, _i, _i, _vp]),
+    'cpf_wallish2018_rows': (_i, [_vp, _vp, _i, _vp, _vp, _i, _i64, _vp, _vp, _i, _i, _vp]),
     'cpf_eh_pk': (_i, [_vp, _vp, _i64, _i, _vp, _i, _d, _d, _d, _i, _vp, _vp, _i, _i, _vp]),
     'cpf_measure_fp64_peak': (_i, [_i, ctypes.POINTER(_d)]),
 }

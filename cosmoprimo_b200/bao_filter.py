@@ -57,6 +57,17 @@ class BasePowerSpectrumBAOFilter(object):
             pk = interp(k)
         return pk
 
+    def _evaluate_rows(self, k):
+        """The same values with one ROW per spectrum, (ncols, nk), written directly by the spline kernel (``cpf_spline_eval_t``) -- the layout
+        ``cpf_wallish2018_rows`` fetches with bulk copies -- or None when the interpolator is not one of this package's."""
+        from .interpolator import PowerSpectrumInterpolator1D, PowerSpectrumInterpolator2D, _scaled
+        interp = self.pk_interpolator
+        if type(interp) is PowerSpectrumInterpolator1D:
+            return _scaled(interp._interp.eval_rows(k), interp._rsigma8sq)
+        if type(interp) is PowerSpectrumInterpolator2D and interp._is2d and np.ndim(interp.z) > 0:
+            return interp(k, interp.z, ignore_growth=True, rows=True)
+        return None
+
     def set_pk(self, pk_interpolator, cosmo=None):
         """Evaluate the input spectrum on :attr:`k` (ref:92-102)."""
         if cosmo is not None: self._cosmo = cosmo
@@ -98,12 +109,17 @@ class Wallish2018PowerSpectrumBAOFilter(BasePowerSpectrumBAOFilter):
         lib = _lib.load()
         _lib.require_device()
         klin = np.linspace(self.pk_interpolator.extrap_kmin, 2., 4096)                       # ref:364
-        pklin = self._evaluate(klin)                                                          # ref:365-369
-        pklin = pklin.reshape(pklin.shape[0], -1)
+        pklin = self._evaluate_rows(klin)                                                     # ref:365-369, one row per spectrum where the interpolator can
+        rows = pklin is not None
+        if rows:
+            pklin = pklin.reshape(-1, klin.size)
+        else:
+            pklin = self._evaluate(klin)
+            pklin = pklin.reshape(pklin.shape[0], -1)
         lin, out_in = _buf.as_input(pklin, dtype='f8'), _buf.as_input(self.pk, dtype='f8')
         if lin.on_device != out_in.on_device:
             raise ValueError('pk_interpolator returned host and device arrays for the two grids')
-        ncols = int(lin.shape[1])
+        ncols = int(lin.shape[0 if rows else 1])
         if ncols != int(out_in.shape[1]):
             raise ValueError('pk_interpolator returned {} and {} spectra on the two grids'.format(ncols, out_in.shape[1]))
         device = lin.device if lin.on_device else (self._device if self._device is not None else _buf.default_device())
@@ -120,8 +136,8 @@ class Wallish2018PowerSpectrumBAOFilter(BasePowerSpectrumBAOFilter):
             boxes_ptr = boxes.ctypes.data
             stream = None
         res = _buf.empty_like_kind(out_in, (self.k.size, ncols), dtype='f8')
-        rc = lib.cpf_wallish2018(kl.ptr, lin.ptr, 4096, ko.ptr, out_in.ptr, self.k.size, ncols, res.ptr, boxes_ptr,
-                                 int(lin.on_device), device, stream)
+        entry = lib.cpf_wallish2018_rows if rows else lib.cpf_wallish2018
+        rc = entry(kl.ptr, lin.ptr, 4096, ko.ptr, out_in.ptr, self.k.size, ncols, res.ptr, boxes_ptr, int(lin.on_device), device, stream)
         _lib.check(rc)
         self.pknow = res.obj
         self.pk = out_in.obj

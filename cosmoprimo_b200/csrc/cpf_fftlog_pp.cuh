@@ -19,12 +19,12 @@
 //   * the rows of the next pair are prefetched into L2 while the current pair is transformed.
 #pragma once
 
+#include "cpf_async.h"
 #include "cpf_fft_core.h"
 
 namespace cpf {
 
 // ---- tensor-memory helpers (tcgen05, 32x32b shape: thread i of a warp <-> lane 32*(warp%4)+i) ------------------
-__device__ __forceinline__ uint32_t pp_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void tmem_alloc_all(uint32_t* slot) {   // whole TMEM (512 columns); one warp
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(pp_smem_u32(slot)) : "memory");
@@ -90,27 +90,6 @@ __device__ __forceinline__ bool named_sync_or(const int id, const int nthreads, 
 }
 __device__ __forceinline__ void named_arrive(const int id, const int nthreads) {
   asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-
-// ---- mbarrier + bulk copy (TMA, non-tensor form) ------------------------------------------------------------------
-__device__ __forceinline__ void mbar_init(uint64_t* bar, const unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(pp_smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, const unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pp_smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, const unsigned parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
-      ::"r"(pp_smem_u32(bar)), "r"(parity)
-      : "memory");
-}
-// global -> shared bulk copy of `bytes` (multiple of 16, both addresses 16-byte aligned), completion counted on `bar`
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, const unsigned bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(pp_smem_u32(dst)), "l"(src), "r"(bytes), "r"(pp_smem_u32(bar))
-               : "memory");
 }
 
 // ---- per-thread table record (host builds it, see build_pp_tables in cpf_fftlog.cu) ---------------------------

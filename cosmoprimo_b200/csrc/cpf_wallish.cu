@@ -13,6 +13,7 @@
 #include <string.h>
 #include <vector>
 
+#include "cpf_async.h"
 #include "cpf_common.h"
 #include "cpf_fastmath.h"
 #include "cpf_fft_core.h"
@@ -36,7 +37,8 @@ struct WallishTables {
 
 struct WallishArgs {
   const double* klin;     // [4096]
-  const double* pklin;    // [4096, ld]
+  const double* pklin;    // [4096, ld], or with lin_rows [ncols, 4096]: one contiguous row per spectrum (the layout cpf_spline_eval_t writes)
+  int lin_rows;
   const double* pkout;    // [nk, ld]
   double* pknow;          // [nk, ld]
   long long ncols;
@@ -193,8 +195,48 @@ __device__ __forceinline__ void wallish_copy_edges(const WallishArgs& a, const i
 // ROLL: the samples land in the (free) buffer by asynchronous 16-byte copies, the logarithms are taken in place by a rolled loop
 template <bool ROLL>
 __device__ __forceinline__ void wallish_load_log(const WallishArgs& a, const WallishSmem& sm, const int t, const long long col0, const bool has1,
-                                                 double2 (&v)[16]) {
+                                                 double2 (&v)[16], uint64_t* bar, unsigned& bar_parity) {
   typedef WallishGeo G;
+  if (a.lin_rows) {
+    // one contiguous 32 KB row per spectrum: two bulk copies per pair instead of 4096 16-byte requests through the L1 tag stage; row a lands in
+    // raw[0, 4096), row b in raw[4096, 8192); every thread takes the logarithms of its own 16 + 16 samples in place, then picks them up
+    double* raw = reinterpret_cast<double*>(sm.B);
+    if (t == 0) {
+      mbar_expect_tx(bar, has1 ? 2u * G::N * 8u : G::N * 8u);
+      bulk_g2s(raw, a.pklin + col0 * G::N, G::N * 8u, bar);
+      if (has1) bulk_g2s(raw + G::N, a.pklin + (col0 + 1) * G::N, G::N * 8u, bar);
+    }
+    wallish_copy_edges(a, t, col0, has1);
+    mbar_wait(bar, bar_parity);
+    bar_parity ^= 1u;
+#pragma unroll 1
+    for (int r4 = 0; r4 < 16; r4 += 4) {                // four samples per step: their k and shared-memory loads are in flight together
+      double k[4], xa[4], xb[4];
+      int j[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        double sign;
+        j[i] = makhoul_src(t + 256 * (r4 + i), sign);
+        k[i] = __ldg(a.klin + j[i]);
+        xa[i] = raw[j[i]];
+        xb[i] = has1 ? raw[G::N + j[i]] : xa[i];
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const double sign = t + 256 * (r4 + i) < G::N / 2 ? 1. : -1.;
+        raw[j[i]] = sign * fast_log(k[i] * xa[i]);
+        raw[G::N + j[i]] = sign * fast_log(k[i] * xb[i]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      double sign;
+      const int j = makhoul_src(t + 256 * r, sign);
+      v[r] = mk2(raw[j], raw[G::N + j]);
+    }
+    __syncthreads();                                     // pass 1 of the FFT scatters into other threads' slots
+    return;
+  }
   if (!ROLL) {
 #pragma unroll
     for (int r = 0; r < 16; ++r) {
@@ -430,7 +472,11 @@ __global__ void __launch_bounds__(256, 2) wallish_fused_kernel(const WallishArgs
   const WallishSmem sm(smem_raw);
   const int t = threadIdx.x;
   const long long npairs = (a.ncols + 1) / 2;
-  if (t < 32) sm.wtab[t] = a.wtab[t];            // visible after the barriers of the first FFT
+  __shared__ __align__(8) uint64_t s_bar;        // completion of the bulk copies of the rows layout
+  unsigned bar_parity = 0;
+  if (t == 0) { mbar_init(&s_bar, 1); mbar_fence_init(); }
+  if (t < 32) sm.wtab[t] = a.wtab[t];
+  __syncthreads();
   for (long long pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
     const long long col0 = 2 * pair;
     const bool has1 = col0 + 1 < a.ncols;     // odd column count: the last pair repeats its column
@@ -443,12 +489,12 @@ __global__ void __launch_bounds__(256, 2) wallish_fused_kernel(const WallishArgs
     if (V & 1) {
 #pragma unroll 1
       for (int leg = 0; leg < 2; ++leg) {
-        if (leg == 0) wallish_load_log<(V & 2) != 0>(a, sm, t, col0, has1, v);
+        if (leg == 0) wallish_load_log<(V & 2) != 0>(a, sm, t, col0, has1, v, &s_bar, bar_parity);
         fft4096(t, v, sm.B, a.tw1, a.tw2);
         if (leg == 0) wallish_middle(a, sm, t, col0, has1, v, d);
       }
     } else {
-      wallish_load_log<(V & 2) != 0>(a, sm, t, col0, has1, v);
+      wallish_load_log<(V & 2) != 0>(a, sm, t, col0, has1, v, &s_bar, bar_parity);
       stamp(0);
       fft4096(t, v, sm.B, a.tw1, a.tw2);
       stamp(1);
@@ -462,6 +508,7 @@ __global__ void __launch_bounds__(256, 2) wallish_fused_kernel(const WallishArgs
     stamp(4);
     wallish_final(a, sm, t, col0, has1, d);
     stamp(5);
+    fence_proxy_async_smem();                             // this pair's writes to the buffer are ordered before the next pair's bulk copies into it
     __syncthreads();                                      // the buffer goes back to the next pair's FFT
   }
 }
@@ -605,8 +652,8 @@ int cpf_dst(int type, const double* in, int nx, int64_t ncols, double* out, int 
   return CPF_OK;
 }
 
-int cpf_wallish2018(const double* klin, const double* pklin, int nlin, const double* kout, const double* pkout, int nk,
-                    int64_t ncols, double* pknow, int32_t* boxes, int on_device, int device, void* stream_) {
+static int wallish2018_impl(const double* klin, const double* pklin, int nlin, const double* kout, const double* pkout, int nk,
+                            int64_t ncols, double* pknow, int32_t* boxes, int on_device, int device, void* stream_, const int lin_rows) {
   if (nlin != WallishGeo::N) return fail(CPF_EUNSUPPORTED, "cpf_wallish2018: nlin must be %d (bao_filter.py:364), got %d", WallishGeo::N, nlin);
   if (nk < 2) return fail(CPF_EINVAL, "cpf_wallish2018: nk = %d", nk);
   if (ncols < 0) return fail(CPF_EINVAL, "cpf_wallish2018: negative column count");
@@ -679,6 +726,8 @@ int cpf_wallish2018(const double* klin, const double* pklin, int nlin, const dou
   CPF_CUDA(cudaMemcpyAsync(d_tab.p, h_tab.data(), tab_bytes, cudaMemcpyHostToDevice, stream));
   WallishArgs a;
   a.klin = p_klin; a.pklin = p_pklin; a.pkout = p_pkout; a.pknow = p_pknow; a.ncols = ncols; a.ld = ncols;
+  a.lin_rows = lin_rows ? 1 : 0;
+  if (lin_rows && (uintptr_t)p_pklin % 16 != 0) return fail(CPF_EINVAL, "cpf_wallish2018_rows: pklin must be 16-byte aligned");
   a.vec = (ncols % 2 == 0) && ((uintptr_t)p_pklin % 16 == 0) && ((uintptr_t)p_pkout % 16 == 0) && ((uintptr_t)p_pknow % 16 == 0);
   a.boxes = p_boxes;
   a.dbg = nullptr;
@@ -730,6 +779,16 @@ int cpf_wallish2018(const double* klin, const double* pklin, int nlin, const dou
             (double)h[1] / npairs, (double)h[2] / npairs, (double)h[3] / npairs, (double)h[4] / npairs, (double)h[5] / npairs);
   }
   return CPF_OK;
+}
+
+int cpf_wallish2018(const double* klin, const double* pklin, int nlin, const double* kout, const double* pkout, int nk,
+                    int64_t ncols, double* pknow, int32_t* boxes, int on_device, int device, void* stream) {
+  return wallish2018_impl(klin, pklin, nlin, kout, pkout, nk, ncols, pknow, boxes, on_device, device, stream, 0);
+}
+
+int cpf_wallish2018_rows(const double* klin, const double* pklin_rows, int nlin, const double* kout, const double* pkout, int nk,
+                         int64_t ncols, double* pknow, int32_t* boxes, int on_device, int device, void* stream) {
+  return wallish2018_impl(klin, pklin_rows, nlin, kout, pkout, nk, ncols, pknow, boxes, on_device, device, stream, 1);
 }
 
 }  // extern "C"

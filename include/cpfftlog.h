@@ -162,6 +162,12 @@ int cpf_dst(int type /*2 or 3*/, const double* in, int nx, int64_t ncols, double
 int cpf_wallish2018(const double* klin, const double* pklin, int nlin, const double* kout, const double* pkout,
                     int nk, int64_t ncols, double* pknow, int32_t* boxes,
                     int on_device, int device, void* stream);
+/* The same filter with the linear-grid spectra handed over one ROW per spectrum, pklin_rows [ncols, nlin] -- the layout cpf_spline_eval_t
+ * writes (`pk_interpolator(klin)` evaluated as rows): the kernel fetches a pair of spectra with two 32 KB bulk copies instead of 4096
+ * strided 16-byte requests.  pkout / pknow / boxes as above (reference layout); results are bit-identical to cpf_wallish2018.
+ * pklin_rows must be 16-byte aligned. */
+int cpf_wallish2018_rows(const double* klin, const double* pklin_rows, int nlin, const double* kout, const double* pkout,
+                         int nk, int64_t ncols, double* pknow, int32_t* boxes, int on_device, int device, void* stream);
 
 /* ---- on-device Eisenstein & Hu linear P(k, z): replaces, for B flat LCDM cosmologies without massive neutrinos,
  * `Cosmology(..., engine='eisenstein_hu').get_fourier().pk_interpolator()(k, z)` (eisenstein_hu.py:34-92 coefficients,

@@ -245,6 +245,54 @@ def test_wallish_seeded_batch_vs_oracle():
     assert np.max(np.abs(filt_dd.pknow.cpu().numpy() / ref_d - 1.)) < 1e-10
 
 
+@pytest.mark.parametrize('ncols', [1, 6, 7])
+def test_wallish_rows_entry_is_bit_identical(ncols):
+    """cpf_wallish2018_rows (linear-grid spectra one row per spectrum, fetched by bulk copies) == cpf_wallish2018 (reference layout) bit for bit,
+    boxes included: host arrays (even / odd column counts) and device arrays; and the filter class takes the rows entry for this package's
+    interpolators (1-D on host and device tables, 2-D) with the same result as the reference layout."""
+    torch = pytest.importorskip('torch')
+    lib = _lib.load()
+    d = load_golden('wallish_golden.npz').data
+    klin, pklin, kout, pkout = (np.ascontiguousarray(d['w0_%s' % n]) for n in ['klin', 'pklin', 'kout', 'pkout'])
+    pklin, pkout = (np.ascontiguousarray(np.tile(a, (1, 2))[:, :ncols]) for a in (pklin, pkout))          # the golden has six columns
+    assert pklin.shape == (4096, ncols) and pkout.shape == (kout.size, ncols)
+    rows = np.ascontiguousarray(pklin.T)
+    out = [np.empty_like(pkout) for _ in range(2)]
+    boxes = [np.empty((ncols, 4), dtype='i4') for _ in range(2)]
+    _lib.check(lib.cpf_wallish2018(klin.ctypes.data, pklin.ctypes.data, 4096, kout.ctypes.data, pkout.ctypes.data, kout.size, ncols, out[0].ctypes.data, boxes[0].ctypes.data, 0, 0, None))
+    _lib.check(lib.cpf_wallish2018_rows(klin.ctypes.data, rows.ctypes.data, 4096, kout.ctypes.data, pkout.ctypes.data, kout.size, ncols, out[1].ctypes.data, boxes[1].ctypes.data, 0, 0, None))
+    assert np.array_equal(out[0], out[1], equal_nan=True) and np.array_equal(boxes[0], boxes[1])
+    t = {name: torch.from_numpy(a).cuda() for name, a in dict(klin=klin, rows=rows, kout=kout, pkout=pkout).items()}
+    dout = torch.empty_like(t['pkout'])
+    _lib.check(lib.cpf_wallish2018_rows(t['klin'].data_ptr(), t['rows'].data_ptr(), 4096, t['kout'].data_ptr(), t['pkout'].data_ptr(), kout.size, ncols, dout.data_ptr(), None, 1, 0,
+                                        torch.cuda.current_stream().cuda_stream))
+    assert np.array_equal(dout.cpu().numpy(), out[0], equal_nan=True)
+
+
+def test_wallish_filter_class_uses_rows_for_own_interpolators():
+    torch = pytest.importorskip('torch')
+    from cosmoprimo_b200.interpolator import PowerSpectrumInterpolator2D
+    ktab = np.geomspace(1e-4, 50., 300)
+    pk = S.eh_pk(ktab, S.lhs_cosmologies(5, seed=11)).T.copy()                              # (nk, 5)
+    for table in (pk, torch.from_numpy(pk).cuda()):
+        interp = PowerSpectrumInterpolator1D(ktab, table)
+        filt = PowerSpectrumBAOFilter(interp, engine='wallish2018_cuda')
+        assert filt._evaluate_rows(filt.k) is not None
+        klin = np.linspace(interp.extrap_kmin, 2., 4096)
+        pklin, pkout = interp(klin), interp(filt.k)
+        to_np = lambda a: a.cpu().numpy() if hasattr(a, 'cpu') else np.asarray(a)
+        ref = PowerSpectrumBAOFilter(fake_interpolator(klin, to_np(pklin), filt.k, to_np(pkout)), engine='wallish2018_cuda')       # reference layout
+        assert np.array_equal(to_np(filt._boxes), ref._boxes)
+        assert np.max(np.abs(to_np(filt.pknow) / ref.pknow - 1.)) < 1e-12              # (eval_t and eval differ by the rounding of their exp10 only)
+    z = np.linspace(0., 1., 6)
+    interp2 = PowerSpectrumInterpolator2D(ktab, z, pk[:, :1] * (1. + z)[None, :]**-2)
+    filt2 = PowerSpectrumBAOFilter(interp2, engine='wallish2018_cuda')
+    assert filt2.pknow.shape == (filt2.k.size, z.size) and np.isfinite(filt2.pknow).all()
+    klin = np.linspace(interp2.extrap_kmin, 2., 4096)
+    ref2 = PowerSpectrumBAOFilter(fake_interpolator(klin, interp2(klin, z), filt2.k, interp2(filt2.k, z)), engine='wallish2018_cuda')
+    assert np.array_equal(filt2._boxes, ref2._boxes) and np.max(np.abs(filt2.pknow / ref2.pknow - 1.)) < 1e-12
+
+
 def test_dst_matches_scipy():
     """cpf_dst == scipy.fftpack.dst / idst (type 2, ortho, axis 0) that the reference calls (bao_filter.py:372, 412)."""
     from scipy import fftpack

@@ -1,4 +1,5 @@
-"""Profiler driver: cpf_wallish2018 over N device-resident spectra, a few repetitions (python tools/lab/wallish_run.py [ncols] [reps])."""
+"""Profiler driver: cpf_wallish2018 over N device-resident spectra, a few repetitions (python tools/lab/wallish_run.py [ncols] [reps] [rows]):
+`rows` = the linear-grid spectra handed over one row per spectrum (cpf_wallish2018_rows), checked against the column entry."""
 import os
 import sys
 import time
@@ -24,6 +25,18 @@ kl, ko = torch.from_numpy(klin).cuda(), torch.from_numpy(kout).cuda()
 out = torch.empty_like(pkout)
 stream = torch.cuda.current_stream().cuda_stream
 call = lambda: _lib.check(lib.cpf_wallish2018(kl.data_ptr(), pklin.data_ptr(), 4096, ko.data_ptr(), pkout.data_ptr(), kout.size, ncols, out.data_ptr(), None, 1, 0, stream))
+if len(sys.argv) > 3 and sys.argv[3] == 'rows':
+    call()
+    torch.cuda.synchronize()
+    ref = out.clone()
+    rows = interp._interp.eval_rows(klin)                      # (ncols, 4096)
+    assert tuple(rows.shape) == (ncols, 4096)
+    call = lambda: _lib.check(lib.cpf_wallish2018_rows(kl.data_ptr(), rows.data_ptr(), 4096, ko.data_ptr(), pkout.data_ptr(), kout.size, ncols, out.data_ptr(), None, 1, 0, stream))
+    out.zero_()
+    call()
+    torch.cuda.synchronize()
+    same = bool(torch.equal(out, ref)) or bool(((out == ref) | (torch.isnan(out) & torch.isnan(ref))).all())
+    print('rows entry vs column entry: bit-identical = {}, max |diff/ref| = {:.2e}'.format(same, float(((out - ref).abs() / ref.abs()).nan_to_num(0.).max())))
 call()
 torch.cuda.synchronize()
 t0 = time.perf_counter()
