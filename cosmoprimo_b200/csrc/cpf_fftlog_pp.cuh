@@ -233,10 +233,12 @@ __global__ void __launch_bounds__(512, 1) fftlog_pp_kernel(const FftlogArgs a, c
 
       // a register pass followed by its twiddles (chunks of 4 from TMEM, next chunk in flight while this one is used)
       // and the scatter to shared memory
-      auto twiddle_store = [&](double2 (&w)[16], const int nw, const uint32_t col, double2* dst, const int stride) {
-        // w[0..nw) are the DFT outputs; w[k] *= tw[k] for k >= 1; then dst[k * stride] = w[k]
+      auto twiddle_store = [&](double2 (&w)[16], const int nw, const uint32_t col, double2* dst, const int stride, auto dft) {
+        // dft() turns w[0..nw) into the DFT outputs (the first chunk of twiddles arrives behind its butterflies); w[k] *= tw[k] for k >= 1;
+        // then dst[k * stride] = w[k]
         Tm4 tw[2];
         tmem_ld4(col, tw[0]);
+        dft();
         tmem_wait4(tw[0]);
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
@@ -263,8 +265,7 @@ __global__ void __launch_bounds__(512, 1) fftlog_pp_kernel(const FftlogArgs a, c
           double2 w[16];
 #pragma unroll
           for (int n1 = 0; n1 < R1; ++n1) w[bitrev(n1, G::B1)] = v[n1 * G::C + c];
-          dft_dit<R1, HALF_IN, false>(w);
-          twiddle_store(w, R1, tb + PP_COL_TW1 + 4 * (c * R1), S + n2, RS);
+          twiddle_store(w, R1, tb + PP_COL_TW1 + 4 * (c * R1), S + n2, RS, [&]() { dft_dit<R1, HALF_IN, false>(w); });
         }
       };
       auto pass2 = [&]() {
@@ -273,8 +274,7 @@ __global__ void __launch_bounds__(512, 1) fftlog_pp_kernel(const FftlogArgs a, c
         double2 w[16];
 #pragma unroll
         for (int m1 = 0; m1 < 16; ++m1) w[bitrev(m1, 4)] = row[16 * m1];
-        dft_dit<16, false, false>(w);
-        twiddle_store(w, 16, tb + PP_COL_TW2, row, 16);
+        twiddle_store(w, 16, tb + PP_COL_TW2, row, 16, [&]() { dft_dit<16, false, false>(w); });
       };
 
       // ---- FFT #1 ----
@@ -297,11 +297,11 @@ __global__ void __launch_bounds__(512, 1) fftlog_pp_kernel(const FftlogArgs a, c
         for (int m2 = 0; m2 < 16; ++m2) v[bitrev(m2, 4)] = row[m2];
       }
       gbar();   // pass-3 reads of S are done before FFT #2 overwrites it (nothing below touches S before pass 1 stores)
-      dft_dit<16, false, false>(v);
       // ---- kernel multiply ----
       {
         Tm4 tu[2];
         tmem_ld4(tb + PP_COL_UT, tu[0]);
+        dft_dit<16, false, false>(v);
         tmem_wait4(tu[0]);
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
