@@ -690,7 +690,8 @@ def run_secondary(args):
                                                                  out.data_ptr(), None, 1, 0, stream)), reps=3, warm=1)
     # the entry the filter class uses: the linear-grid spectra one row per spectrum (what the spline kernel writes), fetched by bulk copies
     pklin_rows = interp._interp.eval_rows(klin)
-    tw = gpu_time(lambda: _lib.check(lib.cpf_wallish2018_rows(kl.data_ptr(), pklin_rows.data_ptr(), 4096, ko.data_ptr(), pkout.data_ptr(), filt.k.size, ncols,
+    kout_h = np.ascontiguousarray(filt.k)
+    tw = gpu_time(lambda: _lib.check(lib.cpf_wallish2018_rows(klin.ctypes.data, pklin_rows.data_ptr(), 4096, kout_h.ctypes.data, pkout.data_ptr(), filt.k.size, ncols,
                                                               out.data_ptr(), None, 1, 0, stream)), reps=3, warm=1)
     tf = gpu_time(lambda: filt(interp), reps=3, warm=1)
     pl_cpu, po_cpu = pklin[:, :32].cpu().numpy(), pkout[:, :32].cpu().numpy()
@@ -698,7 +699,7 @@ def run_secondary(args):
     # parity at the BASELINE size (VERDICT r1 missing 6): boxes of every one of the 65 536 columns from the timed entry point, against the oracle on
     # a strided sample of 1024 columns (bit-identical inputs): number of columns whose four box indices differ (expected 0) and max |pknow/ref - 1|
     boxes = torch.empty((ncols, 4), dtype=torch.int32, device='cuda')
-    _lib.check(lib.cpf_wallish2018_rows(kl.data_ptr(), pklin_rows.data_ptr(), 4096, ko.data_ptr(), pkout.data_ptr(), filt.k.size, ncols, out.data_ptr(), boxes.data_ptr(), 1, 0, stream))
+    _lib.check(lib.cpf_wallish2018_rows(klin.ctypes.data, pklin_rows.data_ptr(), 4096, kout_h.ctypes.data, pkout.data_ptr(), filt.k.size, ncols, out.data_ptr(), boxes.data_ptr(), 1, 0, stream))
     torch.cuda.synchronize()
     sample = np.arange(0, ncols, ncols // 1024)
     ref_s, dbg_s = WO.wallish2018(klin, pklin[:, sample].cpu().numpy(), filt.k, pkout[:, sample].cpu().numpy(), return_debug=True)

@@ -126,7 +126,10 @@ class Wallish2018PowerSpectrumBAOFilter(BasePowerSpectrumBAOFilter):
         if lin.on_device:
             torch = _buf._torch()
             dev = torch.device('cuda', device)
-            kl, ko = _buf.as_input(torch.as_tensor(klin, device=dev)), _buf.as_input(torch.as_tensor(self.k, device=dev))
+            if rows:          # the rows entry takes the two grids as host arrays (cached plan: no copy, no synchronisation)
+                kl, ko = _buf.as_input(klin), _buf.as_input(self.k)
+            else:
+                kl, ko = _buf.as_input(torch.as_tensor(klin, device=dev)), _buf.as_input(torch.as_tensor(self.k, device=dev))
             boxes = torch.empty((ncols, 4), dtype=torch.int32, device=dev)
             boxes_ptr = boxes.data_ptr()
             stream = _buf.current_stream(device)

@@ -601,6 +601,69 @@ static int wallish_tables(int device, WallishTables* out) {
   return CPF_OK;
 }
 
+// Everything cpf_wallish2018 derives from the two wavenumber grids (bao_filter.py:364, 413-431), cached per (device, klin, kout) together
+// with its device image: [facT | qh | qth | 1/klin | klin] (doubles) then [slotT | qstart | qinfo] (ints).  Entries live until evicted
+// (at most kWallishPlans per process; the eviction synchronises the device before it frees the image).
+struct WallishGridPlan {
+  int device, cap_limit;
+  std::vector<double> klin, kout;
+  WallishFinalPlan fp;
+  void* d_tab = nullptr;
+  const double* d_klin() const { return reinterpret_cast<const double*>(d_tab) + fp.facT.size() + fp.qh.size() + kout.size() + klin.size(); }
+};
+static std::mutex g_gp_mutex;
+static std::vector<WallishGridPlan*> g_gp;
+constexpr size_t kWallishPlans = 8;
+
+static int wallish_grid_plan(int device, const std::vector<double>& klin, const std::vector<double>& kout, int cap_limit, const WallishGridPlan** out) {
+  std::lock_guard<std::mutex> lock(g_gp_mutex);
+  for (size_t i = 0; i < g_gp.size(); ++i) {
+    WallishGridPlan* e = g_gp[i];
+    if (e->device == device && e->cap_limit == cap_limit && e->klin.size() == klin.size() && e->kout.size() == kout.size() &&
+        memcmp(e->klin.data(), klin.data(), klin.size() * sizeof(double)) == 0 && memcmp(e->kout.data(), kout.data(), kout.size() * sizeof(double)) == 0) {
+      g_gp.erase(g_gp.begin() + i);          // most recently used last
+      g_gp.push_back(e);
+      *out = e;
+      return CPF_OK;
+    }
+  }
+  const int nlin = (int)klin.size(), nk = (int)kout.size();
+  for (int i = 1; i < nlin; ++i) if (!(klin[i] > klin[i - 1])) return fail(CPF_EINVAL, "cpf_wallish2018: klin must be strictly increasing");
+  for (int i = 1; i < nk; ++i) if (!(kout[i] > kout[i - 1])) return fail(CPF_EINVAL, "cpf_wallish2018: kout must be strictly increasing");
+  WallishGridPlan* e = new WallishGridPlan();
+  e->device = device; e->cap_limit = cap_limit; e->klin = klin; e->kout = kout;
+  const std::string why = wallish_final_plan(klin.data(), nlin, kout.data(), nk, &e->fp, cap_limit);
+  if (!why.empty()) { delete e; return fail(CPF_EINVAL, "cpf_wallish2018: %s", why.c_str()); }
+  const WallishFinalPlan& fp = e->fp;
+  const size_t n_fac = fp.facT.size(), n_qh = fp.qh.size(), n_slot = fp.slotT.size(), n_qs = fp.qstart.size(), n_qi = fp.qinfo.size();
+  const size_t tab_bytes = (n_fac + n_qh + (size_t)nk + 2 * (size_t)nlin) * sizeof(double) + (n_slot + n_qs + n_qi) * sizeof(int);
+  std::vector<char> h_tab(tab_bytes);
+  double* pd = reinterpret_cast<double*>(h_tab.data());
+  memcpy(pd, fp.facT.data(), n_fac * sizeof(double));
+  memcpy(pd + n_fac, fp.qh.data(), n_qh * sizeof(double));
+  for (int q = 0; q < nk; ++q) {                                          // _tophat(self.k, kmax=1, scale=20) (:425-431)
+    const double k = kout[q];
+    pd[n_fac + n_qh + q] = k > 1. ? exp(-400. * (k - 1.) * (k - 1.)) : 1.;
+  }
+  for (int i = 0; i < nlin; ++i) { pd[n_fac + n_qh + nk + i] = 1. / klin[i]; pd[n_fac + n_qh + nk + nlin + i] = klin[i]; }
+  int* pi = reinterpret_cast<int*>(pd + n_fac + n_qh + nk + 2 * (size_t)nlin);
+  memcpy(pi, fp.slotT.data(), n_slot * sizeof(int));
+  memcpy(pi + n_slot, fp.qstart.data(), n_qs * sizeof(int));
+  memcpy(pi + n_slot + n_qs, fp.qinfo.data(), n_qi * sizeof(int));
+  if (int rc = upload(&e->d_tab, h_tab.data(), tab_bytes)) { delete e; return rc; }
+  if (g_gp.size() >= kWallishPlans) {
+    WallishGridPlan* old = g_gp.front();
+    g_gp.erase(g_gp.begin());
+    DeviceGuard g(old->device);
+    cudaDeviceSynchronize();               // a launch may still read the image
+    cudaFree(old->d_tab);
+    delete old;
+  }
+  g_gp.push_back(e);
+  *out = e;
+  return CPF_OK;
+}
+
 static int check_device(const char* who, int device) {
   int ndev = 0;
   CPF_TRY(cpf_device_count(&ndev));
@@ -665,9 +728,11 @@ static int wallish2018_impl(const double* klin, const double* pklin, int nlin, c
   WallishTables wt;
   CPF_TRY(wallish_tables(device, &wt));
 
-  // the two wavenumber grids are needed on the host (knot selection, interval search, spline factors) and on the device
+  // The two wavenumber grids are needed on the host (knot selection, interval search, spline factors); everything derived from them is cached
+  // per (device, klin, kout) with its device copy (wallish_grid_plan).  The rows entry takes the grids as HOST arrays: no device-to-host copy,
+  // no synchronisation, and with device spectra the call is asynchronous on the stream.
   std::vector<double> h_klin(nlin), h_kout(nk);
-  if (on_device) {
+  if (on_device && !lin_rows) {
     CPF_CUDA(cudaMemcpyAsync(h_klin.data(), klin, nlin * sizeof(double), cudaMemcpyDeviceToHost, stream));
     CPF_CUDA(cudaMemcpyAsync(h_kout.data(), kout, nk * sizeof(double), cudaMemcpyDeviceToHost, stream));
     CPF_CUDA(cudaStreamSynchronize(stream));
@@ -675,55 +740,29 @@ static int wallish2018_impl(const double* klin, const double* pklin, int nlin, c
     h_klin.assign(klin, klin + nlin);
     h_kout.assign(kout, kout + nk);
   }
-  for (int i = 1; i < nlin; ++i) if (!(h_klin[i] > h_klin[i - 1])) return fail(CPF_EINVAL, "cpf_wallish2018: klin must be strictly increasing");
-  for (int i = 1; i < nk; ++i) if (!(h_kout[i] > h_kout[i - 1])) return fail(CPF_EINVAL, "cpf_wallish2018: kout must be strictly increasing");
-  WallishFinalPlan fp;
   const char* cap_env = getenv("CPF_WALLISH_SLOT_CAP");                   // tests: forces the multi-round evaluation
-  const std::string why = wallish_final_plan(h_klin.data(), nlin, h_kout.data(), nk, &fp, cap_env ? atoi(cap_env) : 0);
-  if (!why.empty()) return fail(CPF_EINVAL, "cpf_wallish2018: %s", why.c_str());
-  std::vector<double> h_qth(nk);
-  for (int q = 0; q < nk; ++q) {                                          // _tophat(self.k, kmax=1, scale=20) (:425-431)
-    const double k = h_kout[q];
-    h_qth[q] = k > 1. ? exp(-400. * (k - 1.) * (k - 1.)) : 1.;
-  }
+  const WallishGridPlan* gp = nullptr;
+  CPF_TRY(wallish_grid_plan(device, h_klin, h_kout, cap_env ? atoi(cap_env) : 0, &gp));
+  const WallishFinalPlan& fp = gp->fp;
 
   const size_t lin_bytes = (size_t)nlin * ncols * sizeof(double), out_bytes = (size_t)nk * ncols * sizeof(double);
-  ScratchBuf d_klin, d_pklin, d_pkout, d_pknow, d_boxes, d_tab;
-  const double *p_klin = klin, *p_pklin = pklin, *p_pkout = pkout;
+  ScratchBuf d_pklin, d_pkout, d_pknow, d_boxes;
+  const double *p_klin = gp->d_klin(), *p_pklin = pklin, *p_pkout = pkout;
   double* p_pknow = pknow;
   int* p_boxes = boxes;
   if (!on_device) {
-    CPF_CUDA(d_klin.alloc(nlin * sizeof(double), stream));
     CPF_CUDA(d_pklin.alloc(lin_bytes, stream));
     CPF_CUDA(d_pkout.alloc(out_bytes, stream));
     CPF_CUDA(d_pknow.alloc(out_bytes, stream));
-    CPF_CUDA(cudaMemcpyAsync(d_klin.p, klin, nlin * sizeof(double), cudaMemcpyHostToDevice, stream));
     CPF_CUDA(cudaMemcpyAsync(d_pklin.p, pklin, lin_bytes, cudaMemcpyHostToDevice, stream));
     CPF_CUDA(cudaMemcpyAsync(d_pkout.p, pkout, out_bytes, cudaMemcpyHostToDevice, stream));
-    p_klin = (const double*)d_klin.p; p_pklin = (const double*)d_pklin.p; p_pkout = (const double*)d_pkout.p;
+    p_pklin = (const double*)d_pklin.p; p_pkout = (const double*)d_pkout.p;
     p_pknow = (double*)d_pknow.p;
     if (boxes) {
       CPF_CUDA(d_boxes.alloc((size_t)ncols * 4 * sizeof(int), stream));
       p_boxes = (int*)d_boxes.p;
     }
   }
-  // the tables of the final stage in one allocation / one copy: doubles first (facT, qh, qth, rklin), then the ints (slotT, qstart, qinfo)
-  const size_t n_fac = fp.facT.size(), n_qh = fp.qh.size(), n_slot = fp.slotT.size(), n_qs = fp.qstart.size(), n_qi = fp.qinfo.size();
-  const size_t tab_bytes = (n_fac + n_qh + (size_t)nk + (size_t)nlin) * sizeof(double) + (n_slot + n_qs + n_qi) * sizeof(int);
-  std::vector<char> h_tab(tab_bytes);
-  {
-    double* pd = reinterpret_cast<double*>(h_tab.data());
-    memcpy(pd, fp.facT.data(), n_fac * sizeof(double));
-    memcpy(pd + n_fac, fp.qh.data(), n_qh * sizeof(double));
-    memcpy(pd + n_fac + n_qh, h_qth.data(), (size_t)nk * sizeof(double));
-    for (int i = 0; i < nlin; ++i) pd[n_fac + n_qh + nk + i] = 1. / h_klin[i];
-    int* pi = reinterpret_cast<int*>(pd + n_fac + n_qh + nk + nlin);
-    memcpy(pi, fp.slotT.data(), n_slot * sizeof(int));
-    memcpy(pi + n_slot, fp.qstart.data(), n_qs * sizeof(int));
-    memcpy(pi + n_slot + n_qs, fp.qinfo.data(), n_qi * sizeof(int));
-  }
-  CPF_CUDA(d_tab.alloc(tab_bytes, stream));
-  CPF_CUDA(cudaMemcpyAsync(d_tab.p, h_tab.data(), tab_bytes, cudaMemcpyHostToDevice, stream));
   WallishArgs a;
   a.klin = p_klin; a.pklin = p_pklin; a.pkout = p_pkout; a.pknow = p_pknow; a.ncols = ncols; a.ld = ncols;
   a.lin_rows = lin_rows ? 1 : 0;
@@ -736,14 +775,14 @@ static int wallish2018_impl(const double* klin, const double* pklin, int nlin, c
   a.tw1 = wt.tw1; a.tw2 = wt.tw2; a.twd = wt.twd; a.wtab = wt.wtab;
   a.i0 = fp.i0; a.i1 = fp.i1; a.nl = fp.nl; a.nr = fp.nr; a.lz = fp.lz; a.rz = fp.rz; a.nmid = fp.nmid; a.nc = fp.nc; a.nk = nk;
   a.nrounds = fp.nrounds; a.slbase = fp.slbase;
-  a.fc.facT = reinterpret_cast<const double*>(d_tab.p);
+  a.fc.facT = reinterpret_cast<const double*>(gp->d_tab);
   a.fc.t0 = fp.ut0; a.fc.t1 = fp.ut1; a.fc.Lw = fp.uLw; a.fc.cp = fp.ucp; a.fc.P = fp.uP; a.fc.Q = fp.uQ;
-  a.qh = a.fc.facT + n_fac;
-  a.qth = a.qh + n_qh;
+  a.qh = a.fc.facT + fp.facT.size();
+  a.qth = a.qh + fp.qh.size();
   a.rklin = a.qth + nk;
-  a.slotT = reinterpret_cast<const int*>(a.rklin + nlin);
-  a.qstart = a.slotT + n_slot;
-  a.qinfo = a.qstart + n_qs;
+  a.slotT = reinterpret_cast<const int*>(a.rklin + 2 * (size_t)nlin);        // (the device copy of klin sits behind rklin)
+  a.qstart = a.slotT + fp.slotT.size();
+  a.qinfo = a.qstart + fp.qstart.size();
   int sms = 0;
   CPF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
   const long long npairs = (ncols + 1) / 2;
@@ -770,8 +809,8 @@ static int wallish2018_impl(const double* klin, const double* pklin, int nlin, c
     CPF_CUDA(cudaMemcpyAsync(pknow, p_pknow, out_bytes, cudaMemcpyDeviceToHost, stream));
     if (boxes) CPF_CUDA(cudaMemcpyAsync(boxes, p_boxes, (size_t)ncols * 4 * sizeof(int), cudaMemcpyDeviceToHost, stream));
   }
-  // the host table image must outlive its upload; scratch is stream-ordered
-  CPF_CUDA(cudaStreamSynchronize(stream));
+  // host results must have landed when the call returns; device results are stream-ordered (scratch memory too)
+  if (!on_device || a.dbg) CPF_CUDA(cudaStreamSynchronize(stream));
   if (a.dbg) {
     unsigned long long h[8];
     CPF_CUDA(cudaMemcpy(h, a.dbg, sizeof(h), cudaMemcpyDeviceToHost));

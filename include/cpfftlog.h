@@ -165,6 +165,8 @@ int cpf_wallish2018(const double* klin, const double* pklin, int nlin, const dou
 /* The same filter with the linear-grid spectra handed over one ROW per spectrum, pklin_rows [ncols, nlin] -- the layout cpf_spline_eval_t
  * writes (`pk_interpolator(klin)` evaluated as rows): the kernel fetches a pair of spectra with two 32 KB bulk copies instead of 4096
  * strided 16-byte requests.  pkout / pknow / boxes as above (reference layout); results are bit-identical to cpf_wallish2018.
+ * klin and kout are HOST arrays here whatever on_device says (the knot selection needs them on the host; everything derived from them is
+ * cached per grid pair), so with device spectra the call neither copies nor synchronises: it is asynchronous on the stream.
  * pklin_rows must be 16-byte aligned. */
 int cpf_wallish2018_rows(const double* klin, const double* pklin_rows, int nlin, const double* kout, const double* pkout,
                          int nk, int64_t ncols, double* pknow, int32_t* boxes, int on_device, int device, void* stream);

@@ -264,7 +264,7 @@ def test_wallish_rows_entry_is_bit_identical(ncols):
     assert np.array_equal(out[0], out[1], equal_nan=True) and np.array_equal(boxes[0], boxes[1])
     t = {name: torch.from_numpy(a).cuda() for name, a in dict(klin=klin, rows=rows, kout=kout, pkout=pkout).items()}
     dout = torch.empty_like(t['pkout'])
-    _lib.check(lib.cpf_wallish2018_rows(t['klin'].data_ptr(), t['rows'].data_ptr(), 4096, t['kout'].data_ptr(), t['pkout'].data_ptr(), kout.size, ncols, dout.data_ptr(), None, 1, 0,
+    _lib.check(lib.cpf_wallish2018_rows(klin.ctypes.data, t['rows'].data_ptr(), 4096, kout.ctypes.data, t['pkout'].data_ptr(), kout.size, ncols, dout.data_ptr(), None, 1, 0,        # grids: host
                                         torch.cuda.current_stream().cuda_stream))
     assert np.array_equal(dout.cpu().numpy(), out[0], equal_nan=True)
 

@@ -31,7 +31,7 @@ if len(sys.argv) > 3 and sys.argv[3] == 'rows':
     ref = out.clone()
     rows = interp._interp.eval_rows(klin)                      # (ncols, 4096)
     assert tuple(rows.shape) == (ncols, 4096)
-    call = lambda: _lib.check(lib.cpf_wallish2018_rows(kl.data_ptr(), rows.data_ptr(), 4096, ko.data_ptr(), pkout.data_ptr(), kout.size, ncols, out.data_ptr(), None, 1, 0, stream))
+    call = lambda: _lib.check(lib.cpf_wallish2018_rows(klin.ctypes.data, rows.data_ptr(), 4096, kout.ctypes.data, pkout.data_ptr(), kout.size, ncols, out.data_ptr(), None, 1, 0, stream))
     out.zero_()
     call()
     torch.cuda.synchronize()
