@@ -197,7 +197,7 @@ class Interpolator1D(object):
         if want_device:
             torch = _buf._torch()
             if not q_on_device:
-                q = torch.as_tensor(q, device=torch.device('cuda', dev))
+                q = _device_copy(np.ascontiguousarray(q), dev)          # cached by content: the same grids come back call after call
             qbuf = _buf.as_input(q.contiguous(), dtype='f8')
             out = _buf.empty_like_kind(qbuf, (nq, self._ncols), dtype='f8')
             stream = _buf.current_stream(dev)
