@@ -259,35 +259,51 @@ __global__ void __launch_bounds__(128) spline_eval_kernel(const double* __restri
 
 // transposed evaluation: out[col, q] (rows = splines: the layout cpf_fftlog reads), 32 x 32 tiles through shared memory so
 // that both the knot-matrix reads (contiguous in col) and the stores (contiguous in q) are coalesced
+#define SPLINE_EVALT_Q 128          // queries per block: 8 groups of 16 consecutive queries; 32 columns per block
 __global__ void __launch_bounds__(256) spline_eval_t_kernel(const double* __restrict__ x, const double* __restrict__ y,
                                                             const double* __restrict__ s, const long long ncols,
                                                             const double* __restrict__ qx, const int* __restrict__ qi, const int nq,
                                                             const int nu, const int log_y, double* __restrict__ out) {
-  __shared__ double tile[32][33];
+  __shared__ double tile[SPLINE_EVALT_Q][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const long long c0 = (long long)blockIdx.x * 32;
-  const int q0 = blockIdx.y * 32;
+  const int q0 = blockIdx.y * SPLINE_EVALT_Q;
   const long long col = c0 + tx;
-  for (int qq = ty; qq < 32; qq += 8) {
-    const int q = q0 + qq;
+  // a thread takes 16 consecutive queries of its column and keeps the knot values / slopes while they stay in one interval
+  int have = -2;
+  double x0 = 0., x1 = 0., y0 = 0., y1 = 0., s0 = 0., s1 = 0.;
+#pragma unroll 4
+  for (int j = 0; j < 16; ++j) {
+    const int qq = 16 * ty + j, q = q0 + qq;
     double r = 0.;
     if (q < nq && col < ncols) {
-      const int i = qi[q];
+      const int i = __ldg(qi + q);
       if (i < 0) {
         r = nan("");
       } else {
-        const long long o = (long long)i * ncols + col;
-        r = spline_poly(x[i], x[i + 1], y[o], y[o + ncols], s[o], s[o + ncols], qx[q], nu);
+        if (i != have) {
+          const long long o = (long long)i * ncols + col;
+          if (i == have + 1) { x0 = x1; y0 = y1; s0 = s1; }
+          else { x0 = __ldg(x + i); y0 = y[o]; s0 = s[o]; }
+          x1 = __ldg(x + i + 1); y1 = y[o + ncols]; s1 = s[o + ncols];
+          have = i;
+        }
+        r = spline_poly(x0, x1, y0, y1, s0, s1, __ldg(qx + q), nu);
         if (log_y) r = exp10(r);
       }
     }
     tile[qq][tx] = r;
   }
   __syncthreads();
+  // one warp per column: 128 consecutive queries = four 256-byte runs of a row of the result
   for (int cc = ty; cc < 32; cc += 8) {
     const long long c = c0 + cc;
-    const int q = q0 + tx;
-    if (c < ncols && q < nq) out[c * nq + q] = tile[tx][cc];
+    if (c >= ncols) continue;
+#pragma unroll
+    for (int k = 0; k < SPLINE_EVALT_Q / 32; ++k) {
+      const int q = q0 + 32 * k + tx;
+      if (q < nq) __stcs(out + c * nq + q, tile[32 * k + tx][cc]);
+    }
   }
 }
 
@@ -572,7 +588,7 @@ static int spline_eval_impl(const cpf_spline* sp, const double* xq, int nq, int 
   if (nq == 0 || sp->ncols == 0) return CPF_OK;
   if (!xq || !out) return fail(CPF_EINVAL, "cpf_spline_eval: null buffer");
   if (!transposed && nq > 65535) return fail(CPF_EUNSUPPORTED, "cpf_spline_eval: more than 65535 query points in one call");
-  if (transposed && (nq + 31) / 32 > 65535) return fail(CPF_EUNSUPPORTED, "cpf_spline_eval_t: more than 2 M query points in one call");
+  if (transposed && (nq + 31) / 32 > 65535) return fail(CPF_EUNSUPPORTED, "cpf_spline_eval_t: more than 2 M query points in one call");   // (grid.y has room for four times that)
   DeviceGuard guard(sp->device);
   cudaStream_t stream = (cudaStream_t)stream_;
   const size_t cells = (size_t)nq * (size_t)sp->ncols;
@@ -592,7 +608,7 @@ static int spline_eval_impl(const cpf_spline* sp, const double* xq, int nq, int 
   spline_query_kernel<<<(nq + 127) / 128, 128, 0, stream>>>(sp->d_x, sp->nx, d_xq, nq, sp->extrap, sp->log_x, sp->xmin_raw, sp->xmax_raw,
                                                           (double*)qx.p, (int*)qi.p);
   if (transposed) {
-    dim3 grid((unsigned)((sp->ncols + 31) / 32), (unsigned)((nq + 31) / 32));
+    dim3 grid((unsigned)((sp->ncols + 31) / 32), (unsigned)((nq + SPLINE_EVALT_Q - 1) / SPLINE_EVALT_Q));
     spline_eval_t_kernel<<<grid, 256, 0, stream>>>(sp->d_x, sp->d_y, sp->d_s, sp->ncols, (const double*)qx.p, (const int*)qi.p, nq, nu,
                                                    sp->log_y, d_out);
   } else {
