@@ -227,6 +227,9 @@ int main() {
   run_mio<1>("LDS.128 only", sink, d_cycles);
   run_mio<8>("STS.128 only", sink, d_cycles);
   run_mio<9>("LDS.128 + STS.128", sink, d_cycles);
+  run_mio<4>("SHFL x16 only", sink, d_cycles);
+  run_mio<13>("LDS.128 + STS.128 + SHFL x16", sink, d_cycles);
+  run_mio<12>("STS.128 + SHFL x16", sink, d_cycles);
   run_mio<2>("tcgen05.ld x16 (wait each)", sink, d_cycles);
   run_mio<3>("LDS.128 + tcgen05.ld", sink, d_cycles);
   {
