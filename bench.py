@@ -701,7 +701,7 @@ def run_secondary(args):
     boxes = torch.empty((ncols, 4), dtype=torch.int32, device='cuda')
     _lib.check(lib.cpf_wallish2018_rows(klin.ctypes.data, pklin_rows.data_ptr(), 4096, kout_h.ctypes.data, pkout.data_ptr(), filt.k.size, ncols, out.data_ptr(), boxes.data_ptr(), 1, 0, stream))
     torch.cuda.synchronize()
-    sample = np.arange(0, ncols, ncols // 1024)
+    sample = np.arange(0, ncols, ncols // 4096)
     ref_s, dbg_s = WO.wallish2018(klin, pklin[:, sample].cpu().numpy(), filt.k, pkout[:, sample].cpu().numpy(), return_debug=True)
     mism = np.any(boxes.cpu().numpy()[sample] != dbg_s['boxes'], axis=1)
     perr = np.abs(out[:, sample].cpu().numpy() / ref_s - 1.)
