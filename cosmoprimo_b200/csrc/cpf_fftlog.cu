@@ -21,7 +21,10 @@
 #include <stdlib.h>
 #include <string.h>
 #include <atomic>
+#include <condition_variable>
+#include <deque>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 #include "cpf_common.h"
@@ -515,9 +518,14 @@ cudaMemPool_t scratch_pool(int device) {
   return pool;
 }
 
+// One-time table upload.  cudaMemcpy from pageable memory returns once the data sits in the driver's staging buffer: the DMA into *dptr
+// may still be in flight on the legacy stream, and the kernels that read the table run on non-blocking streams (the staging pool's, the
+// caller's), which do not wait for it.  So the legacy stream is drained before the table is handed out (r4o: the first chunks of a
+// host-buffer call read a table that had not landed yet, once the host side stopped being slow enough to hide it).
 int upload(void** dptr, const void* src, size_t bytes) {
   CPF_CUDA(cudaMalloc(dptr, bytes ? bytes : 1));
   CPF_CUDA(cudaMemcpy(*dptr, src, bytes, cudaMemcpyHostToDevice));
+  CPF_CUDA(cudaStreamSynchronize(cudaStreamLegacy));
   return CPF_OK;
 }
 
@@ -696,6 +704,8 @@ struct StagePool {
   cudaEvent_t out_free[kNumStage];  // D2H of buffer i finished
   cudaEvent_t start;
   std::mutex busy;                  // host-pointer calls on one device are serialised
+  void* h_bounce[kNumStage] = {};   // page-locked bounce buffers for pageable input (HostCopyPool), grown on demand
+  size_t h_bounce_bytes = 0;
 };
 static std::mutex g_stage_mutex;
 static std::vector<StagePool*> g_stage_pools;
@@ -985,6 +995,7 @@ static int ticket_acquire(int device, TicketLease* lease, bool* ok) {
     CPF_CUDA(cudaMemset(ring->counters, 0, (size_t)kTicketSlots * kTicketSlotWords * sizeof(unsigned)));
     CPF_CUDA(cudaMalloc(&ring->finished, kTicketSlots * sizeof(unsigned)));
     CPF_CUDA(cudaMemset(ring->finished, 0, kTicketSlots * sizeof(unsigned)));
+    CPF_CUDA(cudaStreamSynchronize(cudaStreamLegacy));      // the memsets run on the legacy stream, the kernels on non-blocking ones
     CPF_CUDA(cudaHostAlloc(&host, kTicketSlots * sizeof(unsigned), cudaHostAllocMapped | cudaHostAllocPortable));
     memset(host, 0, kTicketSlots * sizeof(unsigned));
     ring->done_host = static_cast<volatile unsigned*>(host);
@@ -1349,6 +1360,66 @@ static bool pinned_device_pointer(const void* host, void** dev) {
   return true;
 }
 
+// Pageable host input (an ordinary numpy array): cudaMemcpyAsync stages such memory through the driver's own bounce buffer on the calling
+// thread at ~10 GB/s and blocks while it does.  Instead a few persistent worker threads copy every chunk, in slices, into page-locked
+// buffers of the staging pool one chunk ahead of its H2D copy (CPF_HOST_THREADS, default 8, 0 = let the driver do it).
+static bool is_pageable_host(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return true; }
+  return at.type == cudaMemoryTypeUnregistered;
+}
+struct HostCopyPool {
+  struct Job { char* dst; const char* src; size_t bytes; std::atomic<int>* pending; };
+  std::mutex m;
+  std::condition_variable cv, done;
+  std::deque<Job> q;
+  int nthreads = 0;
+  void worker() {
+    for (;;) {
+      Job j;
+      {
+        std::unique_lock<std::mutex> lock(m);
+        cv.wait(lock, [&] { return !q.empty(); });
+        j = q.front();
+        q.pop_front();
+      }
+      memcpy(j.dst, j.src, j.bytes);
+      if (j.pending->fetch_sub(1) == 1) {
+        std::lock_guard<std::mutex> lock(m);
+        done.notify_all();
+      }
+    }
+  }
+  // copy `bytes` in up to nthreads slices; *pending counts the slices still running
+  void submit(char* dst, const char* src, size_t bytes, std::atomic<int>* pending) {
+    const size_t slice = ((bytes + nthreads - 1) / nthreads + 4095) & ~(size_t)4095;
+    int n = 0;
+    for (size_t o = 0; o < bytes; o += slice) ++n;
+    pending->store(n);
+    std::lock_guard<std::mutex> lock(m);
+    for (size_t o = 0; o < bytes; o += slice) q.push_back({dst + o, src + o, bytes - o < slice ? bytes - o : slice, pending});
+    cv.notify_all();
+  }
+  void wait(std::atomic<int>* pending) {
+    std::unique_lock<std::mutex> lock(m);
+    done.wait(lock, [&] { return pending->load() == 0; });
+  }
+};
+static HostCopyPool* host_copy_pool() {          // created on first use, lives until the process exits (the workers are detached)
+  static HostCopyPool* pool = [] {
+    const char* e = getenv("CPF_HOST_THREADS");
+    int n = e ? atoi(e) : 8;
+    const int hw = (int)std::thread::hardware_concurrency();
+    if (hw > 0 && n > hw) n = hw;
+    if (n <= 0) return (HostCopyPool*)nullptr;
+    HostCopyPool* p = new HostCopyPool();
+    p->nthreads = n;
+    for (int i = 0; i < n; ++i) std::thread([p] { p->worker(); }).detach();
+    return p;
+  }();
+  return pool;
+}
+
 // Chunk sizes (rows) of a staged host-pointer call: small chunks at both ends so that the pipeline fills and drains
 // quickly (the first H2D and the last D2H are not overlapped with anything), `cap`-sized chunks in the middle where
 // per-chunk overheads matter.  Every chunk but the last has an even number of rows.
@@ -1428,11 +1499,51 @@ static int run_staged(int device, const double* in, size_t in_row_doubles, doubl
   CPF_CUDA(cudaStreamWaitEvent(sp->d2h, sp->start, 0));
   int rc = CPF_OK;
   long long first = 0;
+  // pageable input: worker threads fill page-locked bounce buffers one chunk ahead (see HostCopyPool)
+  HostCopyPool* hpool = (!in_dev && rows * (long long)in_row_doubles * 8 >= (4LL << 20) && is_pageable_host(in)) ? host_copy_pool() : nullptr;
+  std::atomic<int> bounce_pending[kNumStage];
+  std::vector<long long> chunk_first(sched.size() + 1, 0);
+  for (size_t c = 0; c < sched.size(); ++c) chunk_first[c + 1] = chunk_first[c] + sched[c];
+  if (hpool) {
+    const size_t need = (size_t)buf_rows * in_row_doubles * sizeof(double);
+    if (sp->h_bounce_bytes < need) {
+      for (int i = 0; i < kNumStage; ++i) { if (sp->h_bounce[i]) cudaFreeHost(sp->h_bounce[i]); sp->h_bounce[i] = nullptr; }
+      sp->h_bounce_bytes = 0;
+      bool ok = true;
+      for (int i = 0; i < max_buf && ok; ++i) ok = cudaHostAlloc(&sp->h_bounce[i], need, cudaHostAllocPortable) == cudaSuccess;
+      if (ok) sp->h_bounce_bytes = need;
+      else { cudaGetLastError(); hpool = nullptr; }        // no page-locked memory to spare: the driver stages the copies
+    }
+  }
+  auto bounce_fill = [&](const size_t c) -> cudaError_t {   // start copying chunk c into its bounce buffer
+    const int i = (int)(c % nbuf);
+    if (c >= (size_t)nbuf) {                                 // the H2D copy of chunk c - nbuf has left the buffer
+      const cudaError_t e = cudaEventSynchronize(sp->in_ready[i]);
+      if (e != cudaSuccess) return e;
+    }
+    hpool->submit((char*)sp->h_bounce[i], (const char*)(in + (size_t)chunk_first[c] * in_row_doubles), (size_t)sched[c] * in_row_doubles * sizeof(double),
+                  &bounce_pending[i]);
+    return cudaSuccess;
+  };
+  if (hpool) {
+    const cudaError_t e = bounce_fill(0);
+    if (e != cudaSuccess) rc = fail(CPF_ECUDA, "event sync: %s", cudaGetErrorString(e));
+  }
   for (size_t c = 0; c < sched.size() && rc == CPF_OK; ++c) {
     const int i = (int)(c % nbuf);
     const bool reused = c >= (size_t)nbuf;
     const long long cnt = sched[c];
     const double* src = in + (size_t)first * in_row_doubles;
+    if (hpool) {
+      // the next chunk goes into its bounce buffer while this one crosses the link (one buffer only: this chunk, now)
+      const size_t ahead = nbuf > 1 ? c + 1 : c;
+      if (ahead > 0 && ahead < sched.size()) {
+        const cudaError_t e = bounce_fill(ahead);
+        if (e != cudaSuccess) { rc = fail(CPF_ECUDA, "event sync: %s", cudaGetErrorString(e)); break; }
+      }
+      hpool->wait(&bounce_pending[i]);
+      src = (const double*)sp->h_bounce[i];
+    }
     double* dst = out_base + (size_t)first * out_row_doubles;
     const double* d_in = src;
     double* d_out = dst;
