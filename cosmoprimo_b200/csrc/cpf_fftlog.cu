@@ -1464,6 +1464,31 @@ static int run_staged(int device, const double* in, size_t in_row_doubles, doubl
   CPF_TRY(stage_pool(device, &sp));
   std::lock_guard<std::mutex> lock(sp->busy);
   const size_t row_bytes = (in_row_doubles > out_row_doubles ? in_row_doubles : out_row_doubles) * sizeof(double);
+  // Small calls (a single transform, the reference's configs[0]): nothing to overlap, so no chunks, events or copy streams: copy in,
+  // run, copy out on one stream: a third of the API calls of the pipelined path (83 -> ~50 us for one nk = 1024 transform from Python).
+  if ((size_t)rows * row_bytes <= (256u << 10) && !host_direct_out_enabled()) {
+    ScratchBuf din1, dout1;
+    const double* d_in = in;
+    double* d_out = out;
+    const size_t in_bytes = (size_t)rows * in_row_doubles * sizeof(double), out_bytes = (size_t)rows * out_row_doubles * sizeof(double);
+    if (!in_dev) {
+      CPF_CUDA(din1.alloc(in_bytes, sp->comp));
+      CPF_CUDA(cudaMemcpyAsync(din1.p, in, in_bytes, cudaMemcpyHostToDevice, sp->comp));
+      d_in = (const double*)din1.p;
+    }
+    if (!out_dev) {
+      CPF_CUDA(dout1.alloc(out_bytes, sp->comp));
+      d_out = (double*)dout1.p;
+    }
+    if (in_dev || out_dev) {                      // one side lives on the caller's stream: order the internal stream after / before it
+      CPF_CUDA(cudaEventRecord(sp->start, user_stream));
+      CPF_CUDA(cudaStreamWaitEvent(sp->comp, sp->start, 0));
+    }
+    CPF_TRY(body(0LL, rows, d_in, d_out, sp->comp));
+    if (!out_dev) CPF_CUDA(cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, sp->comp));
+    CPF_CUDA(cudaStreamSynchronize(sp->comp));
+    return CPF_OK;
+  }
   // tuning knobs (bytes / count): CPF_STAGE_CAP_KB (largest chunk), CPF_STAGE_SMALL_KB (first and last chunk), CPF_STAGE_NBUF
   size_t cap_bytes = 16u << 20, small_bytes = 1u << 20;
   int max_buf = 4;

@@ -456,6 +456,19 @@ class FFTlog(object):
 
 # -- device plan, built lazily and re-validated against the (public, mutable) tables on every call ------------------
 
+def _probe(t):
+    """Bytes of 16 values spread over a table (first and last included): the cheap fingerprint of the per-call re-validation."""
+    flat = t.reshape(-1)
+    n = flat.size
+    idx = _PROBE_IDX.get(n)
+    if idx is None:
+        idx = _PROBE_IDX[n] = np.linspace(0, n - 1, 16).astype('i8') if n > 16 else np.arange(n)
+    return flat[idx].tobytes() + t.dtype.char.encode()
+
+
+_PROBE_IDX = {}
+
+
 def _device_plan_for(self, device):
     """
     The tables are public attributes that subclasses rescale after the engine exists (ref:117 then 280, 319, 330,
@@ -468,15 +481,15 @@ def _device_plan_for(self, device):
     entry = self._dev_plans.get(device, None)
     if entry is not None:
         snap, dplan, seen = entry
-        # fast path (a deep comparison of the three (P, N) tables costs as much as a small transform): the same array objects as at the
-        # last validation and an unchanged 1-in-8 sample of their values (whole-array rescalings, the way subclasses and inv() modify the
-        # tables, always show up in it); anything else goes through the deep comparison below
-        if all(a is b for a, b in zip(seen, (self.padded_prefactor, self.padded_u, self.padded_postfactor))) and \
-                all(s.shape == t.shape and s.dtype == t.dtype and np.array_equal(s[..., ::8], t[..., ::8]) and np.array_equal(s[..., -1], t[..., -1])
-                    for s, t in zip(snap, (pre, u, post))):
+        # fast path (a deep comparison of the three (P, N) tables costs as much as a small transform, a 1-in-8 sample a third of a
+        # single-transform call): the same array objects as at the last validation and 16 unchanged probe values per table (whole-array
+        # rescalings, the way subclasses and inv() modify the tables, show up in every one of them); anything else goes through the deep
+        # comparison below
+        if all(a is b for a, b in zip(seen[:3], (self.padded_prefactor, self.padded_u, self.padded_postfactor))) and \
+                all(t.shape == s.shape and _probe(t) == pb for s, t, pb in zip(snap, (pre, u, post), seen[3])):
             return dplan
         if all(s.shape == t.shape and s.dtype == t.dtype and np.array_equal(s, t) for s, t in zip(snap, (pre, u, post))):
-            self._dev_plans[device] = (snap, dplan, (self.padded_prefactor, self.padded_u, self.padded_postfactor))
+            self._dev_plans[device] = (snap, dplan, (self.padded_prefactor, self.padded_u, self.padded_postfactor, tuple(_probe(t) for t in (pre, u, post))))
             return dplan
     P, N = self.x.shape[0], self.padded_size
     if pre.shape != (P, N) or post.shape != (P, N) or u.shape != (P, N // 2 + 1):
@@ -487,7 +500,7 @@ def _device_plan_for(self, device):
         raise TypeError('complex padded_prefactor (inv() of a complex=True transform) is not supported: the real-input FFT of the reference '
                         '(numpy.fft.rfft, ref fftlog.py:540) rejects it as well')
     snap, dplan = _shared_device_plan(self.x.shape[-1], N, P, self.padded_size_in_left, self.padded_size_out_left, pre, u, post, device)
-    self._dev_plans[device] = (snap, dplan, (self.padded_prefactor, self.padded_u, self.padded_postfactor))
+    self._dev_plans[device] = (snap, dplan, (self.padded_prefactor, self.padded_u, self.padded_postfactor, tuple(_probe(t) for t in (pre, u, post))))
     return dplan
 
 
