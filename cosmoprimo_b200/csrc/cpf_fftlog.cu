@@ -20,6 +20,7 @@
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 #include <atomic>
 #include <condition_variable>
 #include <deque>
@@ -1409,17 +1410,25 @@ struct HostCopyPool {
   }
 };
 static HostCopyPool* host_copy_pool() {          // created on first use, lives until the process exits (the workers are detached)
-  static HostCopyPool* pool = [] {
+  static std::mutex mu;
+  static HostCopyPool* pool = nullptr;
+  static long owner = -1;                         // threads do not survive fork(): a child process makes its own pool
+  std::lock_guard<std::mutex> lock(mu);
+  const long me = (long)getpid();
+  if (owner != me) {
+    owner = me;
+    pool = nullptr;
     const char* e = getenv("CPF_HOST_THREADS");
     int n = e ? atoi(e) : 8;
     const int hw = (int)std::thread::hardware_concurrency();
     if (hw > 0 && n > hw) n = hw;
-    if (n <= 0) return (HostCopyPool*)nullptr;
-    HostCopyPool* p = new HostCopyPool();
-    p->nthreads = n;
-    for (int i = 0; i < n; ++i) std::thread([p] { p->worker(); }).detach();
-    return p;
-  }();
+    if (n > 0) {
+      HostCopyPool* p = new HostCopyPool();
+      p->nthreads = n;
+      for (int i = 0; i < n; ++i) std::thread([p] { p->worker(); }).detach();
+      pool = p;
+    }
+  }
   return pool;
 }
 
