@@ -293,6 +293,45 @@ def test_wallish_filter_class_uses_rows_for_own_interpolators():
     assert np.array_equal(filt2._boxes, ref2._boxes) and np.max(np.abs(filt2.pknow / ref2.pknow - 1.)) < 1e-12
 
 
+def test_new_entry_points_reject_bad_input():
+    """Error behaviour of the round-2 entry points through the C ABI: bad knots / misaligned rows / null buffers give CPF_EINVAL (ValueError in
+    the Python layer), never a crash."""
+    torch = pytest.importorskip('torch')
+    lib = _lib.load()
+    y = np.abs(np.random.default_rng(0).standard_normal((8, 3))) + 1.
+    flags = np.zeros(3, dtype='u1')
+    handle = ctypes.c_void_p()
+    x_bad = np.array([1e-7, 1e-6, 1., 2., 3., 2.5, 5., 6., 7., 8., 9., 1e2])          # 8 + 4 knots, not increasing
+    with pytest.raises(ValueError):
+        _lib.check(lib.cpf_spline_create_padlog(ctypes.byref(handle), x_bad.ctypes.data, y.ctypes.data, 8, 3, 0, flags.ctypes.data, 0, 0, None))
+    x_neg = np.array([-1., 1e-6, 1., 2., 3., 4., 5., 6., 7., 8., 9., 1e2])
+    with pytest.raises(ValueError):
+        _lib.check(lib.cpf_spline_create_padlog(ctypes.byref(handle), x_neg.ctypes.data, y.ctypes.data, 8, 3, 0, flags.ctypes.data, 0, 0, None))
+    with pytest.raises(ValueError):
+        _lib.check(lib.cpf_spline_create_padlog(ctypes.byref(handle), x_neg.ctypes.data, None, 8, 3, 0, flags.ctypes.data, 0, 0, None))
+    assert not handle.value
+    # NaN screening on a device table: all-NaN column -> 1, partly NaN -> 2, clean -> 0; negative counts as NaN only with the log rule
+    t = torch.from_numpy(y.copy()).cuda()
+    t[:, 0] = float('nan'); t[2, 1] = -1.
+    _lib.check(lib.cpf_column_nan_flags(t.data_ptr(), 8, 3, 1, flags.ctypes.data, 0, torch.cuda.current_stream().cuda_stream))
+    assert flags.tolist() == [1, 2, 0]
+    _lib.check(lib.cpf_column_nan_flags(t.data_ptr(), 8, 3, 0, flags.ctypes.data, 0, torch.cuda.current_stream().cuda_stream))
+    assert flags.tolist() == [1, 0, 0]
+    # rows entry of the Wallish2018 filter: misaligned rows pointer, non-increasing grid
+    d = load_golden('wallish_golden.npz').data
+    klin, kout = np.ascontiguousarray(d['w0_klin']), np.ascontiguousarray(d['w0_kout'])
+    rows = np.ascontiguousarray(np.concatenate([[0.], d['w0_pklin'][:, 0]]))               # rows[1:] is 8 bytes off a 16-byte boundary
+    pkout, out = np.ascontiguousarray(d['w0_pkout'][:, :1]), np.empty((kout.size, 1))
+    assert rows[1:].ctypes.data % 16 == 8
+    rows_d = torch.from_numpy(rows).cuda()
+    pk_d, out_d = torch.from_numpy(pkout).cuda(), torch.from_numpy(out).cuda()
+    with pytest.raises(ValueError):
+        _lib.check(lib.cpf_wallish2018_rows(klin.ctypes.data, rows_d.data_ptr() + 8, 4096, kout.ctypes.data, pk_d.data_ptr(), kout.size, 1, out_d.data_ptr(), None, 1, 0, None))
+    kbad = klin.copy(); kbad[100] = kbad[99]
+    with pytest.raises(ValueError):
+        _lib.check(lib.cpf_wallish2018_rows(kbad.ctypes.data, rows_d.data_ptr(), 4096, kout.ctypes.data, pk_d.data_ptr(), kout.size, 1, out_d.data_ptr(), None, 1, 0, None))
+
+
 def test_dst_matches_scipy():
     """cpf_dst == scipy.fftpack.dst / idst (type 2, ortho, axis 0) that the reference calls (bao_filter.py:372, 412)."""
     from scipy import fftpack
