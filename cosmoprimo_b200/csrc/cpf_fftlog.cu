@@ -1240,6 +1240,11 @@ static int launch_pp8k(const cpf_plan* pl, const FftlogArgs& a, cudaStream_t str
   cfg.numAttrs = (pdl_env && pdl_env[0] == '0') ? 0 : 1;
   FftlogArgs b = a;
   b.tickets = nullptr;
+  // phase offset between the two chains of a pair: chain 1 idles this long after the barrier that follows the input, so that its
+  // shared-memory phases fall on chain 0's fp64 phases instead of on its shared-memory phases (r5b/r5c: 0 ns 26.07, 400 ns 26.38, 800 ns
+  // 26.72, 1600 ns 26.61, 2400 ns 25.16 M transforms/s); CPF_PP8K_SKEW_NS overrides
+  b.ahead = 800;
+  if (const char* e = getenv("CPF_PP8K_SKEW_NS")) b.ahead = atoi(e);
   CPF_CUDA(cudaLaunchKernelEx(&cfg, kern, b, (const double2*)pl->d_pp8k, pl->d_tw2_256, pl->d_tw8192));
   return CPF_OK;
 }

@@ -14,6 +14,8 @@
 //   * each chain is the ping-pong kernel's register FFT (cpf_fft_core.h) on the group's own exchange buffer with group barriers; the
 //     groups meet three times per pair: after the input is in registers (the staging buffer is refilled), and around the exchange of
 //     the chain results (group 0 finishes output rows 0..7, group 1 rows 8..15);
+//   * the chains run the same phases, so chain 1 is held back by 0.8 us after the first of those meetings: its shared-memory phases then fall
+//     on chain 0's fp64 phases (+2.5 %);
 //   * programmatic dependent launch and non-finite handling as in the other persistent kernels.
 #pragma once
 
@@ -199,6 +201,7 @@ __global__ void __launch_bounds__(512, 1) fftlog_pp8k_kernel(const FftlogArgs a,
       // ---- FFT #1 ----
       pass1(v);
       const bool row_a_bad = __syncthreads_or(bad_a);                     // every thread has its samples in registers
+      if (a.ahead > 0 && g == 1) __nanosleep((unsigned)a.ahead);          // phase offset between the two chains (launch_pp8k)
       if (TMA && threadIdx.x == 0 && pair + stride < a.pairs_per_p) stage_rows(p, pair + stride);
       pass2();
       const bool row_b_bad = named_sync_or(1 + g, T, bad_b);              // both groups loaded the same rows: the same flags in both
