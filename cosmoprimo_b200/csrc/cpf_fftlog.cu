@@ -1093,11 +1093,14 @@ static int launch_stream(const cpf_plan* pl, const FftlogArgs& a, cudaStream_t s
   // the shared-memory pipe, and later the fp64 pipe, at the same moments.  Warps 4..7 of a group (the second warp of each sub-partition) idle
   // 250 ns after the SECOND group barrier of a pair, which takes them out of step (r5f-r5h: 78.2 -> 79.8 M transforms/s over 200 launches,
   // 77.0 -> 77.8 M over 20; 150-500 ns all give this, 550 ns and more lose; after the first barrier instead: +0.4 %).
-  // CPF_STREAM_WSKEW2_NS / CPF_STREAM_WSKEW_NS (first barrier) / CPF_STREAM_WSKEW_MASK (which warps: warp index & mask) override.
-  s.wskew_ns = 0;
+  // CPF_STREAM_WSKEW2_NS / CPF_STREAM_WSKEW_NS (first barrier) / CPF_STREAM_WSKEW_INV (first barrier: the other warps) /
+  // CPF_STREAM_WSKEW_MASK (which warps: warp index & mask) override.
+  s.wskew_ns = 300;          // ... and warps 0..3 idle 300 ns after the FIRST group barrier (the other half: r5o/r5p, another +0.6 %)
   if (const char* e = getenv("CPF_STREAM_WSKEW_NS")) s.wskew_ns = atoi(e);
   s.wskew_mask = 4;
   if (const char* e = getenv("CPF_STREAM_WSKEW_MASK")) s.wskew_mask = atoi(e);
+  s.wskew_inv = 1;
+  if (const char* e = getenv("CPF_STREAM_WSKEW_INV")) s.wskew_inv = atoi(e);
   s.wskew2_ns = 250;
   if (const char* e = getenv("CPF_STREAM_WSKEW2_NS")) s.wskew2_ns = atoi(e);
 #ifdef CPF_LAB

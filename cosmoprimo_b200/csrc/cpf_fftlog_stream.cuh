@@ -96,9 +96,10 @@ struct StreamArgs {
   int off_in, off_out;      // N/4 - in_left, N/4 - out_left
   int lines;                // 128-byte lines per input row
   long long* dbg;           // lab builds: per-CTA time stamps (globaltimer ns), else null
+  int wskew_inv;            // ... the first-barrier offset applies to the OTHER warps (default)
   int wskew_mask;           // phase offset inside a group (launch_stream): warps with (warp index & mask) != 0 idle ...
   int wskew2_ns;            // ... this long after the second group barrier of a pair (default 250 ns)
-  int wskew_ns;             // ... and this long after the first (default 0)
+  int wskew_ns;             // ... and this long after the first (default 300 ns, on the other warps)
   int skew_ns;              // lab builds: group 1 starts its first pair this much later (phase offset between the groups)
   unsigned* tickets;        // dynamic scheduling (TMA variant, grid >= P): one self-resetting ticket counter per plan row, else null
   unsigned* t_finished;     // ... with the slot's CTA exit counter and completion word (ticket_release, cpf_fftlog.cu)
@@ -341,7 +342,7 @@ __global__ void __launch_bounds__(512, 1) fftlog_stream_kernel(const StreamArgs 
         st_p1(tau, v8, S, tb);
       }
       if (!(ABL & 1)) row_a_bad = named_sync_or(1 + g, T, bad_a);
-      if (a.wskew_ns > 0 && (warp & a.wskew_mask)) __nanosleep((unsigned)a.wskew_ns);
+      if (a.wskew_ns > 0 && ((warp & a.wskew_mask) != 0) != (a.wskew_inv != 0)) __nanosleep((unsigned)a.wskew_ns);
       if (TMA && tau == 0) {                                                  // every thread of the group has its samples in registers
         if (dynamic) {
           const int tn = st_draw_ticket(a.tickets + p, ticket_wrap);
