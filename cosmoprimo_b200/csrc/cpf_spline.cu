@@ -17,6 +17,7 @@
 
 #include "cpf_common.h"
 #include "cpf_spline_core.h"
+#include "cpf_fastmath.h"
 
 namespace cpf {
 
@@ -51,7 +52,7 @@ void spline_factor_host(const double* x, const int nx, const int bc, double* fac
 // optional log10 of the abscissae / ordinates (Interpolator1D's interp_x='log' / interp_fun='log', jax.py:152-153)
 __global__ void log10_kernel(const double* __restrict__ in, double* __restrict__ out, const long long count, const int apply) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (i < count) out[i] = apply ? log10(in[i]) : in[i];
+  if (i < count) out[i] = apply ? fast_log10(in[i]) : in[i];
 }
 
 
@@ -69,12 +70,12 @@ __global__ void __launch_bounds__(128) padlog_kernel(const double* __restrict__ 
   int bad = 0;
 #pragma unroll 4
   for (int i = r0; i < r1; ++i) {
-    const double v = log10(__ldcs(y + (long long)i * ncols + col));
+    const double v = fast_log10(__ldcs(y + (long long)i * ncols + col));
     bad += isnan(v) ? 1 : 0;
     ly[(long long)(i + 2) * ncols + col] = v;
   }
   if (blockIdx.y == 0) {                         // continuation below the table: slope of the two lowest samples
-    const double a = log10(y[col]), b = log10(y[ncols + col]);
+    const double a = fast_log10(y[col]), b = fast_log10(y[ncols + col]);
     const double x0 = lx[2], slope = (b - a) / (lx[3] - x0);
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
@@ -84,7 +85,7 @@ __global__ void __launch_bounds__(128) padlog_kernel(const double* __restrict__ 
     }
   }
   if (blockIdx.y == gridDim.y - 1) {             // continuation above the table: slope of the two highest samples
-    const double a = log10(y[(long long)(nx - 2) * ncols + col]), b = log10(y[(long long)(nx - 1) * ncols + col]);
+    const double a = fast_log10(y[(long long)(nx - 2) * ncols + col]), b = fast_log10(y[(long long)(nx - 1) * ncols + col]);
     const double x1 = lx[nx + 1], slope = (b - a) / (x1 - lx[nx]);
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
@@ -251,7 +252,7 @@ __global__ void __launch_bounds__(128) spline_eval_kernel(const double* __restri
         have = i;
       }
       r = spline_poly(x0, x1, y0, y1, s0, s1, __ldg(qx + q), nu);
-      if (log_y) r = exp10(r);   // 10**tmp, jax.py:191
+      if (log_y) r = fast_exp10(r);   // 10**tmp, jax.py:191
     }
     __stcs(out + (long long)q * ncols + col, r);
   }
@@ -289,7 +290,7 @@ __global__ void __launch_bounds__(256) spline_eval_t_kernel(const double* __rest
           have = i;
         }
         r = spline_poly(x0, x1, y0, y1, s0, s1, __ldg(qx + q), nu);
-        if (log_y) r = exp10(r);
+        if (log_y) r = fast_exp10(r);
       }
     }
     tile[qq][tx] = r;

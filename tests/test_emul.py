@@ -34,3 +34,15 @@ def test_spline_window_weights_emulation():
         res = subprocess.run([exe], capture_output=True, text=True)
     assert res.returncode == 0, res.stdout
     assert 'OK' in res.stdout
+
+
+def test_fastmath_against_libm():
+    """cpf_fastmath.h (fast_log / fast_exp of the Wallish2018 kernel, fast_log10 / fast_exp10 of the spline kernels) against long-double libm:
+    every function < 2 ulp over 2 M arguments, special values as libm."""
+    here = os.path.dirname(os.path.abspath(__file__))
+    with tempfile.TemporaryDirectory() as tmp:
+        exe = os.path.join(tmp, 'emul_fastmath')
+        subprocess.run(['g++', '-O2', '-std=c++17', '-o', exe, os.path.join(here, 'emul', 'emul_fastmath.cpp')], check=True)
+        res = subprocess.run([exe], capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout
+    assert 'OK' in res.stdout
