@@ -211,7 +211,8 @@ __global__ void __launch_bounds__(128) spline_backward_kernel(const double* __re
 // ---- evaluation ----------------------------------------------------------------------------------------------------
 // Everything that depends on the query only -- log10 of the abscissa, bounds test, interval search -- is done once per query
 // by spline_query_kernel (it used to be repeated by every thread: ~3/4 of the instructions of an evaluation);
-// qx[q] = (transformed) abscissa, qi[q] = interval index, or -1 when the result is NaN.
+// qi[q] = interval index, or -1 when the result is NaN; qx[q] = offset of the (transformed) abscissa from the left knot of its interval,
+// qx[nq + q] = 1 / width of the interval (the one division of spline_poly: it used to be taken per column and query).
 __global__ void spline_query_kernel(const double* __restrict__ x, const int nx, const double* __restrict__ xq, const int nq,
                                     const int extrap, const int log_x, const double xmin_raw, const double xmax_raw,
                                     double* __restrict__ qx, int* __restrict__ qi) {
@@ -221,8 +222,10 @@ __global__ void spline_query_kernel(const double* __restrict__ x, const int nx, 
   // bounds are tested on the raw abscissa, before the log10 (jax.py:188-189)
   const bool inside = raw >= xmin_raw && raw <= xmax_raw;
   const double xv = log_x ? log10(raw) : raw;
-  qx[q] = xv;
-  qi[q] = ((!inside && !extrap) || !(xv == xv)) ? -1 : spline_interval(x, nx, xv);
+  const int i = ((!inside && !extrap) || !(xv == xv)) ? -1 : spline_interval(x, nx, xv);
+  qi[q] = i;
+  qx[q] = i < 0 ? 0. : xv - x[i];
+  qx[nq + q] = i < 0 ? 0. : 1. / (x[i + 1] - x[i]);
 }
 
 // out[q, col]: block = (column tile, SPLINE_EVAL_Q consecutive queries).  A thread keeps the knot values and slopes of its column while
@@ -237,21 +240,24 @@ __global__ void __launch_bounds__(128) spline_eval_kernel(const double* __restri
   const long long col = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (col >= ncols) return;
   int have = -2;
-  double x0 = 0., x1 = 0., y0 = 0., y1 = 0., s0 = 0., s1 = 0.;
+  double y1 = 0., s1 = 0.;
+  SplineCubic cub = {0., 0., 0., 0.};
   for (int q = q0; q < q1; ++q) {
     const int i = __ldg(qi + q);
     double r;
     if (i < 0) {
       r = nan("");
     } else {
-      if (i != have) {
+      if (i != have) {                                               // coefficients once per (interval, column)
         const long long o = (long long)i * ncols + col;
-        if (i == have + 1) { x0 = x1; y0 = y1; s0 = s1; }           // the next interval shares a knot
-        else { x0 = __ldg(x + i); y0 = y[o]; s0 = s[o]; }
-        x1 = __ldg(x + i + 1); y1 = y[o + ncols]; s1 = s[o + ncols];
+        double y0, s0;
+        if (i == have + 1) { y0 = y1; s0 = s1; }                     // the next interval shares a knot
+        else { y0 = y[o]; s0 = s[o]; }
+        y1 = y[o + ncols]; s1 = s[o + ncols];
+        cub = spline_coeffs(__ldg(qx + nq + q), y0, y1, s0, s1);
         have = i;
       }
-      r = spline_poly(x0, x1, y0, y1, s0, s1, __ldg(qx + q), nu);
+      r = spline_cubic_eval(cub, __ldg(qx + q), nu);
       if (log_y) r = fast_exp10(r);   // 10**tmp, jax.py:191
     }
     __stcs(out + (long long)q * ncols + col, r);
@@ -272,7 +278,8 @@ __global__ void __launch_bounds__(256) spline_eval_t_kernel(const double* __rest
   const long long col = c0 + tx;
   // a thread takes 16 consecutive queries of its column and keeps the knot values / slopes while they stay in one interval
   int have = -2;
-  double x0 = 0., x1 = 0., y0 = 0., y1 = 0., s0 = 0., s1 = 0.;
+  double y1 = 0., s1 = 0.;
+  SplineCubic cub = {0., 0., 0., 0.};
 #pragma unroll 4
   for (int j = 0; j < 16; ++j) {
     const int qq = 16 * ty + j, q = q0 + qq;
@@ -284,12 +291,14 @@ __global__ void __launch_bounds__(256) spline_eval_t_kernel(const double* __rest
       } else {
         if (i != have) {
           const long long o = (long long)i * ncols + col;
-          if (i == have + 1) { x0 = x1; y0 = y1; s0 = s1; }
-          else { x0 = __ldg(x + i); y0 = y[o]; s0 = s[o]; }
-          x1 = __ldg(x + i + 1); y1 = y[o + ncols]; s1 = s[o + ncols];
+          double y0, s0;
+          if (i == have + 1) { y0 = y1; s0 = s1; }
+          else { y0 = y[o]; s0 = s[o]; }
+          y1 = y[o + ncols]; s1 = s[o + ncols];
+          cub = spline_coeffs(__ldg(qx + nq + q), y0, y1, s0, s1);
           have = i;
         }
-        r = spline_poly(x0, x1, y0, y1, s0, s1, __ldg(qx + q), nu);
+        r = spline_cubic_eval(cub, __ldg(qx + q), nu);
         if (log_y) r = fast_exp10(r);
       }
     }
@@ -604,7 +613,7 @@ static int spline_eval_impl(const cpf_spline* sp, const double* xq, int nq, int 
     d_out = (double*)dout.p;
   }
   ScratchBuf qx, qi;
-  CPF_CUDA(qx.alloc(nq * sizeof(double), stream));
+  CPF_CUDA(qx.alloc(2 * (size_t)nq * sizeof(double), stream));
   CPF_CUDA(qi.alloc(nq * sizeof(int), stream));
   spline_query_kernel<<<(nq + 127) / 128, 128, 0, stream>>>(sp->d_x, sp->nx, d_xq, nq, sp->extrap, sp->log_x, sp->xmin_raw, sp->xmax_raw,
                                                           (double*)qx.p, (int*)qi.p);

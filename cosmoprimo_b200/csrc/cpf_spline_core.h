@@ -99,6 +99,23 @@ CPF_SHD double spline_poly(const double x0, const double x1, const double y0, co
 }
 
 
+// The same polynomial in two steps, for kernels that evaluate many points per interval: the coefficients once per (interval, column) from
+// idx = 1 / (x1 - x0) (a property of the interval: computed once per query point, not per column), then a Horner step per point at d = xv - x0.
+struct SplineCubic { double c0, c1, c2, c3; };
+CPF_SHD SplineCubic spline_coeffs(const double idx, const double y0, const double y1, const double s0, const double s1) {
+  const double m = (y1 - y0) * idx;
+  const double t = (s0 + s1 - 2. * m) * idx;
+  SplineCubic c;
+  c.c0 = t * idx; c.c1 = (m - s0) * idx - t; c.c2 = s0; c.c3 = y0;
+  return c;
+}
+CPF_SHD double spline_cubic_eval(const SplineCubic& c, const double d, const int nu) {
+  if (nu == 0) return c.c3 + d * (c.c2 + d * (c.c1 + d * c.c0));
+  if (nu == 1) return c.c2 + d * (2. * c.c1 + d * 3. * c.c0);
+  if (nu == 2) return 2. * c.c1 + 6. * c.c0 * d;
+  return 6. * c.c0;
+}
+
 // ---- windowed evaluation weights -----------------------------------------------------------------------------------
 // The spline value at xv is linear in the ordinates: S(xv) = sum_j w_j y_j.  The slope system is strictly diagonally
 // dominant, so the influence of y_j on the slopes of the interval [x_i, x_{i+1}] holding xv decays like (2-sqrt 3)^|i-j|
