@@ -1101,6 +1101,8 @@ static int launch_stream(const cpf_plan* pl, const FftlogArgs& a, cudaStream_t s
   if (const char* e = getenv("CPF_STREAM_WSKEW_MASK")) s.wskew_mask = atoi(e);
   s.wskew_inv = 1;
   if (const char* e = getenv("CPF_STREAM_WSKEW_INV")) s.wskew_inv = atoi(e);
+  s.early = 1;
+  if (const char* e = getenv("CPF_STREAM_EARLY")) s.early = atoi(e);
   s.wskew2_ns = 250;
   if (const char* e = getenv("CPF_STREAM_WSKEW2_NS")) s.wskew2_ns = atoi(e);
 #ifdef CPF_LAB

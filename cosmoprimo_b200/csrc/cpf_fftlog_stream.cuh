@@ -101,6 +101,7 @@ struct StreamArgs {
   int wskew2_ns;            // ... this long after the second group barrier of a pair (default 250 ns)
   int wskew_ns;             // ... and this long after the first (default 300 ns, on the other warps)
   int skew_ns;              // lab builds: group 1 starts its first pair this much later (phase offset between the groups)
+  int early;                // the first ticket is drawn and the first pair's rows are prefetched into L2 BEFORE the dependency wait (default 1)
   unsigned* tickets;        // dynamic scheduling (TMA variant, grid >= P): one self-resetting ticket counter per plan row, else null
   unsigned* t_finished;     // ... with the slot's CTA exit counter and completion word (ticket_release, cpf_fftlog.cu)
   unsigned* t_done;
@@ -296,17 +297,20 @@ __global__ void __launch_bounds__(512, 1) fftlog_stream_kernel(const StreamArgs 
     __syncthreads();
     tmem_fence_after();
     ST_STAMP(2);
-    // everything above read plan tables only; rows may have been written by the previous kernel of the stream
-    if (first_pair) asm volatile("griddepcontrol.wait;" ::: "memory");
+    // everything above read plan tables only; rows may have been written by the previous kernel of the stream.  What does not READ caller
+    // data happens before the dependency wait, while the previous grid drains: the first ticket (the counters belong to this launch) and an L2
+    // prefetch of the first pair's rows (L2 is the coherence point: a line prefetched early still shows every later write of the previous
+    // grid); the bulk copies themselves follow the wait.
+    if (first_pair && !a.early) asm volatile("griddepcontrol.wait;" ::: "memory");
     if (dynamic) {
-      if (tau == 0) {
-        const int t0 = st_draw_ticket(a.tickets + p, ticket_wrap);
-        s_next[g] = t0;
-        if (t0 < pair_hi) stage_rows(p, t0);
-      }
+      if (tau == 0) s_next[g] = st_draw_ticket(a.tickets + p, ticket_wrap);
       named_sync(1 + g, T);
       pair = s_next[g];
-    } else
+    }
+    if (first_pair && a.early) {
+      if (TMA && pair < pair_hi) prefetch_rows(p, pair);
+      asm volatile("griddepcontrol.wait;" ::: "memory");
+    }
     if (TMA && tau == 0 && pair < pair_hi) stage_rows(p, pair);     // nobody reads the staging buffer any more (barrier above)
 
     while (pair < pair_hi) {
