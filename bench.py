@@ -443,8 +443,8 @@ def run_ours(args):
         roof = {'bound': 'fp64', 'achieved': ach_tflops, 'peak': f64_tflops, 'unit': 'TFLOP/s', 'frac': ach_tflops / f64_tflops}
     else:
         roof = {'bound': 'hbm', 'achieved': ach_gbs, 'peak': hbm_gbs, 'unit': 'GB/s', 'frac': ach_gbs / hbm_gbs}
-    # DRAM bytes of one launch of the step's kernel from the committed `ncu --set full` capture (profiles/r6b_ncu_stream_kernel.txt)
-    roof.update({'traffic': 347174912, 'traffic_unit': 'bytes/launch (dram__bytes_read.sum + dram__bytes_write.sum = 201 869 568 + 145 305 344 of one launch under ncu --set full: profiles/r6b_ncu_stream_kernel.txt, cited not measured in this run)', 'kernel': 'fftlog_stream_kernel<fullwin, tma-staged rows, dynamic pairs> (CPF_FFTLOG_KERNEL=%s)' % os.environ.get('CPF_FFTLOG_KERNEL', 'auto'), 'launch_ms': 1e3 * t_launch,
+    # DRAM bytes of one launch of the step's kernel from the committed `ncu --set full` capture (profiles/r6m_ncu_stream_kernel.txt)
+    roof.update({'traffic': 346772480, 'traffic_unit': 'bytes/launch (dram__bytes_read.sum + dram__bytes_write.sum = 201 870 848 + 144 901 632 of one launch of the final kernel under ncu --set full: profiles/r6m_ncu_stream_kernel.txt, cited not measured in this run)', 'kernel': 'fftlog_stream_kernel<fullwin, tma-staged rows, dynamic pairs> (CPF_FFTLOG_KERNEL=%s)' % os.environ.get('CPF_FFTLOG_KERNEL', 'auto'), 'launch_ms': 1e3 * t_launch,
                  'algorithmic_flops_per_launch': per_step * FLOPS_PER_TRANSFORM, 'algorithmic_bytes_per_launch': per_step * BYTES_PER_TRANSFORM,
                  'peak_source': 'fp64: DFMA microbenchmark in this run (cpf_measure_fp64_peak); hbm: ' + hbm_src,
                  'hbm': {'achieved': ach_gbs, 'peak': hbm_gbs, 'unit': 'GB/s', 'frac': ach_gbs / hbm_gbs},
