@@ -77,6 +77,25 @@ int main() {
     }
   }
   printf("worst relative error %.3e\n", worst);
+  // the evaluation kernels' two-step form (spline_coeffs once per interval and column, spline_cubic_eval per point, with the interval's
+  // reciprocal width from spline_query_kernel) against spline_poly: the same arithmetic, value and three derivatives
+  {
+    double worst2 = 0.;
+    unsigned long long st = 88172645463325252ull;
+    auto rnd = [&]() { st ^= st << 13; st ^= st >> 7; st ^= st << 17; return (double)(st >> 11) / 9007199254740992.; };
+    for (int it = 0; it < 200000; ++it) {
+      const double x0 = -3. + 6. * rnd(), x1 = x0 + 1e-3 + rnd(), y0 = -5. + 10. * rnd(), y1 = y0 + rnd() - 0.5, s0 = 4. * rnd() - 2., s1 = 4. * rnd() - 2.;
+      const double xv = x0 + (x1 - x0) * (1.4 * rnd() - 0.2);
+      const SplineCubic c = spline_coeffs(1. / (x1 - x0), y0, y1, s0, s1);
+      for (int nu = 0; nu < 4; ++nu) {
+        const double a = spline_poly(x0, x1, y0, y1, s0, s1, xv, nu), b = spline_cubic_eval(c, xv - x0, nu);
+        const double err = fabs(a - b) / fmax(fabs(a), 1e-300);
+        if (err > worst2) worst2 = err;
+        if (!(a == b || err < 1e-15)) { ++bad; if (bad < 10) printf("two-step evaluation: nu %d %.17g vs %.17g\n", nu, a, b); }
+      }
+    }
+    printf("two-step evaluation against spline_poly: worst relative difference %.3e\n", worst2);
+  }
   if (bad) { printf("FAILED %d\n", bad); return 1; }
   printf("OK\n");
   return 0;
