@@ -549,10 +549,12 @@ int cpf_spline_create_padlog(cpf_spline** out, const double* x_padded, const dou
       SP_CUDA(cudaMemsetAsync(counts.p, 0, (size_t)ncols * sizeof(int), stream));
       const dim3 grid((unsigned)((ncols + 127) / 128), (unsigned)((nx + PADLOG_ROWS - 1) / PADLOG_ROWS));
       padlog_kernel<<<grid, 128, 0, stream>>>(src_y, sp->d_x, nx, ncols, sp->d_y, (int*)counts.p);
-      SP_CUDA(cudaMemcpyAsync(h_counts.data(), counts.p, (size_t)ncols * sizeof(int), cudaMemcpyDeviceToHost, stream));
     }
-    // NaN columns propagate through their own (independent) solves, so the fit does not wait for the flags
+    // NaN columns propagate through their own (independent) solves, so the fit does not wait for the flags; the copy of the counts into
+    // pageable host memory blocks the host, so it is queued behind the fit kernels (it used to sit between the logarithms and the fit and
+    // left the device idle while the host came back to launch them)
     if ((rc = spline_fit_device(sp->d_x, sp->d_y, np, ncols, 0, sp->d_s, (double*)fac.p, stream, true)) != CPF_OK) break;
+    if (ncols > 0) SP_CUDA(cudaMemcpyAsync(h_counts.data(), counts.p, (size_t)ncols * sizeof(int), cudaMemcpyDeviceToHost, stream));
     SP_CUDA(cudaStreamSynchronize(stream));     // flags for the caller; the caller's host arrays may go away
 #undef SP_CUDA
   } while (0);
